@@ -1,0 +1,345 @@
+// Fused multi-head self-attention forward on tcgen05 (sm_100a): softmax(Q K^T * scale) V with the score tile
+// held in tensor memory and never written to HBM.
+//
+// One CTA owns 128 consecutive token rows (a "query tile") of one head. For every 128-token block of keys of the
+// same sample:   S = Q K^T  (UMMA 128x128xhd, fp32 in TMEM)  ->  four softmax warps read S, one row per thread,
+// keep a running max / sum (online softmax, fp32) and write P = exp2(..) as bf16 into shared memory in the
+// swizzled K-major UMMA layout  ->  O_blk = P V (UMMA 128xhdx128, V supplied pre-transposed so both operands
+// are K-major)  ->  the softmax warps fold O_blk into per-thread fp32 output rows.
+// Samples with fewer than 128 tokens share a tile; a block-diagonal mask keeps them independent.
+//
+// Warp roles (192 threads): warps 0..3 = softmax / output rows, warp 4 = TMA producer, warp 5 = TMEM + MMA issuer.
+#include <string.h>
+
+#include "common.cuh"
+#include "host.h"
+#include "../../include/idf_b200.h"
+
+namespace idf {
+
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TMEM_COLS = 256;  // S: columns [0,128), O_blk: columns [128, 128+hd)
+
+struct AttnParams {
+  CUtensorMap tmQK;  // (M, 2C) bf16, box (SWZ/2, 128)
+  CUtensorMap tmVT;  // (C, M)  bf16, box (64, HD)
+  __nv_bfloat16* out;
+  long long ld_out;
+  int M, T, C;
+  int t_shift;     // log2(T)
+  int nblk;        // key blocks per query tile
+  int kv_stages;   // 1 or 2
+  float scale_log2e;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);  // bytes per Q/K row in shared memory
+  constexpr int QK_BYTES = 128 * SWZ;
+  constexpr int V_BYTES = 2 * HD * 128;  // two boxes of (HD rows x 64 keys)
+  constexpr int P_BYTES = 2 * 128 * 128; // two blocks of (128 rows x 64 keys)
+  constexpr int KV_BYTES = QK_BYTES + V_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_q = smem;
+  uint8_t* smem_p = smem + QK_BYTES;
+  uint8_t* smem_kv = smem_p + P_BYTES;  // [kv_stages][K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + p.kv_stages * KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x;
+  const int head = blockIdx.y;
+  const int row0 = tile_m * 128;
+  // first key row of this tile's key range
+  const int kv_base = (p.T >= 128) ? (row0 >> p.t_shift) << p.t_shift : row0;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQK);
+    tma_prefetch_desc(&p.tmVT);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, QK_BYTES);
+      tma_load_2d(smem_q, &p.tmQK, q_full, head * HD, row0);
+      for (int j = 0; j < p.nblk; ++j) {
+        const int st = j % p.kv_stages;
+        const uint32_t ph = (j / p.kv_stages) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&kv_full[st], KV_BYTES);
+        uint8_t* k_dst = smem_kv + st * KV_BYTES;
+        uint8_t* v_dst = k_dst + QK_BYTES;
+        const int kv0 = kv_base + j * 128;
+        tma_load_2d(k_dst, &p.tmQK, &kv_full[st], p.C + head * HD, kv0);
+        tma_load_2d(v_dst, &p.tmVT, &kv_full[st], kv0, head * HD);
+        tma_load_2d(v_dst + HD * 128, &p.tmVT, &kv_full[st], kv0 + 64, head * HD);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
+      const uint64_t dq = umma_desc_kmajor(smem_u32(smem_q), SWZ);
+      const uint64_t dp0 = umma_desc_kmajor(smem_u32(smem_p), 128);
+      const uint64_t dp1 = umma_desc_kmajor(smem_u32(smem_p + 128 * 128), 128);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < p.nblk; ++j) {
+        const int st = j % p.kv_stages;
+        const uint32_t ph = (j / p.kv_stages) & 1;
+        uint8_t* k_src = smem_kv + st * KV_BYTES;
+        uint8_t* v_src = k_src + QK_BYTES;
+        mbar_wait(&kv_full[st], ph);
+        if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t dk = umma_desc_kmajor(smem_u32(k_src), SWZ);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full);
+
+        mbar_wait(p_full, j & 1);
+        tc_fence_after_sync();
+        const uint64_t dv0 = umma_desc_kmajor(smem_u32(v_src), 128);
+        const uint64_t dv1 = umma_desc_kmajor(smem_u32(v_src + HD * 128), 128);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t da = (k < 4 ? dp0 : dp1) + 2 * (k & 3);
+          const uint64_t db = (k < 4 ? dv0 : dv1) + 2 * (k & 3);
+          umma_bf16(tmem_o, da, db, idesc_o, k != 0);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output (warps 0..3)
+    const int r = warp * 32 + lane;  // row of the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const long long m = (long long)row0 + r;
+    const bool masked = p.T < 128;
+    const int row_seg = r >> p.t_shift;
+    const float c = p.scale_log2e;
+
+    float o_acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+
+    for (int j = 0; j <= p.nblk; ++j) {
+      if (j > 0) {
+        // fold the previous block's P V into the running output
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int d0 = 0; d0 < HD; d0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(tmem_o + lane_addr + d0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) o_acc[d0 + d] += __uint_as_float(v[d]);
+        }
+      }
+      if (j == p.nblk) break;
+
+      mbar_wait(s_full, j & 1);
+      tc_fence_after_sync();
+
+      // pass A: row maximum over the valid keys
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        if (masked && p.T >= 32 && ((ch * 32) >> p.t_shift) != row_seg) continue;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + lane_addr + ch * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(v[i]);
+          if (masked && ((ch * 32 + i) >> p.t_shift) != row_seg) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = fast_exp2((m_run - m_new) * c);  // first block: exp2(-inf) = 0
+      const float mc = m_new * c;
+      l_run *= alpha;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) o_acc[d] *= alpha;
+      m_run = m_new;
+
+      // pass B: P = exp2(S*c - m*c) -> bf16 -> swizzled shared memory; running sum in fp32
+      float psum = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint8_t* prow = smem_p + (ch >> 1) * (128 * 128) + r * 128;
+        const bool skip = masked && p.T >= 32 && ((ch * 32) >> p.t_shift) != row_seg;
+        uint32_t v[32];
+        if (!skip) {
+          tmem_ld_32x32(tmem_s + lane_addr + ch * 32, v);
+          tmem_ld_wait();
+        }
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = 0.f;
+          if (!skip) {
+            const bool ok = !masked || (((ch * 32 + i) >> p.t_shift) == row_seg);
+            e = ok ? fast_exp2(fmaf(__uint_as_float(v[i]), c, -mc)) : 0.f;
+          }
+          pv[i] = e;
+          psum += e;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((ch & 1) * 4 + q) ^ (r & 7);
+          uint4 o;
+          o.x = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
+          o.y = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
+          o.z = pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]);
+          o.w = pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
+        }
+      }
+      l_run += psum;
+
+      // S has been consumed: the next Q K^T may overwrite it; P is ready for the P V product.
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty);
+        mbar_arrive(p_full);
+      }
+    }
+
+    if (m < p.M) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* dst = p.out + m * p.ld_out + head * HD;
+#pragma unroll
+      for (int d0 = 0; d0 < HD; d0 += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(o_acc[d0 + 0] * inv, o_acc[d0 + 1] * inv);
+        o.y = pack_bf16x2(o_acc[d0 + 2] * inv, o_acc[d0 + 3] * inv);
+        o.z = pack_bf16x2(o_acc[d0 + 4] * inv, o_acc[d0 + 5] * inv);
+        o.w = pack_bf16x2(o_acc[d0 + 6] * inv, o_acc[d0 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + d0) = o;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
+template <int HD>
+static int launch_attention(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
+  constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
+  const int smem = 128 * SWZ + 2 * 128 * 128 + p.kv_stages * (128 * SWZ + 2 * HD * 128) + 1024 + 128;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                        "attention: cudaFuncSetAttribute");
+    if (rc != IDF_OK) return rc;
+    smem_set = smem;
+  }
+  attention_kernel<HD><<<dim3(tiles, heads), ATT_THREADS, smem, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "attention launch");
+}
+
+}  // namespace idf
+
+using namespace idf;
+
+extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out,
+                                 int64_t ld_out, int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale,
+                                 idf_stream_t stream) {
+  if (!qk || !vt || !out) return fail(IDF_ERR_ARG, "attention: null pointer");
+  if (T < 16 || (T & (T - 1)) != 0) return fail(IDF_ERR_UNSUPPORTED, "attention: T = %d must be a power of two >= 16", T);
+  if (M <= 0 || M % T != 0) return fail(IDF_ERR_ARG, "attention: M = %d not a multiple of T = %d", M, T);
+  const int C = heads * head_dim;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || ld_out % 8 != 0 || head_dim % 8 != 0)
+    return fail(IDF_ERR_ARG, "attention: output alignment");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out;
+  p.M = M; p.T = T; p.C = C;
+  p.t_shift = 0;
+  while ((1 << p.t_shift) < T) ++p.t_shift;
+  p.nblk = T >= 128 ? T / 128 : 1;
+  p.kv_stages = p.nblk > 1 ? 2 : 1;
+  p.scale_log2e = scale * 1.4426950408889634f;
+
+  const int swz = head_dim <= 16 ? 32 : (head_dim <= 32 ? 64 : 128);
+  const CUtensorMapSwizzle swz_enum = swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc;
+  {
+    const uint64_t dims[2] = {(uint64_t)(2 * C), (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)ld_qk * 2};
+    const uint32_t box[2] = {(uint32_t)(swz / 2), 128u};
+    if ((rc = encode_tmap(&p.tmQK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qk, 2, dims, strides, box, swz_enum)) != IDF_OK)
+      return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)M, (uint64_t)C};
+    const uint64_t strides[1] = {(uint64_t)ld_vt * 2};
+    const uint32_t box[2] = {64u, (uint32_t)head_dim};
+    if ((rc = encode_tmap(&p.tmVT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, vt, 2, dims, strides, box,
+                          CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
+      return rc;
+  }
+  const int tiles = (M + 127) / 128;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (head_dim) {
+    case 16: return launch_attention<16>(p, tiles, heads, s);
+    case 32: return launch_attention<32>(p, tiles, heads, s);
+    case 48: return launch_attention<48>(p, tiles, heads, s);
+    case 64: return launch_attention<64>(p, tiles, heads, s);
+    default: return fail(IDF_ERR_UNSUPPORTED, "attention: head_dim %d not in {16,32,48,64}", head_dim);
+  }
+}

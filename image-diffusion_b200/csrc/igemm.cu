@@ -1,0 +1,406 @@
+// Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (sm_100a).
+//
+//   D[m, n] = sum_k A[m, k] * W[n, k]      m = pixel (n, h, w) of a channels-last activation, k = (tap, cin)
+//
+// A tiles are never materialised: for every filter tap the TMA engine fetches a (tile_n, tile_h, tile_w, 64ch)
+// box of the NHWC activation at the tap's (dh, dw) offset; coordinates that fall outside the image are
+// zero-filled by the TMA unit, which is exactly the convolution's zero padding. The box lands in shared memory
+// as 128 rows x 128 bytes with the 128-byte swizzle, i.e. the canonical K-major UMMA operand. Weights are a plain
+// 2-D (N, K) bf16 matrix. One elected thread issues tcgen05.mma (128 x BLOCK_N x 16) with the fp32 accumulator
+// in tensor memory; four epilogue warps read it back (one accumulator row per thread), fuse bias / time bias /
+// residual / padding mask, and hand a bf16 tile to a TMA store.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include <string.h>
+
+#include "common.cuh"
+#include "host.h"
+#include "../../include/idf_b200.h"
+
+namespace idf {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KiB
+constexpr int TMEM_COLS = 128;
+constexpr int IGEMM_THREADS = 192;
+constexpr int IGEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum : int { F_RES = 1, F_ZERO_PAD = 2, F_VT = 4, F_OUT_F32 = 8 };
+
+struct IgemmParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB;
+  CUtensorMap tmC;
+  CUtensorMap tmR;
+  int kb_seg0;   // k-blocks (of 64) in segment 0
+  int kb_total;  // k-blocks in both segments
+  int cb[2];     // channel blocks per tap, per segment
+  int taps[2];
+  int H, W, HW;
+  int tile_w, tile_h, tile_n;
+  int tiles_per_img;  // HW / 128 when HW >= 128, else 0
+  int matrix;         // 1: A is a plain (rows, cols) matrix walked 128 rows at a time along the w axis
+  int M, N;
+  int flags;
+  const float* bias;
+  const float* rowbias;
+  const int* rowbias_idx;
+  int rowbias_ld;
+  __nv_bfloat16* vt;
+  int vt_col0;
+  long long vt_ld;
+  float* out_f32;
+  long long out_f32_ld;
+};
+
+__global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;                                  // [STAGES][16 KiB]
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;         // [STAGES][16 KiB]
+  uint8_t* stage_c = smem;                                 // epilogue staging aliases A stages 0..1 (32 KiB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint64_t* res_bar = bars + 2 * STAGES + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  const int tile_m = blockIdx.x;
+  const int n0 = blockIdx.y * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+    if (p.kb_total > p.kb_seg0) tma_prefetch_desc(&p.tmA[1]);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(res_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int img0, h0, w0 = 0;
+      if (p.matrix) {
+        img0 = 0;
+        h0 = 0;
+        w0 = tile_m * BLOCK_M;
+      } else if (p.tiles_per_img > 0) {
+        img0 = tile_m / p.tiles_per_img;
+        h0 = (tile_m % p.tiles_per_img) * p.tile_h;
+      } else {
+        img0 = tile_m * p.tile_n;
+        h0 = 0;
+      }
+      int seg = 0, tap = 0, cbk = 0;
+      for (int kb = 0; kb < p.kb_total; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+        int dh = 0, dw = 0;
+        if (p.taps[seg] == 9) {
+          dh = tap / 3 - 1;
+          dw = tap % 3 - 1;
+        }
+        tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0);
+        tma_load_2d(smem_b + s * B_STAGE_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+        if (++cbk == p.cb[seg]) {
+          cbk = 0;
+          if (++tap == p.taps[seg]) {
+            tap = 0;
+            ++seg;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      for (int kb = 0; kb < p.kb_total; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after_sync();
+        const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + s * A_STAGE_BYTES), 128);
+        const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + s * B_STAGE_BYTES), 128);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advancing 16 bf16 (32 bytes) along K inside the swizzle row = +2 in the 16-byte address field
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);    // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps, 128 threads)
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may touch
+    const int r = quad * 32 + lane;        // accumulator row within the tile
+    const int et = threadIdx.x - 64;       // 0..127
+    const long long m = (long long)tile_m * BLOCK_M + r;
+    const bool row_ok = m < p.M;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after_sync();
+
+    const bool to_vt = (p.flags & F_VT) && n0 >= p.vt_col0;
+    const bool to_f32 = (p.flags & F_OUT_F32) != 0;
+    const bool staged = !to_vt && !to_f32;
+
+    if ((p.flags & F_RES) && staged) {
+      if (et == 0) {
+        mbar_expect_tx(res_bar, 2 * BLOCK_M * 128);
+        tma_load_2d(stage_c, &p.tmR, res_bar, n0, tile_m * BLOCK_M);
+        tma_load_2d(stage_c + BLOCK_M * 128, &p.tmR, res_bar, n0 + 64, tile_m * BLOCK_M);
+      }
+      mbar_wait(res_bar, 0);
+    }
+
+    int sample = 0;
+    bool zero_row = false;
+    if (p.rowbias != nullptr || (p.flags & F_ZERO_PAD)) {
+      const long long mm = row_ok ? m : 0;
+      sample = (int)(mm / p.HW);
+      const int pix = (int)(mm % p.HW);
+      if (p.flags & F_ZERO_PAD) zero_row = (pix / p.W == p.H - 1) || (pix % p.W == p.W - 1);
+    }
+    const float* rb = nullptr;
+    if (p.rowbias != nullptr) {
+      const int rrow = p.rowbias_idx ? p.rowbias_idx[sample] : sample;
+      rb = p.rowbias + (long long)rrow * p.rowbias_ld + n0;
+    }
+
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+      if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          acc[4 * j + 0] += b.x;
+          acc[4 * j + 1] += b.y;
+          acc[4 * j + 2] += b.z;
+          acc[4 * j + 3] += b.w;
+        }
+      }
+      if (rb != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(rb + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          acc[4 * j + 0] += b.x;
+          acc[4 * j + 1] += b.y;
+          acc[4 * j + 2] += b.z;
+          acc[4 * j + 3] += b.w;
+        }
+      }
+      if (staged) {
+        // staging layout = two TMA boxes of (128 rows x 64 cols), 128-byte swizzled
+        uint8_t* box = stage_c + (c >> 1) * (BLOCK_M * 128) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+          uint4* slot = reinterpret_cast<uint4*>(box + chunk * 16);
+          if (p.flags & F_RES) {
+            const uint4 rv = *slot;
+            acc[8 * q + 0] += bf16_lo(rv.x);
+            acc[8 * q + 1] += bf16_hi(rv.x);
+            acc[8 * q + 2] += bf16_lo(rv.y);
+            acc[8 * q + 3] += bf16_hi(rv.y);
+            acc[8 * q + 4] += bf16_lo(rv.z);
+            acc[8 * q + 5] += bf16_hi(rv.z);
+            acc[8 * q + 6] += bf16_lo(rv.w);
+            acc[8 * q + 7] += bf16_hi(rv.w);
+          }
+          uint4 o;
+          if (zero_row) {
+            o = make_uint4(0u, 0u, 0u, 0u);
+          } else {
+            o.x = pack_bf16x2(acc[8 * q + 0], acc[8 * q + 1]);
+            o.y = pack_bf16x2(acc[8 * q + 2], acc[8 * q + 3]);
+            o.z = pack_bf16x2(acc[8 * q + 4], acc[8 * q + 5]);
+            o.w = pack_bf16x2(acc[8 * q + 6], acc[8 * q + 7]);
+          }
+          *slot = o;
+        }
+      } else if (to_vt) {
+        if (row_ok) {
+          __nv_bfloat16* dst = p.vt + (long long)(n0 - p.vt_col0 + c * 32) * p.vt_ld + m;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[(long long)j * p.vt_ld] = __float2bfloat16_rn(acc[j]);
+        }
+      } else {
+        if (row_ok) {
+          float4* dst = reinterpret_cast<float4*>(p.out_f32 + m * p.out_f32_ld + n0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(acc[4 * j + 0], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+      }
+    }
+    if (staged) {
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        tma_store_2d(&p.tmC, stage_c, n0, tile_m * BLOCK_M);
+        tma_store_2d(&p.tmC, stage_c + BLOCK_M * 128, n0 + 64, tile_m * BLOCK_M);
+        tma_store_commit();
+        tma_store_wait_all();
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+static int make_act_map(CUtensorMap* tm, const idf_nhwc_t& a, int tile_w, int tile_h, int tile_n) {
+  const uint64_t dims[4] = {(uint64_t)a.c, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.n};
+  const uint64_t strides[3] = {(uint64_t)a.sw * 2, (uint64_t)a.sh * 2, (uint64_t)a.sn * 2};
+  const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)tile_w, (uint32_t)tile_h, (uint32_t)tile_n};
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.ptr, 4, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+static int make_mat_map(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint32_t box_cols, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {ld * 2};
+  const uint32_t box[2] = {box_cols, box_rows};
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace idf
+
+using namespace idf;
+
+extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
+  if (a == nullptr || a->a[0].ptr == nullptr || a->w == nullptr || a->out == nullptr)
+    return fail(IDF_ERR_ARG, "idf_conv2d_igemm: null argument");
+  const idf_nhwc_t& x0 = a->a[0];
+  const int nseg = a->a[1].ptr != nullptr ? 2 : 1;
+  for (int s = 0; s < nseg; ++s) {
+    const idf_nhwc_t& x = a->a[s];
+    if (x.n != x0.n || x.h != x0.h || x.w != x0.w) return fail(IDF_ERR_ARG, "igemm: segments disagree on n/h/w");
+    if (x.c <= 0 || x.c % BLOCK_K != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: channels %d not a multiple of 64", x.c);
+    if (a->taps[s] != 1 && a->taps[s] != 9) return fail(IDF_ERR_ARG, "igemm: taps must be 1 or 9");
+  }
+  if (a->N <= 0 || a->N % BLOCK_N != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d not a multiple of %d", a->N, BLOCK_N);
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int H = x0.h, W = x0.w, HW = H * W;
+  const long long M = (long long)x0.n * HW;
+  if (M <= 0 || M > 0x7fffffffLL) return fail(IDF_ERR_ARG, "igemm: bad M");
+  // M-tile geometry: 128 consecutive NHWC pixels = tile_n images x tile_h rows x tile_w columns.
+  const bool is_matrix = x0.n == 1 && x0.h == 1 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
+  if (is_matrix) {
+    p.matrix = 1; p.tile_w = BLOCK_M; p.tile_h = 1; p.tile_n = 1; p.tiles_per_img = 0;
+  } else if (W > BLOCK_M) {
+    return fail(IDF_ERR_UNSUPPORTED, "igemm: image width %d > 128", W);
+  } else if (HW >= BLOCK_M) {
+    if (BLOCK_M % W != 0 || HW % BLOCK_M != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: %dx%d image does not tile", H, W);
+    p.tile_w = W; p.tile_h = BLOCK_M / W; p.tile_n = 1; p.tiles_per_img = HW / BLOCK_M;
+  } else {
+    if (BLOCK_M % HW != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: %dx%d image does not tile", H, W);
+    p.tile_w = W; p.tile_h = H; p.tile_n = BLOCK_M / HW; p.tiles_per_img = 0;
+  }
+  int rc;
+  int ktot = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if ((rc = make_act_map(&p.tmA[s], a->a[s], p.tile_w, p.tile_h, p.tile_n)) != IDF_OK) return rc;
+    p.cb[s] = a->a[s].c / BLOCK_K;
+    p.taps[s] = a->taps[s];
+    ktot += a->taps[s] * a->a[s].c;
+  }
+  if (nseg == 1) { p.cb[1] = 1; p.taps[1] = 1; }
+  p.kb_seg0 = a->taps[0] * p.cb[0];
+  p.kb_total = ktot / BLOCK_K;
+  if (a->ldw < ktot) return fail(IDF_ERR_ARG, "igemm: ldw %lld < K %d", (long long)a->ldw, ktot);
+  if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, BLOCK_N)) != IDF_OK)
+    return rc;
+
+  p.H = a->epi_h > 0 ? a->epi_h : H;
+  p.W = a->epi_w > 0 ? a->epi_w : W;
+  p.HW = p.H * p.W;
+  p.M = (int)M; p.N = a->N;
+  p.bias = a->bias;
+  p.rowbias = a->rowbias;
+  p.rowbias_idx = a->rowbias_idx;
+  p.rowbias_ld = a->rowbias_ld;
+  if (a->rowbias != nullptr && (a->rowbias_ld % 4 != 0 || (reinterpret_cast<uintptr_t>(a->rowbias) & 15)))
+    return fail(IDF_ERR_ARG, "igemm: rowbias must be 16-byte aligned with ld %% 4 == 0");
+  if (a->bias != nullptr && (reinterpret_cast<uintptr_t>(a->bias) & 15))
+    return fail(IDF_ERR_ARG, "igemm: bias must be 16-byte aligned");
+  if (a->zero_pad_last) p.flags |= F_ZERO_PAD;
+  if (a->out_f32) {
+    if (a->res != nullptr || a->vt != nullptr) return fail(IDF_ERR_UNSUPPORTED, "igemm: fp32 output excludes res/vt");
+    if (a->ldo % 4 != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15)) return fail(IDF_ERR_ARG, "igemm: fp32 out alignment");
+    p.flags |= F_OUT_F32;
+    p.out_f32 = reinterpret_cast<float*>(a->out);
+    p.out_f32_ld = a->ldo;
+  } else {
+    int out_cols = a->N;
+    if (a->vt != nullptr) {
+      if (a->vt_col0 % BLOCK_N != 0 || a->vt_col0 <= 0 || a->vt_col0 >= a->N)
+        return fail(IDF_ERR_ARG, "igemm: vt_col0 must be a positive multiple of %d below N", BLOCK_N);
+      p.flags |= F_VT;
+      p.vt = reinterpret_cast<__nv_bfloat16*>(a->vt);
+      p.vt_col0 = a->vt_col0;
+      p.vt_ld = a->vt_ld;
+      out_cols = a->vt_col0;
+    }
+    if ((rc = make_mat_map(&p.tmC, a->out, (uint64_t)M, (uint64_t)out_cols, (uint64_t)a->ldo, 64, BLOCK_M)) != IDF_OK)
+      return rc;
+    if (a->res != nullptr) {
+      p.flags |= F_RES;
+      if ((rc = make_mat_map(&p.tmR, a->res, (uint64_t)M, (uint64_t)out_cols, (uint64_t)a->ldres, 64, BLOCK_M)) != IDF_OK)
+        return rc;
+    }
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    if ((rc = check_cuda(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM),
+                         "igemm: cudaFuncSetAttribute")) != IDF_OK)
+      return rc;
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((M + BLOCK_M - 1) / BLOCK_M), (unsigned)(a->N / BLOCK_N));
+  igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return check_cuda(cudaGetLastError(), "igemm launch");
+}

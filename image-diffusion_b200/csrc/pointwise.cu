@@ -1,0 +1,534 @@
+// Bandwidth- and latency-bound pieces of the path: timestep/class embedding, the fused CFG + DDPM posterior
+// step, the VQ nearest-code search, the tiny-channel edge convolutions and a few layout movers.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/idf_b200.h"
+
+namespace idf {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------
+// embedding path
+// ---------------------------------------------------------------------------------------------
+// e[r, j] = sin(t_r / factor_j) for j < D/2, cos(t_r / factor_{j - D/2}) otherwise  (components.py:442-443)
+__global__ void sincos_kernel(const int64_t* __restrict__ t, const float* __restrict__ factor,
+                              float* __restrict__ e, int R, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * D) return;
+  const int r = i / D, j = i % D, half = D / 2;
+  const float arg = (float)t[r] / factor[j < half ? j : j - half];
+  e[i] = j < half ? sinf(arg) : cosf(arg);
+}
+
+// Y[r, j] = act_out( b[j] + sum_k W[j, k] * X[r, k] + mask[r] * cls[ctx[r], j] ), one warp per output column,
+// rows in register chunks of 8 so each weight row is streamed once per chunk.
+template <bool SILU_OUT>
+__global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restrict__ X, int ldx,
+                                                          const float* __restrict__ W, const float* __restrict__ b,
+                                                          float* __restrict__ Y, int ldy, int R, int K, int J,
+                                                          const float* __restrict__ cls,
+                                                          const int64_t* __restrict__ ctx,
+                                                          const float* __restrict__ mask) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= J) return;
+  const float4* w4 = reinterpret_cast<const float4*>(W + (long long)j * K);
+  for (int r0 = 0; r0 < R; r0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k4 = lane; k4 < K / 4; k4 += 32) {
+      const float4 w = __ldg(w4 + k4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (r0 + i < R) {
+          const float4 xv = *reinterpret_cast<const float4*>(X + (long long)(r0 + i) * ldx + k4 * 4);
+          acc[i] = fmaf(w.x, xv.x, acc[i]);
+          acc[i] = fmaf(w.y, xv.y, acc[i]);
+          acc[i] = fmaf(w.z, xv.z, acc[i]);
+          acc[i] = fmaf(w.w, xv.w, acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i;
+        if (r < R) {
+          float v = acc[i] + b[j];
+          if (cls != nullptr && ctx != nullptr) {
+            const float mk = mask ? mask[r] : 1.f;
+            v += mk * cls[(long long)ctx[r] * J + j];
+          }
+          Y[(long long)r * ldy + j] = SILU_OUT ? silu_f(v) : v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CFG mix + DDPM ancestral step (diffusion.py:55, components.py:405-424)
+// ---------------------------------------------------------------------------------------------
+__global__ void cfg_posterior_kernel(const float* __restrict__ xt, const float* __restrict__ ec,
+                                     const float* __restrict__ eu, const float* __restrict__ z,
+                                     const float* __restrict__ cfg, const int64_t* __restrict__ t, int t_stride,
+                                     const float* __restrict__ betas, const float* __restrict__ alphas,
+                                     const float* __restrict__ acp, const float* __restrict__ sacp,
+                                     const float* __restrict__ somacp, float* __restrict__ x_prev,
+                                     float* __restrict__ x0_out, int N, int chw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * chw) return;
+  const int n = (int)(i / chw);
+  const int tn = (int)t[(long long)n * t_stride];
+  const int t_first = (int)t[0];
+  const float x = xt[i];
+  const float u = eu[i];
+  const float eps = u + cfg[n] * (ec[i] - u);
+  const float b = betas[tn];
+  const float so = somacp[tn];
+  if (x0_out != nullptr) {
+    float x0 = (x - so * eps) / sacp[tn];
+    x0_out[i] = fminf(fmaxf(x0, -1.f), 1.f);
+  }
+  float mean = x - (b * eps) / so;
+  mean = mean / sqrtf(alphas[tn]);
+  if (t_first == 0) {
+    x_prev[i] = mean;
+  } else {
+    float var = (1.f - acp[tn - 1]) / (1.f - acp[tn]);
+    var = var * b;
+    x_prev[i] = mean + sqrtf(var) * z[i];
+  }
+}
+
+__global__ void add_noise_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                 const int64_t* __restrict__ t, const float* __restrict__ sacp,
+                                 const float* __restrict__ somacp, float* __restrict__ out, int N, int chw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * chw) return;
+  const int tn = (int)t[i / chw];
+  out[i] = sacp[tn] * x[i] + somacp[tn] * noise[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// VQ nearest code: one warp per latent vector, codebook (augmented with its norms) in shared memory,
+// lanes stride over the codes, warp-shuffle (distance, index) min-reduction with first-index tie break.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb,
+                                                        int64_t* __restrict__ idx_out, float* __restrict__ zq_out,
+                                                        int rows, int size) {
+  extern __shared__ float s_cb[];  // [size][DIM + 1]: code, |code|^2
+  for (int i = threadIdx.x; i < size; i += blockDim.x) {
+    float nrm = 0.f;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      const float e = cb[(long long)i * DIM + d];
+      s_cb[i * (DIM + 1) + d] = e;
+      nrm += e * e;  // pow(2).sum(-1): sequential over the last dim
+    }
+    s_cb[i * (DIM + 1) + DIM] = nrm;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    float xv[DIM];
+    float xn = 0.f;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      xv[d] = z[(long long)row * DIM + d];
+      xn += xv[d] * xv[d];
+    }
+    float best = INFINITY;
+    int best_i = 0x7fffffff;
+    for (int i = lane; i < size; i += 32) {
+      // x1_ . x2_ with x1_ = [-2x, |x|^2, 1], x2_ = [e, 1, |e|^2]; K = DIM + 2 products accumulated in order
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) acc = fmaf(-2.f * xv[d], s_cb[i * (DIM + 1) + d], acc);
+      acc = fmaf(xn, 1.f, acc);
+      acc = fmaf(1.f, s_cb[i * (DIM + 1) + DIM], acc);
+      const float dist = sqrtf(fmaxf(acc, 0.f));
+      if (dist < best) {  // strict: keeps the first minimal index within the lane's ascending walk
+        best = dist;
+        best_i = i;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob < best || (ob == best && oi < best_i)) {
+        best = ob;
+        best_i = oi;
+      }
+    }
+    if (lane == 0) idx_out[row] = (int64_t)best_i;
+    if (zq_out != nullptr && lane < DIM) zq_out[(long long)row * DIM + lane] = s_cb[best_i * (DIM + 1) + lane];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// edge convolutions with a handful of channels on one side
+// ---------------------------------------------------------------------------------------------
+// fp32 NCHW (Cin <= 8) -> bf16 NHWC, 3x3 s1 p1. One thread = one pixel x 8 output channels.
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __restrict__ x,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ bias,
+                                                                __nv_bfloat16* __restrict__ y, long long ldy, int B,
+                                                                int H, int W, int Cout) {
+  extern __shared__ float s_w[];  // [CIN*9][Cout] + bias[Cout]
+  const int K = CIN * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int o = i / K, k = i % K;  // w is OIHW = [o][k]
+    s_w[k * Cout + o] = w[i];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[K * Cout + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int groups = Cout / 8;
+  const long long total = (long long)B * H * W * groups;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(it % groups);
+    const long long pix = it / groups;
+    const int wq = (int)(pix % W);
+    const int hq = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float patch[CIN * 9];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int hh = hq + kh - 1, ww = wq + kw - 1;
+          patch[c * 9 + kh * 3 + kw] =
+              (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((long long)b * CIN + c) * H + hh) * W + ww] : 0.f;
+        }
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = s_w[K * Cout + g * 8 + o];
+#pragma unroll
+    for (int k = 0; k < CIN * 9; ++k) {
+      const float4 wa = *reinterpret_cast<const float4*>(&s_w[k * Cout + g * 8]);
+      const float4 wb = *reinterpret_cast<const float4*>(&s_w[k * Cout + g * 8 + 4]);
+      acc[0] = fmaf(patch[k], wa.x, acc[0]); acc[1] = fmaf(patch[k], wa.y, acc[1]);
+      acc[2] = fmaf(patch[k], wa.z, acc[2]); acc[3] = fmaf(patch[k], wa.w, acc[3]);
+      acc[4] = fmaf(patch[k], wb.x, acc[4]); acc[5] = fmaf(patch[k], wb.y, acc[5]);
+      acc[6] = fmaf(patch[k], wb.z, acc[6]); acc[7] = fmaf(patch[k], wb.w, acc[7]);
+    }
+    uint4 o4;
+    o4.x = pack_bf16x2(acc[0], acc[1]);
+    o4.y = pack_bf16x2(acc[2], acc[3]);
+    o4.z = pack_bf16x2(acc[4], acc[5]);
+    o4.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(y + pix * ldy + g * 8) = o4;
+  }
+}
+
+// bf16 NHWC -> fp32 NCHW (Cout <= 8), 3x3 s1 p1. One warp = one pixel; lanes stride over (tap, 8-channel vector).
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                                 const float* __restrict__ w,
+                                                                 const float* __restrict__ bias,
+                                                                 float* __restrict__ y, int B, int Cin, int H,
+                                                                 int W) {
+  extern __shared__ float s_w[];  // [9][Cin][COUT]
+  for (int i = threadIdx.x; i < COUT * Cin * 9; i += blockDim.x) {
+    const int o = i / (Cin * 9), rem = i % (Cin * 9), c = rem / 9, tap = rem % 9;  // OIHW
+    s_w[(tap * Cin + c) * COUT + o] = w[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int vec_per_tap = Cin / 8;
+  const int items = 9 * vec_per_tap;
+  const long long total = (long long)B * H * W;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long long pix = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix < total;
+       pix += (long long)gridDim.x * warps_per_block) {
+    const int wq = (int)(pix % W);
+    const int hq = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    for (int it = lane; it < items; it += 32) {
+      const int tap = it / vec_per_tap, vv = it % vec_per_tap;
+      const int hh = hq + tap / 3 - 1, ww = wq + tap % 3 - 1;
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      const uint4 raw =
+          *reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * ldx + vv * 8);
+      float f[8];
+      f[0] = bf16_lo(raw.x); f[1] = bf16_hi(raw.x); f[2] = bf16_lo(raw.y); f[3] = bf16_hi(raw.y);
+      f[4] = bf16_lo(raw.z); f[5] = bf16_hi(raw.z); f[6] = bf16_lo(raw.w); f[7] = bf16_hi(raw.w);
+      const float* wp = &s_w[(tap * Cin + vv * 8) * COUT];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(f[e], wp[e * COUT + o], acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o)
+      for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o)
+        y[(((long long)b * COUT + o) * H + hq) * W + wq] = acc[o] + (bias ? bias[o] : 0.f);
+    }
+  }
+}
+
+// fp32 NCHW 1x1 convolution with tiny channel counts (decoder's first conv, encoder's last conv).
+__global__ void conv1x1_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ bias, float* __restrict__ y, int B, int Cin, int Cout,
+                                     int HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * Cout * HW) return;
+  const int p = (int)(i % HW);
+  const int o = (int)((i / HW) % Cout);
+  const int b = (int)(i / ((long long)HW * Cout));
+  float acc = 0.f;
+  for (int c = 0; c < Cin; ++c) acc = fmaf(x[((long long)b * Cin + c) * HW + p], w[o * Cin + c], acc);
+  y[i] = acc + (bias ? bias[o] : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout movers (16-byte vectors over channels-last bf16)
+// ---------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
+                                  long long ldy, int B, int H, int W, int C) {
+  const int vec = C / 8;
+  const long long total = (long long)B * (2 * H) * (2 * W) * vec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    const long long opix = i / vec;
+    const int ow = (int)(opix % (2 * W));
+    const int oh = (int)((opix / (2 * W)) % (2 * H));
+    const int b = (int)(opix / ((long long)4 * W * H));
+    const long long ipix = ((long long)b * H + (oh >> 1)) * W + (ow >> 1);
+    *reinterpret_cast<uint4*>(y + opix * ldy + v * 8) = *reinterpret_cast<const uint4*>(x + ipix * ldx + v * 8);
+  }
+}
+
+__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
+                                 int B, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2, vec = C / 8;
+  const long long total = (long long)B * OH * OW * 9 * vec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    const int tap = (int)((i / vec) % 9);
+    const long long opix = i / ((long long)vec * 9);
+    const int ow = (int)(opix % OW);
+    const int oh = (int)((opix / OW) % OH);
+    const int b = (int)(opix / ((long long)OW * OH));
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (oh < OH - 1 && ow < OW - 1) {
+      const int hh = 2 * oh + tap / 3, ww = 2 * ow + tap % 3;
+      val = *reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * ldx + v * 8);
+    }
+    *reinterpret_cast<uint4*>(y + opix * (9LL * C) + (long long)tap * C + v * 8) = val;
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long ldy, int B,
+                                    int C, int HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * C * HW) return;
+  const int c = (int)(i % C);
+  const long long pix = i / C;
+  const int p = (int)(pix % HW);
+  const int b = (int)(pix / HW);
+  y[pix * ldy + c] = __float2bfloat16_rn(x[((long long)b * C + c) * HW + p]);
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restrict__ y, int B,
+                                    int C, int HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * C * HW) return;
+  const int p = (int)(i % HW);
+  const int c = (int)((i / HW) % C);
+  const int b = (int)(i / ((long long)HW * C));
+  y[i] = __bfloat162float(x[((long long)b * HW + p) * ldx + c]);
+}
+
+static inline unsigned blocks_for(long long n, int threads, int cap = 148 * 16) {
+  long long b = (n + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace idf
+
+using namespace idf;
+
+extern "C" int idf_embed_time_class(const int64_t* t, const int64_t* ctx, const float* ctx_mask, int32_t R,
+                                    int32_t D, const float* factor, const float* w1, const float* b1, const float* w2,
+                                    const float* b2, const float* class_w, const float* wp, const float* bp,
+                                    int32_t P, float* out, float* scratch, idf_stream_t stream) {
+  if (!t || !factor || !w1 || !b1 || !w2 || !b2 || !wp || !bp || !out || !scratch)
+    return fail(IDF_ERR_ARG, "embed: null pointer");
+  if (R <= 0 || D <= 0 || D % 8 != 0 || P <= 0) return fail(IDF_ERR_ARG, "embed: bad shape");
+  if (ctx != nullptr && class_w == nullptr) return fail(IDF_ERR_ARG, "embed: ctx without class_w");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* e = scratch;               // (R, D)    sin/cos, later silu(temb)
+  float* h1 = scratch + (long long)R * D;  // (R, 4D)
+  sincos_kernel<<<(R * D + 255) / 256, 256, 0, s>>>(t, factor, e, R, D);
+  const int wpb = 8;  // warps per block
+  linear_rows_kernel<true><<<(4 * D + wpb - 1) / wpb, 256, 0, s>>>(e, D, w1, b1, h1, 4 * D, R, D, 4 * D, nullptr,
+                                                                   nullptr, nullptr);
+  // temb = Linear2(h1) + mask * class_w[ctx]; every consumer applies SiLU first (components.py:486), so store that
+  linear_rows_kernel<true><<<(D + wpb - 1) / wpb, 256, 0, s>>>(h1, 4 * D, w2, b2, e, D, R, 4 * D, D, class_w, ctx,
+                                                               ctx_mask);
+  linear_rows_kernel<false><<<(P + wpb - 1) / wpb, 256, 0, s>>>(e, D, wp, bp, out, P, R, D, P, nullptr, nullptr,
+                                                                nullptr);
+  return check_cuda(cudaGetLastError(), "embed launch");
+}
+
+extern "C" int idf_cfg_posterior_step(const float* xt, const float* eps_cond, const float* eps_uncond,
+                                      const float* noise, const float* cfg, const int64_t* t, int32_t t_stride,
+                                      const float* betas, const float* alphas, const float* alpha_cum_prod,
+                                      const float* sqrt_alpha_cum_prod, const float* sqrt_one_minus_alpha_cum_prod,
+                                      float* x_prev, float* x0_out, int32_t N, int32_t chw, idf_stream_t stream) {
+  if (!xt || !eps_cond || !eps_uncond || !noise || !cfg || !t || !betas || !alphas || !alpha_cum_prod ||
+      !sqrt_alpha_cum_prod || !sqrt_one_minus_alpha_cum_prod || !x_prev)
+    return fail(IDF_ERR_ARG, "cfg_posterior: null pointer");
+  const long long n = (long long)N * chw;
+  cfg_posterior_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      xt, eps_cond, eps_uncond, noise, cfg, t, t_stride, betas, alphas, alpha_cum_prod, sqrt_alpha_cum_prod,
+      sqrt_one_minus_alpha_cum_prod, x_prev, x0_out, N, chw);
+  return check_cuda(cudaGetLastError(), "cfg_posterior launch");
+}
+
+extern "C" int idf_add_noise(const float* x, const float* noise, const int64_t* t, const float* sqrt_alpha_cum_prod,
+                             const float* sqrt_one_minus_alpha_cum_prod, float* out, int32_t N, int32_t chw,
+                             idf_stream_t stream) {
+  if (!x || !noise || !t || !out) return fail(IDF_ERR_ARG, "add_noise: null pointer");
+  const long long n = (long long)N * chw;
+  add_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, noise, t, sqrt_alpha_cum_prod, sqrt_one_minus_alpha_cum_prod, out, N, chw);
+  return check_cuda(cudaGetLastError(), "add_noise launch");
+}
+
+extern "C" int idf_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, float* zq_out, int32_t rows,
+                             int32_t dim, int32_t size, idf_stream_t stream) {
+  if (!z || !codebook || !idx_out) return fail(IDF_ERR_ARG, "vq_argmin: null pointer");
+  if (rows <= 0 || size <= 0) return fail(IDF_ERR_ARG, "vq_argmin: bad shape");
+  const int smem = size * (dim + 1) * 4;
+  if (smem > 48 * 1024) return fail(IDF_ERR_UNSUPPORTED, "vq_argmin: codebook does not fit shared memory");
+  const unsigned grid = blocks_for((long long)rows, 8, 148 * 8);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (dim) {
+    case 3: vq_argmin_kernel<3><<<grid, 256, smem, s>>>(z, codebook, idx_out, zq_out, rows, size); break;
+    case 4: vq_argmin_kernel<4><<<grid, 256, smem, s>>>(z, codebook, idx_out, zq_out, rows, size); break;
+    case 8: vq_argmin_kernel<8><<<grid, 256, smem, s>>>(z, codebook, idx_out, zq_out, rows, size); break;
+    default: return fail(IDF_ERR_UNSUPPORTED, "vq_argmin: dim %d not in {3,4,8}", dim);
+  }
+  return check_cuda(cudaGetLastError(), "vq_argmin launch");
+}
+
+extern "C" int idf_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int64_t ldy,
+                                     int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout,
+                                     idf_stream_t stream) {
+  if (!x || !w || !y) return fail(IDF_ERR_ARG, "conv_small_cin: null pointer");
+  if (Cout % 8 != 0 || ldy % 8 != 0) return fail(IDF_ERR_ARG, "conv_small_cin: Cout and ldy must be multiples of 8");
+  const int smem = (Cin * 9 + 1) * Cout * 4;
+  if (smem > 48 * 1024) return fail(IDF_ERR_UNSUPPORTED, "conv_small_cin: weights exceed 48 KiB");
+  const long long total = (long long)B * H * W * (Cout / 8);
+  const unsigned grid = blocks_for(total, 256);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  switch (Cin) {
+    case 3: conv3x3_small_cin_kernel<3><<<grid, 256, smem, s>>>(x, w, bias, yp, ldy, B, H, W, Cout); break;
+    case 4: conv3x3_small_cin_kernel<4><<<grid, 256, smem, s>>>(x, w, bias, yp, ldy, B, H, W, Cout); break;
+    default: return fail(IDF_ERR_UNSUPPORTED, "conv_small_cin: Cin %d not in {3,4}", Cin);
+  }
+  return check_cuda(cudaGetLastError(), "conv_small_cin launch");
+}
+
+template <int COUT>
+static int launch_small_cout(const __nv_bfloat16* x, long long ldx, const float* w, const float* bias, float* y, int B,
+                             int Cin, int H, int W, cudaStream_t s) {
+  const int smem = 9 * Cin * COUT * 4;
+  static int smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(conv3x3_small_cout_kernel<COUT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                        "conv_small_cout: cudaFuncSetAttribute");
+    if (rc != IDF_OK) return rc;
+    smem_set = smem;
+  }
+  const unsigned grid = blocks_for((long long)B * H * W, 8, 148 * 8);
+  conv3x3_small_cout_kernel<COUT><<<grid, 256, smem, s>>>(x, ldx, w, bias, y, B, Cin, H, W);
+  return check_cuda(cudaGetLastError(), "conv_small_cout launch");
+}
+
+extern "C" int idf_conv3x3_small_cout(const void* x, int64_t ldx, const float* w, const float* bias, float* y,
+                                      int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout,
+                                      idf_stream_t stream) {
+  if (!x || !w || !y) return fail(IDF_ERR_ARG, "conv_small_cout: null pointer");
+  if (Cin % 8 != 0 || ldx % 8 != 0) return fail(IDF_ERR_ARG, "conv_small_cout: Cin and ldx must be multiples of 8");
+  if (9 * Cin * Cout * 4 > 200 * 1024) return fail(IDF_ERR_UNSUPPORTED, "conv_small_cout: weights exceed shared memory");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  switch (Cout) {
+    case 3: return launch_small_cout<3>(xp, ldx, w, bias, y, B, Cin, H, W, s);
+    case 6: return launch_small_cout<6>(xp, ldx, w, bias, y, B, Cin, H, W, s);
+    default: return fail(IDF_ERR_UNSUPPORTED, "conv_small_cout: Cout %d not in {3,6}", Cout);
+  }
+}
+
+extern "C" int idf_conv1x1_small_f32(const float* x, const float* w, const float* bias, float* y, int32_t B,
+                                     int32_t Cin, int32_t Cout, int32_t HW, idf_stream_t stream) {
+  if (!x || !w || !y) return fail(IDF_ERR_ARG, "conv1x1_small: null pointer");
+  const long long n = (long long)B * Cout * HW;
+  conv1x1_small_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, w, bias, y, B, Cin, Cout, HW);
+  return check_cuda(cudaGetLastError(), "conv1x1_small launch");
+}
+
+extern "C" int idf_upsample_nearest2x(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t B, int32_t H,
+                                      int32_t W, int32_t C, idf_stream_t stream) {
+  if (!x || !y) return fail(IDF_ERR_ARG, "upsample: null pointer");
+  if (C % 8 != 0 || ldx % 8 != 0 || ldy % 8 != 0) return fail(IDF_ERR_ARG, "upsample: C/ld must be multiples of 8");
+  const long long total = (long long)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, B, H, W, C);
+  return check_cuda(cudaGetLastError(), "upsample launch");
+}
+
+extern "C" int idf_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                             idf_stream_t stream) {
+  if (!x || !y) return fail(IDF_ERR_ARG, "im2col_s2: null pointer");
+  if (C % 8 != 0 || ldx % 8 != 0 || H % 2 != 0 || W % 2 != 0) return fail(IDF_ERR_ARG, "im2col_s2: bad shape");
+  const long long total = (long long)B * (H / 2) * (W / 2) * 9 * (C / 8);
+  im2col_s2_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+  return check_cuda(cudaGetLastError(), "im2col_s2 launch");
+}
+
+extern "C" int idf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t ldy, int32_t B, int32_t C, int32_t HW,
+                                         idf_stream_t stream) {
+  if (!x || !y) return fail(IDF_ERR_ARG, "nchw_to_nhwc: null pointer");
+  const long long n = (long long)B * C * HW;
+  nchw_to_nhwc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y), ldy, B, C, HW);
+  return check_cuda(cudaGetLastError(), "nchw_to_nhwc launch");
+}
+
+extern "C" int idf_nhwc_bf16_to_nchw_f32(const void* x, int64_t ldx, float* y, int32_t B, int32_t C, int32_t HW,
+                                         idf_stream_t stream) {
+  if (!x || !y) return fail(IDF_ERR_ARG, "nhwc_to_nchw: null pointer");
+  const long long n = (long long)B * C * HW;
+  nhwc_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, y, B, C, HW);
+  return check_cuda(cudaGetLastError(), "nhwc_to_nchw launch");
+}

@@ -1,0 +1,116 @@
+"""ctypes binding of libidf_b200.so (see include/idf_b200.h). The library is the only compute path: if it is
+missing or a call fails, an exception is raised — there is no eager/PyTorch or CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libidf_b200.so")
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class NHWC(C.Structure):
+    _fields_ = [("ptr", _vp), ("n", _i32), ("h", _i32), ("w", _i32), ("c", _i32),
+                ("sn", _i64), ("sh", _i64), ("sw", _i64)]
+
+
+class IgemmArgs(C.Structure):
+    _fields_ = [
+        ("a", NHWC * 2), ("taps", _i32 * 2),
+        ("w", _vp), ("ldw", _i64), ("N", _i32),
+        ("out", _vp), ("ldo", _i64), ("out_f32", _i32),
+        ("bias", _vp), ("rowbias", _vp), ("rowbias_idx", _vp), ("rowbias_ld", _i32),
+        ("res", _vp), ("ldres", _i64),
+        ("vt", _vp), ("vt_col0", _i32), ("vt_ld", _i64),
+        ("zero_pad_last", _i32), ("epi_h", _i32), ("epi_w", _i32),
+    ]
+
+
+# name -> argtypes (the trailing stream argument is appended automatically)
+_SIGNATURES = {
+    "idf_conv2d_igemm": [C.POINTER(IgemmArgs)],
+    "idf_groupnorm_silu": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32],
+    "idf_attention_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32],
+    "idf_softmax_rows": [_vp, _i64, _vp, _i64, _i32, _i32, _f32],
+    "idf_embed_time_class": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    "idf_cfg_posterior_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32],
+    "idf_add_noise": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32],
+    "idf_vq_argmin": [_vp, _vp, _vp, _vp, _i32, _i32, _i32],
+    "idf_conv3x3_small_cin": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32],
+    "idf_conv3x3_small_cout": [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32],
+    "idf_conv1x1_small_f32": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32],
+    "idf_upsample_nearest2x": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32],
+    "idf_im2col_s2": [_vp, _i64, _vp, _i32, _i32, _i32, _i32],
+    "idf_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i64, _i32, _i32, _i32],
+    "idf_nhwc_bf16_to_nchw_f32": [_vp, _i64, _vp, _i32, _i32, _i32],
+}
+EXPORTS = sorted(list(_SIGNATURES) + ["idf_last_error", "idf_abi_version"])
+
+_lib = None
+launch_count = 0  # kernels-launching C-ABI calls made through this module (bench.py reports it)
+
+
+def load() -> C.CDLL:
+    """Loads the shared library (once). Raises NativeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} is missing: run `python __graft_entry__.py build` (or image-diffusion_b200/csrc/build.py). "
+            "There is no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.idf_last_error.restype = C.c_char_p
+    lib.idf_last_error.argtypes = []
+    lib.idf_abi_version.restype = C.c_int
+    lib.idf_abi_version.argtypes = []
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = list(argtypes) + [_vp]
+    _lib = lib
+    return lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int | None:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def call(name: str, *args) -> None:
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args, _stream())
+    launch_count += 1
+    if rc != 0:
+        raise NativeError(f"{name} failed (code {rc}): {lib.idf_last_error().decode()}")
+
+
+def nhwc_view(t: torch.Tensor | None, n: int = 0, h: int = 0, w: int = 0, c: int = 0, ld: int | None = None) -> NHWC:
+    """View over a (rows, ld) bf16 matrix holding an (n, h, w) pixel grid with `c` channels starting at t's pointer."""
+    v = NHWC()
+    if t is None:
+        v.ptr = None
+        return v
+    ld = int(ld if ld is not None else t.stride(-2))
+    v.ptr = t.data_ptr()
+    v.n, v.h, v.w, v.c = n, h, w, c
+    v.sw, v.sh, v.sn = ld, ld * w, ld * w * h
+    return v
+
+
+def matrix_view(t: torch.Tensor, rows: int, cols: int, ld: int | None = None) -> NHWC:
+    return nhwc_view(t, 1, 1, rows, cols, ld)

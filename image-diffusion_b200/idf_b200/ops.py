@@ -1,0 +1,155 @@
+"""Tensor-level wrappers over the C ABI. Activations are channels-last bf16 matrices of shape (B*H*W, C) (possibly
+column slices of a wider buffer, so the row stride may exceed C). Nothing here computes in PyTorch."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import native
+from .native import IgemmArgs, call, matrix_view, nhwc_view, ptr
+
+
+def _check_bf16_rows(t: torch.Tensor, name: str) -> None:
+    if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D bf16 matrix with unit column stride, got {t.dtype} {tuple(t.shape)} "
+                         f"strides {t.stride()}")
+
+
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """OIHW fp32 -> (O, KH*KW*I) bf16, tap-major then input channel (the igemm K order)."""
+    o, i, kh, kw = w.shape
+    return w.detach().permute(0, 2, 3, 1).reshape(o, kh * kw * i).to(torch.bfloat16).contiguous()
+
+
+def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
+          res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None) -> torch.Tensor:
+    """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view."""
+    a = IgemmArgs()
+    if not 1 <= len(segs) <= 2:
+        raise ValueError("igemm takes one or two input segments")
+    for i, (t, (n, h, wd), c, taps) in enumerate(segs):
+        _check_bf16_rows(t, f"igemm segment {i}")
+        a.a[i] = nhwc_view(t, n, h, wd, c)
+        a.taps[i] = taps
+    if len(segs) == 1:
+        a.a[1] = nhwc_view(None)
+        a.taps[1] = 1
+    _check_bf16_rows(w, "igemm weight")
+    a.w, a.ldw, a.N = w.data_ptr(), w.stride(0), n_out
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    a.out_f32 = 1 if out.dtype == torch.float32 else 0
+    a.bias = ptr(bias)
+    a.rowbias = ptr(rowbias)
+    a.rowbias_idx = ptr(rowbias_idx)
+    a.rowbias_ld = rowbias.stride(0) if rowbias is not None else 0
+    a.res = ptr(res)
+    a.ldres = res.stride(0) if res is not None else 0
+    a.vt = ptr(vt)
+    a.vt_col0 = vt_col0
+    a.vt_ld = vt.stride(0) if vt is not None else 0
+    a.zero_pad_last = 1 if zero_pad_last else 0
+    a.epi_h, a.epi_w = epi_hw if epi_hw is not None else (0, 0)
+    call("idf_conv2d_igemm", a)
+    return out
+
+
+def groupnorm_silu(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, B: int, HW: int, C: int,
+                   groups: int, silu: bool, eps: float = 1e-5) -> torch.Tensor:
+    _check_bf16_rows(x, "groupnorm x")
+    _check_bf16_rows(y, "groupnorm y")
+    call("idf_groupnorm_silu", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gamma.data_ptr(), beta.data_ptr(),
+         B, HW, C, groups, eps, 1 if silu else 0)
+    return y
+
+
+def attention(qk: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, M: int, T: int, heads: int, head_dim: int):
+    _check_bf16_rows(qk, "attention qk")
+    _check_bf16_rows(vt, "attention vt")
+    _check_bf16_rows(out, "attention out")
+    call("idf_attention_fwd", qk.data_ptr(), qk.stride(0), vt.data_ptr(), vt.stride(0), out.data_ptr(), out.stride(0),
+         M, T, heads, head_dim, 1.0 / math.sqrt(head_dim))
+    return out
+
+
+def softmax_rows(s: torch.Tensor, out: torch.Tensor, scale: float) -> torch.Tensor:
+    call("idf_softmax_rows", s.data_ptr(), s.stride(0), out.data_ptr(), out.stride(0), s.shape[0], s.shape[1], scale)
+    return out
+
+
+def embed_time_class(t, ctx, ctx_mask, factor, w1, b1, w2, b2, class_w, wp, bp, out, scratch):
+    R, D, P = t.shape[0], factor.shape[0] * 2, wp.shape[0]
+    call("idf_embed_time_class", t.data_ptr(), ptr(ctx), ptr(ctx_mask), R, D, factor.data_ptr(), w1.data_ptr(),
+         b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), ptr(class_w), wp.data_ptr(), bp.data_ptr(), P, out.data_ptr(),
+         scratch.data_ptr())
+    return out
+
+
+def cfg_posterior_step(xt, eps_c, eps_u, noise, cfg, t, sched, x_prev, x0_out=None):
+    N = xt.shape[0]
+    chw = xt.numel() // N
+    t_stride = 0 if t.numel() == 1 else 1
+    call("idf_cfg_posterior_step", xt.data_ptr(), eps_c.data_ptr(), eps_u.data_ptr(), noise.data_ptr(), cfg.data_ptr(),
+         t.data_ptr(), t_stride, sched.betas.data_ptr(), sched.alphas.data_ptr(), sched.alpha_cum_prod.data_ptr(),
+         sched.sqrt_alpha_cum_prod.data_ptr(), sched.sqrt_one_minus_alpha_cum_prod.data_ptr(), x_prev.data_ptr(),
+         ptr(x0_out), N, chw)
+    return x_prev
+
+
+def add_noise(x, noise, t, sched, out):
+    N = x.shape[0]
+    call("idf_add_noise", x.data_ptr(), noise.data_ptr(), t.data_ptr(), sched.sqrt_alpha_cum_prod.data_ptr(),
+         sched.sqrt_one_minus_alpha_cum_prod.data_ptr(), out.data_ptr(), N, x.numel() // N)
+    return out
+
+
+def vq_argmin(z_rows: torch.Tensor, codebook: torch.Tensor, idx_out: torch.Tensor, zq_out=None):
+    rows, dim = z_rows.shape
+    call("idf_vq_argmin", z_rows.data_ptr(), codebook.data_ptr(), idx_out.data_ptr(), ptr(zq_out), rows, dim,
+         codebook.shape[0])
+    return idx_out
+
+
+def conv3x3_small_cin(x_nchw: torch.Tensor, w: torch.Tensor, bias, y: torch.Tensor):
+    B, Cin, H, W = x_nchw.shape
+    _check_bf16_rows(y, "conv_small_cin y")
+    call("idf_conv3x3_small_cin", x_nchw.data_ptr(), w.data_ptr(), ptr(bias), y.data_ptr(), y.stride(0), B, Cin, H, W,
+         w.shape[0])
+    return y
+
+
+def conv3x3_small_cout(x: torch.Tensor, w: torch.Tensor, bias, y_nchw: torch.Tensor):
+    B, Cout, H, W = y_nchw.shape
+    _check_bf16_rows(x, "conv_small_cout x")
+    call("idf_conv3x3_small_cout", x.data_ptr(), x.stride(0), w.data_ptr(), ptr(bias), y_nchw.data_ptr(), B,
+         w.shape[1], H, W, Cout)
+    return y_nchw
+
+
+def conv1x1_small_f32(x_nchw: torch.Tensor, w: torch.Tensor, bias, y_nchw: torch.Tensor):
+    B, Cin, H, W = x_nchw.shape
+    call("idf_conv1x1_small_f32", x_nchw.data_ptr(), w.data_ptr(), ptr(bias), y_nchw.data_ptr(), B, Cin, w.shape[0],
+         H * W)
+    return y_nchw
+
+
+def upsample_nearest2x(x: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, C: int):
+    call("idf_upsample_nearest2x", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), B, H, W, C)
+    return y
+
+
+def im2col_s2(x: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, C: int):
+    call("idf_im2col_s2", x.data_ptr(), x.stride(0), y.data_ptr(), B, H, W, C)
+    return y
+
+
+def nchw_to_rows(x_nchw: torch.Tensor, y: torch.Tensor):
+    B, Cc, H, W = x_nchw.shape
+    call("idf_nchw_f32_to_nhwc_bf16", x_nchw.data_ptr(), y.data_ptr(), y.stride(0), B, Cc, H * W)
+    return y
+
+
+def rows_to_nchw(x: torch.Tensor, y_nchw: torch.Tensor):
+    B, Cc, H, W = y_nchw.shape
+    call("idf_nhwc_bf16_to_nchw_f32", x.data_ptr(), x.stride(0), y_nchw.data_ptr(), B, Cc, H * W)
+    return y_nchw

@@ -1,0 +1,208 @@
+/*
+ * idf_b200.h — C ABI of libidf_b200.so, the sm_100a kernels behind the drop-in `modules.*` classes.
+ *
+ * The reference (jklimmek/image-diffusion) has no FFI: its boundary is the Python class surface
+ * (modules/unet.py, modules/components.py, modules/diffusion.py, modules/vae.py) and every FLOP is a stock
+ * torch op. Each entry point below names the reference call site(s) (file:line under the reference tree)
+ * whose arithmetic it replaces. The Python host code (image-diffusion_b200/idf_b200) binds these with ctypes.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers borrowed from the caller (torch tensors). The library never allocates
+ *     or frees device memory and keeps no pointer past return.
+ *   - Activations are channels-last (N, H, W, C) bf16 unless stated otherwise; "ld" arguments are row strides
+ *     in ELEMENTS of a (rows, channels) matrix whose rows are pixels/tokens.
+ *   - Every call is asynchronous on `stream` and safe to capture into a CUDA graph (no sync, no allocation).
+ *   - Return value: 0 = OK, non-zero = error (1 bad argument, 2 CUDA error, 3 unsupported shape); the message
+ *     is available from idf_last_error() on the calling thread. Nothing is ever routed to a CPU fallback.
+ */
+#ifndef IDF_B200_H_
+#define IDF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDF_B200_ABI_VERSION 1
+
+typedef struct CUstream_st* idf_stream_t;
+
+const char* idf_last_error(void);
+int idf_abi_version(void);
+
+/* A channels-last activation view: element (n, h, w, c) lives at ptr[n*sn + h*sh + w*sw + c]. A plain
+ * (rows, cols) matrix is the view n = 1, h = 1, w = rows, c = cols, sw = row stride. */
+typedef struct idf_nhwc {
+  const void* ptr;
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw;
+} idf_nhwc_t;
+
+/*
+ * idf_conv2d_igemm — implicit-GEMM convolution / linear layer on tcgen05 tensor cores.
+ *
+ *   out[m, :] = sum_seg sum_tap A_seg[pixel(m) + tap] . W[:, k-range(seg, tap)]^T  (+ epilogue terms)
+ *
+ * Replaces nn.Conv2d 3x3 s1 p1 (components.py:455, 33, 36, 125; unet.py:45,100), nn.Conv2d 1x1
+ * (components.py:501, 43), nn.Linear over tokens (components.py:81-83, 97) and the adds that follow them
+ * (components.py:527 time bias, :533 skip conv, :101 and :48 residual).
+ *
+ *   a[0], a[1]   one or two input segments (a[1].ptr == NULL for one). taps[i] is 9 (3x3, stride 1, zero
+ *                padding 1) or 1. Both segments share n/h/w; channel counts must be multiples of 64.
+ *   w            bf16 (N, ldw) row-major; column order is segment 0 taps (kh, kw) major then channel, followed
+ *                by segment 1 in the same order.
+ *   out          bf16 (M, ldo) written for columns [0, N) when out_f32 == 0, fp32 otherwise. M = n*h*w.
+ *   bias         fp32 [N] or NULL.
+ *   rowbias      fp32 (R, rowbias_ld) or NULL: row rowbias_idx[sample] (or `sample` when idx is NULL) is added
+ *                to every pixel of that sample (the per-sample time-projection bias).
+ *   res          bf16 (M, ldres) residual added in the epilogue, or NULL.
+ *   vt           when non-NULL, output columns >= vt_col0 are NOT written to `out` but transposed into
+ *                vt[(col - vt_col0) * vt_ld + m] (the V^T operand of idf_attention_fwd).
+ *   zero_pad_last  when 1, rows whose pixel is in the last output row or column are written as exact zeros
+ *                (Downsample's ConstantPad2d on the conv OUTPUT, components.py:110-117).
+ *   epi_h/epi_w  image geometry for rowbias / zero_pad_last when the A operand is a flattened matrix
+ *                (e.g. the im2col buffer of idf_im2col_s2); 0 means "use a[0].h / a[0].w".
+ */
+typedef struct idf_igemm_args {
+  idf_nhwc_t a[2];
+  int32_t taps[2];
+  const void* w;
+  int64_t ldw;
+  int32_t N;
+  void* out;
+  int64_t ldo;
+  int32_t out_f32;
+  const float* bias;
+  const float* rowbias;
+  const int32_t* rowbias_idx;
+  int32_t rowbias_ld;
+  const void* res;
+  int64_t ldres;
+  void* vt;
+  int32_t vt_col0;
+  int64_t vt_ld;
+  int32_t zero_pad_last;
+  int32_t epi_h, epi_w; /* output image geometry seen by the epilogue (sample = m / (epi_h*epi_w)); 0 = a[0].h/w */
+} idf_igemm_args;
+
+int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);
+
+/*
+ * idf_groupnorm_silu — GroupNorm(groups, C, eps, affine) optionally followed by SiLU, over a channels-last
+ * (B, HW, C) bf16 tensor; fp32 statistics. Replaces nn.GroupNorm + nn.SiLU (components.py:31-35, 58, 453-454;
+ * unet.py:98-99). x and y are (B*HW, ld) matrices; only C channels are read/written (lets the caller normalise
+ * into / out of a concatenated buffer).
+ */
+int idf_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
+                       int32_t B, int32_t HW, int32_t C, int32_t groups, float eps, int32_t apply_silu,
+                       idf_stream_t stream);
+
+/*
+ * idf_attention_fwd — fused softmax(Q K^T * scale) V per (sample, head), flash style on tcgen05 with the score
+ * tile in TMEM. Replaces components.py:86-94 (head split, QK^T / sqrt(hd), softmax, PV, head merge).
+ *   qk   bf16 (M, ld_qk): columns [0, C) are Q, [C, 2C) are K, C = heads*head_dim, head-major channel blocks.
+ *   vt   bf16 (C, ld_vt): V transposed (channel-major), as written by idf_conv2d_igemm's vt path.
+ *   out  bf16 (M, ld_out), columns [0, C).
+ *   M = B*T tokens; T tokens per sample (power of two, 16 <= T, T | 128 or 128 | T); head_dim in {16,32,48,64}.
+ */
+int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out, int64_t ld_out,
+                      int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale, idf_stream_t stream);
+
+/*
+ * idf_softmax_rows — out[r, :] = softmax(in[r, :] * scale), fp32 in, bf16 out. Used by the single-head
+ * head_dim = 384 attention of the VAE (components.py:91-92) where the score matrix is formed by two GEMMs.
+ */
+int idf_softmax_rows(const float* in, int64_t ld_in, void* out, int64_t ld_out, int32_t rows, int32_t cols,
+                     float scale, idf_stream_t stream);
+
+/*
+ * idf_embed_time_class — TimeEmbedding + class embedding + all per-layer time projections in one call.
+ * Replaces components.py:441-445, unet.py:106-114 and every `time_projs[i](timestep)` (components.py:526).
+ *   t[r]           int64 timestep of row r (R rows).
+ *   ctx[r]         int64 class id or NULL (unconditional); ctx_mask[r] fp32 multiplier or NULL (= 1).
+ *   factor         fp32 [time_dim/2] (the `time_embedding.factor` buffer).
+ *   w1,b1 / w2,b2  fp32 Linear(time_dim, 4*time_dim) / Linear(4*time_dim, time_dim).
+ *   class_w        fp32 (num_classes, time_dim).
+ *   wp, bp         fp32 (P, time_dim) / [P]: every layer's time_projs Linear stacked along rows.
+ *   out            fp32 (R, P): out[r] = wp @ silu(temb[r]) + bp, temb = MLP(sincos(t/factor)) + mask*class_w[ctx].
+ *   scratch        fp32, at least R * 5 * time_dim elements.
+ */
+int idf_embed_time_class(const int64_t* t, const int64_t* ctx, const float* ctx_mask, int32_t R, int32_t time_dim,
+                         const float* factor, const float* w1, const float* b1, const float* w2, const float* b2,
+                         const float* class_w, const float* wp, const float* bp, int32_t P, float* out,
+                         float* scratch, idf_stream_t stream);
+
+/*
+ * idf_cfg_posterior_step — classifier-free-guidance mix fused with the DDPM ancestral step: reads x_t, both
+ * epsilon predictions and the noise once, writes x_{t-1} once. Replaces diffusion.py:55 and
+ * components.py:405-424 (Scheduler.sample_prev_timestep), including the "no noise at t == 0" branch, with the
+ * timestep read on the device (no host sync).
+ *   eps_cond/eps_uncond  fp32 (N, chw); cfg[N] fp32 guidance scale per sample; sample n uses timestep
+ *   t[n * t_stride] (t_stride = 0: one device scalar for the batch) and, like the reference, the no-noise branch
+ *   is decided by t[0]; tables are the Scheduler's fp32 [num_steps] vectors.
+ *   x0_out may be NULL (the reference computes x0 and drops it).
+ */
+int idf_cfg_posterior_step(const float* xt, const float* eps_cond, const float* eps_uncond, const float* noise,
+                           const float* cfg, const int64_t* t, int32_t t_stride, const float* betas,
+                           const float* alphas,
+                           const float* alpha_cum_prod, const float* sqrt_alpha_cum_prod,
+                           const float* sqrt_one_minus_alpha_cum_prod, float* x_prev, float* x0_out, int32_t N,
+                           int32_t chw, idf_stream_t stream);
+
+/* idf_add_noise — sqrt(acp[t_n]) * x + sqrt(1 - acp[t_n]) * noise with per-sample t (components.py:399-403). */
+int idf_add_noise(const float* x, const float* noise, const int64_t* t, const float* sqrt_alpha_cum_prod,
+                  const float* sqrt_one_minus_alpha_cum_prod, float* out, int32_t N, int32_t chw,
+                  idf_stream_t stream);
+
+/*
+ * idf_vq_argmin — nearest codebook entry per latent vector, reproducing torch.cdist's matmul formulation
+ * (components.py:272-275): d2 = x1_ . x2_ with x1_ = [-2x, |x|^2, 1], x2_ = [e, 1, |e|^2], clamp_min(0), sqrt,
+ * first minimal index. z is fp32 (rows, dim) row-major, codebook fp32 (size, dim); idx_out int64 [rows];
+ * zq_out (optional) fp32 (rows, dim) receives codebook[idx].
+ */
+int idf_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, float* zq_out, int32_t rows,
+                  int32_t dim, int32_t size, idf_stream_t stream);
+
+/*
+ * idf_conv3x3_small_cin — direct 3x3 s1 p1 convolution for tiny Cin (the 3-channel latent): fp32 NCHW in,
+ * bf16 NHWC out. Replaces unet.py:45,116 (in_conv) and components.py:207-208 (decoder 1x1 folded by the
+ * caller + 3x3). w is fp32 OIHW, bias fp32 [Cout]; Cout % 8 == 0, Cin <= 8.
+ */
+int idf_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int64_t ldy, int32_t B,
+                          int32_t Cin, int32_t H, int32_t W, int32_t Cout, idf_stream_t stream);
+
+/*
+ * idf_conv3x3_small_cout — direct 3x3 s1 p1 convolution for tiny Cout: bf16 NHWC in (already normalised and
+ * activated), fp32 NCHW out. Replaces unet.py:100 (out_conv's Conv2d) and components.py:240,178. w fp32 OIHW.
+ */
+int idf_conv3x3_small_cout(const void* x, int64_t ldx, const float* w, const float* bias, float* y, int32_t B,
+                           int32_t Cin, int32_t H, int32_t W, int32_t Cout, idf_stream_t stream);
+
+/* idf_conv1x1_small_f32 — fp32 NCHW 1x1 convolution with a handful of channels (components.py:207 decoder's
+ * first conv, components.py:179 encoder's last conv). w fp32 (Cout, Cin). */
+int idf_conv1x1_small_f32(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin,
+                          int32_t Cout, int32_t HW, idf_stream_t stream);
+
+/* idf_upsample_nearest2x — nn.Upsample(scale_factor=2) (components.py:124,128) on channels-last bf16. */
+int idf_upsample_nearest2x(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t B, int32_t H, int32_t W,
+                           int32_t C, idf_stream_t stream);
+
+/*
+ * idf_im2col_s2 — gathers the 3x3 stride-2 pad-0 patches of Downsample (components.py:110) into a
+ * (B*OH*OW, 9*C) bf16 matrix with OH = H/2, OW = W/2; rows of the padded last output row/column are zero. The
+ * GEMM that follows runs with zero_pad_last = 1.
+ */
+int idf_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                  idf_stream_t stream);
+
+/* idf_nchw_f32_to_nhwc_bf16 / idf_nhwc_bf16_to_nchw_f32 — layout + dtype conversion at the module boundary. */
+int idf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t ldy, int32_t B, int32_t C, int32_t HW,
+                              idf_stream_t stream);
+int idf_nhwc_bf16_to_nchw_f32(const void* x, int64_t ldx, float* y, int32_t B, int32_t C, int32_t HW,
+                              idf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDF_B200_H_ */

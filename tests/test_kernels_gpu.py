@@ -1,0 +1,291 @@
+"""Kernel-level parity (B200): every C-ABI kernel against the same op in plain PyTorch fp32 on the same inputs.
+
+Inputs are rounded to bf16 first where the kernel consumes bf16, so the only differences left are fp32
+accumulation order and the final bf16 rounding of the output: tolerances are a few bf16 ulps of the output scale.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from idf_b200 import ops
+    return ops
+
+
+def rows(x_nchw):
+    """NCHW fp32 -> (B*H*W, C) bf16 channels-last matrix."""
+    B, C, H, W = x_nchw.shape
+    return x_nchw.permute(0, 2, 3, 1).reshape(B * H * W, C).to(torch.bfloat16).contiguous()
+
+
+def unrows(y, B, H, W):
+    return y.float().reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
+
+
+def rel_err(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H", [
+    (2, 128, 128, 32), (3, 256, 384, 16), (5, 384, 512, 8), (9, 512, 512, 4), (1, 512, 128, 32),
+    (2, 1024, 384, 8), (1, 128, 128, 64), (1, 128, 128, 128), (1, 64, 128, 4),
+])
+def test_conv3x3_igemm(B, Cin, Cout, H):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + Cin + Cout + H)
+    x = torch.randn(B, Cin, H, H, device=DEV, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, device=DEV, generator=g)
+    xr = rows(x)
+    out = torch.empty(B * H * H, Cout, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(xr, (B, H, H), Cin, 9)], ops.pack_conv_weight(w), Cout, out, bias=b)
+    ref = F.conv2d(bf(x), bf(w), b, padding=1)
+    got = unrows(out, B, H, H)
+    assert rel_err(got, ref) < 6e-3, rel_err(got, ref)
+    assert (got - ref).abs().max().item() < 0.06
+
+
+def test_conv3x3_rowbias_and_fused_skip():
+    """second_half conv3x3 + 1x1 skip conv as one two-segment GEMM, plus a per-sample time bias."""
+    ops = _ops()
+    B, C1, C2, Cout, H = 3, 256, 128, 256, 16
+    g = torch.Generator(device=DEV).manual_seed(7)
+    h = torch.randn(B, C1, H, H, device=DEV, generator=g)
+    x = torch.randn(B, C2, H, H, device=DEV, generator=g)
+    w3 = torch.randn(Cout, C1, 3, 3, device=DEV, generator=g) / math.sqrt(9 * C1)
+    w1 = torch.randn(Cout, C2, 1, 1, device=DEV, generator=g) / math.sqrt(C2)
+    b = torch.randn(Cout, device=DEV, generator=g)
+    table = torch.randn(4, 512, device=DEV, generator=g)
+    idx = torch.tensor([2, 0, 3], device=DEV, dtype=torch.int32)
+    wcat = torch.cat([ops.pack_conv_weight(w3), ops.pack_conv_weight(w1)], dim=1).contiguous()
+    out = torch.empty(B * H * H, Cout, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(rows(h), (B, H, H), C1, 9), (rows(x), (B, H, H), C2, 1)], wcat, Cout, out, bias=b,
+              rowbias=table[:, 128:128 + Cout], rowbias_idx=idx)
+    ref = F.conv2d(bf(h), bf(w3), b, padding=1) + F.conv2d(bf(x), bf(w1))
+    ref = ref + table[idx.long(), 128:128 + Cout][:, :, None, None]
+    got = unrows(out, B, H, H)
+    assert rel_err(got, ref) < 6e-3, rel_err(got, ref)
+
+
+def test_linear_residual_strided_output():
+    """out_proj + residual written into the right half of a concatenated buffer."""
+    ops = _ops()
+    M, K, N = 3 * 256, 384, 384
+    g = torch.Generator(device=DEV).manual_seed(11)
+    a = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    b = torch.randn(N, device=DEV, generator=g)
+    res = torch.randn(M, N, device=DEV, generator=g).to(torch.bfloat16)
+    cat = torch.zeros(M, 2 * N, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(a, (1, 1, M), K, 1)], w, N, cat[:, N:], bias=b, res=res)
+    ref = a.float() @ w.float().t() + b + res.float()
+    assert rel_err(cat[:, N:].float(), ref) < 6e-3
+    assert cat[:, :N].abs().max().item() == 0.0
+
+
+def test_gemm_small_m_and_f32_out():
+    ops = _ops()
+    M, K, N = 16, 512, 1536
+    g = torch.Generator(device=DEV).manual_seed(13)
+    a = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.igemm([(a, (1, 1, M), K, 1)], w, N, out)
+    ref = a.float() @ w.float().t()
+    assert rel_err(out, ref) < 1e-4, rel_err(out, ref)
+
+
+@pytest.mark.parametrize("B,T,heads,hd", [
+    (2, 1024, 8, 32), (1, 1024, 8, 16), (3, 256, 8, 48), (2, 256, 8, 32), (4, 64, 8, 64), (3, 64, 8, 48),
+    (9, 16, 8, 64), (1, 16, 8, 64),
+])
+def test_qkv_attention(B, T, heads, hd):
+    """QKV projection (V written transposed) followed by the fused attention kernel."""
+    ops = _ops()
+    Cc = heads * hd
+    M = B * T
+    g = torch.Generator(device=DEV).manual_seed(B * 100 + T + hd)
+    x = torch.randn(M, Cc, device=DEV, generator=g).to(torch.bfloat16)
+    wqkv = (torch.randn(3 * Cc, Cc, device=DEV, generator=g) * (1.5 / math.sqrt(Cc))).to(torch.bfloat16)
+    bqkv = torch.randn(3 * Cc, device=DEV, generator=g) * 0.1
+    qk = torch.empty(M, 2 * Cc, device=DEV, dtype=torch.bfloat16)
+    vt = torch.empty(Cc, M, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(x, (1, 1, M), Cc, 1)], wqkv, 3 * Cc, qk, bias=bqkv, vt=vt, vt_col0=2 * Cc)
+    qkv_ref = x.float() @ wqkv.float().t() + bqkv
+    assert rel_err(qk.float(), qkv_ref[:, :2 * Cc]) < 6e-3
+    assert rel_err(vt.float().t(), qkv_ref[:, 2 * Cc:]) < 6e-3
+
+    out = torch.empty(M, Cc, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qk, vt, out, M, T, heads, hd)
+    q = qk[:, :Cc].float().reshape(B, T, heads, hd).transpose(1, 2)
+    k = qk[:, Cc:].float().reshape(B, T, heads, hd).transpose(1, 2)
+    v = vt.float().t().reshape(B, T, heads, hd).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(M, Cc)
+    err = rel_err(out.float(), ref)
+    assert err < 1.5e-2, err
+
+
+@pytest.mark.parametrize("B,C,H,silu", [(3, 128, 32, True), (2, 384, 16, True), (2, 768, 16, True),
+                                        (5, 1024, 8, True), (4, 512, 4, False), (1, 256, 64, True)])
+def test_groupnorm_silu(B, C, H, silu):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(C + H)
+    x = torch.randn(B, C, H, H, device=DEV, generator=g) * 1.7 + 0.3
+    gamma = 1 + 0.2 * torch.randn(C, device=DEV, generator=g)
+    beta = 0.2 * torch.randn(C, device=DEV, generator=g)
+    xr = rows(x)
+    y = torch.empty_like(xr)
+    ops.groupnorm_silu(xr, y, gamma, beta, B, H * H, C, 32, silu)
+    ref = F.group_norm(bf(x), 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    got = unrows(y, B, H, H)
+    assert (got - ref).abs().max().item() < 0.04
+    assert rel_err(got, ref) < 5e-3
+
+
+def test_embed_time_class():
+    ops = _ops()
+    D, P, R = 512, 4864, 7
+    g = torch.Generator(device=DEV).manual_seed(3)
+    factor = 10000 ** (torch.arange(0, D // 2, dtype=torch.float32, device=DEV) / (D // 2))
+    w1 = torch.randn(4 * D, D, device=DEV, generator=g) / math.sqrt(D)
+    b1 = torch.randn(4 * D, device=DEV, generator=g) * 0.1
+    w2 = torch.randn(D, 4 * D, device=DEV, generator=g) / math.sqrt(4 * D)
+    b2 = torch.randn(D, device=DEV, generator=g) * 0.1
+    cw = torch.randn(3, D, device=DEV, generator=g)
+    wp = torch.randn(P, D, device=DEV, generator=g) / math.sqrt(D)
+    bp = torch.randn(P, device=DEV, generator=g) * 0.1
+    t = torch.tensor([0, 1, 17, 500, 998, 999, 999], device=DEV)
+    ctx = torch.tensor([0, 1, 2, 0, 1, 2, 0], device=DEV)
+    mask = torch.tensor([1, 1, 0, 1, 0, 1, 1], device=DEV, dtype=torch.float32)
+    out = torch.empty(R, P, device=DEV)
+    scratch = torch.empty(R * 5 * D, device=DEV)
+    ops.embed_time_class(t, ctx, mask, factor, w1, b1, w2, b2, cw, wp, bp, out, scratch)
+    with torch.no_grad():
+        e = t[:, None] / factor
+        e = torch.cat([torch.sin(e), torch.cos(e)], -1)
+        temb = F.linear(F.silu(F.linear(e, w1, b1)), w2, b2) + mask[:, None] * cw[ctx]
+        ref = F.linear(F.silu(temb), wp, bp)
+    assert (out - ref).abs().max().item() < 2e-3, (out - ref).abs().max().item()
+    out2 = torch.empty(R, P, device=DEV)
+    ops.embed_time_class(t, None, None, factor, w1, b1, w2, b2, cw, wp, bp, out2, scratch)
+    temb = F.linear(F.silu(F.linear(e, w1, b1)), w2, b2)
+    ref2 = F.linear(F.silu(temb), wp, bp)
+    assert (out2 - ref2).abs().max().item() < 2e-3
+
+
+def test_small_channel_convs_and_movers():
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    B, H = 3, 32
+    x = torch.randn(B, 3, H, H, device=DEV, generator=g)
+    w = torch.randn(128, 3, 3, 3, device=DEV, generator=g) / math.sqrt(27)
+    b = torch.randn(128, device=DEV, generator=g)
+    y = torch.empty(B * H * H, 128, device=DEV, dtype=torch.bfloat16)
+    ops.conv3x3_small_cin(x, w, b, y)
+    ref = F.conv2d(x, w, b, padding=1)
+    assert rel_err(unrows(y, B, H, H), ref) < 4e-3
+
+    hcl = torch.randn(B, 128, H, H, device=DEV, generator=g)
+    w2 = torch.randn(3, 128, 3, 3, device=DEV, generator=g) / math.sqrt(9 * 128)
+    b2 = torch.randn(3, device=DEV, generator=g)
+    out = torch.empty(B, 3, H, H, device=DEV)
+    ops.conv3x3_small_cout(rows(hcl), w2, b2, out)
+    ref = F.conv2d(bf(hcl), w2, b2, padding=1)
+    assert (out - ref).abs().max().item() < 1e-4
+
+    w11 = torch.randn(3, 3, device=DEV, generator=g)
+    b11 = torch.randn(3, device=DEV, generator=g)
+    o11 = torch.empty_like(x)
+    ops.conv1x1_small_f32(x, w11, b11, o11)
+    assert (o11 - F.conv2d(x, w11[:, :, None, None], b11)).abs().max().item() < 1e-5
+
+    xs = torch.randn(2, 256, 8, 8, device=DEV, generator=g)
+    up = torch.empty(2 * 16 * 16, 256, device=DEV, dtype=torch.bfloat16)
+    ops.upsample_nearest2x(rows(xs), up, 2, 8, 8, 256)
+    assert torch.equal(unrows(up, 2, 16, 16), F.interpolate(bf(xs), scale_factor=2))
+
+    back = torch.empty(2, 256, 8, 8, device=DEV)
+    ops.rows_to_nchw(ops.nchw_to_rows(xs, torch.empty(2 * 64, 256, device=DEV, dtype=torch.bfloat16)), back)
+    assert torch.equal(back, bf(xs))
+
+
+@pytest.mark.parametrize("B,C,H", [(2, 256, 32), (3, 384, 16), (5, 512, 8)])
+def test_downsample_im2col_gemm(B, C, H):
+    """Conv2d(C, C, 3, stride 2, pad 0) followed by ConstantPad2d((0,1,0,1)) on the OUTPUT."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(C)
+    x = torch.randn(B, C, H, H, device=DEV, generator=g)
+    w = torch.randn(C, C, 3, 3, device=DEV, generator=g) / math.sqrt(9 * C)
+    b = torch.randn(C, device=DEV, generator=g)
+    OH = H // 2
+    col = torch.empty(B * OH * OH, 9 * C, device=DEV, dtype=torch.bfloat16)
+    ops.im2col_s2(rows(x), col, B, H, H, C)
+    out = torch.empty(B * OH * OH, C, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(col, (1, 1, B * OH * OH), 9 * C, 1)], ops.pack_conv_weight(w), C, out, bias=b, zero_pad_last=True,
+              epi_hw=(OH, OH))
+    ref = F.pad(F.conv2d(bf(x), bf(w), b, stride=2), (0, 1, 0, 1))
+    got = unrows(out, B, OH, OH)
+    assert rel_err(got, ref) < 6e-3
+    assert got[:, :, -1, :].abs().max().item() == 0.0 and got[:, :, :, -1].abs().max().item() == 0.0
+
+
+def test_cfg_posterior_step():
+    ops = _ops()
+    from types import SimpleNamespace
+    T = 1000
+    betas = torch.linspace(1e-4 ** 0.5, 0.02 ** 0.5, T, device=DEV) ** 2
+    alphas = 1 - betas
+    acp = torch.cumprod(alphas, 0)
+    sched = SimpleNamespace(betas=betas, alphas=alphas, alpha_cum_prod=acp, sqrt_alpha_cum_prod=acp.sqrt(),
+                            sqrt_one_minus_alpha_cum_prod=(1 - acp).sqrt())
+    g = torch.Generator(device=DEV).manual_seed(9)
+    N = 6
+    xt, ec, eu, z = (torch.randn(N, 3, 32, 32, device=DEV, generator=g) for _ in range(4))
+    cfg = torch.tensor([1, 3, 5, 7, 9, 2], device=DEV, dtype=torch.float32)
+    for step in (999, 500, 1, 0):
+        t = torch.full((N,), step, device=DEV, dtype=torch.long)
+        out = torch.empty_like(xt)
+        x0 = torch.empty_like(xt)
+        ops.cfg_posterior_step(xt, ec, eu, z, cfg, t, sched, out, x0)
+        eps = eu + cfg.long()[:, None, None, None] * (ec - eu)
+        so, sa = sched.sqrt_one_minus_alpha_cum_prod[t].view(-1, 1, 1, 1), sched.sqrt_alpha_cum_prod[t].view(-1, 1, 1, 1)
+        x0_ref = ((xt - so * eps) / sa).clamp(-1, 1)
+        mean = (xt - betas[t].view(-1, 1, 1, 1) * eps / so) / alphas[t].view(-1, 1, 1, 1).sqrt()
+        if step > 0:
+            var = (1 - acp[t - 1]) / (1 - acp[t]) * betas[t]
+            mean = mean + (var ** 0.5).view(-1, 1, 1, 1) * z
+        assert (out - mean).abs().max().item() <= 1e-5 * mean.abs().max().item()
+        assert (x0 - x0_ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("spread", ["default_init", "normal"])
+def test_vq_argmin_bit_exact(spread):
+    """Indices must equal torch.cdist(...).argmin on the same device, including near-ties."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(21)
+    B, size, dim = 16, 1024, 3
+    z = torch.randn(B, 1024, dim, device=DEV, generator=g)
+    if spread == "default_init":
+        cb = (torch.rand(size, dim, device=DEV, generator=g) * 2 - 1) / size
+    else:
+        cb = torch.randn(size, dim, device=DEV, generator=g)
+    ref = torch.cdist(z, cb[None].repeat(B, 1, 1)).argmin(dim=-1).view(-1)
+    idx = torch.empty(B * 1024, device=DEV, dtype=torch.long)
+    zq = torch.empty(B * 1024, dim, device=DEV)
+    ops.vq_argmin(z.reshape(-1, dim).contiguous(), cb, idx, zq)
+    mism = (idx != ref).sum().item()
+    assert mism == 0, f"{mism} / {idx.numel()} indices differ"
+    assert torch.equal(zq, cb[ref])
