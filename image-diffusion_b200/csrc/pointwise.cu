@@ -119,32 +119,49 @@ __global__ void add_noise_kernel(const float* __restrict__ x, const float* __res
 // VQ nearest code: one warp per latent vector, codebook (augmented with its norms) in shared memory,
 // lanes stride over the codes, warp-shuffle (distance, index) min-reduction with first-index tie break.
 // ---------------------------------------------------------------------------------------------
+// |v|^2 exactly as ATen's CUDA reduce kernel evaluates v.pow(2).sum(-1) for a tiny last dimension: squares are
+// rounded separately (no FMA), lane i of a power-of-two-wide group sums elements i, i+w, ... and the group is
+// folded with a halving tree. For DIM = 3 this is (v0^2 + v2^2) + v1^2, verified bit-for-bit on B200
+// (tools/diag_cdist.py); other DIMs follow the same scheme but are unverified.
+template <int DIM>
+__device__ __forceinline__ float aten_sumsq(const float (&v)[DIM]) {
+  constexpr int WIDTH = DIM >= 8 ? 8 : (DIM >= 4 ? 4 : (DIM >= 2 ? 2 : 1));
+  float part[WIDTH];
+#pragma unroll
+  for (int i = 0; i < WIDTH; ++i) {
+    part[i] = __fmul_rn(v[i], v[i]);
+#pragma unroll
+    for (int j = i + WIDTH; j < DIM; j += WIDTH) part[i] = __fadd_rn(part[i], __fmul_rn(v[j], v[j]));
+  }
+#pragma unroll
+  for (int off = WIDTH / 2; off > 0; off >>= 1)
+#pragma unroll
+    for (int i = 0; i < off; ++i) part[i] = __fadd_rn(part[i], part[i + off]);
+  return part[0];
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb,
                                                         int64_t* __restrict__ idx_out, float* __restrict__ zq_out,
                                                         int rows, int size) {
   extern __shared__ float s_cb[];  // [size][DIM + 1]: code, |code|^2
   for (int i = threadIdx.x; i < size; i += blockDim.x) {
-    float nrm = 0.f;
+    float ev[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
-      const float e = cb[(long long)i * DIM + d];
-      s_cb[i * (DIM + 1) + d] = e;
-      nrm += e * e;  // pow(2).sum(-1): sequential over the last dim
+      ev[d] = cb[(long long)i * DIM + d];
+      s_cb[i * (DIM + 1) + d] = ev[d];
     }
-    s_cb[i * (DIM + 1) + DIM] = nrm;
+    s_cb[i * (DIM + 1) + DIM] = aten_sumsq<DIM>(ev);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
     float xv[DIM];
-    float xn = 0.f;
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      xv[d] = z[(long long)row * DIM + d];
-      xn += xv[d] * xv[d];
-    }
+    for (int d = 0; d < DIM; ++d) xv[d] = z[(long long)row * DIM + d];
+    const float xn = aten_sumsq<DIM>(xv);
     float best = INFINITY;
     int best_i = 0x7fffffff;
     for (int i = lane; i < size; i += 32) {

@@ -11,6 +11,10 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+# the PyTorch side must be true fp32 (cuDNN/cuBLAS default to TF32 for convolutions)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 DEV = "cuda"
 
 
