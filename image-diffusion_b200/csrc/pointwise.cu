@@ -80,7 +80,7 @@ __global__ void cfg_posterior_kernel(const float* __restrict__ xt, const float* 
                                      const float* __restrict__ betas, const float* __restrict__ alphas,
                                      const float* __restrict__ acp, const float* __restrict__ sacp,
                                      const float* __restrict__ somacp, float* __restrict__ x_prev,
-                                     float* __restrict__ x0_out, int N, int chw) {
+                                     float* __restrict__ x_prev_dup, float* __restrict__ x0_out, int N, int chw) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * chw) return;
   const int n = (int)(i / chw);
@@ -97,13 +97,14 @@ __global__ void cfg_posterior_kernel(const float* __restrict__ xt, const float* 
   }
   float mean = x - (b * eps) / so;
   mean = mean / sqrtf(alphas[tn]);
-  if (t_first == 0) {
-    x_prev[i] = mean;
-  } else {
+  float out = mean;
+  if (t_first != 0) {
     float var = (1.f - acp[tn - 1]) / (1.f - acp[tn]);
     var = var * b;
-    x_prev[i] = mean + sqrtf(var) * z[i];
+    out = mean + sqrtf(var) * z[i];
   }
+  x_prev[i] = out;  // may alias xt: every thread reads its own element before writing it
+  if (x_prev_dup != nullptr) x_prev_dup[i] = out;
 }
 
 __global__ void add_noise_kernel(const float* __restrict__ x, const float* __restrict__ noise,
@@ -143,7 +144,7 @@ __device__ __forceinline__ float aten_sumsq(const float (&v)[DIM]) {
 template <int DIM>
 __global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb,
                                                         int64_t* __restrict__ idx_out, float* __restrict__ zq_out,
-                                                        int rows, int size) {
+                                                        int rows, int size, int hw) {
   extern __shared__ float s_cb[];  // [size][DIM + 1]: code, |code|^2
   for (int i = threadIdx.x; i < size; i += blockDim.x) {
     float ev[DIM];
@@ -160,7 +161,11 @@ __global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict_
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
     float xv[DIM];
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) xv[d] = z[(long long)row * DIM + d];
+    // hw > 0: z and zq are NCHW tensors with hw pixels per image (row = image * hw + pixel); else row-major rows
+    const long long base = hw > 0 ? ((long long)(row / hw) * DIM * hw + row % hw) : (long long)row * DIM;
+    const long long dstride = hw > 0 ? hw : 1;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) xv[d] = z[base + d * dstride];
     const float xn = aten_sumsq<DIM>(xv);
     float best = INFINITY;
     int best_i = 0x7fffffff;
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict_
       }
     }
     if (lane == 0) idx_out[row] = (int64_t)best_i;
-    if (zq_out != nullptr && lane < DIM) zq_out[(long long)row * DIM + lane] = s_cb[best_i * (DIM + 1) + lane];
+    if (zq_out != nullptr && lane < DIM) zq_out[base + lane * dstride] = s_cb[best_i * (DIM + 1) + lane];
   }
 }
 
@@ -414,14 +419,15 @@ extern "C" int idf_cfg_posterior_step(const float* xt, const float* eps_cond, co
                                       const float* noise, const float* cfg, const int64_t* t, int32_t t_stride,
                                       const float* betas, const float* alphas, const float* alpha_cum_prod,
                                       const float* sqrt_alpha_cum_prod, const float* sqrt_one_minus_alpha_cum_prod,
-                                      float* x_prev, float* x0_out, int32_t N, int32_t chw, idf_stream_t stream) {
+                                      float* x_prev, float* x_prev_dup, float* x0_out, int32_t N, int32_t chw,
+                                      idf_stream_t stream) {
   if (!xt || !eps_cond || !eps_uncond || !noise || !cfg || !t || !betas || !alphas || !alpha_cum_prod ||
       !sqrt_alpha_cum_prod || !sqrt_one_minus_alpha_cum_prod || !x_prev)
     return fail(IDF_ERR_ARG, "cfg_posterior: null pointer");
   const long long n = (long long)N * chw;
   cfg_posterior_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       xt, eps_cond, eps_uncond, noise, cfg, t, t_stride, betas, alphas, alpha_cum_prod, sqrt_alpha_cum_prod,
-      sqrt_one_minus_alpha_cum_prod, x_prev, x0_out, N, chw);
+      sqrt_one_minus_alpha_cum_prod, x_prev, x_prev_dup, x0_out, N, chw);
   return check_cuda(cudaGetLastError(), "cfg_posterior launch");
 }
 
@@ -436,7 +442,7 @@ extern "C" int idf_add_noise(const float* x, const float* noise, const int64_t* 
 }
 
 extern "C" int idf_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, float* zq_out, int32_t rows,
-                             int32_t dim, int32_t size, idf_stream_t stream) {
+                             int32_t dim, int32_t size, int32_t nchw_hw, idf_stream_t stream) {
   if (!z || !codebook || !idx_out) return fail(IDF_ERR_ARG, "vq_argmin: null pointer");
   if (rows <= 0 || size <= 0) return fail(IDF_ERR_ARG, "vq_argmin: bad shape");
   const int smem = size * (dim + 1) * 4;
@@ -444,9 +450,9 @@ extern "C" int idf_vq_argmin(const float* z, const float* codebook, int64_t* idx
   const unsigned grid = blocks_for((long long)rows, 8, 148 * 8);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (dim) {
-    case 3: vq_argmin_kernel<3><<<grid, 256, smem, s>>>(z, codebook, idx_out, zq_out, rows, size); break;
-    case 4: vq_argmin_kernel<4><<<grid, 256, smem, s>>>(z, codebook, idx_out, zq_out, rows, size); break;
-    case 8: vq_argmin_kernel<8><<<grid, 256, smem, s>>>(z, codebook, idx_out, zq_out, rows, size); break;
+    case 3: vq_argmin_kernel<3><<<grid, 256, smem, s>>>(z, codebook, idx_out, zq_out, rows, size, nchw_hw); break;
+    case 4: vq_argmin_kernel<4><<<grid, 256, smem, s>>>(z, codebook, idx_out, zq_out, rows, size, nchw_hw); break;
+    case 8: vq_argmin_kernel<8><<<grid, 256, smem, s>>>(z, codebook, idx_out, zq_out, rows, size, nchw_hw); break;
     default: return fail(IDF_ERR_UNSUPPORTED, "vq_argmin: dim %d not in {3,4,8}", dim);
   }
   return check_cuda(cudaGetLastError(), "vq_argmin launch");

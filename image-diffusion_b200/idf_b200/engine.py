@@ -1,0 +1,371 @@
+"""Execution engines: turn a parameter tree (drop-in Unet / VAE module) into a fixed sequence of C-ABI kernel calls
+over persistent channels-last bf16 workspaces. One engine instance serves one (batch, resolution); the whole call
+sequence is allocation-free after the first run, so it can be captured into a CUDA graph.
+
+Kernel sequence per DiffusionBlock layer (reference components.py:518-536):
+  GN+SiLU -> conv3x3 (+bias +time bias) -> GN+SiLU -> [conv3x3 (+) 1x1 skip conv] -> GN -> QKV GEMM (V transposed)
+  -> fused attention -> out_proj GEMM (+bias +residual)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .spec import unet_blocks, vae_program
+
+BF16 = torch.bfloat16
+
+
+class Act:
+    """A channels-last activation: 2-D bf16 view of shape (B*H*W, C) (row stride may exceed C)."""
+    __slots__ = ("t", "B", "H", "W", "C")
+
+    def __init__(self, t, B, H, W, C):
+        self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+
+    @property
+    def M(self):
+        return self.B * self.H * self.W
+
+    @property
+    def grid(self):
+        return (self.B, self.H, self.W)
+
+
+class Workspace:
+    """Named persistent device buffers; a name is allocated once and reused by every later call."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, rows, cols, dtype=BF16):
+        key = (name, rows, cols, dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(rows, cols, device=self.device, dtype=dtype)
+            self.bufs[key] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+def _f32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _Packed:
+    """bf16 / fp32 device copies of a module's parameters in the layouts the kernels consume; rebuilt whenever a
+    parameter has been modified in place or replaced (optimizer step, load_state_dict, .to())."""
+
+    def __init__(self, module):
+        self.module = module
+        self.key = None
+        self.w = {}
+
+    def stale(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+        if key != self.key:
+            self.key = key
+            return True
+        return False
+
+    def sd(self):
+        return {k: v for k, v in self.module.state_dict().items()}
+
+
+# =================================================================================================
+# UNet
+# =================================================================================================
+class UnetEngine:
+    def __init__(self, module, arch, device):
+        self.m, self.arch, self.device = module, arch, device
+        self.packed = _Packed(module)
+        self.ws = Workspace(device)
+        self.L, self.heads, self.G = arch["num_res_layers"], arch["num_heads"], arch["num_groups"]
+        self.downs, self.mids, self.ups = unet_blocks(arch)
+        for _, cin, cout in self.downs + self.mids + self.ups:
+            if cin % 64 or cout % 128:
+                raise ValueError(f"UnetEngine: block {cin}->{cout}: the tcgen05 path needs Cin % 64 == 0 and "
+                                 f"Cout % 128 == 0")
+        self.P = 0
+        self.tp_off = {}
+        for p, _, cout in self.downs + self.mids + self.ups:
+            for l in range(self.L):
+                self.tp_off[(p, l)] = self.P
+                self.P += cout
+
+    # ---------------------------------------------------------------------------------------------
+    def prepare(self):
+        if not self.packed.stale():
+            return
+        sd = self.packed.sd()
+        w = {}
+        pk = ops.pack_conv_weight
+        for p, cin, cout in self.downs + self.mids + self.ups:
+            for l in range(self.L):
+                a = f"{p}.self_attns.{l}"
+                w[f"{p}.{l}.w1"] = pk(sd[f"{p}.first_halfs.{l}.layers.2.weight"])
+                w[f"{p}.{l}.b1"] = _f32(sd[f"{p}.first_halfs.{l}.layers.2.bias"])
+                w[f"{p}.{l}.w2"] = torch.cat([pk(sd[f"{p}.second_halfs.{l}.layers.2.weight"]),
+                                             pk(sd[f"{p}.residuals.{l}.weight"])], dim=1).contiguous()
+                w[f"{p}.{l}.b2"] = _f32(sd[f"{p}.second_halfs.{l}.layers.2.bias"] + sd[f"{p}.residuals.{l}.bias"])
+                w[f"{p}.{l}.wqkv"] = torch.cat([sd[a + ".to_q.weight"], sd[a + ".to_k.weight"],
+                                                sd[a + ".to_v.weight"]], dim=0).to(BF16).contiguous()
+                w[f"{p}.{l}.bqkv"] = _f32(torch.cat([sd[a + ".to_q.bias"], sd[a + ".to_k.bias"],
+                                                     sd[a + ".to_v.bias"]]))
+                w[f"{p}.{l}.wo"] = sd[a + ".out_proj.weight"].detach().to(BF16).contiguous()
+                w[f"{p}.{l}.bo"] = _f32(sd[a + ".out_proj.bias"])
+                for n, key in (("g1", f"{p}.first_halfs.{l}.layers.0"), ("g2", f"{p}.second_halfs.{l}.layers.0"),
+                               ("g3", a + ".groupnorm")):
+                    w[f"{p}.{l}.{n}w"] = _f32(sd[key + ".weight"])
+                    w[f"{p}.{l}.{n}b"] = _f32(sd[key + ".bias"])
+        for i in range(len(self.downs)):
+            w[f"down.{i}.w"] = pk(sd[f"downsamples.{i}.down.weight"])
+            w[f"down.{i}.b"] = _f32(sd[f"downsamples.{i}.down.bias"])
+            w[f"up.{i}.w"] = pk(sd[f"upsamples.{i}.conv.weight"])
+            w[f"up.{i}.b"] = _f32(sd[f"upsamples.{i}.conv.bias"])
+        w["in.w"], w["in.b"] = _f32(sd["in_conv.weight"]), _f32(sd["in_conv.bias"])
+        w["out.gw"], w["out.gb"] = _f32(sd["out_conv.0.weight"]), _f32(sd["out_conv.0.bias"])
+        w["out.w"], w["out.b"] = _f32(sd["out_conv.2.weight"]), _f32(sd["out_conv.2.bias"])
+        w["t.factor"] = _f32(sd["time_embedding.factor"])
+        w["t.w1"], w["t.b1"] = _f32(sd["time_embedding.embeddings.0.weight"]), _f32(sd["time_embedding.embeddings.0.bias"])
+        w["t.w2"], w["t.b2"] = _f32(sd["time_embedding.embeddings.2.weight"]), _f32(sd["time_embedding.embeddings.2.bias"])
+        w["t.cls"] = _f32(sd["class_embedding.weight"])
+        order = [(p, l) for p, _, _ in self.downs + self.mids + self.ups for l in range(self.L)]
+        w["t.wp"] = _f32(torch.cat([sd[f"{p}.time_projs.{l}.1.weight"] for p, l in order], dim=0))
+        w["t.bp"] = _f32(torch.cat([sd[f"{p}.time_projs.{l}.1.bias"] for p, l in order], dim=0))
+        self.packed.w = w
+
+    # ---------------------------------------------------------------------------------------------
+    def _block(self, p, x: Act, cout, table, idx, final_dst=None) -> Act:
+        w, ws, G = self.packed.w, self.ws, self.G
+        B, H, W = x.grid
+        M, HW = x.M, x.H * x.W
+        hd = cout // self.heads
+        for l in range(self.L):
+            cin = x.C
+            k = f"{p}.{l}"
+            h1 = ws.get("h1", M, cin)
+            ops.groupnorm_silu(x.t, h1, w[k + ".g1w"], w[k + ".g1b"], B, HW, cin, G, True)
+            y1 = ws.get("y1", M, cout)
+            off = self.tp_off[(p, l)]
+            ops.igemm([(h1, x.grid, cin, 9)], w[k + ".w1"], cout, y1, bias=w[k + ".b1"],
+                      rowbias=table[:, off:off + cout], rowbias_idx=idx)
+            h2 = ws.get("h2", M, cout)
+            ops.groupnorm_silu(y1, h2, w[k + ".g2w"], w[k + ".g2b"], B, HW, cout, G, True)
+            x2 = ws.get("x2", M, cout)
+            ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"])
+            h3 = ws.get("h3", M, cout)
+            ops.groupnorm_silu(x2, h3, w[k + ".g3w"], w[k + ".g3b"], B, HW, cout, G, False)
+            qk = ws.get("qk", M, 2 * cout)
+            vt = ws.get("vt", cout, M)
+            ops.igemm([(h3, (1, 1, M), cout, 1)], w[k + ".wqkv"], 3 * cout, qk, bias=w[k + ".bqkv"], vt=vt,
+                      vt_col0=2 * cout)
+            o = ws.get("o", M, cout)
+            ops.attention(qk, vt, o, M, HW, self.heads, hd)
+            if l == self.L - 1 and final_dst is not None:
+                dst = final_dst
+            else:
+                dst = ws.get("xa" if (l % 2 == 0) else "xb", M, cout)
+            ops.igemm([(o, (1, 1, M), cout, 1)], w[k + ".wo"], cout, dst, bias=w[k + ".bo"], res=x2)
+            x = Act(dst, B, H, W, cout)
+        return x
+
+    def run(self, x_nchw, t_rows, ctx_rows, mask_rows, row_idx, out_nchw):
+        """x_nchw fp32 (B, z, H, W) -> out_nchw fp32 (B, z, H, W).
+
+        t_rows int64 (R,), ctx_rows int64 (R,) or None, mask_rows fp32 (R,) or None describe R distinct
+        (timestep, class) embedding rows; row_idx int32 (B,) maps each sample to its row (None: R == B, identity).
+        """
+        self.prepare()
+        w, ws = self.packed.w, self.ws
+        B, _, H, W = x_nchw.shape
+        R = t_rows.shape[0]
+        D = self.arch["time_dim"]
+        table = ws.get("tp_table", R, self.P, torch.float32)
+        scratch = ws.get("tp_scratch", R, 5 * D, torch.float32)
+        ops.embed_time_class(t_rows, ctx_rows, mask_rows, w["t.factor"], w["t.w1"], w["t.b1"], w["t.w2"], w["t.b2"],
+                             w["t.cls"], w["t.wp"], w["t.bp"], table, scratch)
+        ch = list(self.arch["channels"])
+        a0 = ws.get("in", B * H * W, ch[0])
+        ops.conv3x3_small_cin(x_nchw, w["in.w"], w["in.b"], a0)
+        x = Act(a0, B, H, W, ch[0])
+        cats = []
+        for i, (p, cin, cout) in enumerate(self.downs):
+            cat = ws.get(f"cat{i}", x.M, 2 * cout)
+            cats.append(cat)
+            x = self._block(p, x, cout, table, row_idx, final_dst=cat[:, cout:])
+            col = ws.get("col", x.M // 4, 9 * cout)
+            ops.im2col_s2(x.t, col, x.B, x.H, x.W, cout)
+            nxt = ws.get("dn", x.M // 4, cout)
+            ops.igemm([(col, (1, 1, x.M // 4), 9 * cout, 1)], w[f"down.{i}.w"], cout, nxt, bias=w[f"down.{i}.b"],
+                      zero_pad_last=True, epi_hw=(x.H // 2, x.W // 2))
+            x = Act(nxt, x.B, x.H // 2, x.W // 2, cout)
+        for p, cin, cout in self.mids:
+            x = self._block(p, x, cout, table, row_idx)
+        for i, (p, cin, cout) in enumerate(self.ups):
+            c = x.C
+            up = ws.get("up", 4 * x.M, c)
+            ops.upsample_nearest2x(x.t, up, x.B, x.H, x.W, c)
+            cat = cats.pop()
+            ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), c, 9)], w[f"up.{i}.w"], c, cat[:, :c], bias=w[f"up.{i}.b"])
+            x = self._block(p, Act(cat, x.B, 2 * x.H, 2 * x.W, 2 * c), cout, table, row_idx)
+        h = ws.get("h1", x.M, x.C)
+        ops.groupnorm_silu(x.t, h, w["out.gw"], w["out.gb"], x.B, x.H * x.W, x.C, self.G, True)
+        ops.conv3x3_small_cout(h, w["out.w"], w["out.b"], out_nchw)
+        return out_nchw
+
+
+# =================================================================================================
+# VAE encoder / decoder
+# =================================================================================================
+class VaeEngine:
+    """Runs Encoder.down / Decoder.up (components.py:133-246) for one (batch, resolution)."""
+
+    def __init__(self, module, arch, device):
+        self.m, self.arch, self.device = module, arch, device
+        self.packed = _Packed(module)
+        self.ws = Workspace(device)
+        self.G, self.heads = arch["num_groups"], arch["num_heads"]
+
+    def prepare(self):
+        if not self.packed.stale():
+            return
+        sd = self.packed.sd()
+        w = {}
+        pk = ops.pack_conv_weight
+        for part, prefix in (("encoder", "encoder.down"), ("decoder", "decoder.up")):
+            for kind, i, cin, cout in vae_program(self.arch, part):
+                p = f"{prefix}.{i}"
+                if kind in ("conv1x1", "conv3x3"):
+                    w[p + ".w"], w[p + ".b"] = _f32(sd[p + ".weight"]), _f32(sd[p + ".bias"])
+                elif kind == "res":
+                    w[p + ".g1w"], w[p + ".g1b"] = _f32(sd[p + ".branch.0.weight"]), _f32(sd[p + ".branch.0.bias"])
+                    w[p + ".g2w"], w[p + ".g2b"] = _f32(sd[p + ".branch.3.weight"]), _f32(sd[p + ".branch.3.bias"])
+                    w[p + ".w1"], w[p + ".b1"] = pk(sd[p + ".branch.2.weight"]), _f32(sd[p + ".branch.2.bias"])
+                    if cin != cout:
+                        w[p + ".w2"] = torch.cat([pk(sd[p + ".branch.5.weight"]),
+                                                  pk(sd[p + ".residual_wrapper.weight"])], dim=1).contiguous()
+                        w[p + ".b2"] = _f32(sd[p + ".branch.5.bias"] + sd[p + ".residual_wrapper.bias"])
+                    else:
+                        w[p + ".w2"], w[p + ".b2"] = pk(sd[p + ".branch.5.weight"]), _f32(sd[p + ".branch.5.bias"])
+                elif kind == "attn":
+                    w[p + ".gw"], w[p + ".gb"] = _f32(sd[p + ".groupnorm.weight"]), _f32(sd[p + ".groupnorm.bias"])
+                    w[p + ".wqkv"] = torch.cat([sd[p + ".to_q.weight"], sd[p + ".to_k.weight"],
+                                                sd[p + ".to_v.weight"]], dim=0).to(BF16).contiguous()
+                    w[p + ".bqkv"] = _f32(torch.cat([sd[p + ".to_q.bias"], sd[p + ".to_k.bias"], sd[p + ".to_v.bias"]]))
+                    w[p + ".wo"], w[p + ".bo"] = sd[p + ".out_proj.weight"].detach().to(BF16).contiguous(), _f32(sd[p + ".out_proj.bias"])
+                elif kind in ("up", "down"):
+                    n = "conv" if kind == "up" else "down"
+                    w[p + ".w"], w[p + ".b"] = pk(sd[f"{p}.{n}.weight"]), _f32(sd[f"{p}.{n}.bias"])
+                elif kind == "gn_silu":
+                    w[p + ".gw"], w[p + ".gb"] = _f32(sd[p + ".weight"]), _f32(sd[p + ".bias"])
+        self.packed.w = w
+
+    # ---- layer runners -------------------------------------------------------------------------
+    def _res(self, p, x: Act, cout) -> Act:
+        w, ws, G = self.packed.w, self.ws, self.G
+        B, H, W = x.grid
+        M, HW, cin = x.M, x.H * x.W, x.C
+        h1 = ws.get("h1", M, cin)
+        ops.groupnorm_silu(x.t, h1, w[p + ".g1w"], w[p + ".g1b"], B, HW, cin, G, True)
+        y1 = ws.get("y1", M, cout)
+        ops.igemm([(h1, x.grid, cin, 9)], w[p + ".w1"], cout, y1, bias=w[p + ".b1"])
+        h2 = ws.get("h2", M, cout)
+        ops.groupnorm_silu(y1, h2, w[p + ".g2w"], w[p + ".g2b"], B, HW, cout, G, True)
+        dst = ws.get("xa" if x.t is not self.ws.bufs.get(("xa", M, cout, BF16)) else "xb", M, cout)
+        if cin != cout:
+            ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[p + ".w2"], cout, dst, bias=w[p + ".b2"])
+        else:
+            ops.igemm([(h2, x.grid, cout, 9)], w[p + ".w2"], cout, dst, bias=w[p + ".b2"], res=x.t)
+        return Act(dst, B, H, W, cout)
+
+    def _attn(self, p, x: Act) -> Act:
+        """GroupNorm -> QKV -> softmax(QK^T/sqrt(hd)) V -> out_proj + x (components.py:64-103). head_dim <= 64 uses
+        the fused kernel; the VAE's single 384-wide head forms the score matrix with two GEMMs per sample."""
+        w, ws = self.packed.w, self.ws
+        B, H, W = x.grid
+        M, T, C = x.M, x.H * x.W, x.C
+        hd = C // self.heads
+        h3 = ws.get("h3", M, C)
+        ops.groupnorm_silu(x.t, h3, w[p + ".gw"], w[p + ".gb"], B, T, C, self.G, False)
+        qk = ws.get("qk", M, 2 * C)
+        vt = ws.get("vt", C, M)
+        ops.igemm([(h3, (1, 1, M), C, 1)], w[p + ".wqkv"], 3 * C, qk, bias=w[p + ".bqkv"], vt=vt, vt_col0=2 * C)
+        o = ws.get("o", M, C)
+        if hd in (16, 32, 48, 64):
+            ops.attention(qk, vt, o, M, T, self.heads, hd)
+        else:
+            if T % 128 or hd % 128:
+                raise ValueError(f"VaeEngine attention: T={T}, head_dim={hd} unsupported by the GEMM-pair path")
+            s = ws.get("scores", T, T, torch.float32)
+            pm = ws.get("probs", T, T)
+            scale = 1.0 / (hd ** 0.5)
+            for b in range(B):
+                for hh in range(self.heads):
+                    rows = slice(b * T, (b + 1) * T)
+                    q = qk[rows, hh * hd:(hh + 1) * hd]
+                    kk = qk[rows, C + hh * hd:C + (hh + 1) * hd]
+                    ops.igemm([(q, (1, 1, T), hd, 1)], kk, T, s)                      # S = Q K^T  (fp32)
+                    ops.softmax_rows(s, pm, scale)                                     # P = softmax(S / sqrt(hd))
+                    ops.igemm([(pm, (1, 1, T), T, 1)], vt[hh * hd:(hh + 1) * hd, rows], hd,
+                              o[rows, hh * hd:(hh + 1) * hd])                          # O = P V
+        dst = ws.get("xa" if x.t is not self.ws.bufs.get(("xa", M, C, BF16)) else "xb", M, C)
+        ops.igemm([(o, (1, 1, M), C, 1)], w[p + ".wo"], C, dst, bias=w[p + ".bo"], res=x.t)
+        return Act(dst, B, H, W, C)
+
+    def _run(self, part, prefix, x_nchw, out_nchw):
+        self.prepare()
+        w, ws = self.packed.w, self.ws
+        B, _, H, W = x_nchw.shape
+        prog = vae_program(self.arch, part)
+        x = None
+        cur = x_nchw
+        for n, (kind, i, cin, cout) in enumerate(prog):
+            p = f"{prefix}.{i}"
+            if kind == "conv1x1":  # tiny channel count, stays fp32 NCHW
+                dst = out_nchw if n == len(prog) - 1 else ws.get(f"c11_{p}", B * cout, cur.shape[2] * cur.shape[3],
+                                                               torch.float32).view(B, cout, cur.shape[2], cur.shape[3])
+                if x is not None:  # encoder tail: previous conv3x3 wrote fp32 NCHW into `cur`
+                    pass
+                ops.conv1x1_small_f32(cur, w[p + ".w"].view(cout, cin), w[p + ".b"], dst)
+                cur = dst
+            elif kind == "conv3x3" and x is None:  # first wide conv: fp32 NCHW -> bf16 rows
+                a0 = ws.get("in", B * H * W, cout)
+                ops.conv3x3_small_cin(cur, w[p + ".w"], w[p + ".b"], a0)
+                x = Act(a0, B, H, W, cout)
+            elif kind == "conv3x3":  # last narrow conv: bf16 rows -> fp32 NCHW
+                last = n == len(prog) - 1
+                dst = out_nchw if last else ws.get("tail", B * cout, x.H * x.W, torch.float32).view(B, cout, x.H, x.W)
+                ops.conv3x3_small_cout(x.t, w[p + ".w"], w[p + ".b"], dst)
+                cur = dst
+            elif kind == "res":
+                x = self._res(p, x, cout)
+            elif kind == "attn":
+                x = self._attn(p, x)
+            elif kind == "gn_silu":
+                h = ws.get("h1", x.M, x.C)
+                ops.groupnorm_silu(x.t, h, w[p + ".gw"], w[p + ".gb"], x.B, x.H * x.W, x.C, self.G, True)
+                x = Act(h, x.B, x.H, x.W, x.C)
+            elif kind == "up":
+                up = ws.get("up", 4 * x.M, x.C)
+                ops.upsample_nearest2x(x.t, up, x.B, x.H, x.W, x.C)
+                dst = ws.get("xa", 4 * x.M, cout)
+                ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), x.C, 9)], w[p + ".w"], cout, dst, bias=w[p + ".b"])
+                x = Act(dst, x.B, 2 * x.H, 2 * x.W, cout)
+            elif kind == "down":
+                col = ws.get("col", x.M // 4, 9 * x.C)
+                ops.im2col_s2(x.t, col, x.B, x.H, x.W, x.C)
+                dst = ws.get("xa", x.M // 4, cout)
+                ops.igemm([(col, (1, 1, x.M // 4), 9 * x.C, 1)], w[p + ".w"], cout, dst, bias=w[p + ".b"],
+                          zero_pad_last=True, epi_hw=(x.H // 2, x.W // 2))
+                x = Act(dst, x.B, x.H // 2, x.W // 2, cout)
+        return out_nchw
+
+    def decode(self, z_nchw, out_nchw):
+        return self._run("decoder", "decoder.up", z_nchw, out_nchw)
+
+    def encode(self, x_nchw, out_nchw):
+        return self._run("encoder", "encoder.down", x_nchw, out_nchw)

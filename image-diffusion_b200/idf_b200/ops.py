@@ -85,14 +85,14 @@ def embed_time_class(t, ctx, ctx_mask, factor, w1, b1, w2, b2, class_w, wp, bp, 
     return out
 
 
-def cfg_posterior_step(xt, eps_c, eps_u, noise, cfg, t, sched, x_prev, x0_out=None):
+def cfg_posterior_step(xt, eps_c, eps_u, noise, cfg, t, sched, x_prev, x0_out=None, x_prev_dup=None):
     N = xt.shape[0]
     chw = xt.numel() // N
     t_stride = 0 if t.numel() == 1 else 1
     call("idf_cfg_posterior_step", xt.data_ptr(), eps_c.data_ptr(), eps_u.data_ptr(), noise.data_ptr(), cfg.data_ptr(),
          t.data_ptr(), t_stride, sched.betas.data_ptr(), sched.alphas.data_ptr(), sched.alpha_cum_prod.data_ptr(),
          sched.sqrt_alpha_cum_prod.data_ptr(), sched.sqrt_one_minus_alpha_cum_prod.data_ptr(), x_prev.data_ptr(),
-         ptr(x0_out), N, chw)
+         ptr(x_prev_dup), ptr(x0_out), N, chw)
     return x_prev
 
 
@@ -103,10 +103,15 @@ def add_noise(x, noise, t, sched, out):
     return out
 
 
-def vq_argmin(z_rows: torch.Tensor, codebook: torch.Tensor, idx_out: torch.Tensor, zq_out=None):
-    rows, dim = z_rows.shape
-    call("idf_vq_argmin", z_rows.data_ptr(), codebook.data_ptr(), idx_out.data_ptr(), ptr(zq_out), rows, dim,
-         codebook.shape[0])
+def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, idx_out: torch.Tensor, zq_out=None):
+    """z: fp32 (rows, dim) row-major, or an NCHW (B, dim, H, W) tensor (rows are then (image, pixel))."""
+    if z.dim() == 4:
+        B, dim, H, W = z.shape
+        rows, hw = B * H * W, H * W
+    else:
+        (rows, dim), hw = z.shape, 0
+    call("idf_vq_argmin", z.data_ptr(), codebook.data_ptr(), idx_out.data_ptr(), ptr(zq_out), rows, dim,
+         codebook.shape[0], hw)
     return idx_out
 
 

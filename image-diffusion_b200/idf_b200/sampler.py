@@ -1,0 +1,88 @@
+"""CFG DDPM sampling loop (reference modules/diffusion.py:46-56) as one CUDA-graph replay per step.
+
+A step = one batch-doubled UNet pass (rows [0, N) conditional, rows [N, 2N) unconditional — the reference's two
+calls, diffusion.py:53-54) + the fused guidance-mix / posterior kernel that advances x_t in place. The per-step
+embedding work is done for the (num_classes + 1) distinct (timestep, class) rows only; samples index into that
+table. Nothing inside the step synchronises with the host.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import native, ops
+
+
+class CfgSampler:
+    def __init__(self, unet, scheduler, labels: torch.Tensor, cfg_scales: torch.Tensor, latent_shape, use_graph=True):
+        dev = labels.device
+        self.unet, self.sched = unet, scheduler._on(dev)
+        self.N = N = labels.shape[0]
+        self.shape = (N, *latent_shape)
+        K = unet.num_classes
+        self.engine = unet.engine(2 * N, latent_shape[1], latent_shape[2])
+        # embedding rows: classes 0..K-1 (conditional) and one masked row (unconditional)
+        self.t_rows = torch.zeros(K + 1, device=dev, dtype=torch.int64)
+        self.ctx_rows = torch.cat([torch.arange(K, device=dev), torch.zeros(1, device=dev, dtype=torch.int64)])
+        self.mask_rows = torch.cat([torch.ones(K, device=dev), torch.zeros(1, device=dev)]).to(torch.float32)
+        self.row_idx = torch.cat([labels.to(torch.int32), torch.full((N,), K, device=dev, dtype=torch.int32)])
+        self.cfg = cfg_scales.to(device=dev, dtype=torch.float32).contiguous()
+        self.xx = torch.zeros(2 * N, *latent_shape, device=dev, dtype=torch.float32)   # [x_t ; x_t]
+        self.eps = torch.empty_like(self.xx)                                            # [eps_cond ; eps_uncond]
+        self.z = torch.zeros(N, *latent_shape, device=dev, dtype=torch.float32)
+        self.use_graph = use_graph
+        self.graph = None
+        self.launches_per_step = None
+
+    def _step(self):
+        N = self.N
+        self.engine.run(self.xx, self.t_rows, self.ctx_rows, self.mask_rows, self.row_idx, self.eps)
+        ops.cfg_posterior_step(self.xx[:N], self.eps[:N], self.eps[N:], self.z, self.cfg, self.t_rows[:1], self.sched,
+                               self.xx[:N], None, self.xx[N:])
+
+    def _ensure_graph(self):
+        if self.graph is not None or not self.use_graph:
+            return
+        keep = self.xx.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._step()  # warm-up: allocates workspaces, packs weights, sets kernel attributes
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        before = native.launch_count
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step()
+        self.launches_per_step = native.launch_count - before
+        self.graph = g
+        self.xx.copy_(keep)
+
+    def set_latent(self, x_T: torch.Tensor):
+        self.xx[:self.N].copy_(x_T)
+        self.xx[self.N:].copy_(x_T)
+
+    @property
+    def latent(self) -> torch.Tensor:
+        return self.xx[:self.N]
+
+    def step(self, i: int, noise: torch.Tensor | None = None):
+        """Advance x_i -> x_{i-1}. `noise` injects the step's N(0,1) draw; None draws it from the global CUDA
+        generator exactly where the reference does (components.py:423: randn_like(xt), skipped at i == 0)."""
+        self._ensure_graph()
+        self.t_rows.fill_(i)
+        if i > 0:
+            if noise is None:
+                self.z.normal_()
+            else:
+                self.z.copy_(noise)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+
+    def run(self, x_T: torch.Tensor, steps=None, noises=None) -> torch.Tensor:
+        self.set_latent(x_T)
+        steps = list(reversed(range(self.sched.num_steps))) if steps is None else list(steps)
+        for k, i in enumerate(steps):
+            self.step(i, None if noises is None else noises[k])
+        return self.latent

@@ -141,14 +141,16 @@ int idf_embed_time_class(const int64_t* t, const int64_t* ctx, const float* ctx_
  *   eps_cond/eps_uncond  fp32 (N, chw); cfg[N] fp32 guidance scale per sample; sample n uses timestep
  *   t[n * t_stride] (t_stride = 0: one device scalar for the batch) and, like the reference, the no-noise branch
  *   is decided by t[0]; tables are the Scheduler's fp32 [num_steps] vectors.
- *   x0_out may be NULL (the reference computes x0 and drops it).
+ *   x_prev may alias xt (in-place step). x_prev_dup (optional) receives a second copy of x_{t-1}: the
+ *   unconditional half of the batch-doubled UNet input. x0_out may be NULL (the reference computes x0 and
+ *   drops it).
  */
 int idf_cfg_posterior_step(const float* xt, const float* eps_cond, const float* eps_uncond, const float* noise,
                            const float* cfg, const int64_t* t, int32_t t_stride, const float* betas,
                            const float* alphas,
                            const float* alpha_cum_prod, const float* sqrt_alpha_cum_prod,
-                           const float* sqrt_one_minus_alpha_cum_prod, float* x_prev, float* x0_out, int32_t N,
-                           int32_t chw, idf_stream_t stream);
+                           const float* sqrt_one_minus_alpha_cum_prod, float* x_prev, float* x_prev_dup,
+                           float* x0_out, int32_t N, int32_t chw, idf_stream_t stream);
 
 /* idf_add_noise — sqrt(acp[t_n]) * x + sqrt(1 - acp[t_n]) * noise with per-sample t (components.py:399-403). */
 int idf_add_noise(const float* x, const float* noise, const int64_t* t, const float* sqrt_alpha_cum_prod,
@@ -158,11 +160,12 @@ int idf_add_noise(const float* x, const float* noise, const int64_t* t, const fl
 /*
  * idf_vq_argmin — nearest codebook entry per latent vector, reproducing torch.cdist's matmul formulation
  * (components.py:272-275): d2 = x1_ . x2_ with x1_ = [-2x, |x|^2, 1], x2_ = [e, 1, |e|^2], clamp_min(0), sqrt,
- * first minimal index. z is fp32 (rows, dim) row-major, codebook fp32 (size, dim); idx_out int64 [rows];
- * zq_out (optional) fp32 (rows, dim) receives codebook[idx].
+ * first minimal index. codebook is fp32 (size, dim); idx_out int64 [rows]. With nchw_hw == 0, z (and the optional
+ * zq_out = codebook[idx]) are fp32 (rows, dim) row-major; with nchw_hw = H*W they are NCHW tensors and
+ * row = image * H*W + pixel (the "B C H W -> B (H W) C" rearrange of components.py:269 folded into the addressing).
  */
 int idf_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, float* zq_out, int32_t rows,
-                  int32_t dim, int32_t size, idf_stream_t stream);
+                  int32_t dim, int32_t size, int32_t nchw_hw, idf_stream_t stream);
 
 /*
  * idf_conv3x3_small_cin — direct 3x3 s1 p1 convolution for tiny Cin (the 3-channel latent): fp32 NCHW in,
