@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — CFG UNet denoise throughput (img-steps/s) of the B200-native sampling path.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K    # the reference algorithm on the host CPU (oracle port)
+
+A "step" is one classifier-free-guided DDPM denoising step over one batch of 48 latents (BASELINE.json configs[1]:
+3 classes x 16 images, 32x32x3 latents, the ~60M-parameter diff-kl-lin-32x32 UNet): a batch-doubled UNet pass (96
+forwards) plus the fused guidance-mix / posterior update, i.e. 48 img-steps. With N GPUs every rank runs its own
+batch of 48 (batch-sharded sampling, no per-step cross-GPU traffic): weak scaling, value = total img-steps/s.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "image-diffusion_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+GFLOP_PER_IMG_STEP = 45.510  # 2 UNet forwards, SURVEY.md §8(d) / BASELINE.md §3 (matmul-class FLOPs only)
+BATCH = 48
+README_IMG_STEPS_PER_S = 37.5  # 27 images x 1000 steps in "~12 minutes" on an unnamed GPU
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return p.get("bf16_tflops_sustained", 1373.8), p.get("hbm_gbs", 6546.9), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower() == "active"})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def build_models(dev):
+    from modules.components import Scheduler
+    from modules.unet import Unet
+    from modules.vae import VAE
+    from oracle.ref_path import UNET_ARCH, VAE_KL_ARCH  # architecture constants only (configs/*.yaml values)
+    torch.manual_seed(2018)  # configs/diff-kl-lin-32x32.yaml:32 — random-init weights, default init
+    unet = Unet(**UNET_ARCH).to(dev).eval()
+    vae = VAE(**VAE_KL_ARCH).to(dev).eval()
+    return unet, vae, Scheduler(1000, 1e-4, 0.02, "linear", dev)
+
+
+def cpu_reference_rate(steps, warmup, batch=8, threads=None):
+    """The reference algorithm (oracle port, fp32 torch on CPU): img-steps/s of CFG steps on `batch` latents."""
+    from oracle import ref_path as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        torch.manual_seed(2018)
+        sd = O.seeded_state_dict(O.unet_param_shapes(O.UNET_ARCH), 2018)
+        sched = O.SchedulerTables(1000)
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(batch, 3, 32, 32, generator=g)
+        labels = torch.tensor(([0, 1, 2] * batch)[:batch])
+        cfg = torch.full((batch,), 3)
+        times = []
+        for k in range(warmup + steps):
+            z = torch.randn(batch, 3, 32, 32, generator=g)
+            t0 = time.perf_counter()
+            x = O.cfg_sample(sd, O.UNET_ARCH, sched, x, labels, cfg, [z], steps=[500])
+            if k >= warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * len(times) / total, total / len(times), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 8))
+    rate, sec_per_step, threads = cpu_reference_rate(steps, 1)
+    sample = f"{steps} CFG steps (2 UNet fwd + mix + posterior) on batch 8, fp32 torch CPU, step i=500"
+    line = {
+        "impl": "reference", "metric": "CFG UNet denoise img-steps/s (32x32x3 latents, diff-kl-lin-32x32 UNet)",
+        "value": rate, "unit": "img-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] bounded sample: CFG DDPM denoise steps, batch 8 of 48, random-init UNet",
+                   "note": "reference algorithm = oracle/ref_path.py (functional restatement pinned on reference "
+                           "golden vectors); the reference itself is not pip-installable (no setup.py/pyproject)"},
+        "cpu_baseline": {"value": rate, "unit": "img-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "img-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def igemm_roofline(sampler, peak_tflops, peak_kind):
+    """Live CUDA-event timing of every kernel of one eager step; returns the roofline object of the dominant kernel
+    (the tcgen05 implicit GEMM) plus a per-kernel time breakdown."""
+    from idf_b200 import native
+    records = []
+    orig_call = native.call
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        flops = 0.0
+        if name == "idf_conv2d_igemm":
+            g = a[0]
+            m = g.a[0].n * g.a[0].h * g.a[0].w
+            k = g.taps[0] * g.a[0].c + (g.taps[1] * g.a[1].c if g.a[1].ptr else 0)
+            flops = 2.0 * m * g.N * k
+        records.append((name, e0, e1, flops))
+
+    from idf_b200 import ops
+    keep = sampler.xx.clone()
+    try:
+        native.call = timed_call
+        ops.call = timed_call
+        torch.cuda._sleep(int(4e7))  # let the host queue the whole step so kernels run back to back
+        sampler._step()
+        torch.cuda.synchronize()
+    finally:
+        native.call = orig_call
+        ops.call = orig_call
+        sampler.xx.copy_(keep)
+    by = {}
+    for name, e0, e1, fl in records:
+        d = by.setdefault(name, [0.0, 0, 0.0])
+        d[0] += e0.elapsed_time(e1)
+        d[1] += 1
+        d[2] += fl
+    total = sum(v[0] for v in by.values())
+    ms, n, fl = by["idf_conv2d_igemm"]
+    achieved = fl / (ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "igemm_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    roof = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM, all conv/linear layers)",
+            "achieved": achieved, "peak": peak_tflops, "peak_kind": f"bf16 dense sustained, of {peak_kind}",
+            "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
+            "launches_per_step": n, "avg_launch_ms": ms / n, "flops_per_launch": fl / n,
+            "share_of_step": ms / total}
+    breakdown = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])}
+    return roof, breakdown
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-job", action="store_true", help="also time the full 1000-step sample + decode")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    warmup = max(args.warmup, 3)
+    peak_tflops, _, peak_kind = load_peaks()
+
+    from idf_b200 import native
+    from idf_b200.sampler import CfgSampler
+    with torch.no_grad():
+        unet, vae, sched = build_models(dev)
+        labels = torch.tensor([0, 1, 2] * (BATCH // 3), device=dev)
+        cfg = torch.full((BATCH,), 3, device=dev)
+        sampler = CfgSampler(unet, sched, labels, cfg, (3, 32, 32))
+        gen = torch.Generator(device=dev).manual_seed(rank)
+        x_T = torch.randn(BATCH, 3, 32, 32, device=dev, generator=gen)
+        sampler.set_latent(x_T)
+        total = warmup + args.steps
+        timesteps = [999 - (k % 999) for k in range(total)]  # i = 999, 998, ... (never the noise-free i = 0)
+        for k in range(warmup):
+            sampler.step(timesteps[k])
+        torch.cuda.synchronize()
+        # ---------------- device-timed region: K graph replays, inputs resident in HBM
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(warmup, total):
+            sampler.step(timesteps[k])
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        clock_info = clocks.stop() if rank == 0 else None
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        # ---------------- end-to-end: host buffers, H2D noise + D2H latent every step, wall clock
+        h_noise = torch.randn(BATCH, 3, 32, 32).pin_memory()
+        h_out = torch.empty(BATCH, 3, 32, 32).pin_memory()
+        d_noise = torch.empty(BATCH, 3, 32, 32, device=dev)
+        e2e_steps = args.steps
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        w0 = time.perf_counter()
+        for k in range(e2e_steps):
+            d_noise.copy_(h_noise, non_blocking=True)
+            sampler.step(timesteps[warmup + k], noise=d_noise)
+            h_out.copy_(sampler.latent, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - w0
+        if dist is not None:
+            t = torch.tensor([e2e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = t.item()
+        finite = bool(torch.isfinite(h_out).all())
+
+        extra = {}
+        roof, breakdown = None, None
+        if rank == 0:
+            roof, breakdown = igemm_roofline(sampler, peak_tflops, peak_kind)
+            # decode stage (once per job) timed for context
+            z0 = sampler.latent.clone()
+            vae.decode(z0)
+            torch.cuda.synchronize()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            vae.decode(z0)
+            d1.record()
+            torch.cuda.synchronize()
+            extra["kl_decode_ms_batch48"] = d0.elapsed_time(d1)
+            if args.full_job:
+                from modules.diffusion import Diffusion
+                dfn = Diffusion(vae, unet, sched, "a,b,c", "cuda")
+                torch.cuda.synchronize()
+                f0 = time.perf_counter()
+                imgs = dfn.sample(3, num_images=16, seed=0).cpu()
+                extra["full_job_s_1000_steps_plus_decode"] = time.perf_counter() - f0
+                extra["full_job_finite"] = bool(torch.isfinite(imgs).all())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    value = world * BATCH * args.steps / (ms * 1e-3)
+    e2e_value = world * BATCH * e2e_steps / e2e_s
+    line = {
+        "metric": "CFG UNet denoise img-steps/s (32x32x3 latents, diff-kl-lin-32x32 UNet)",
+        "value": value, "unit": "img-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": value / README_IMG_STEPS_PER_S,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": "configs[1]: CFG DDPM sampling steps, batch 48 (3 classes x 16) per GPU, cfg scale 3, "
+                        "linear schedule, UNet 60.5M params random init; step = 96 UNet forwards + fused CFG/posterior",
+            "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"batch-sharded x{world}",
+            "l2": "per-step working set (121 MB bf16 weights + >1 GB activations) exceeds the 126 MB L2",
+            "vs_baseline_note": "README's ~37.5 img-steps/s: 27-image grid, unnamed GPU, fp32 eager",
+            "pct_tensor_peak": value / world * GFLOP_PER_IMG_STEP * 1e9 / (peak_tflops * 1e12),
+            "gflop_per_img_step": GFLOP_PER_IMG_STEP, "finite": finite, **extra,
+        },
+        "clocks": clock_info,
+        "e2e": {"value": e2e_value, "unit": "img-steps/s", "h2d_bytes_per_step": h_noise.numel() * 4,
+                "d2h_bytes_per_step": h_out.numel() * 4,
+                "how": "per step: pinned-host noise -> device, CfgSampler.step (graph replay), latent -> pinned "
+                       "host, stream sync; wall clock"},
+        "gpu_launches": sampler.launches_per_step * args.steps,
+        "roofline": roof,
+        "kernel_breakdown_ms_per_step": breakdown,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        rate, sec, threads = cpu_reference_rate(3, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "img-steps/s", "cores": threads, "kind": "port",
+                                "sample": "3 CFG steps (2 UNet fwd + mix + posterior) on batch 8 of the same "
+                                          "workload, oracle port of the reference, fp32 torch on the host CPU"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,14 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
 }
 
+constexpr double GN_FIX = 268435456.0;  // 2^28
+__device__ __forceinline__ unsigned long long to_fixed(float v) {
+  return static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v) * GN_FIX));
+}
+__device__ __forceinline__ float from_fixed(unsigned long long v) {
+  return static_cast<float>(static_cast<double>(static_cast<long long>(v)) * (1.0 / GN_FIX));
+}
+
 // grid = (B, slabs). A slab is `gps` consecutive groups = gps*cpg channels = V 16-byte vectors per pixel.
 // Thread t owns vector (t % V) of pixels (t / V), (t / V) + rows_per_iter, ...
 template <bool SILU>
@@ -23,16 +31,18 @@ __global__ void __launch_bounds__(512) groupnorm_kernel(const __nv_bfloat16* __r
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int HW, int cpg, int gps,
                                                         int V, float eps) {
-  __shared__ float s_sum[GN_MAX_GPS];
-  __shared__ float s_sq[GN_MAX_GPS];
+  // Group sums are accumulated as Q36.28 fixed point: integer addition is associative, so the shared-memory
+  // atomics give bit-identical statistics from run to run (and across batch sizes) in any arrival order.
+  __shared__ unsigned long long s_sum[GN_MAX_GPS];
+  __shared__ unsigned long long s_sq[GN_MAX_GPS];
   const int b = blockIdx.x;
   const int c0 = blockIdx.y * gps * cpg;
   const int v = threadIdx.x % V;
   const int prow = threadIdx.x / V;
   const int rows_per_iter = blockDim.x / V;
   if (threadIdx.x < GN_MAX_GPS) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
+    s_sum[threadIdx.x] = 0ull;
+    s_sq[threadIdx.x] = 0ull;
   }
   __syncthreads();
 
@@ -75,15 +85,15 @@ __global__ void __launch_bounds__(512) groupnorm_kernel(const __nv_bfloat16* __r
     for (int e = 0; e < 8; ++e) {
       const int g = (v * 8 + e) / cpg;
       if (g != g_prev) {
-        atomicAdd(&s_sum[g_prev], as);
-        atomicAdd(&s_sq[g_prev], aq);
+        atomicAdd(&s_sum[g_prev], to_fixed(as));
+        atomicAdd(&s_sq[g_prev], to_fixed(aq));
         as = 0.f; aq = 0.f; g_prev = g;
       }
       as += s[e];
       aq += q[e];
     }
-    atomicAdd(&s_sum[g_prev], as);
-    atomicAdd(&s_sq[g_prev], aq);
+    atomicAdd(&s_sum[g_prev], to_fixed(as));
+    atomicAdd(&s_sq[g_prev], to_fixed(aq));
   }
   __syncthreads();
 
@@ -93,8 +103,8 @@ __global__ void __launch_bounds__(512) groupnorm_kernel(const __nv_bfloat16* __r
   for (int e = 0; e < 8; ++e) {
     const int cl = v * 8 + e;
     const int g = cl / cpg;
-    const float mean = s_sum[g] * inv_cnt;
-    const float var = fmaxf(s_sq[g] * inv_cnt - mean * mean, 0.f);
+    const float mean = from_fixed(s_sum[g]) * inv_cnt;
+    const float var = fmaxf(from_fixed(s_sq[g]) * inv_cnt - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
     const float ga = gamma[c0 + cl], be = beta[c0 + cl];
     sc[e] = rstd * ga;

@@ -84,6 +84,7 @@ class UnetEngine:
         self.packed = _Packed(module)
         self.ws = Workspace(device)
         self.L, self.heads, self.G = arch["num_res_layers"], arch["num_heads"], arch["num_groups"]
+        self.taps = None  # debugging aid: set to a dict to collect fp32 copies of intermediate activations
         self.downs, self.mids, self.ups = unet_blocks(arch)
         for _, cin, cout in self.downs + self.mids + self.ups:
             if cin % 64 or cout % 128:
@@ -139,6 +140,10 @@ class UnetEngine:
         self.packed.w = w
 
     # ---------------------------------------------------------------------------------------------
+    def _tap(self, name, t2d):
+        if self.taps is not None:
+            self.taps[name] = t2d.float().clone()
+
     def _block(self, p, x: Act, cout, table, idx, final_dst=None) -> Act:
         w, ws, G = self.packed.w, self.ws, self.G
         B, H, W = x.grid
@@ -170,6 +175,10 @@ class UnetEngine:
             else:
                 dst = ws.get("xa" if (l % 2 == 0) else "xb", M, cout)
             ops.igemm([(o, (1, 1, M), cout, 1)], w[k + ".wo"], cout, dst, bias=w[k + ".bo"], res=x2)
+            if self.taps is not None:
+                for nm, tt in (("h1", h1), ("y1", y1), ("h2", h2), ("x2", x2), ("h3", h3), ("qk", qk), ("o", o),
+                               ("out", dst)):
+                    self._tap(f"{k}.{nm}", tt)
             x = Act(dst, B, H, W, cout)
         return x
 
@@ -191,6 +200,8 @@ class UnetEngine:
         ch = list(self.arch["channels"])
         a0 = ws.get("in", B * H * W, ch[0])
         ops.conv3x3_small_cin(x_nchw, w["in.w"], w["in.b"], a0)
+        self._tap("table", table)
+        self._tap("in", a0)
         x = Act(a0, B, H, W, ch[0])
         cats = []
         for i, (p, cin, cout) in enumerate(self.downs):
@@ -202,6 +213,7 @@ class UnetEngine:
             nxt = ws.get("dn", x.M // 4, cout)
             ops.igemm([(col, (1, 1, x.M // 4), 9 * cout, 1)], w[f"down.{i}.w"], cout, nxt, bias=w[f"down.{i}.b"],
                       zero_pad_last=True, epi_hw=(x.H // 2, x.W // 2))
+            self._tap(f"down.{i}", nxt)
             x = Act(nxt, x.B, x.H // 2, x.W // 2, cout)
         for p, cin, cout in self.mids:
             x = self._block(p, x, cout, table, row_idx)
@@ -211,6 +223,7 @@ class UnetEngine:
             ops.upsample_nearest2x(x.t, up, x.B, x.H, x.W, c)
             cat = cats.pop()
             ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), c, 9)], w[f"up.{i}.w"], c, cat[:, :c], bias=w[f"up.{i}.b"])
+            self._tap(f"up.{i}", cat)
             x = self._block(p, Act(cat, x.B, 2 * x.H, 2 * x.W, 2 * c), cout, table, row_idx)
         h = ws.get("h1", x.M, x.C)
         ops.groupnorm_silu(x.t, h, w["out.gw"], w["out.gb"], x.B, x.H * x.W, x.C, self.G, True)
