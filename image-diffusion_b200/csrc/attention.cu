@@ -9,6 +9,7 @@
 // Samples with fewer than 128 tokens share a tile; a block-diagonal mask keeps them independent.
 //
 // Warp roles (192 threads): warps 0..3 = softmax / output rows, warp 4 = TMA producer, warp 5 = TMEM + MMA issuer.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -275,6 +276,281 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Software-pipelined variant for long sequences (>= 3 key blocks per query tile). One CTA per SM:
+//   * S is double-buffered in TMEM: the MMA thread issues Q K_{j+2}^T as soon as the softmax warps have pulled
+//     S_j into registers, so the next score tile is always ready when they come back for it;
+//   * P and the per-block output O_blk are double-buffered too: P_j V_j runs on the tensor core while the softmax
+//     warps already work on block j+1; O_blk_j is folded into the fp32 output rows one iteration late;
+//   * each softmax thread holds its whole 128-wide score row in registers (one TMEM read per score).
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+hd) O1 [320,320+hd) -> 512 allocated.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ATTP_TMEM_COLS = 512;
+constexpr int ATTP_KSTAGES = 4;
+constexpr int ATTP_VSTAGES = 3;
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
+  constexpr int QK_BYTES = 128 * SWZ;
+  constexpr int V_BYTES = 2 * HD * 128;
+  constexpr int P_BYTES = 2 * 128 * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_q = smem;
+  uint8_t* smem_p = smem_q + QK_BYTES;                    // [2][P_BYTES]
+  uint8_t* smem_k = smem_p + 2 * P_BYTES;                 // [ATTP_KSTAGES][QK_BYTES]
+  uint8_t* smem_v = smem_k + ATTP_KSTAGES * QK_BYTES;     // [ATTP_VSTAGES][V_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + ATTP_VSTAGES * V_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;                       // [4]
+  uint64_t* k_empty = k_full + ATTP_KSTAGES;         // [4]
+  uint64_t* v_full = k_empty + ATTP_KSTAGES;         // [3]
+  uint64_t* v_empty = v_full + ATTP_VSTAGES;         // [3]
+  uint64_t* s_full = v_empty + ATTP_VSTAGES;         // [2]
+  uint64_t* s_empty = s_full + 2;                    // [2]
+  uint64_t* p_full = s_empty + 2;                    // [2]
+  uint64_t* o_full = p_full + 2;                     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x;
+  const int head = blockIdx.y;
+  const int row0 = tile_m * 128;
+  const int kv_base = (row0 >> p.t_shift) << p.t_shift;
+  const int n = p.nblk;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQK);
+    tma_prefetch_desc(&p.tmVT);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATTP_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < ATTP_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, ATTP_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, QK_BYTES);
+      tma_load_2d(smem_q, &p.tmQK, q_full, head * HD, row0);
+      auto load_k = [&](int j) {
+        const int st = j % ATTP_KSTAGES;
+        mbar_wait(&k_empty[st], ((j / ATTP_KSTAGES) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], QK_BYTES);
+        tma_load_2d(smem_k + st * QK_BYTES, &p.tmQK, &k_full[st], p.C + head * HD, kv_base + j * 128);
+      };
+      auto load_v = [&](int j) {
+        const int st = j % ATTP_VSTAGES;
+        mbar_wait(&v_empty[st], ((j / ATTP_VSTAGES) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], V_BYTES);
+        uint8_t* dst = smem_v + st * V_BYTES;
+        tma_load_2d(dst, &p.tmVT, &v_full[st], kv_base + j * 128, head * HD);
+        tma_load_2d(dst + HD * 128, &p.tmVT, &v_full[st], kv_base + j * 128 + 64, head * HD);
+      };
+      load_k(0);
+      if (n > 1) load_k(1);
+      for (int j = 0; j < n; ++j) {
+        load_v(j);
+        if (j + 2 < n) load_k(j + 2);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
+      const uint64_t dq = umma_desc_kmajor(smem_u32(smem_q), SWZ);
+      auto issue_s = [&](int j) {  // S[j & 1] = Q K_j^T
+        const int st = j % ATTP_KSTAGES;
+        mbar_wait(&k_full[st], (j / ATTP_KSTAGES) & 1);
+        tc_fence_after_sync();
+        const uint64_t dk = umma_desc_kmajor(smem_u32(smem_k + st * QK_BYTES), SWZ);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem_base + (j & 1) * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[j & 1]);
+        umma_commit(&k_empty[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (n > 1) issue_s(1);
+      for (int j = 0; j < n; ++j) {
+        const int b = j & 1;
+        const int vs = j % ATTP_VSTAGES;
+        mbar_wait(&p_full[b], (j >> 1) & 1);
+        mbar_wait(&v_full[vs], (j / ATTP_VSTAGES) & 1);
+        tc_fence_after_sync();
+        const uint8_t* pb = smem_p + b * P_BYTES;
+        const uint8_t* vb = smem_v + vs * V_BYTES;
+        const uint64_t dp0 = umma_desc_kmajor(smem_u32(pb), 128);
+        const uint64_t dp1 = umma_desc_kmajor(smem_u32(pb + 128 * 128), 128);
+        const uint64_t dv0 = umma_desc_kmajor(smem_u32(vb), 128);
+        const uint64_t dv1 = umma_desc_kmajor(smem_u32(vb + HD * 128), 128);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + 256 + b * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), (k < 4 ? dv0 : dv1) + 2 * (k & 3),
+                    idesc_o, k != 0);
+        umma_commit(&o_full[b]);
+        umma_commit(&v_empty[vs]);
+        if (j + 2 < n) {
+          mbar_wait(&s_empty[b], (j >> 1) & 1);
+          issue_s(j + 2);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output rows (warps 0..3)
+    const int r = warp * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const long long m = (long long)row0 + r;
+    const float c = p.scale_log2e;
+    float o_acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < n; ++j) {
+      const int b = j & 1;
+      mbar_wait(&s_full[b], (j >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32(tmem_base + b * 128 + lane_addr + ch * 32, sv[ch]);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[b]);  // S_j now lives in registers
+
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(sv[ch][i]));
+      const float mrow = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                               fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      const float m_new = fmaxf(m_run, mrow);
+      const float alpha = fast_exp2((m_run - m_new) * c);
+      const float mc = m_new * c;
+      m_run = m_new;
+
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+      uint8_t* pbuf = smem_p + b * P_BYTES;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint8_t* prow = pbuf + (ch >> 1) * (128 * 128) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            e[i] = fast_exp2(fmaf(__uint_as_float(sv[ch][8 * q + i]), c, -mc));
+            ps[i & 3] += e[i];
+          }
+          uint4 o;
+          o.x = pack_bf16x2(e[0], e[1]);
+          o.y = pack_bf16x2(e[2], e[3]);
+          o.z = pack_bf16x2(e[4], e[5]);
+          o.w = pack_bf16x2(e[6], e[7]);
+          const int chunk = ((ch & 1) * 4 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+      l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+
+      if (j > 0) {  // fold block j-1 (computed at scale m_{j-1}) into the running output
+        const int pb = (j - 1) & 1;
+        mbar_wait(&o_full[pb], ((j - 1) >> 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int d0 = 0; d0 < HD; d0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(tmem_base + 256 + pb * 64 + lane_addr + d0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) o_acc[d0 + d] += __uint_as_float(v[d]);
+        }
+      }
+      if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o_acc[d] *= alpha;
+      }
+    }
+    {
+      const int pb = (n - 1) & 1;
+      mbar_wait(&o_full[pb], ((n - 1) >> 1) & 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int d0 = 0; d0 < HD; d0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + 256 + pb * 64 + lane_addr + d0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o_acc[d0 + d] += __uint_as_float(v[d]);
+      }
+    }
+    if (m < p.M) {
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* dst = p.out + m * p.ld_out + head * HD;
+#pragma unroll
+      for (int d0 = 0; d0 < HD; d0 += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(o_acc[d0 + 0] * inv, o_acc[d0 + 1] * inv);
+        o.y = pack_bf16x2(o_acc[d0 + 2] * inv, o_acc[d0 + 3] * inv);
+        o.z = pack_bf16x2(o_acc[d0 + 4] * inv, o_acc[d0 + 5] * inv);
+        o.w = pack_bf16x2(o_acc[d0 + 6] * inv, o_acc[d0 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + d0) = o;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, ATTP_TMEM_COLS);
+  }
+}
+
+template <int HD>
+static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
+  constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
+  const int smem = 128 * SWZ + 2 * (2 * 128 * 128) + ATTP_KSTAGES * 128 * SWZ + ATTP_VSTAGES * 2 * HD * 128 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(attention_pipe_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                        "attention_pipe: cudaFuncSetAttribute");
+    if (rc != IDF_OK) return rc;
+    attr_set = true;
+  }
+  attention_pipe_kernel<HD><<<dim3(tiles, heads), ATT_THREADS, smem, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "attention_pipe launch");
+}
+
 template <int HD>
 static int launch_attention(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
@@ -335,6 +611,19 @@ extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, 
   }
   const int tiles = (M + 127) / 128;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static const int pipe_min_blocks = [] {
+    const char* e = getenv("IDF_ATTN_PIPE_MIN_BLOCKS");
+    return e ? atoi(e) : 3;
+  }();
+  if (p.nblk >= pipe_min_blocks) {
+    switch (head_dim) {
+      case 16: return launch_attention_pipe<16>(p, tiles, heads, s);
+      case 32: return launch_attention_pipe<32>(p, tiles, heads, s);
+      case 48: return launch_attention_pipe<48>(p, tiles, heads, s);
+      case 64: return launch_attention_pipe<64>(p, tiles, heads, s);
+      default: break;
+    }
+  }
   switch (head_dim) {
     case 16: return launch_attention<16>(p, tiles, heads, s);
     case 32: return launch_attention<32>(p, tiles, heads, s);

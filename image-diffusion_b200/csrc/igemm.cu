@@ -253,17 +253,31 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
           *slot = o;
         }
       } else if (to_vt) {
-        if (row_ok) {
-          __nv_bfloat16* dst = p.vt + (long long)(n0 - p.vt_col0 + c * 32) * p.vt_ld + m;
+        // transpose through shared memory: stage_c is viewed as [128 columns][128 rows] bf16
+        __nv_bfloat16* tcol = reinterpret_cast<__nv_bfloat16*>(stage_c) + (c * 32) * BLOCK_M + r;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[(long long)j * p.vt_ld] = __float2bfloat16_rn(acc[j]);
-        }
+        for (int j = 0; j < 32; ++j) tcol[j * BLOCK_M] = __float2bfloat16_rn(acc[j]);
       } else {
         if (row_ok) {
           float4* dst = reinterpret_cast<float4*>(p.out_f32 + m * p.out_f32_ld + n0 + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             dst[j] = make_float4(acc[4 * j + 0], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
+      }
+    }
+    if (to_vt) {
+      // coalesced write-out of the transposed tile: 16 threads cover one 256-byte channel row
+      named_bar_sync(1, 128);
+      const long long m0 = (long long)tile_m * BLOCK_M;
+      __nv_bfloat16* gbase = p.vt + (long long)(n0 - p.vt_col0) * p.vt_ld + m0;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int q = i * 128 + et;
+        const int col = q >> 4, part = q & 15;
+        if (m0 + part * 8 < p.M) {
+          const uint4 v = *reinterpret_cast<const uint4*>(stage_c + col * (BLOCK_M * 2) + part * 16);
+          *reinterpret_cast<uint4*>(gbase + (long long)col * p.vt_ld + part * 8) = v;
         }
       }
     }
@@ -381,6 +395,8 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
       p.flags |= F_VT;
       p.vt = reinterpret_cast<__nv_bfloat16*>(a->vt);
       p.vt_col0 = a->vt_col0;
+      if (a->vt_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(a->vt) & 15) || M % 8 != 0)
+        return fail(IDF_ERR_ARG, "igemm: vt needs 16-byte alignment, vt_ld %% 8 == 0 and M %% 8 == 0");
       p.vt_ld = a->vt_ld;
       out_cols = a->vt_col0;
     }

@@ -198,60 +198,60 @@ __global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 // edge convolutions with a handful of channels on one side
 // ---------------------------------------------------------------------------------------------
-// fp32 NCHW (Cin <= 8) -> bf16 NHWC, 3x3 s1 p1. One thread = one pixel x 8 output channels.
+// fp32 NCHW (Cin <= 4) -> bf16 NHWC, 3x3 s1 p1. Thread (lane) owns 4 output channels and keeps their 4*9*CIN
+// weights in registers; a warp covers 128 output channels of one pixel at a time: the 9*CIN patch values are
+// warp-wide broadcast loads and the warp's store is one contiguous 256-byte row segment. With dup_rows > 0 the
+// result is also written `dup_rows` rows further down (the unconditional half of a batch-doubled CFG input).
 template <int CIN>
 __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __restrict__ x,
                                                                 const float* __restrict__ w,
                                                                 const float* __restrict__ bias,
                                                                 __nv_bfloat16* __restrict__ y, long long ldy, int B,
-                                                                int H, int W, int Cout) {
-  extern __shared__ float s_w[];  // [CIN*9][Cout] + bias[Cout]
-  const int K = CIN * 9;
-  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
-    const int o = i / K, k = i % K;  // w is OIHW = [o][k]
-    s_w[k * Cout + o] = w[i];
-  }
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[K * Cout + i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const int groups = Cout / 8;
-  const long long total = (long long)B * H * W * groups;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(it % groups);
-    const long long pix = it / groups;
-    const int wq = (int)(pix % W);
-    const int hq = (int)((pix / W) % H);
-    const int b = (int)(pix / ((long long)W * H));
-    float patch[CIN * 9];
+                                                                int H, int W, int Cout, long long dup_rows) {
+  constexpr int K = CIN * 9;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int cgroups = Cout / 128;  // 128-channel slabs
+  const long long total = (long long)B * H * W * cgroups;
+  const long long warp_id = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * warps_per_block;
+  // consecutive warps of a block walk consecutive pixels of the same slab
+  for (int cg = 0; cg < cgroups; ++cg) {
+    const int co = cg * 128 + lane * 4;
+    float wr[4][K];
+    float bs[4];
 #pragma unroll
-    for (int c = 0; c < CIN; ++c)
+    for (int o = 0; o < 4; ++o) {
+      bs[o] = bias ? bias[co + o] : 0.f;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int hh = hq + kh - 1, ww = wq + kw - 1;
-          patch[c * 9 + kh * 3 + kw] =
-              (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((long long)b * CIN + c) * H + hh) * W + ww] : 0.f;
-        }
-    float acc[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = s_w[K * Cout + g * 8 + o];
-#pragma unroll
-    for (int k = 0; k < CIN * 9; ++k) {
-      const float4 wa = *reinterpret_cast<const float4*>(&s_w[k * Cout + g * 8]);
-      const float4 wb = *reinterpret_cast<const float4*>(&s_w[k * Cout + g * 8 + 4]);
-      acc[0] = fmaf(patch[k], wa.x, acc[0]); acc[1] = fmaf(patch[k], wa.y, acc[1]);
-      acc[2] = fmaf(patch[k], wa.z, acc[2]); acc[3] = fmaf(patch[k], wa.w, acc[3]);
-      acc[4] = fmaf(patch[k], wb.x, acc[4]); acc[5] = fmaf(patch[k], wb.y, acc[5]);
-      acc[6] = fmaf(patch[k], wb.z, acc[6]); acc[7] = fmaf(patch[k], wb.w, acc[7]);
+      for (int k = 0; k < K; ++k) wr[o][k] = w[(long long)(co + o) * K + k];
     }
-    uint4 o4;
-    o4.x = pack_bf16x2(acc[0], acc[1]);
-    o4.y = pack_bf16x2(acc[2], acc[3]);
-    o4.z = pack_bf16x2(acc[4], acc[5]);
-    o4.w = pack_bf16x2(acc[6], acc[7]);
-    *reinterpret_cast<uint4*>(y + pix * ldy + g * 8) = o4;
+    for (long long pix = warp_id; pix < (long long)B * H * W; pix += nwarps) {
+      const int wq = (int)(pix % W);
+      const int hq = (int)((pix / W) % H);
+      const int b = (int)(pix / ((long long)W * H));
+      float acc[4] = {bs[0], bs[1], bs[2], bs[3]};
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int hh = hq + kh - 1, ww = wq + kw - 1;
+            const float v = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                                ? __ldg(&x[(((long long)b * CIN + c) * H + hh) * W + ww])
+                                : 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[o] = fmaf(v, wr[o][c * 9 + kh * 3 + kw], acc[o]);
+          }
+      uint2 o2;
+      o2.x = pack_bf16x2(acc[0], acc[1]);
+      o2.y = pack_bf16x2(acc[2], acc[3]);
+      *reinterpret_cast<uint2*>(y + pix * ldy + co) = o2;
+      if (dup_rows > 0) *reinterpret_cast<uint2*>(y + (pix + dup_rows) * ldy + co) = o2;
+    }
   }
+  (void)total;
 }
 
 // bf16 NHWC -> fp32 NCHW (Cout <= 8), 3x3 s1 p1. One warp = one pixel; lanes stride over (tap, 8-channel vector).
@@ -304,6 +304,63 @@ __global__ void __launch_bounds__(256) conv3x3_small_cout_kernel(const __nv_bflo
         y[(((long long)b * COUT + o) * H + hq) * W + wq] = acc[o] + (bias ? bias[o] : 0.f);
     }
   }
+}
+
+
+// Tiled variant: one CTA = a (TH x TW) pixel tile of one image (TH*TW = 128 threads, one output pixel each). The
+// (TH+2) x (TW+2) input halo tile is staged once in shared memory (rows padded by 16 bytes so that the per-pixel
+// 16-byte reads of a warp fall in distinct banks); weights are read as warp-wide broadcasts.
+template <int COUT>
+__global__ void __launch_bounds__(128) conv3x3_small_cout_tiled_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                       long long ldx, const float* __restrict__ w,
+                                                                       const float* __restrict__ bias,
+                                                                       float* __restrict__ y, int Cin, int H, int W,
+                                                                       int TH, int TW) {
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  const int pix_bytes = Cin * 2 + 16;
+  float* s_w = reinterpret_cast<float*>(s_raw);                       // [9][Cin][COUT]
+  uint8_t* s_in = s_raw + ((9 * Cin * COUT * 4 + 15) & ~15);          // [(TH+2)*(TW+2)][pix_bytes]
+  for (int i = threadIdx.x; i < COUT * Cin * 9; i += blockDim.x) {
+    const int o = i / (Cin * 9), rem = i % (Cin * 9), c = rem / 9, tap = rem % 9;  // OIHW
+    s_w[(tap * Cin + c) * COUT + o] = w[i];
+  }
+  const int tiles_w = W / TW;
+  const int h0 = (blockIdx.x / tiles_w) * TH, w0 = (blockIdx.x % tiles_w) * TW;
+  const int b = blockIdx.y;
+  const int vec = Cin / 8;
+  const int halo_w = TW + 2;
+  for (int i = threadIdx.x; i < (TH + 2) * halo_w * vec; i += blockDim.x) {
+    const int v = i % vec, pp = i / vec;
+    const int hh = h0 + pp / halo_w - 1, ww = w0 + pp % halo_w - 1;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+      val = *reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * ldx + v * 8);
+    *reinterpret_cast<uint4*>(s_in + pp * pix_bytes + v * 16) = val;
+  }
+  __syncthreads();
+  const int r = threadIdx.x / TW, c = threadIdx.x % TW;
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint8_t* src = s_in + ((r + tap / 3) * halo_w + (c + tap % 3)) * pix_bytes;
+    const float* wt = s_w + tap * Cin * COUT;
+    for (int v = 0; v < vec; ++v) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + v * 16);
+      float f[8];
+      f[0] = bf16_lo(raw.x); f[1] = bf16_hi(raw.x); f[2] = bf16_lo(raw.y); f[3] = bf16_hi(raw.y);
+      f[4] = bf16_lo(raw.z); f[5] = bf16_hi(raw.z); f[6] = bf16_lo(raw.w); f[7] = bf16_hi(raw.w);
+      const float* wp = wt + v * 8 * COUT;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(f[e], wp[e * COUT + o], acc[o]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < COUT; ++o)
+    y[(((long long)b * COUT + o) * H + (h0 + r)) * W + (w0 + c)] = acc[o] + (bias ? bias[o] : 0.f);
 }
 
 // fp32 NCHW 1x1 convolution with tiny channel counts (decoder's first conv, encoder's last conv).
@@ -459,19 +516,18 @@ extern "C" int idf_vq_argmin(const float* z, const float* codebook, int64_t* idx
 }
 
 extern "C" int idf_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int64_t ldy,
-                                     int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout,
+                                     int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t dup,
                                      idf_stream_t stream) {
   if (!x || !w || !y) return fail(IDF_ERR_ARG, "conv_small_cin: null pointer");
-  if (Cout % 8 != 0 || ldy % 8 != 0) return fail(IDF_ERR_ARG, "conv_small_cin: Cout and ldy must be multiples of 8");
-  const int smem = (Cin * 9 + 1) * Cout * 4;
-  if (smem > 48 * 1024) return fail(IDF_ERR_UNSUPPORTED, "conv_small_cin: weights exceed 48 KiB");
-  const long long total = (long long)B * H * W * (Cout / 8);
-  const unsigned grid = blocks_for(total, 256);
+  if (Cout % 128 != 0 || ldy % 4 != 0) return fail(IDF_ERR_ARG, "conv_small_cin: Cout must be a multiple of 128");
+  const long long pixels = (long long)B * H * W;
+  const unsigned grid = blocks_for(pixels, 8 * 4, 148 * 8);  // ~4 pixels per warp at least
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const long long dup_rows = dup ? pixels : 0;
   switch (Cin) {
-    case 3: conv3x3_small_cin_kernel<3><<<grid, 256, smem, s>>>(x, w, bias, yp, ldy, B, H, W, Cout); break;
-    case 4: conv3x3_small_cin_kernel<4><<<grid, 256, smem, s>>>(x, w, bias, yp, ldy, B, H, W, Cout); break;
+    case 3: conv3x3_small_cin_kernel<3><<<grid, 256, 0, s>>>(x, w, bias, yp, ldy, B, H, W, Cout, dup_rows); break;
+    case 4: conv3x3_small_cin_kernel<4><<<grid, 256, 0, s>>>(x, w, bias, yp, ldy, B, H, W, Cout, dup_rows); break;
     default: return fail(IDF_ERR_UNSUPPORTED, "conv_small_cin: Cin %d not in {3,4}", Cin);
   }
   return check_cuda(cudaGetLastError(), "conv_small_cin launch");
@@ -480,6 +536,25 @@ extern "C" int idf_conv3x3_small_cin(const float* x, const float* w, const float
 template <int COUT>
 static int launch_small_cout(const __nv_bfloat16* x, long long ldx, const float* w, const float* bias, float* y, int B,
                              int Cin, int H, int W, cudaStream_t s) {
+  {
+    // tiled path whenever the image splits into 128-pixel tiles and the halo tile fits shared memory
+    const int TW = W >= 32 ? 32 : W;
+    const int TH = 128 / (TW > 0 ? TW : 1);
+    const int tsmem = ((9 * Cin * COUT * 4 + 15) & ~15) + (TH + 2) * (TW + 2) * (Cin * 2 + 16);
+    if (TW * TH == 128 && W % TW == 0 && H % TH == 0 && tsmem <= 100 * 1024) {
+      static int tsmem_set = 0;
+      if (tsmem > 48 * 1024 && tsmem > tsmem_set) {
+        int rc = check_cuda(cudaFuncSetAttribute(conv3x3_small_cout_tiled_kernel<COUT>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, tsmem),
+                            "conv_small_cout tiled: cudaFuncSetAttribute");
+        if (rc != IDF_OK) return rc;
+        tsmem_set = tsmem;
+      }
+      dim3 grid((H / TH) * (W / TW), B);
+      conv3x3_small_cout_tiled_kernel<COUT><<<grid, 128, tsmem, s>>>(x, ldx, w, bias, y, Cin, H, W, TH, TW);
+      return check_cuda(cudaGetLastError(), "conv_small_cout tiled launch");
+    }
+  }
   const int smem = 9 * Cin * COUT * 4;
   static int smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {

@@ -182,8 +182,9 @@ class UnetEngine:
             x = Act(dst, B, H, W, cout)
         return x
 
-    def run(self, x_nchw, t_rows, ctx_rows, mask_rows, row_idx, out_nchw):
-        """x_nchw fp32 (B, z, H, W) -> out_nchw fp32 (B, z, H, W).
+    def run(self, x_nchw, t_rows, ctx_rows, mask_rows, row_idx, out_nchw, dup_input=False):
+        """x_nchw fp32 (B, z, H, W) -> out_nchw fp32 (B, z, H, W). With dup_input the network runs at batch 2*B on
+        [x ; x] (CFG batch doubling; out_nchw then has 2*B samples) without materialising the doubled input.
 
         t_rows int64 (R,), ctx_rows int64 (R,) or None, mask_rows fp32 (R,) or None describe R distinct
         (timestep, class) embedding rows; row_idx int32 (B,) maps each sample to its row (None: R == B, identity).
@@ -191,6 +192,8 @@ class UnetEngine:
         self.prepare()
         w, ws = self.packed.w, self.ws
         B, _, H, W = x_nchw.shape
+        if dup_input:
+            B *= 2
         R = t_rows.shape[0]
         D = self.arch["time_dim"]
         table = ws.get("tp_table", R, self.P, torch.float32)
@@ -199,7 +202,7 @@ class UnetEngine:
                              w["t.cls"], w["t.wp"], w["t.bp"], table, scratch)
         ch = list(self.arch["channels"])
         a0 = ws.get("in", B * H * W, ch[0])
-        ops.conv3x3_small_cin(x_nchw, w["in.w"], w["in.b"], a0)
+        ops.conv3x3_small_cin(x_nchw, w["in.w"], w["in.b"], a0, dup=dup_input)
         self._tap("table", table)
         self._tap("in", a0)
         x = Act(a0, B, H, W, ch[0])

@@ -44,7 +44,7 @@ _SIGNATURES = {
     "idf_cfg_posterior_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32],
     "idf_add_noise": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32],
     "idf_vq_argmin": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32],
-    "idf_conv3x3_small_cin": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32],
+    "idf_conv3x3_small_cin": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32],
     "idf_conv3x3_small_cout": [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32],
     "idf_conv1x1_small_f32": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32],
     "idf_upsample_nearest2x": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32],

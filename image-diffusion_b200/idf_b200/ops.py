@@ -115,11 +115,12 @@ def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, idx_out: torch.Tensor, zq
     return idx_out
 
 
-def conv3x3_small_cin(x_nchw: torch.Tensor, w: torch.Tensor, bias, y: torch.Tensor):
+def conv3x3_small_cin(x_nchw: torch.Tensor, w: torch.Tensor, bias, y: torch.Tensor, dup: bool = False):
+    """dup=True also writes the result to rows [B*H*W, 2*B*H*W) of y (batch-doubled CFG input)."""
     B, Cin, H, W = x_nchw.shape
     _check_bf16_rows(y, "conv_small_cin y")
     call("idf_conv3x3_small_cin", x_nchw.data_ptr(), w.data_ptr(), ptr(bias), y.data_ptr(), y.stride(0), B, Cin, H, W,
-         w.shape[0])
+         w.shape[0], 1 if dup else 0)
     return y
 
 

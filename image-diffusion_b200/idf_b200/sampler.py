@@ -26,8 +26,8 @@ class CfgSampler:
         self.mask_rows = torch.cat([torch.ones(K, device=dev), torch.zeros(1, device=dev)]).to(torch.float32)
         self.row_idx = torch.cat([labels.to(torch.int32), torch.full((N,), K, device=dev, dtype=torch.int32)])
         self.cfg = cfg_scales.to(device=dev, dtype=torch.float32).contiguous()
-        self.xx = torch.zeros(2 * N, *latent_shape, device=dev, dtype=torch.float32)   # [x_t ; x_t]
-        self.eps = torch.empty_like(self.xx)                                            # [eps_cond ; eps_uncond]
+        self.xx = torch.zeros(N, *latent_shape, device=dev, dtype=torch.float32)        # x_t (fp32 state)
+        self.eps = torch.empty(2 * N, *latent_shape, device=dev, dtype=torch.float32)  # [eps_cond ; eps_uncond]
         self.z = torch.zeros(N, *latent_shape, device=dev, dtype=torch.float32)
         self.use_graph = use_graph
         self.graph = None
@@ -35,9 +35,9 @@ class CfgSampler:
 
     def _step(self):
         N = self.N
-        self.engine.run(self.xx, self.t_rows, self.ctx_rows, self.mask_rows, self.row_idx, self.eps)
-        ops.cfg_posterior_step(self.xx[:N], self.eps[:N], self.eps[N:], self.z, self.cfg, self.t_rows[:1], self.sched,
-                               self.xx[:N], None, self.xx[N:])
+        self.engine.run(self.xx, self.t_rows, self.ctx_rows, self.mask_rows, self.row_idx, self.eps, dup_input=True)
+        ops.cfg_posterior_step(self.xx, self.eps[:N], self.eps[N:], self.z, self.cfg, self.t_rows[:1], self.sched,
+                               self.xx)
 
     def _ensure_graph(self):
         if self.graph is not None or not self.use_graph:
@@ -58,12 +58,11 @@ class CfgSampler:
         self.xx.copy_(keep)
 
     def set_latent(self, x_T: torch.Tensor):
-        self.xx[:self.N].copy_(x_T)
-        self.xx[self.N:].copy_(x_T)
+        self.xx.copy_(x_T)
 
     @property
     def latent(self) -> torch.Tensor:
-        return self.xx[:self.N]
+        return self.xx
 
     def step(self, i: int, noise: torch.Tensor | None = None):
         """Advance x_i -> x_{i-1}. `noise` injects the step's N(0,1) draw; None draws it from the global CUDA

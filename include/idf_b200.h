@@ -170,10 +170,11 @@ int idf_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, float
 /*
  * idf_conv3x3_small_cin — direct 3x3 s1 p1 convolution for tiny Cin (the 3-channel latent): fp32 NCHW in,
  * bf16 NHWC out. Replaces unet.py:45,116 (in_conv) and components.py:207-208 (decoder 1x1 folded by the
- * caller + 3x3). w is fp32 OIHW, bias fp32 [Cout]; Cout % 8 == 0, Cin <= 8.
+ * caller + 3x3). w is fp32 OIHW, bias fp32 [Cout]; Cout % 128 == 0, Cin in {3, 4}. With dup != 0 the B*H*W output
+ * rows are also written to rows [B*H*W, 2*B*H*W): cond and uncond halves of a batch-doubled CFG pass share x_t.
  */
 int idf_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int64_t ldy, int32_t B,
-                          int32_t Cin, int32_t H, int32_t W, int32_t Cout, idf_stream_t stream);
+                          int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t dup, idf_stream_t stream);
 
 /*
  * idf_conv3x3_small_cout — direct 3x3 s1 p1 convolution for tiny Cout: bf16 NHWC in (already normalised and
