@@ -9,6 +9,7 @@
 // Samples with fewer than 128 tokens share a tile; a block-diagonal mask keeps them independent.
 //
 // Warp roles (192 threads): warps 0..3 = softmax / output rows, warp 4 = TMA producer, warp 5 = TMEM + MMA issuer.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -31,6 +32,8 @@ struct AttnParams {
   int nblk;        // key blocks per query tile
   int kv_stages;   // 1 or 2
   float scale_log2e;
+  int dbg;  // ablation switches for profiling (IDF_ATTN_DBG), 0 in production
+  long long* trace;  // dbg & 16: per-event clock64 trace of CTA (0, 0)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, QK_BYTES);
       tma_load_2d(smem_q, &p.tmQK, q_full, head * HD, row0);
       for (int j = 0; j < p.nblk; ++j) {
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
       const uint64_t dq = umma_desc_kmajor(smem_u32(smem_q), SWZ);
@@ -278,20 +281,62 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Software-pipelined variant for long sequences (>= 3 key blocks per query tile). One CTA per SM:
+// Software-pipelined variant for long sequences (>= 3 key blocks per query tile). One CTA (320 threads) per SM:
 //   * S is double-buffered in TMEM: the MMA thread issues Q K_{j+2}^T as soon as the softmax warps have pulled
 //     S_j into registers, so the next score tile is always ready when they come back for it;
 //   * P and the per-block output O_blk are double-buffered too: P_j V_j runs on the tensor core while the softmax
 //     warps already work on block j+1; O_blk_j is folded into the fp32 output rows one iteration late;
-//   * each softmax thread holds its whole 128-wide score row in registers (one TMEM read per score).
+//   * EIGHT softmax warps share the 128 rows: warps q and q+4 own the same 32 TMEM lanes (rows) and split the
+//     128 score columns (and the head_dim output columns) in halves, exchanging their partial row maxima through
+//     shared memory. Two warps per scheduler hide each other's fixed-latency stalls (a single warp issues only
+//     one instruction every ~3.7 cycles here — measured with ncu).
 // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+hd) O1 [320,320+hd) -> 512 allocated.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ATTP_TMEM_COLS = 512;
 constexpr int ATTP_KSTAGES = 4;
 constexpr int ATTP_VSTAGES = 3;
+constexpr int ATTP_THREADS = 384;  // warps 0..7 softmax (2 warpgroups), warp 8 TMA producer, warp 9 TMEM + MMA, 10-11 idle
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* dst) {
+  static_assert(N == 8 || N == 16 || N == 24 || N == 32, "unsupported column count");
+  if constexpr (N == 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(v[i]);
+  } else {
+    if constexpr (N >= 16) {
+      uint32_t v[16];
+      tmem_ld_32x16(taddr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dst[i] = __uint_as_float(v[i]);
+    }
+    if constexpr (N == 8 || N == 24) {
+      constexpr int base = N - 8;
+      uint32_t v[8];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(taddr + base)
+                   : "memory");
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[base + i] = __uint_as_float(v[i]);
+    }
+  }
+}
+
+#define ATT_TRACE(who, ev, jj)                                                                      \
+  do {                                                                                              \
+    if ((p.dbg & 16) && blockIdx.x == 300 && blockIdx.y == 3) {                                     \
+      p.trace[((who) * 16 + (jj)) * 8 + (ev)] = clock64();                                          \
+    }                                                                                               \
+  } while (0)
 
 template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const __grid_constant__ AttnParams p) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
   constexpr int QK_BYTES = 128 * SWZ;
   constexpr int V_BYTES = 2 * HD * 128;
@@ -304,7 +349,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
   uint8_t* smem_p = smem_q + QK_BYTES;                    // [2][P_BYTES]
   uint8_t* smem_k = smem_p + 2 * P_BYTES;                 // [ATTP_KSTAGES][QK_BYTES]
   uint8_t* smem_v = smem_k + ATTP_KSTAGES * QK_BYTES;     // [ATTP_VSTAGES][V_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + ATTP_VSTAGES * V_BYTES);
+  float* xch = reinterpret_cast<float*>(smem_v + ATTP_VSTAGES * V_BYTES);  // [2 parity][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 128);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;                       // [4]
   uint64_t* k_empty = k_full + ATTP_KSTAGES;         // [4]
@@ -323,8 +369,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
   const int row0 = tile_m * 128;
   const int kv_base = (row0 >> p.t_shift) << p.t_shift;
   const int n = p.nblk;
+  if (threadIdx.x == 0) ATT_TRACE(4, 2, 0);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tmQK);
     tma_prefetch_desc(&p.tmVT);
     mbar_init(q_full, 1);
@@ -338,7 +385,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
     }
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, ATTP_TMEM_COLS);
     tmem_relinquish();
   }
@@ -346,10 +393,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) ATT_TRACE(4, 0, 0);
 
-  if (warp == 4) {
+  // register re-balancing between warpgroups: the data-movement warpgroup gives its registers to the two softmax
+  // warpgroups, which keep a whole 128-wide score row per thread
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, QK_BYTES);
       tma_load_2d(smem_q, &p.tmQK, q_full, head * HD, row0);
       auto load_k = [&](int j) {
@@ -357,10 +409,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
         mbar_wait(&k_empty[st], ((j / ATTP_KSTAGES) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], QK_BYTES);
         tma_load_2d(smem_k + st * QK_BYTES, &p.tmQK, &k_full[st], p.C + head * HD, kv_base + j * 128);
+        ATT_TRACE(0, 0, j);
       };
       auto load_v = [&](int j) {
         const int st = j % ATTP_VSTAGES;
         mbar_wait(&v_empty[st], ((j / ATTP_VSTAGES) & 1) ^ 1);
+        ATT_TRACE(0, 1, j);
         mbar_expect_tx(&v_full[st], V_BYTES);
         uint8_t* dst = smem_v + st * V_BYTES;
         tma_load_2d(dst, &p.tmVT, &v_full[st], kv_base + j * 128, head * HD);
@@ -373,15 +427,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
         if (j + 2 < n) load_k(j + 2);
       }
     }
-  } else if (warp == 5) {
+    } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
       const uint64_t dq = umma_desc_kmajor(smem_u32(smem_q), SWZ);
       auto issue_s = [&](int j) {  // S[j & 1] = Q K_j^T
         const int st = j % ATTP_KSTAGES;
         mbar_wait(&k_full[st], (j / ATTP_KSTAGES) & 1);
+        ATT_TRACE(1, 0, j);
         tc_fence_after_sync();
         const uint64_t dk = umma_desc_kmajor(smem_u32(smem_k + st * QK_BYTES), SWZ);
 #pragma unroll
@@ -389,15 +444,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
           umma_bf16(tmem_base + (j & 1) * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
         umma_commit(&s_full[j & 1]);
         umma_commit(&k_empty[st]);
+        ATT_TRACE(1, 1, j);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
-      if (n > 1) issue_s(1);
+      if (n > 1) {
+        // start the second group about half a period late (once group 0 has taken S_0 into registers): with the
+        // two groups out of phase, one group's MUFU-bound exp phase overlaps the other's TMEM reads / max / stores
+        mbar_wait(&s_empty[0], 0);
+        issue_s(1);
+      }
       for (int j = 0; j < n; ++j) {
         const int b = j & 1;
         const int vs = j % ATTP_VSTAGES;
+        // the score buffer is free as soon as its group has pulled S_j into registers (early in its softmax):
+        // issue the group's next Q K^T now so that it is waiting in TMEM when the group comes back for it
+        if (j + 2 < n) {
+          mbar_wait(&s_empty[b], (j >> 1) & 1);
+          issue_s(j + 2);
+        }
         mbar_wait(&p_full[b], (j >> 1) & 1);
+        ATT_TRACE(1, 2, j);
         mbar_wait(&v_full[vs], (j / ATTP_VSTAGES) & 1);
+        ATT_TRACE(1, 3, j);
         tc_fence_after_sync();
         const uint8_t* pb = smem_p + b * P_BYTES;
         const uint8_t* vb = smem_v + vs * V_BYTES;
@@ -405,57 +474,94 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
         const uint64_t dp1 = umma_desc_kmajor(smem_u32(pb + 128 * 128), 128);
         const uint64_t dv0 = umma_desc_kmajor(smem_u32(vb), 128);
         const uint64_t dv1 = umma_desc_kmajor(smem_u32(vb + HD * 128), 128);
+        if (!(p.dbg & 8)) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_bf16(tmem_base + 256 + b * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), (k < 4 ? dv0 : dv1) + 2 * (k & 3),
-                    idesc_o, k != 0);
+                    idesc_o, (j >= 2) || (k != 0));  // accumulate over the group's key blocks
+        }
         umma_commit(&o_full[b]);
         umma_commit(&v_empty[vs]);
-        if (j + 2 < n) {
-          mbar_wait(&s_empty[b], (j >> 1) & 1);
-          issue_s(j + 2);
-        }
+        ATT_TRACE(1, 4, j);
       }
     }
+    }
   } else {
-    // ------------------------------------------------------------------ softmax + output rows (warps 0..3)
-    const int r = warp * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ------------------------------------------------------------------ softmax + output rows (warps 0..7)
+    // Two independent warpgroups: group g (warps 4g..4g+3, one row per thread) runs the online softmax over the
+    // key blocks j = g, g+2, g+4, ... with its own S / P / O_blk buffers and its own running (max, sum, output).
+    // The groups are naturally out of phase, so on every scheduler one warp's MUFU phase overlaps the other
+    // warp's TMEM loads, max reduction, packing and stores. The two partial results are merged at the end.
+    const int quad = warp & 3;
+    const int g = warp >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const long long m = (long long)row0 + r;
     const float c = p.scale_log2e;
-    float o_acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    // The output rows accumulate in TMEM across the group's key blocks (P V with accumulate). The softmax uses a
+    // possibly stale row maximum m_used: P = exp2((S - m_used) * c) stays exact arithmetic as long as it cannot
+    // overflow, so the accumulator is only rescaled when the true maximum outgrows m_used by more than 2^8
+    // (rare after the first block). No per-block read-back of the output rows.
+    float m_run = -INFINITY, l_run = 0.f;  // m_run = m_used
+    uint8_t* pbuf = smem_p + g * P_BYTES;
+    const uint32_t tmem_o = tmem_base + 256 + g * 64 + lane_addr;
 
-    for (int j = 0; j < n; ++j) {
-      const int b = j & 1;
-      mbar_wait(&s_full[b], (j >> 1) & 1);
+    int k = 0;
+    for (int j = g; j < n; j += 2, ++k) {
+      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 0, j);
+      mbar_wait(&s_full[g], k & 1);
+      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 1, j);
       tc_fence_after_sync();
       uint32_t sv[4][32];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32(tmem_base + b * 128 + lane_addr + ch * 32, sv[ch]);
+      for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32(tmem_base + g * 128 + lane_addr + ch * 32, sv[ch]);
       tmem_ld_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);  // S_j now lives in registers
+      if (lane == 0) mbar_arrive(&s_empty[g]);  // S_j now lives in registers
+      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 2, j);
 
-      float mx[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx[i & 7] = fmaxf(mx[i & 7], __uint_as_float(sv[ch][i]));
-      const float mrow = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
-                               fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-      const float m_new = fmaxf(m_run, mrow);
-      const float alpha = fast_exp2((m_run - m_new) * c);
-      const float mc = m_new * c;
-      m_run = m_new;
+        for (int i = 0; i < 32; i += 2)
+          mx[(i >> 1) & 3] = fmaxf(mx[(i >> 1) & 3],
+                                   fmaxf(__uint_as_float(sv[ch][i]), __uint_as_float(sv[ch][i + 1])));  // FMNMX3
+      const float mrow = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+
+      if (k > 0) {
+        // P_{k-1} V has to be complete before P is overwritten (and before the accumulator may be rescaled)
+        if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 3, j);
+        mbar_wait(&o_full[g], (k - 1) & 1);
+        if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 4, j);
+      }
+      const bool grow = (mrow - m_run) * c > 8.0f;  // first block: m_run = -inf -> true
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mrow : m_run;
+        const float alpha = fast_exp2((m_run - m_new) * c);  // 1 for rows that keep their maximum
+        m_run = m_new;
+        l_run *= alpha;
+        if (k > 0) {
+          tc_fence_after_sync();
+#pragma unroll
+          for (int d0 = 0; d0 < HD; d0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_o + d0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
+            tmem_st_32x16(tmem_o + d0, v);
+          }
+          tmem_st_wait();
+          tc_fence_before_sync();
+        }
+      }
+      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 5, j);
+      const float mc = m_run * c;
 
       float ps[4] = {0.f, 0.f, 0.f, 0.f};
-      uint8_t* pbuf = smem_p + b * P_BYTES;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint8_t* prow = pbuf + (ch >> 1) * (128 * 128) + r * 128;
@@ -478,50 +584,55 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
-      l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
-
-      if (j > 0) {  // fold block j-1 (computed at scale m_{j-1}) into the running output
-        const int pb = (j - 1) & 1;
-        mbar_wait(&o_full[pb], ((j - 1) >> 1) & 1);
-        tc_fence_after_sync();
-#pragma unroll
-        for (int d0 = 0; d0 < HD; d0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x16(tmem_base + 256 + pb * 64 + lane_addr + d0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int d = 0; d < 16; ++d) o_acc[d0 + d] += __uint_as_float(v[d]);
-        }
-      }
-      if (__any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll
-        for (int d = 0; d < HD; ++d) o_acc[d] *= alpha;
-      }
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 6, j);
+      l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
     }
-    {
-      const int pb = (n - 1) & 1;
-      mbar_wait(&o_full[pb], ((n - 1) >> 1) & 1);
+    float o_acc[HD];
+    if (k > 0) {  // all of this group's P V products are complete: fetch its output rows
+      mbar_wait(&o_full[g], (k - 1) & 1);
       tc_fence_after_sync();
 #pragma unroll
       for (int d0 = 0; d0 < HD; d0 += 16) {
         uint32_t v[16];
-        tmem_ld_32x16(tmem_base + 256 + pb * 64 + lane_addr + d0, v);
+        tmem_ld_32x16(tmem_o + d0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int d = 0; d < 16; ++d) o_acc[d0 + d] += __uint_as_float(v[d]);
+        for (int d = 0; d < 16; ++d) o_acc[d0 + d] = __uint_as_float(v[d]);
       }
+    } else {
+#pragma unroll
+      for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
     }
-    if (m < p.M) {
-      const float inv = 1.f / l_run;
+    // merge the two groups' partial softmax states: group 1 publishes (m, l, O) through shared memory (the P
+    // buffers are free once every P V product has completed), group 0 combines and writes the output rows
+    named_bar_sync(1, 256);
+    float* mrg = reinterpret_cast<float*>(smem_p);  // [HD + 2][128]: column-major so lanes hit distinct banks
+    if (g == 1) {
+      mrg[0 * 128 + r] = m_run;
+      mrg[1 * 128 + r] = l_run;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) mrg[(2 + d) * 128 + r] = o_acc[d];
+    }
+    named_bar_sync(1, 256);
+    if (g == 0 && m < p.M) {
+      const float m_b = mrg[0 * 128 + r], l_b = mrg[1 * 128 + r];
+      const float m_tot = fmaxf(m_run, m_b);
+      const float sa = fast_exp2((m_run - m_tot) * c);
+      const float sb = fast_exp2((m_b - m_tot) * c);  // 0 when group 1 had no block (m_b = -inf)
+      const float inv = 1.f / (l_run * sa + l_b * sb);
+      const float wa = sa * inv, wb = sb * inv;
       __nv_bfloat16* dst = p.out + m * p.ld_out + head * HD;
 #pragma unroll
       for (int d0 = 0; d0 < HD; d0 += 8) {
+        float f[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) f[d] = o_acc[d0 + d] * wa + mrg[(2 + d0 + d) * 128 + r] * wb;
         uint4 o;
-        o.x = pack_bf16x2(o_acc[d0 + 0] * inv, o_acc[d0 + 1] * inv);
-        o.y = pack_bf16x2(o_acc[d0 + 2] * inv, o_acc[d0 + 3] * inv);
-        o.z = pack_bf16x2(o_acc[d0 + 4] * inv, o_acc[d0 + 5] * inv);
-        o.w = pack_bf16x2(o_acc[d0 + 6] * inv, o_acc[d0 + 7] * inv);
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
         *reinterpret_cast<uint4*>(dst + d0) = o;
       }
     }
@@ -529,7 +640,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) {
+  if (threadIdx.x == 0) ATT_TRACE(4, 1, 0);
+  if (warp == 9) {
     __syncwarp();
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, ATTP_TMEM_COLS);
@@ -539,7 +651,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_pipe_kernel(const __
 template <int HD>
 static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
-  const int smem = 128 * SWZ + 2 * (2 * 128 * 128) + ATTP_KSTAGES * 128 * SWZ + ATTP_VSTAGES * 2 * HD * 128 + 1024 + 256;
+  const int smem = 128 * SWZ + 2 * (2 * 128 * 128) + ATTP_KSTAGES * 128 * SWZ + ATTP_VSTAGES * 2 * HD * 128 +
+                   2 * 2 * 128 * 4 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(attention_pipe_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
@@ -547,7 +660,7 @@ static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cuda
     if (rc != IDF_OK) return rc;
     attr_set = true;
   }
-  attention_pipe_kernel<HD><<<dim3(tiles, heads), ATT_THREADS, smem, stream>>>(p);
+  attention_pipe_kernel<HD><<<dim3(tiles, heads), ATTP_THREADS, smem, stream>>>(p);
   return check_cuda(cudaGetLastError(), "attention_pipe launch");
 }
 
@@ -589,6 +702,18 @@ extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, 
   p.nblk = T >= 128 ? T / 128 : 1;
   p.kv_stages = p.nblk > 1 ? 2 : 1;
   p.scale_log2e = scale * 1.4426950408889634f;
+  {
+    static const int dbg = [] { const char* e = getenv("IDF_ATTN_DBG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
+    static long long* trace = nullptr;
+    if ((dbg & 16) && trace == nullptr) {
+      cudaMalloc(&trace, 5 * 16 * 8 * sizeof(long long));
+      cudaMemset(trace, 0, 5 * 16 * 8 * sizeof(long long));
+      FILE* f = fopen("/tmp/idf_attn_trace_ptr", "w");
+      if (f) { fprintf(f, "%llu", (unsigned long long)trace); fclose(f); }
+    }
+    p.trace = trace;
+  }
 
   const int swz = head_dim <= 16 ? 32 : (head_dim <= 32 ? 64 : 128);
   const CUtensorMapSwizzle swz_enum = swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B

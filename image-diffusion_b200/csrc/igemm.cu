@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (elect.sync, not `lane == 0`: ptxas then knows a single thread runs the loop and feeds the uniform datapath
+    //  of UTMALDG / UTCHMMA directly instead of wrapping every issue in a warp-uniformisation loop)
+    if (elect_one()) {
       int img0, h0, w0 = 0;
       if (p.matrix) {
         img0 = 0;
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
       for (int kb = 0; kb < p.kb_total; ++kb) {
         const int s = kb % STAGES;
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
     const bool staged = !to_vt && !to_f32;
 
     if ((p.flags & F_RES) && staged) {
-      if (et == 0) {
+      if (warp == 2 && elect_one()) {
         mbar_expect_tx(res_bar, 2 * BLOCK_M * 128);
         tma_load_2d(stage_c, &p.tmR, res_bar, n0, tile_m * BLOCK_M);
         tma_load_2d(stage_c + BLOCK_M * 128, &p.tmR, res_bar, n0 + 64, tile_m * BLOCK_M);
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
     if (staged) {
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
-      if (et == 0) {
+      if (warp == 2 && elect_one()) {
         tma_store_2d(&p.tmC, stage_c, n0, tile_m * BLOCK_M);
         tma_store_2d(&p.tmC, stage_c + BLOCK_M * 128, n0 + 64, tile_m * BLOCK_M);
         tma_store_commit();

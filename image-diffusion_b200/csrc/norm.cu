@@ -1,7 +1,5 @@
 // GroupNorm (+ SiLU) over channels-last bf16 activations, and the row softmax used by the VAE attention.
 // Both are memory-bound: 16-byte vector accesses, fp32 statistics, second pass served from L2.
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 #include "host.h"
 #include "../../include/idf_b200.h"
@@ -17,110 +15,121 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
 }
 
-constexpr double GN_FIX = 268435456.0;  // 2^28
-__device__ __forceinline__ unsigned long long to_fixed(float v) {
-  return static_cast<unsigned long long>(__double2ll_rn(static_cast<double>(v) * GN_FIX));
-}
-__device__ __forceinline__ float from_fixed(unsigned long long v) {
-  return static_cast<float>(static_cast<double>(static_cast<long long>(v)) * (1.0 / GN_FIX));
+// ---------------------------------------------------------------------------------------------------------------
+// Standalone GroupNorm(+SiLU). grid = (B, slabs); a slab is `gps` consecutive groups = V (<= VP) 16-byte vectors
+// per pixel. Lane l of a warp owns vector (l % VP) of pixel row (l / VP), so a warp reads 32/VP whole pixel slabs
+// per sweep (coalesced) and lanes holding the same vector are reduced with a fixed xor-shuffle tree. Per-warp
+// per-channel partials are then summed over warps and over the channels of a group in a fixed order: the
+// statistics are bit-identical from run to run and independent of the batch size (no atomics anywhere).
+// Pass 2 re-reads the slab (L2) and writes the normalised, activated bf16 output.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GN_MAX_WARPS = 12;
+
+// silu(t) = t * sigmoid(t) = h + h * tanh(h) with h = t / 2: one MUFU op instead of two (ex2 + rcp); the
+// approximation error (~2^-11 relative) is far below the bf16 rounding of the stored result.
+__device__ __forceinline__ float silu_tanh(float t) {
+  const float h = 0.5f * t;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
 }
 
-// grid = (B, slabs). A slab is `gps` consecutive groups = gps*cpg channels = V 16-byte vectors per pixel.
-// Thread t owns vector (t % V) of pixels (t / V), (t / V) + rows_per_iter, ...
-template <bool SILU>
-__global__ void __launch_bounds__(512) groupnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
-                                                        __nv_bfloat16* __restrict__ y, long long ldy,
-                                                        const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, int HW, int cpg, int gps,
-                                                        int V, float eps) {
-  // Group sums are accumulated as Q36.28 fixed point: integer addition is associative, so the shared-memory
-  // atomics give bit-identical statistics from run to run (and across batch sizes) in any arrival order.
-  __shared__ unsigned long long s_sum[GN_MAX_GPS];
-  __shared__ unsigned long long s_sq[GN_MAX_GPS];
+template <bool SILU, int VP>
+__global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                      long long ldx, __nv_bfloat16* __restrict__ y,
+                                                                      long long ldy, const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta, int HW, int cpg,
+                                                                      int gps, int V, float eps) {
+  __shared__ float ch_s[GN_MAX_WARPS][VP * 8];
+  __shared__ float ch_q[GN_MAX_WARPS][VP * 8];
+  __shared__ float ct_s[VP * 8];
+  __shared__ float ct_q[VP * 8];
+  __shared__ float g_mean[GN_MAX_GPS];
+  __shared__ float g_rstd[GN_MAX_GPS];
+  constexpr int RPW = 32 / VP;  // pixel rows per warp per sweep
   const int b = blockIdx.x;
   const int c0 = blockIdx.y * gps * cpg;
-  const int v = threadIdx.x % V;
-  const int prow = threadIdx.x / V;
-  const int rows_per_iter = blockDim.x / V;
-  if (threadIdx.x < GN_MAX_GPS) {
-    s_sum[threadIdx.x] = 0ull;
-    s_sq[threadIdx.x] = 0ull;
-  }
-  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int v = lane % VP, prl = lane / VP;
+  const bool active = v < V;
+  const int rows_per_iter = nwarps * RPW;
 
   const __nv_bfloat16* xb = x + (long long)b * HW * ldx + c0 + v * 8;
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-  int pix = prow;
-  for (; pix + 3 * rows_per_iter < HW; pix += 4 * rows_per_iter) {
-    uint4 r0 = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
-    uint4 r1 = *reinterpret_cast<const uint4*>(xb + (long long)(pix + rows_per_iter) * ldx);
-    uint4 r2 = *reinterpret_cast<const uint4*>(xb + (long long)(pix + 2 * rows_per_iter) * ldx);
-    uint4 r3 = *reinterpret_cast<const uint4*>(xb + (long long)(pix + 3 * rows_per_iter) * ldx);
-    float f[8];
-    unpack8(r0, f);
+  if (active) {
+    int pix = warp * RPW + prl;
+    for (; pix + 3 * rows_per_iter < HW; pix += 4 * rows_per_iter) {
+      uint4 r[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
-    unpack8(r1, f);
+      for (int i = 0; i < 4; ++i) r[i] = *reinterpret_cast<const uint4*>(xb + (long long)(pix + i * rows_per_iter) * ldx);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
-    unpack8(r2, f);
+      for (int i = 0; i < 4; ++i) {
+        float f[8];
+        unpack8(r[i], f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
-    unpack8(r3, f);
+        for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+      }
+    }
+    for (; pix < HW; pix += rows_per_iter) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
+      float f[8];
+      unpack8(r0, f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+    }
   }
-  for (; pix < HW; pix += rows_per_iter) {
-    uint4 r0 = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
-    float f[8];
-    unpack8(r0, f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
-  }
-  // fold the 8 channel lanes into their groups, then one shared atomic per (thread, group)
-  {
-    int g_prev = (v * 8) / cpg;
-    float as = 0.f, aq = 0.f;
+  for (int off = VP; off < 32; off <<= 1) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int g = (v * 8 + e) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&s_sum[g_prev], to_fixed(as));
-        atomicAdd(&s_sq[g_prev], to_fixed(aq));
-        as = 0.f; aq = 0.f; g_prev = g;
-      }
-      as += s[e];
-      aq += q[e];
+      s[e] += __shfl_xor_sync(0xffffffffu, s[e], off);
+      q[e] += __shfl_xor_sync(0xffffffffu, q[e], off);
     }
-    atomicAdd(&s_sum[g_prev], to_fixed(as));
-    atomicAdd(&s_sq[g_prev], to_fixed(aq));
+  }
+  if (prl == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ch_s[warp][v * 8 + e] = s[e]; ch_q[warp][v * 8 + e] = q[e]; }
   }
   __syncthreads();
+  if (threadIdx.x < V * 8) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < nwarps; ++w) { a += ch_s[w][threadIdx.x]; c += ch_q[w][threadIdx.x]; }
+    ct_s[threadIdx.x] = a;
+    ct_q[threadIdx.x] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x < gps) {
+    float a = 0.f, c = 0.f;
+    for (int k = 0; k < cpg; ++k) { a += ct_s[threadIdx.x * cpg + k]; c += ct_q[threadIdx.x * cpg + k]; }
+    const float inv_cnt = 1.f / ((float)HW * (float)cpg);
+    const float mean = a * inv_cnt;
+    const float var = fmaxf(c * inv_cnt - mean * mean, 0.f);
+    g_mean[threadIdx.x] = mean;
+    g_rstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  if (!active) return;
 
-  const float inv_cnt = 1.f / ((float)HW * (float)cpg);
   float sc[8], sh[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int cl = v * 8 + e;
     const int g = cl / cpg;
-    const float mean = from_fixed(s_sum[g]) * inv_cnt;
-    const float var = fmaxf(from_fixed(s_sq[g]) * inv_cnt - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
     const float ga = gamma[c0 + cl], be = beta[c0 + cl];
-    sc[e] = rstd * ga;
-    sh[e] = be - mean * rstd * ga;
+    sc[e] = g_rstd[g] * ga;
+    sh[e] = be - g_mean[g] * g_rstd[g] * ga;
   }
   __nv_bfloat16* yb = y + (long long)b * HW * ldy + c0 + v * 8;
-  for (pix = prow; pix < HW; pix += rows_per_iter) {
-    uint4 r0 = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
+  for (int pix = warp * RPW + prl; pix < HW; pix += rows_per_iter) {
+    const uint4 r0 = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
     float f[8];
     unpack8(r0, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float t = fmaf(f[e], sc[e], sh[e]);
-      if (SILU) t = t / (1.f + __expf(-t));
+      if (SILU) t = silu_tanh(t);
       f[e] = t;
     }
     uint4 o;
@@ -129,120 +138,6 @@ __global__ void __launch_bounds__(512) groupnorm_kernel(const __nv_bfloat16* __r
     o.z = pack_bf16x2(f[4], f[5]);
     o.w = pack_bf16x2(f[6], f[7]);
     *reinterpret_cast<uint4*>(yb + (long long)pix * ldy) = o;
-  }
-}
-
-
-// Single-read variant: the pixels of one (sample, slab) are split over a thread-block cluster. Every CTA keeps its
-// pixels in registers, publishes fixed-point partial sums in its shared memory, the cluster exchanges them through
-// distributed shared memory, and each CTA normalises its own registers: one HBM read + one write per element.
-constexpr int GN_MAXP = 8;
-template <bool SILU>
-__global__ void __launch_bounds__(512) groupnorm_cluster_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
-                                                                __nv_bfloat16* __restrict__ y, long long ldy,
-                                                                const float* __restrict__ gamma,
-                                                                const float* __restrict__ beta, int HW, int cpg,
-                                                                int gps, int V, float eps, int cs) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  __shared__ unsigned long long s_sum[GN_MAX_GPS];
-  __shared__ unsigned long long s_sq[GN_MAX_GPS];
-  const int rank = (int)cluster.block_rank();
-  const int b = blockIdx.x / cs;
-  const int c0 = blockIdx.y * gps * cpg;
-  const int v = threadIdx.x % V;
-  const int prow = threadIdx.x / V;
-  const int rows_per_iter = blockDim.x / V;
-  const int ppc = HW / cs;  // pixels per CTA
-  if (threadIdx.x < GN_MAX_GPS) {
-    s_sum[threadIdx.x] = 0ull;
-    s_sq[threadIdx.x] = 0ull;
-  }
-  __syncthreads();
-  const long long row0 = (long long)b * HW + (long long)rank * ppc;
-  const __nv_bfloat16* xb = x + row0 * ldx + c0 + v * 8;
-  uint4 held[GN_MAXP];
-  float s[8], q[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-#pragma unroll
-  for (int i = 0; i < GN_MAXP; ++i) {
-    const int pix = prow + i * rows_per_iter;
-    held[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (pix < ppc) held[i] = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
-  }
-#pragma unroll
-  for (int i = 0; i < GN_MAXP; ++i) {
-    float f[8];
-    unpack8(held[i], f);  // out-of-range slots hold zeros and add nothing
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
-  }
-  {
-    int g_prev = (v * 8) / cpg;
-    float as = 0.f, aq = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int g = (v * 8 + e) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&s_sum[g_prev], to_fixed(as));
-        atomicAdd(&s_sq[g_prev], to_fixed(aq));
-        as = 0.f; aq = 0.f; g_prev = g;
-      }
-      as += s[e];
-      aq += q[e];
-    }
-    atomicAdd(&s_sum[g_prev], to_fixed(as));
-    atomicAdd(&s_sq[g_prev], to_fixed(aq));
-  }
-  cluster.sync();
-  // every CTA sums the cluster's partials itself (integer addition: any order gives the same bits)
-  __shared__ unsigned long long t_sum[GN_MAX_GPS];
-  __shared__ unsigned long long t_sq[GN_MAX_GPS];
-  if (threadIdx.x < gps) {
-    unsigned long long a = 0ull, c = 0ull;
-    for (int r = 0; r < cs; ++r) {
-      a += *cluster.map_shared_rank(&s_sum[threadIdx.x], r);
-      c += *cluster.map_shared_rank(&s_sq[threadIdx.x], r);
-    }
-    t_sum[threadIdx.x] = a;
-    t_sq[threadIdx.x] = c;
-  }
-  cluster.sync();  // nobody may exit (or proceed) while a peer still reads its partials
-
-  const float inv_cnt = 1.f / ((float)HW * (float)cpg);
-  float sc[8], sh[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int cl = v * 8 + e;
-    const int g = cl / cpg;
-    const float mean = from_fixed(t_sum[g]) * inv_cnt;
-    const float var = fmaxf(from_fixed(t_sq[g]) * inv_cnt - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float ga = gamma[c0 + cl], be = beta[c0 + cl];
-    sc[e] = rstd * ga;
-    sh[e] = be - mean * rstd * ga;
-  }
-  __nv_bfloat16* yb = y + row0 * ldy + c0 + v * 8;
-#pragma unroll
-  for (int i = 0; i < GN_MAXP; ++i) {
-    const int pix = prow + i * rows_per_iter;
-    if (pix < ppc) {
-      float f[8];
-      unpack8(held[i], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float t = fmaf(f[e], sc[e], sh[e]);
-        if (SILU) t = t / (1.f + __expf(-t));
-        f[e] = t;
-      }
-      uint4 o;
-      o.x = pack_bf16x2(f[0], f[1]);
-      o.y = pack_bf16x2(f[2], f[3]);
-      o.z = pack_bf16x2(f[4], f[5]);
-      o.w = pack_bf16x2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(yb + (long long)pix * ldy) = o;
-    }
   }
 }
 
@@ -299,56 +194,29 @@ extern "C" int idf_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t l
   if (!x || !y || !gamma || !beta) return fail(IDF_ERR_ARG, "groupnorm: null pointer");
   if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups != 0) return fail(IDF_ERR_ARG, "groupnorm: bad shape");
   const int cpg = C / groups;
-  int gps = (groups % 8 == 0) ? 8 : groups;
-  if (gps > GN_MAX_GPS) return fail(IDF_ERR_UNSUPPORTED, "groupnorm: %d groups per slab", gps);
-  if ((gps * cpg) % 8 != 0) return fail(IDF_ERR_UNSUPPORTED, "groupnorm: slab of %d channels not a multiple of 8", gps * cpg);
+  // groups per slab: as many as possible (<= 8) while a slab stays <= 8 sixteen-byte vectors wide
+  int gps = 0;
+  for (int d = 8; d >= 1; --d)
+    if (groups % d == 0 && (d * cpg) % 8 == 0 && d * cpg / 8 <= 8) { gps = d; break; }
+  if (gps == 0) return fail(IDF_ERR_UNSUPPORTED, "groupnorm: %d channels in %d groups does not split into slabs", C, groups);
   const int V = gps * cpg / 8;
-  if (V > 512) return fail(IDF_ERR_UNSUPPORTED, "groupnorm: slab too wide");
   if (ldx % 8 != 0 || ldy % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
     return fail(IDF_ERR_ARG, "groupnorm: 16-byte alignment required");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
-  int threads = (384 / V) * V;
-  if (threads == 0) threads = V;
-  {
-    // cluster path: split the pixels of a sample over up to 8 CTAs so each thread holds <= GN_MAXP vectors
-    int cs = 8;
-    while (cs > 1 && (HW % cs != 0 || HW / cs < 16)) cs >>= 1;
-    const int ppc = HW / cs;
-    int th = threads;
-    while (th / V > ppc && th > V) th -= V;
-    const int per_thread = (ppc + th / V - 1) / (th / V);
-    if (per_thread <= GN_MAXP) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(B * cs, groups / gps);
-      cfg.blockDim = dim3(th);
-      cfg.dynamicSmemBytes = 0;
-      cfg.stream = s;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = cs;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      cudaError_t e;
-      if (apply_silu)
-        e = cudaLaunchKernelEx(&cfg, groupnorm_cluster_kernel<true>, xp, (long long)ldx, yp, (long long)ldy, gamma, beta,
-                               (int)HW, cpg, gps, V, eps, cs);
-      else
-        e = cudaLaunchKernelEx(&cfg, groupnorm_cluster_kernel<false>, xp, (long long)ldx, yp, (long long)ldy, gamma, beta,
-                               (int)HW, cpg, gps, V, eps, cs);
-      return check_cuda(e, "groupnorm cluster launch");
-    }
-  }
-  // small images: do not launch more pixel rows than exist
-  while (threads / V > HW && threads > V) threads -= V;
+  const int VP = V <= 4 ? 4 : 8;
+  int warps = GN_MAX_WARPS;
+  while (warps > 1 && (warps - 1) * (32 / VP) >= HW) --warps;  // tiny images: no idle warps
   dim3 grid(B, groups / gps);
-  if (apply_silu)
-    groupnorm_kernel<true><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
-  else
-    groupnorm_kernel<false><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
+  const int threads = warps * 32;
+  if (VP == 4) {
+    if (apply_silu) groupnorm_kernel<true, 4><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
+    else groupnorm_kernel<false, 4><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
+  } else {
+    if (apply_silu) groupnorm_kernel<true, 8><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
+    else groupnorm_kernel<false, 8><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
+  }
   return check_cuda(cudaGetLastError(), "groupnorm launch");
 }
 
