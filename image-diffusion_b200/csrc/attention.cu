@@ -281,16 +281,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Software-pipelined variant for long sequences (>= 3 key blocks per query tile). One CTA (320 threads) per SM:
-//   * S is double-buffered in TMEM: the MMA thread issues Q K_{j+2}^T as soon as the softmax warps have pulled
-//     S_j into registers, so the next score tile is always ready when they come back for it;
-//   * P and the per-block output O_blk are double-buffered too: P_j V_j runs on the tensor core while the softmax
-//     warps already work on block j+1; O_blk_j is folded into the fp32 output rows one iteration late;
-//   * EIGHT softmax warps share the 128 rows: warps q and q+4 own the same 32 TMEM lanes (rows) and split the
-//     128 score columns (and the head_dim output columns) in halves, exchanging their partial row maxima through
-//     shared memory. Two warps per scheduler hide each other's fixed-latency stalls (a single warp issues only
-//     one instruction every ~3.7 cycles here — measured with ncu).
-// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+hd) O1 [320,320+hd) -> 512 allocated.
+// Pipelined variant for samples with >= 256 tokens. One CTA (384 threads) per SM owns TWO query tiles (256 rows)
+// of one head; every K / V block is fetched once and used for both tiles.
+//   * warpgroup g (warps 4g..4g+3, one row per thread) runs the online softmax of query tile g; the two groups
+//     are started half a period apart so that one group's MUFU-bound exp phase overlaps the other group's TMEM
+//     reads, max reduction and stores (a single warp per scheduler reaches only ~60% of the MUFU rate);
+//   * the MMA thread issues Q_g K_{j+1}^T as soon as group g has pulled S_g(j) into registers, so the next score
+//     tile is waiting in TMEM when the group comes back for it;
+//   * the output rows accumulate in TMEM over all key blocks (lazy rescaling, see below): no per-block read-back.
+// TMEM columns: S_0 [0,128) S_1 [128,256) O_0 [256,256+hd) O_1 [320,320+hd) -> 512 allocated.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ATTP_TMEM_COLS = 512;
 constexpr int ATTP_KSTAGES = 4;
@@ -345,8 +344,8 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* smem_q = smem;
-  uint8_t* smem_p = smem_q + QK_BYTES;                    // [2][P_BYTES]
+  uint8_t* smem_q = smem;                                 // [2][QK_BYTES]: query tiles 0 and 1
+  uint8_t* smem_p = smem_q + 2 * QK_BYTES;                // [2][P_BYTES]
   uint8_t* smem_k = smem_p + 2 * P_BYTES;                 // [ATTP_KSTAGES][QK_BYTES]
   uint8_t* smem_v = smem_k + ATTP_KSTAGES * QK_BYTES;     // [ATTP_VSTAGES][V_BYTES]
   float* xch = reinterpret_cast<float*>(smem_v + ATTP_VSTAGES * V_BYTES);  // [2 parity][2 halves][128 rows]
@@ -364,9 +363,8 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x;
   const int head = blockIdx.y;
-  const int row0 = tile_m * 128;
+  const int row0 = blockIdx.x * 256;  // two query tiles per CTA (same sample: T >= 256)
   const int kv_base = (row0 >> p.t_shift) << p.t_shift;
   const int n = p.nblk;
   if (threadIdx.x == 0) ATT_TRACE(4, 2, 0);
@@ -402,8 +400,9 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
     if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      mbar_expect_tx(q_full, QK_BYTES);
+      mbar_expect_tx(q_full, 2 * QK_BYTES);
       tma_load_2d(smem_q, &p.tmQK, q_full, head * HD, row0);
+      tma_load_2d(smem_q + QK_BYTES, &p.tmQK, q_full, head * HD, row0 + 128);
       auto load_k = [&](int j) {
         const int st = j % ATTP_KSTAGES;
         mbar_wait(&k_empty[st], ((j / ATTP_KSTAGES) & 1) ^ 1);
@@ -425,64 +424,67 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
       for (int j = 0; j < n; ++j) {
         load_v(j);
         if (j + 2 < n) load_k(j + 2);
-      }
+      }  // (K runs two blocks ahead of V: S(j+1) is issued while the softmax of block j is still running)
     }
     } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
-      const uint64_t dq = umma_desc_kmajor(smem_u32(smem_q), SWZ);
-      auto issue_s = [&](int j) {  // S[j & 1] = Q K_j^T
+      const uint64_t dq[2] = {umma_desc_kmajor(smem_u32(smem_q), SWZ),
+                              umma_desc_kmajor(smem_u32(smem_q + QK_BYTES), SWZ)};
+      auto issue_s = [&](int g, int j) {  // S_g = Q_g K_j^T
         const int st = j % ATTP_KSTAGES;
-        mbar_wait(&k_full[st], (j / ATTP_KSTAGES) & 1);
-        ATT_TRACE(1, 0, j);
-        tc_fence_after_sync();
+        if (g == 0) {
+          mbar_wait(&k_full[st], (j / ATTP_KSTAGES) & 1);
+          ATT_TRACE(1, 0, j);
+          tc_fence_after_sync();
+        }
         const uint64_t dk = umma_desc_kmajor(smem_u32(smem_k + st * QK_BYTES), SWZ);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tmem_base + (j & 1) * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[j & 1]);
-        umma_commit(&k_empty[st]);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + g * 128, dq[g] + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[g]);
+        if (g == 1) umma_commit(&k_empty[st]);  // both tiles have consumed K_j
         ATT_TRACE(1, 1, j);
       };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      if (n > 1) {
-        // start the second group about half a period late (once group 0 has taken S_0 into registers): with the
-        // two groups out of phase, one group's MUFU-bound exp phase overlaps the other's TMEM reads / max / stores
-        mbar_wait(&s_empty[0], 0);
-        issue_s(1);
-      }
-      for (int j = 0; j < n; ++j) {
-        const int b = j & 1;
+      auto issue_pv = [&](int g, int j) {  // O_g (+)= P_g V_j
         const int vs = j % ATTP_VSTAGES;
-        // the score buffer is free as soon as its group has pulled S_j into registers (early in its softmax):
-        // issue the group's next Q K^T now so that it is waiting in TMEM when the group comes back for it
-        if (j + 2 < n) {
-          mbar_wait(&s_empty[b], (j >> 1) & 1);
-          issue_s(j + 2);
-        }
-        mbar_wait(&p_full[b], (j >> 1) & 1);
+        mbar_wait(&p_full[g], j & 1);
         ATT_TRACE(1, 2, j);
-        mbar_wait(&v_full[vs], (j / ATTP_VSTAGES) & 1);
-        ATT_TRACE(1, 3, j);
+        if (g == 0) mbar_wait(&v_full[vs], (j / ATTP_VSTAGES) & 1);
         tc_fence_after_sync();
-        const uint8_t* pb = smem_p + b * P_BYTES;
+        const uint8_t* pb = smem_p + g * P_BYTES;
         const uint8_t* vb = smem_v + vs * V_BYTES;
         const uint64_t dp0 = umma_desc_kmajor(smem_u32(pb), 128);
         const uint64_t dp1 = umma_desc_kmajor(smem_u32(pb + 128 * 128), 128);
         const uint64_t dv0 = umma_desc_kmajor(smem_u32(vb), 128);
         const uint64_t dv1 = umma_desc_kmajor(smem_u32(vb + HD * 128), 128);
-        if (!(p.dbg & 8)) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + 256 + b * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), (k < 4 ? dv0 : dv1) + 2 * (k & 3),
-                    idesc_o, (j >= 2) || (k != 0));  // accumulate over the group's key blocks
-        }
-        umma_commit(&o_full[b]);
-        umma_commit(&v_empty[vs]);
+          umma_bf16(tmem_base + 256 + g * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), (k < 4 ? dv0 : dv1) + 2 * (k & 3),
+                    idesc_o, (j > 0) || (k != 0));  // accumulate over the key blocks
+        umma_commit(&o_full[g]);
+        if (g == 1) umma_commit(&v_empty[vs]);
         ATT_TRACE(1, 4, j);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0, 0);
+      // start the second tile about half a period late (once group 0 has taken S_0(0) into registers): with the
+      // groups out of phase, one group's MUFU-bound exp phase overlaps the other's TMEM reads / max / stores
+      mbar_wait(&s_empty[0], 0);
+      if (n > 1) issue_s(0, 1);
+      issue_s(1, 0);
+      for (int j = 0; j < n; ++j) {
+        issue_pv(0, j);
+        if (j + 1 < n) {
+          mbar_wait(&s_empty[1], j & 1);
+          issue_s(1, j + 1);
+        }
+        if (j + 2 < n) {
+          mbar_wait(&s_empty[0], (j + 1) & 1);
+          issue_s(0, j + 2);
+        }
+        issue_pv(1, j);
       }
     }
     }
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
     const int g = warp >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const long long m = (long long)row0 + r;
+    const long long m = (long long)row0 + g * 128 + r;
     const float c = p.scale_log2e;
     // The output rows accumulate in TMEM across the group's key blocks (P V with accumulate). The softmax uses a
     // possibly stale row maximum m_used: P = exp2((S - m_used) * c) stays exact arithmetic as long as it cannot
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
     const uint32_t tmem_o = tmem_base + 256 + g * 64 + lane_addr;
 
     int k = 0;
-    for (int j = g; j < n; j += 2, ++k) {
+    for (int j = 0; j < n; ++j, ++k) {
       if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 0, j);
       mbar_wait(&s_full[g], k & 1);
       if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 1, j);
@@ -604,35 +606,16 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
 #pragma unroll
       for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
     }
-    // merge the two groups' partial softmax states: group 1 publishes (m, l, O) through shared memory (the P
-    // buffers are free once every P V product has completed), group 0 combines and writes the output rows
-    named_bar_sync(1, 256);
-    float* mrg = reinterpret_cast<float*>(smem_p);  // [HD + 2][128]: column-major so lanes hit distinct banks
-    if (g == 1) {
-      mrg[0 * 128 + r] = m_run;
-      mrg[1 * 128 + r] = l_run;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) mrg[(2 + d) * 128 + r] = o_acc[d];
-    }
-    named_bar_sync(1, 256);
-    if (g == 0 && m < p.M) {
-      const float m_b = mrg[0 * 128 + r], l_b = mrg[1 * 128 + r];
-      const float m_tot = fmaxf(m_run, m_b);
-      const float sa = fast_exp2((m_run - m_tot) * c);
-      const float sb = fast_exp2((m_b - m_tot) * c);  // 0 when group 1 had no block (m_b = -inf)
-      const float inv = 1.f / (l_run * sa + l_b * sb);
-      const float wa = sa * inv, wb = sb * inv;
+    if (m < p.M) {
+      const float inv = 1.f / l_run;
       __nv_bfloat16* dst = p.out + m * p.ld_out + head * HD;
 #pragma unroll
       for (int d0 = 0; d0 < HD; d0 += 8) {
-        float f[8];
-#pragma unroll
-        for (int d = 0; d < 8; ++d) f[d] = o_acc[d0 + d] * wa + mrg[(2 + d0 + d) * 128 + r] * wb;
         uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]);
-        o.y = pack_bf16x2(f[2], f[3]);
-        o.z = pack_bf16x2(f[4], f[5]);
-        o.w = pack_bf16x2(f[6], f[7]);
+        o.x = pack_bf16x2(o_acc[d0 + 0] * inv, o_acc[d0 + 1] * inv);
+        o.y = pack_bf16x2(o_acc[d0 + 2] * inv, o_acc[d0 + 3] * inv);
+        o.z = pack_bf16x2(o_acc[d0 + 4] * inv, o_acc[d0 + 5] * inv);
+        o.w = pack_bf16x2(o_acc[d0 + 6] * inv, o_acc[d0 + 7] * inv);
         *reinterpret_cast<uint4*>(dst + d0) = o;
       }
     }
@@ -651,7 +634,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
 template <int HD>
 static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
-  const int smem = 128 * SWZ + 2 * (2 * 128 * 128) + ATTP_KSTAGES * 128 * SWZ + ATTP_VSTAGES * 2 * HD * 128 +
+  const int smem = 2 * 128 * SWZ + 2 * (2 * 128 * 128) + ATTP_KSTAGES * 128 * SWZ + ATTP_VSTAGES * 2 * HD * 128 +
                    2 * 2 * 128 * 4 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -660,7 +643,7 @@ static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cuda
     if (rc != IDF_OK) return rc;
     attr_set = true;
   }
-  attention_pipe_kernel<HD><<<dim3(tiles, heads), ATTP_THREADS, smem, stream>>>(p);
+  attention_pipe_kernel<HD><<<dim3((tiles + 1) / 2, heads), ATTP_THREADS, smem, stream>>>(p);
   return check_cuda(cudaGetLastError(), "attention_pipe launch");
 }
 
@@ -740,7 +723,7 @@ extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, 
     const char* e = getenv("IDF_ATTN_PIPE_MIN_BLOCKS");
     return e ? atoi(e) : 3;
   }();
-  if (p.nblk >= pipe_min_blocks) {
+  if (p.nblk >= pipe_min_blocks && T >= 256) {
     switch (head_dim) {
       case 16: return launch_attention_pipe<16>(p, tiles, heads, s);
       case 32: return launch_attention_pipe<32>(p, tiles, heads, s);

@@ -11,6 +11,7 @@
 // residual / padding mask, and hand a bf16 tile to a TMA store.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -304,6 +305,322 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks a static list of output tiles (128 x BN, BN in {128, 192, 256}).
+// The fp32 accumulator is double-buffered in tensor memory, so the epilogue of tile i (TMEM -> registers -> bias /
+// time bias / residual -> bf16 -> swizzled staging -> TMA store) overlaps the TMA + tcgen05.mma mainloop of tile
+// i + 1, and the smem ring keeps streaming across tile boundaries. BN = 256 halves the A re-reads and takes the
+// per-MMA shared-memory traffic below the 128 B/clk limit that bounds 128 x 128 tiles.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PG_THREADS = 192;
+constexpr int PG_STG_BYTES = 2 * BLOCK_M * 128;  // one staging buffer: two (128 rows x 64 cols) swizzled boxes
+
+// BN: tile width; NSTG: epilogue staging buffers (1: long-K tiles whose epilogue hides under the next mainloop;
+// 3: short-K, epilogue-bound tiles - store of group g-1, fill of group g and residual prefetch of group g+1 overlap)
+template <int BN, int NSTG>
+struct PgCfg {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
+  static constexpr int STAGES = (NSTG == 3) ? 4 : ((BN == 128) ? 5 : 4);
+  static constexpr int TMEM_COLS = (BN == 128) ? 256 : 512;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + NSTG * PG_STG_BYTES + 1024 + 256;
+};
+
+template <int BN, int NSTG>
+__global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
+  using Cfg = PgCfg<BN, NSTG>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int GPT = (BN + 127) / 128;  // column groups per tile
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;                                // [STAGES][16 KiB]
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;       // [STAGES][BN * 128]
+  uint8_t* stage_base = smem + STAGES * Cfg::STAGE_BYTES;  // [NSTG][32 KiB] dedicated epilogue staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + NSTG * PG_STG_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint64_t* res_bar = tmem_empty + 2;           // [NSTG]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + NSTG);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = p.N / BN;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+    if (p.kb_total > p.kb_seg0) tma_prefetch_desc(&p.tmA[1]);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    for (int i = 0; i < NSTG; ++i) mbar_init(&res_bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int kc = 0;  // running k-block counter across tiles (ring position)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int tile_m = t / n_tiles, n0 = (t % n_tiles) * BN;
+        int img0, h0, w0 = 0;
+        if (p.matrix) {
+          img0 = 0; h0 = 0; w0 = tile_m * BLOCK_M;
+        } else if (p.tiles_per_img > 0) {
+          img0 = tile_m / p.tiles_per_img;
+          h0 = (tile_m % p.tiles_per_img) * p.tile_h;
+        } else {
+          img0 = tile_m * p.tile_n; h0 = 0;
+        }
+        int seg = 0, tap = 0, cbk = 0;
+        for (int kb = 0; kb < p.kb_total; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          int dh = 0, dw = 0;
+          if (p.taps[seg] == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+          tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0);
+          tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+          if (++cbk == p.cb[seg]) {
+            cbk = 0;
+            if (++tap == p.taps[seg]) { tap = 0; ++seg; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+      int kc = 0, it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        tc_fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.kb_total; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+          tc_fence_after_sync();
+          const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + s * A_STAGE_BYTES), 128);
+          const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + s * Cfg::B_BYTES), 128);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // Work unit = "column group": up to 128 output columns of a tile = one staging buffer. Groups are numbered gc
+    // across tiles; group gc owns staging buffer gc % NSTG.
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const bool has_res = (p.flags & F_RES) != 0;
+    const bool to_f32 = (p.flags & F_OUT_F32) != 0;
+    const bool issuer = (warp == 2) && elect_one();
+    auto group_cols = [&](int cg) { return (BN - cg * 128) < 128 ? (BN - cg * 128) : 128; };
+    auto load_res = [&](int t, int cg, int gc) {  // residual boxes of group (t, cg) -> staging buffer gc % NSTG
+      const int bufi = gc % NSTG;
+      const int gcols = group_cols(cg);
+      const int nc0 = (t % n_tiles) * BN + cg * 128;
+      uint8_t* dst = stage_base + bufi * PG_STG_BYTES;
+      mbar_expect_tx(&res_bar[bufi], (gcols / 64) * BLOCK_M * 128);
+      for (int bx = 0; bx < gcols / 64; ++bx)
+        tma_load_2d(dst + bx * (BLOCK_M * 128), &p.tmR, &res_bar[bufi], nc0 + bx * 64, (t / n_tiles) * BLOCK_M);
+    };
+    int it = 0, gc = 0;
+    if (has_res && issuer && blockIdx.x < total_tiles && !((p.flags & F_VT) || to_f32)) load_res(blockIdx.x, 0, 0);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int tile_m = t / n_tiles, n0 = (t % n_tiles) * BN;
+      const int acc = it & 1;
+      const long long m = (long long)tile_m * BLOCK_M + r;
+      const bool row_ok = m < p.M;
+      const bool to_vt = (p.flags & F_VT) && n0 >= p.vt_col0;
+      const bool staged = !to_vt && !to_f32;
+
+      int sample = 0;
+      bool zero_row = false;
+      if (p.rowbias != nullptr || (p.flags & F_ZERO_PAD)) {
+        const long long mm = row_ok ? m : 0;
+        sample = (int)(mm / p.HW);
+        const int pix = (int)(mm % p.HW);
+        if (p.flags & F_ZERO_PAD) zero_row = (pix / p.W == p.H - 1) || (pix % p.W == p.W - 1);
+      }
+      const float* rb = nullptr;
+      if (p.rowbias != nullptr) {
+        const int rrow = p.rowbias_idx ? p.rowbias_idx[sample] : sample;
+        rb = p.rowbias + (long long)rrow * p.rowbias_ld + n0;
+      }
+
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t tmem_d = tmem_base + acc * BN + lane_addr;
+
+#pragma unroll 1
+      for (int cg = 0; cg < GPT; ++cg, ++gc) {
+        const int gcols = group_cols(cg);
+        const int nc0 = n0 + cg * 128;
+        uint8_t* stage_c = stage_base + (gc % NSTG) * PG_STG_BYTES;
+        // Staging buffer reuse: the TMA store issued NSTG groups ago must have finished READING this buffer; with a
+        // residual prefetch one group ahead, the buffer of group gc+1 (stored NSTG-1 groups ago) must be free too.
+        if (issuer) {
+          if (NSTG >= 3 && has_res) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSTG >= 3 ? NSTG - 2 : 0) : "memory");
+          else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSTG - 1) : "memory");
+        }
+        named_bar_sync(1, 128);
+        if (has_res && staged) {
+          if (NSTG >= 3) {
+            if (issuer) {  // prefetch the next group's residual
+              int nt = t, ncg = cg + 1;
+              if (ncg == GPT) { nt = t + gridDim.x; ncg = 0; }
+              if (nt < total_tiles) load_res(nt, ncg, gc + 1);
+            }
+          } else if (gc > 0) {
+            if (issuer) load_res(t, cg, gc);
+          }
+          mbar_wait(&res_bar[gc % NSTG], (gc / NSTG) & 1);
+        }
+#pragma unroll 1
+        for (int c = 0; c < gcols / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_d + cg * 128 + c * 32, v);
+          tmem_ld_wait();
+          if (cg * 128 + (c + 1) * 32 == BN) {  // last TMEM read of this tile: release the accumulator buffer
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              a[4 * j + 0] += b.x; a[4 * j + 1] += b.y; a[4 * j + 2] += b.z; a[4 * j + 3] += b.w;
+            }
+          }
+          if (rb != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(rb + cg * 128 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              a[4 * j + 0] += b.x; a[4 * j + 1] += b.y; a[4 * j + 2] += b.z; a[4 * j + 3] += b.w;
+            }
+          }
+          if (staged) {
+            uint8_t* box = stage_c + (c >> 1) * (BLOCK_M * 128) + r * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+              uint4* slot = reinterpret_cast<uint4*>(box + chunk * 16);
+              if (has_res) {
+                const uint4 rv = *slot;
+                a[8 * q + 0] += bf16_lo(rv.x); a[8 * q + 1] += bf16_hi(rv.x);
+                a[8 * q + 2] += bf16_lo(rv.y); a[8 * q + 3] += bf16_hi(rv.y);
+                a[8 * q + 4] += bf16_lo(rv.z); a[8 * q + 5] += bf16_hi(rv.z);
+                a[8 * q + 6] += bf16_lo(rv.w); a[8 * q + 7] += bf16_hi(rv.w);
+              }
+              uint4 o;
+              if (zero_row) {
+                o = make_uint4(0u, 0u, 0u, 0u);
+              } else {
+                o.x = pack_bf16x2(a[8 * q + 0], a[8 * q + 1]);
+                o.y = pack_bf16x2(a[8 * q + 2], a[8 * q + 3]);
+                o.z = pack_bf16x2(a[8 * q + 4], a[8 * q + 5]);
+                o.w = pack_bf16x2(a[8 * q + 6], a[8 * q + 7]);
+              }
+              *slot = o;
+            }
+          } else if (to_vt) {
+            __nv_bfloat16* tcol = reinterpret_cast<__nv_bfloat16*>(stage_c) + (c * 32) * BLOCK_M + r;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tcol[j * BLOCK_M] = __float2bfloat16_rn(a[j]);
+          } else if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + m * p.out_f32_ld + nc0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(a[4 * j + 0], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+          }
+        }
+        if (to_vt) {
+          named_bar_sync(1, 128);
+          const long long m0 = (long long)tile_m * BLOCK_M;
+          __nv_bfloat16* gbase = p.vt + (long long)(nc0 - p.vt_col0) * p.vt_ld + m0;
+          for (int i = 0; i < gcols / 8; ++i) {
+            const int q = i * 128 + et;
+            const int col = q >> 4, part = q & 15;
+            if (m0 + part * 8 < p.M) {
+              const uint4 vv = *reinterpret_cast<const uint4*>(stage_c + col * (BLOCK_M * 2) + part * 16);
+              *reinterpret_cast<uint4*>(gbase + (long long)col * p.vt_ld + part * 8) = vv;
+            }
+          }
+          if (issuer) tma_store_commit();  // empty bulk group: keeps "groups pending" == "staging buffers in use"
+        } else if (staged) {
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            for (int bx = 0; bx < gcols / 64; ++bx)
+              tma_store_2d(&p.tmC, stage_c + bx * (BLOCK_M * 128), nc0 + bx * 64, tile_m * BLOCK_M);
+            tma_store_commit();
+          }
+        } else if (issuer) {
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int NSTG>
+static int launch_persist(const IgemmParams& p, cudaStream_t stream) {
+  using Cfg = PgCfg<BN, NSTG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(igemm_persist_kernel<BN, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM),
+                        "igemm_persist: cudaFuncSetAttribute");
+    if (rc != IDF_OK) return rc;
+    attr_set = true;
+  }
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  igemm_persist_kernel<BN, NSTG><<<grid, PG_THREADS, Cfg::SMEM, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "igemm_persist launch");
+}
+
 static int make_act_map(CUtensorMap* tm, const idf_nhwc_t& a, int tile_w, int tile_h, int tile_n) {
   const uint64_t dims[4] = {(uint64_t)a.c, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.n};
   const uint64_t strides[3] = {(uint64_t)a.sw * 2, (uint64_t)a.sh * 2, (uint64_t)a.sn * 2};
@@ -367,7 +684,28 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   p.kb_seg0 = a->taps[0] * p.cb[0];
   p.kb_total = ktot / BLOCK_K;
   if (a->ldw < ktot) return fail(IDF_ERR_ARG, "igemm: ldw %lld < K %d", (long long)a->ldw, ktot);
-  if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, BLOCK_N)) != IDF_OK)
+  // tile width: the persistent kernel takes 256 / 192 / 128 columns per tile; pick the widest that divides N (and
+  // the V^T split point) unless that would leave SMs without a tile
+  static const int legacy = [] { const char* e = getenv("IDF_IGEMM_LEGACY"); return e ? atoi(e) : 0; }();
+  int bn = BLOCK_N;
+  // short-K GEMMs (K <= 1024: QKV / out_proj / skip projections) are epilogue- and memory-bound: narrow tiles with
+  // triple-buffered staging keep loads, residual prefetch and stores in flight together
+  const bool short_k = !legacy && ktot <= 1024;
+  if (!legacy && !short_k) {
+    const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    const int cands[3] = {256, 192, 128};
+    bn = 0;
+    for (int i = 0; i < 3; ++i) {
+      const int c = cands[i];
+      if (a->N % c != 0) continue;
+      if (a->vt != nullptr && a->vt_col0 % c != 0) continue;
+      if (bn == 0) bn = c;                                          // widest legal
+      if (m_tiles * (a->N / c) >= sm_count()) { bn = c; break; }    // widest that still fills the GPU
+      bn = c;                                                       // otherwise keep narrowing
+    }
+    if (bn == 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d has no legal tile width", a->N);
+  }
+  if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, (uint32_t)bn)) != IDF_OK)
     return rc;
 
   p.H = a->epi_h > 0 ? a->epi_h : H;
@@ -417,6 +755,15 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
                          "igemm: cudaFuncSetAttribute")) != IDF_OK)
       return rc;
     attr_set = true;
+  }
+  if (!legacy) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (short_k) return launch_persist<128, 3>(p, st);
+    switch (bn) {
+      case 256: return launch_persist<256, 1>(p, st);
+      case 192: return launch_persist<192, 1>(p, st);
+      default: return launch_persist<128, 1>(p, st);
+    }
   }
   dim3 grid((unsigned)((M + BLOCK_M - 1) / BLOCK_M), (unsigned)(a->N / BLOCK_N));
   igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
