@@ -148,7 +148,7 @@ def igemm_roofline(sampler, peak_tflops, peak_kind):
         flops = 0.0
         if name == "idf_conv2d_igemm":
             g = a[0]
-            m = g.a[0].n * g.a[0].h * g.a[0].w
+            m = (g.s2_batch if g.s2_batch else g.a[0].n) * g.a[0].h * g.a[0].w
             k = g.taps[0] * g.a[0].c + (g.taps[1] * g.a[1].c if g.a[1].ptr else 0)
             flops = 2.0 * m * g.N * k
         records.append((name, e0, e1, flops))

@@ -32,8 +32,7 @@ struct AttnParams {
   int nblk;        // key blocks per query tile
   int kv_stages;   // 1 or 2
   float scale_log2e;
-  int dbg;  // ablation switches for profiling (IDF_ATTN_DBG), 0 in production
-  long long* trace;  // dbg & 16: per-event clock64 trace of CTA (0, 0)
+  int heads;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -292,7 +291,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
 // TMEM columns: S_0 [0,128) S_1 [128,256) O_0 [256,256+hd) O_1 [320,320+hd) -> 512 allocated.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int ATTP_TMEM_COLS = 512;
-constexpr int ATTP_KSTAGES = 4;
+template <int HD> struct AttpK { static constexpr int STAGES = HD > 32 ? 3 : 4; };  // K ring depth (smem budget)
 constexpr int ATTP_VSTAGES = 3;
 constexpr int ATTP_THREADS = 384;  // warps 0..7 softmax (2 warpgroups), warp 8 TMA producer, warp 9 TMEM + MMA, 10-11 idle
 
@@ -327,52 +326,50 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* dst) {
   }
 }
 
-#define ATT_TRACE(who, ev, jj)                                                                      \
-  do {                                                                                              \
-    if ((p.dbg & 16) && blockIdx.x == 300 && blockIdx.y == 3) {                                     \
-      p.trace[((who) * 16 + (jj)) * 8 + (ev)] = clock64();                                          \
-    }                                                                                               \
-  } while (0)
-
 template <int HD>
 __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const __grid_constant__ AttnParams p) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
   constexpr int QK_BYTES = 128 * SWZ;
   constexpr int V_BYTES = 2 * HD * 128;
   constexpr int P_BYTES = 2 * 128 * 128;
+  constexpr int ATTP_KSTAGES = AttpK<HD>::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* smem_q = smem;                                 // [2][QK_BYTES]: query tiles 0 and 1
-  uint8_t* smem_p = smem_q + 2 * QK_BYTES;                // [2][P_BYTES]
+  uint8_t* smem_q = smem;                                 // [2 items][2 tiles][QK_BYTES]
+  uint8_t* smem_p = smem_q + 4 * QK_BYTES;                // [2 groups][P_BYTES]
   uint8_t* smem_k = smem_p + 2 * P_BYTES;                 // [ATTP_KSTAGES][QK_BYTES]
   uint8_t* smem_v = smem_k + ATTP_KSTAGES * QK_BYTES;     // [ATTP_VSTAGES][V_BYTES]
-  float* xch = reinterpret_cast<float*>(smem_v + ATTP_VSTAGES * V_BYTES);  // [2 parity][2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * 2 * 128);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;                       // [4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + ATTP_VSTAGES * V_BYTES);
+  uint64_t* q_full = bars;                           // [2]
+  uint64_t* q_empty = q_full + 2;                    // [2]
+  uint64_t* k_full = q_empty + 2;                    // [4]
   uint64_t* k_empty = k_full + ATTP_KSTAGES;         // [4]
   uint64_t* v_full = k_empty + ATTP_KSTAGES;         // [3]
   uint64_t* v_empty = v_full + ATTP_VSTAGES;         // [3]
-  uint64_t* s_full = v_empty + ATTP_VSTAGES;         // [2]
+  uint64_t* s_full = v_empty + ATTP_VSTAGES;         // [2] per softmax group
   uint64_t* s_empty = s_full + 2;                    // [2]
   uint64_t* p_full = s_empty + 2;                    // [2]
   uint64_t* o_full = p_full + 2;                     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* o_empty = o_full + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int row0 = blockIdx.x * 256;  // two query tiles per CTA (same sample: T >= 256)
-  const int kv_base = (row0 >> p.t_shift) << p.t_shift;
   const int n = p.nblk;
-  if (threadIdx.x == 0) ATT_TRACE(4, 2, 0);
+  // work items: (pair of query tiles, head), dealt round-robin to the persistent CTAs
+  const int pairs = (p.M + 255) / 256;
+  const int total_items = pairs * p.heads;
+  const int my_items = (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int E = my_items * n;  // key blocks this CTA walks through (per softmax group)
+  auto item_head = [&](int item) { return (int)((blockIdx.x + item * gridDim.x) % p.heads); };
+  auto item_row0 = [&](int item) { return (int)((blockIdx.x + item * gridDim.x) / p.heads) * 256; };
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tmQK);
     tma_prefetch_desc(&p.tmVT);
-    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < ATTP_KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < ATTP_VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -380,6 +377,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
       mbar_init(&s_empty[i], 4);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 4);
     }
     fence_mbar_init();
   }
@@ -391,209 +389,203 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) ATT_TRACE(4, 0, 0);
 
   // register re-balancing between warpgroups: the data-movement warpgroup gives its registers to the two softmax
   // warpgroups, which keep a whole 128-wide score row per thread
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 8) {
-    // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * QK_BYTES);
-      tma_load_2d(smem_q, &p.tmQK, q_full, head * HD, row0);
-      tma_load_2d(smem_q + QK_BYTES, &p.tmQK, q_full, head * HD, row0 + 128);
-      auto load_k = [&](int j) {
-        const int st = j % ATTP_KSTAGES;
-        mbar_wait(&k_empty[st], ((j / ATTP_KSTAGES) & 1) ^ 1);
-        mbar_expect_tx(&k_full[st], QK_BYTES);
-        tma_load_2d(smem_k + st * QK_BYTES, &p.tmQK, &k_full[st], p.C + head * HD, kv_base + j * 128);
-        ATT_TRACE(0, 0, j);
-      };
-      auto load_v = [&](int j) {
-        const int st = j % ATTP_VSTAGES;
-        mbar_wait(&v_empty[st], ((j / ATTP_VSTAGES) & 1) ^ 1);
-        ATT_TRACE(0, 1, j);
-        mbar_expect_tx(&v_full[st], V_BYTES);
-        uint8_t* dst = smem_v + st * V_BYTES;
-        tma_load_2d(dst, &p.tmVT, &v_full[st], kv_base + j * 128, head * HD);
-        tma_load_2d(dst + HD * 128, &p.tmVT, &v_full[st], kv_base + j * 128 + 64, head * HD);
-      };
-      load_k(0);
-      if (n > 1) load_k(1);
-      for (int j = 0; j < n; ++j) {
-        load_v(j);
-        if (j + 2 < n) load_k(j + 2);
-      }  // (K runs two blocks ahead of V: S(j+1) is issued while the softmax of block j is still running)
-    }
+      // ------------------------------------------------------------------ TMA producer
+      if (elect_one()) {
+        auto load_q = [&](int item) {
+          const int st = item & 1;
+          mbar_wait(&q_empty[st], ((item >> 1) & 1) ^ 1);
+          mbar_expect_tx(&q_full[st], 2 * QK_BYTES);
+          uint8_t* dst = smem_q + st * 2 * QK_BYTES;
+          tma_load_2d(dst, &p.tmQK, &q_full[st], item_head(item) * HD, item_row0(item));
+          tma_load_2d(dst + QK_BYTES, &p.tmQK, &q_full[st], item_head(item) * HD, item_row0(item) + 128);
+        };
+        auto load_k = [&](int e) {
+          const int item = e / n, j = e % n;
+          if (j == 0) load_q(item);
+          const int st = e % ATTP_KSTAGES;
+          const int kv0 = ((item_row0(item) >> p.t_shift) << p.t_shift) + j * 128;
+          mbar_wait(&k_empty[st], ((e / ATTP_KSTAGES) & 1) ^ 1);
+          mbar_expect_tx(&k_full[st], QK_BYTES);
+          tma_load_2d(smem_k + st * QK_BYTES, &p.tmQK, &k_full[st], p.C + item_head(item) * HD, kv0);
+        };
+        auto load_v = [&](int e) {
+          const int item = e / n, j = e % n;
+          const int st = e % ATTP_VSTAGES;
+          const int kv0 = ((item_row0(item) >> p.t_shift) << p.t_shift) + j * 128;
+          mbar_wait(&v_empty[st], ((e / ATTP_VSTAGES) & 1) ^ 1);
+          mbar_expect_tx(&v_full[st], V_BYTES);
+          uint8_t* dst = smem_v + st * V_BYTES;
+          tma_load_2d(dst, &p.tmVT, &v_full[st], kv0, item_head(item) * HD);
+          tma_load_2d(dst + HD * 128, &p.tmVT, &v_full[st], kv0 + 64, item_head(item) * HD);
+        };
+        if (E > 0) load_k(0);
+        if (E > 1) load_k(1);
+        for (int e = 0; e < E; ++e) {  // K runs two blocks ahead of V (S(e+1) is issued during the softmax of e)
+          load_v(e);
+          if (e + 2 < E) load_k(e + 2);
+        }
+      }
     } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
-      const uint64_t dq[2] = {umma_desc_kmajor(smem_u32(smem_q), SWZ),
-                              umma_desc_kmajor(smem_u32(smem_q + QK_BYTES), SWZ)};
-      auto issue_s = [&](int g, int j) {  // S_g = Q_g K_j^T
-        const int st = j % ATTP_KSTAGES;
-        if (g == 0) {
-          mbar_wait(&k_full[st], (j / ATTP_KSTAGES) & 1);
-          ATT_TRACE(1, 0, j);
+      // ------------------------------------------------------------------ MMA issuer
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
+        auto issue_s = [&](int g, int e) {  // S_g = Q_g K_e^T
+          const int item = e / n, j = e % n;
+          const int st = e % ATTP_KSTAGES;
+          if (g == 0) {
+            if (j == 0) mbar_wait(&q_full[item & 1], (item >> 1) & 1);
+            mbar_wait(&k_full[st], (e / ATTP_KSTAGES) & 1);
+          }
+          if (e > 0) mbar_wait(&s_empty[g], (e - 1) & 1);  // the group has pulled its previous S into registers
           tc_fence_after_sync();
-        }
-        const uint64_t dk = umma_desc_kmajor(smem_u32(smem_k + st * QK_BYTES), SWZ);
+          const uint64_t dq = umma_desc_kmajor(smem_u32(smem_q + ((item & 1) * 2 + g) * QK_BYTES), SWZ);
+          const uint64_t dk = umma_desc_kmajor(smem_u32(smem_k + st * QK_BYTES), SWZ);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + g * 128, dq[g] + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[g]);
-        if (g == 1) umma_commit(&k_empty[st]);  // both tiles have consumed K_j
-        ATT_TRACE(1, 1, j);
-      };
-      auto issue_pv = [&](int g, int j) {  // O_g (+)= P_g V_j
-        const int vs = j % ATTP_VSTAGES;
-        mbar_wait(&p_full[g], j & 1);
-        ATT_TRACE(1, 2, j);
-        if (g == 0) mbar_wait(&v_full[vs], (j / ATTP_VSTAGES) & 1);
-        tc_fence_after_sync();
-        const uint8_t* pb = smem_p + g * P_BYTES;
-        const uint8_t* vb = smem_v + vs * V_BYTES;
-        const uint64_t dp0 = umma_desc_kmajor(smem_u32(pb), 128);
-        const uint64_t dp1 = umma_desc_kmajor(smem_u32(pb + 128 * 128), 128);
-        const uint64_t dv0 = umma_desc_kmajor(smem_u32(vb), 128);
-        const uint64_t dv1 = umma_desc_kmajor(smem_u32(vb + HD * 128), 128);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_base + g * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[g]);
+          if (g == 1) {
+            umma_commit(&k_empty[st]);                         // both tiles have consumed K_e
+            if (j == n - 1) umma_commit(&q_empty[item & 1]);   // ... and this item's Q tiles
+          }
+        };
+        auto issue_pv = [&](int g, int e) {  // O_g (+)= P_g V_e
+          const int item = e / n, j = e % n;
+          const int vs = e % ATTP_VSTAGES;
+          mbar_wait(&p_full[g], e & 1);
+          if (g == 0) mbar_wait(&v_full[vs], (e / ATTP_VSTAGES) & 1);
+          if (j == 0 && item > 0) mbar_wait(&o_empty[g], (item - 1) & 1);  // previous item's output rows were read
+          tc_fence_after_sync();
+          const uint8_t* pb = smem_p + g * P_BYTES;
+          const uint8_t* vb = smem_v + vs * V_BYTES;
+          const uint64_t dp0 = umma_desc_kmajor(smem_u32(pb), 128);
+          const uint64_t dp1 = umma_desc_kmajor(smem_u32(pb + 128 * 128), 128);
+          const uint64_t dv0 = umma_desc_kmajor(smem_u32(vb), 128);
+          const uint64_t dv1 = umma_desc_kmajor(smem_u32(vb + HD * 128), 128);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + 256 + g * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), (k < 4 ? dv0 : dv1) + 2 * (k & 3),
-                    idesc_o, (j > 0) || (k != 0));  // accumulate over the key blocks
-        umma_commit(&o_full[g]);
-        if (g == 1) umma_commit(&v_empty[vs]);
-        ATT_TRACE(1, 4, j);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0, 0);
-      // start the second tile about half a period late (once group 0 has taken S_0(0) into registers): with the
-      // groups out of phase, one group's MUFU-bound exp phase overlaps the other's TMEM reads / max / stores
-      mbar_wait(&s_empty[0], 0);
-      if (n > 1) issue_s(0, 1);
-      issue_s(1, 0);
-      for (int j = 0; j < n; ++j) {
-        issue_pv(0, j);
-        if (j + 1 < n) {
-          mbar_wait(&s_empty[1], j & 1);
-          issue_s(1, j + 1);
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem_base + 256 + g * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), (k < 4 ? dv0 : dv1) + 2 * (k & 3),
+                      idesc_o, (j > 0) || (k != 0));  // accumulate over the item's key blocks
+          umma_commit(&o_full[g]);
+          if (g == 1) umma_commit(&v_empty[vs]);
+        };
+        if (E > 0) {
+          // Group 1 starts about half a period after group 0 (its first S is issued only once group 0 has taken
+          // S_0(0) into registers): with the groups out of phase, one group's MUFU-bound exp phase overlaps the
+          // other's TMEM reads / max reduction / stores. The offset persists across work items.
+          issue_s(0, 0);
+          if (E > 1) issue_s(0, 1);  // waits for s_empty[0](0)
+          else mbar_wait(&s_empty[0], 0);
+          issue_s(1, 0);
+          for (int e = 0; e < E; ++e) {
+            issue_pv(0, e);
+            if (e + 1 < E) issue_s(1, e + 1);
+            if (e + 2 < E) issue_s(0, e + 2);
+            issue_pv(1, e);
+          }
         }
-        if (j + 2 < n) {
-          mbar_wait(&s_empty[0], (j + 1) & 1);
-          issue_s(0, j + 2);
-        }
-        issue_pv(1, j);
       }
     }
-    }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ------------------------------------------------------------------ softmax + output rows (warps 0..7)
-    // Two independent warpgroups: group g (warps 4g..4g+3, one row per thread) runs the online softmax over the
-    // key blocks j = g, g+2, g+4, ... with its own S / P / O_blk buffers and its own running (max, sum, output).
-    // The groups are naturally out of phase, so on every scheduler one warp's MUFU phase overlaps the other
-    // warp's TMEM loads, max reduction, packing and stores. The two partial results are merged at the end.
+    // Warpgroup g (warps 4g..4g+3, one row per thread) owns query tile g of every work item: own S / P / O buffers,
+    // own running (max, sum). The output rows accumulate in TMEM across the item's key blocks (P V with
+    // accumulate). The softmax uses a possibly stale row maximum m_run: P = exp2((S - m_run) * c) is exact
+    // arithmetic as long as it cannot overflow, so the accumulator is only rescaled when the true maximum outgrows
+    // m_run by more than 2^8 (rare after the first block). No per-block read-back of the output rows.
     const int quad = warp & 3;
     const int g = warp >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const long long m = (long long)row0 + g * 128 + r;
     const float c = p.scale_log2e;
-    // The output rows accumulate in TMEM across the group's key blocks (P V with accumulate). The softmax uses a
-    // possibly stale row maximum m_used: P = exp2((S - m_used) * c) stays exact arithmetic as long as it cannot
-    // overflow, so the accumulator is only rescaled when the true maximum outgrows m_used by more than 2^8
-    // (rare after the first block). No per-block read-back of the output rows.
-    float m_run = -INFINITY, l_run = 0.f;  // m_run = m_used
     uint8_t* pbuf = smem_p + g * P_BYTES;
     const uint32_t tmem_o = tmem_base + 256 + g * 64 + lane_addr;
 
-    int k = 0;
-    for (int j = 0; j < n; ++j, ++k) {
-      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 0, j);
-      mbar_wait(&s_full[g], k & 1);
-      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 1, j);
-      tc_fence_after_sync();
-      uint32_t sv[4][32];
+    int e = 0;
+    for (int item = 0; item < my_items; ++item) {
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n; ++j, ++e) {
+        mbar_wait(&s_full[g], e & 1);
+        tc_fence_after_sync();
+        uint32_t sv[4][32];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32(tmem_base + g * 128 + lane_addr + ch * 32, sv[ch]);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[g]);  // S_j now lives in registers
-      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 2, j);
+        for (int ch = 0; ch < 4; ++ch) tmem_ld_32x32(tmem_base + g * 128 + lane_addr + ch * 32, sv[ch]);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[g]);  // S now lives in registers
 
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
+        for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          mx[(i >> 1) & 3] = fmaxf(mx[(i >> 1) & 3],
-                                   fmaxf(__uint_as_float(sv[ch][i]), __uint_as_float(sv[ch][i + 1])));  // FMNMX3
-      const float mrow = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          for (int i = 0; i < 32; i += 2)
+            mx[(i >> 1) & 3] = fmaxf(mx[(i >> 1) & 3],
+                                     fmaxf(__uint_as_float(sv[ch][i]), __uint_as_float(sv[ch][i + 1])));  // FMNMX3
+        const float mrow = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
 
-      if (k > 0) {
-        // P_{k-1} V has to be complete before P is overwritten (and before the accumulator may be rescaled)
-        if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 3, j);
-        mbar_wait(&o_full[g], (k - 1) & 1);
-        if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 4, j);
-      }
-      const bool grow = (mrow - m_run) * c > 8.0f;  // first block: m_run = -inf -> true
-      if (__any_sync(0xffffffffu, grow)) {
-        const float m_new = grow ? mrow : m_run;
-        const float alpha = fast_exp2((m_run - m_new) * c);  // 1 for rows that keep their maximum
-        m_run = m_new;
-        l_run *= alpha;
-        if (k > 0) {
-          tc_fence_after_sync();
+        // P_{j-1} V has to be complete before P is overwritten (and before the accumulator may be rescaled)
+        if (j > 0) mbar_wait(&o_full[g], (e - 1) & 1);
+        const bool grow = (mrow - m_run) * c > 8.0f;  // first block: m_run = -inf -> true
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = grow ? mrow : m_run;
+          const float alpha = fast_exp2((m_run - m_new) * c);  // 1 for rows that keep their maximum
+          m_run = m_new;
+          l_run *= alpha;
+          if (j > 0) {
+            tc_fence_after_sync();
 #pragma unroll
-          for (int d0 = 0; d0 < HD; d0 += 16) {
-            uint32_t v[16];
-            tmem_ld_32x16(tmem_o + d0, v);
-            tmem_ld_wait();
+            for (int d0 = 0; d0 < HD; d0 += 16) {
+              uint32_t v[16];
+              tmem_ld_32x16(tmem_o + d0, v);
+              tmem_ld_wait();
 #pragma unroll
-            for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
-            tmem_st_32x16(tmem_o + d0, v);
+              for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
+              tmem_st_32x16(tmem_o + d0, v);
+            }
+            tmem_st_wait();
+            tc_fence_before_sync();
           }
-          tmem_st_wait();
-          tc_fence_before_sync();
         }
-      }
-      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 5, j);
-      const float mc = m_run * c;
+        const float mc = m_run * c;
 
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint8_t* prow = pbuf + (ch >> 1) * (128 * 128) + r * 128;
+        for (int ch = 0; ch < 4; ++ch) {
+          uint8_t* prow = pbuf + (ch >> 1) * (128 * 128) + r * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float e[8];
+          for (int q = 0; q < 4; ++q) {
+            float ev[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = fast_exp2(fmaf(__uint_as_float(sv[ch][8 * q + i]), c, -mc));
-            ps[i & 3] += e[i];
+            for (int i = 0; i < 8; ++i) {
+              ev[i] = fast_exp2(fmaf(__uint_as_float(sv[ch][8 * q + i]), c, -mc));
+              ps[i & 3] += ev[i];
+            }
+            uint4 o;
+            o.x = pack_bf16x2(ev[0], ev[1]);
+            o.y = pack_bf16x2(ev[2], ev[3]);
+            o.z = pack_bf16x2(ev[4], ev[5]);
+            o.w = pack_bf16x2(ev[6], ev[7]);
+            const int chunk = ((ch & 1) * 4 + q) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
           }
-          uint4 o;
-          o.x = pack_bf16x2(e[0], e[1]);
-          o.y = pack_bf16x2(e[2], e[3]);
-          o.z = pack_bf16x2(e[4], e[5]);
-          o.w = pack_bf16x2(e[6], e[7]);
-          const int chunk = ((ch & 1) * 4 + q) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+        l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[g]);
-      if (lane == 0 && quad == 0) ATT_TRACE(2 + g, 6, j);
-      l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
-    }
-    float o_acc[HD];
-    if (k > 0) {  // all of this group's P V products are complete: fetch its output rows
-      mbar_wait(&o_full[g], (k - 1) & 1);
+      // all of this item's P V products for tile g are complete: fetch the output rows, free the accumulator
+      mbar_wait(&o_full[g], (e - 1) & 1);
       tc_fence_after_sync();
+      float o_acc[HD];
 #pragma unroll
       for (int d0 = 0; d0 < HD; d0 += 16) {
         uint32_t v[16];
@@ -602,28 +594,28 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
 #pragma unroll
         for (int d = 0; d < 16; ++d) o_acc[d0 + d] = __uint_as_float(v[d]);
       }
-    } else {
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[g]);
+      const long long m = (long long)item_row0(item) + g * 128 + r;
+      if (m < p.M) {
+        const float inv = 1.f / l_run;
+        __nv_bfloat16* dst = p.out + m * p.ld_out + item_head(item) * HD;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
-    }
-    if (m < p.M) {
-      const float inv = 1.f / l_run;
-      __nv_bfloat16* dst = p.out + m * p.ld_out + head * HD;
-#pragma unroll
-      for (int d0 = 0; d0 < HD; d0 += 8) {
-        uint4 o;
-        o.x = pack_bf16x2(o_acc[d0 + 0] * inv, o_acc[d0 + 1] * inv);
-        o.y = pack_bf16x2(o_acc[d0 + 2] * inv, o_acc[d0 + 3] * inv);
-        o.z = pack_bf16x2(o_acc[d0 + 4] * inv, o_acc[d0 + 5] * inv);
-        o.w = pack_bf16x2(o_acc[d0 + 6] * inv, o_acc[d0 + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + d0) = o;
+        for (int d0 = 0; d0 < HD; d0 += 8) {
+          uint4 o;
+          o.x = pack_bf16x2(o_acc[d0 + 0] * inv, o_acc[d0 + 1] * inv);
+          o.y = pack_bf16x2(o_acc[d0 + 2] * inv, o_acc[d0 + 3] * inv);
+          o.z = pack_bf16x2(o_acc[d0 + 4] * inv, o_acc[d0 + 5] * inv);
+          o.w = pack_bf16x2(o_acc[d0 + 6] * inv, o_acc[d0 + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + d0) = o;
+        }
       }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (threadIdx.x == 0) ATT_TRACE(4, 1, 0);
   if (warp == 9) {
     __syncwarp();
     tc_fence_after_sync();
@@ -634,8 +626,8 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
 template <int HD>
 static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
-  const int smem = 2 * 128 * SWZ + 2 * (2 * 128 * 128) + ATTP_KSTAGES * 128 * SWZ + ATTP_VSTAGES * 2 * HD * 128 +
-                   2 * 2 * 128 * 4 + 1024 + 256;
+  const int smem = 4 * 128 * SWZ + 2 * (2 * 128 * 128) + AttpK<HD>::STAGES * 128 * SWZ + ATTP_VSTAGES * 2 * HD * 128 +
+                   1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(attention_pipe_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
@@ -643,7 +635,9 @@ static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cuda
     if (rc != IDF_OK) return rc;
     attr_set = true;
   }
-  attention_pipe_kernel<HD><<<dim3((tiles + 1) / 2, heads), ATTP_THREADS, smem, stream>>>(p);
+  const int items = ((tiles + 1) / 2) * heads;
+  const int grid = items < sm_count() ? items : sm_count();
+  attention_pipe_kernel<HD><<<grid, ATTP_THREADS, smem, stream>>>(p);
   return check_cuda(cudaGetLastError(), "attention_pipe launch");
 }
 
@@ -685,18 +679,7 @@ extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, 
   p.nblk = T >= 128 ? T / 128 : 1;
   p.kv_stages = p.nblk > 1 ? 2 : 1;
   p.scale_log2e = scale * 1.4426950408889634f;
-  {
-    static const int dbg = [] { const char* e = getenv("IDF_ATTN_DBG"); return e ? atoi(e) : 0; }();
-    p.dbg = dbg;
-    static long long* trace = nullptr;
-    if ((dbg & 16) && trace == nullptr) {
-      cudaMalloc(&trace, 5 * 16 * 8 * sizeof(long long));
-      cudaMemset(trace, 0, 5 * 16 * 8 * sizeof(long long));
-      FILE* f = fopen("/tmp/idf_attn_trace_ptr", "w");
-      if (f) { fprintf(f, "%llu", (unsigned long long)trace); fclose(f); }
-    }
-    p.trace = trace;
-  }
+  p.heads = heads;
 
   const int swz = head_dim <= 16 ? 32 : (head_dim <= 32 ? 64 : 128);
   const CUtensorMapSwizzle swz_enum = swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
@@ -721,7 +704,7 @@ extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static const int pipe_min_blocks = [] {
     const char* e = getenv("IDF_ATTN_PIPE_MIN_BLOCKS");
-    return e ? atoi(e) : 3;
+    return e ? atoi(e) : 2;
   }();
   if (p.nblk >= pipe_min_blocks && T >= 256) {
     switch (head_dim) {

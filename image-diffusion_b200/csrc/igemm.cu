@@ -45,6 +45,7 @@ struct IgemmParams {
   int tile_w, tile_h, tile_n;
   int tiles_per_img;  // HW / 128 when HW >= 128, else 0
   int matrix;         // 1: A is a plain (rows, cols) matrix walked 128 rows at a time along the w axis
+  int s2_batch;       // > 0: segment 0 holds the 4 parity planes of a stride-2 conv input, stacked along n
   int M, N;
   int flags;
   const float* bias;
@@ -122,12 +123,19 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
-        int dh = 0, dw = 0;
+        int dh = 0, dw = 0, dn = 0;
         if (p.taps[seg] == 9) {
-          dh = tap / 3 - 1;
-          dw = tap % 3 - 1;
+          if (p.s2_batch > 0 && seg == 0) {  // stride 2, pad 0: tap (kh, kw) -> parity plane, shift (kh>>1, kw>>1)
+            const int kh = tap / 3, kw = tap % 3;
+            dn = ((kh & 1) * 2 + (kw & 1)) * p.s2_batch;
+            dh = kh >> 1;
+            dw = kw >> 1;
+          } else {
+            dh = tap / 3 - 1;
+            dw = tap % 3 - 1;
+          }
         }
-        tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0);
+        tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0 + dn);
         tma_load_2d(smem_b + s * B_STAGE_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
         if (++cbk == p.cb[seg]) {
           cbk = 0;
@@ -396,9 +404,19 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           const int s = kc % STAGES;
           mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          int dh = 0, dw = 0;
-          if (p.taps[seg] == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
-          tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0);
+          int dh = 0, dw = 0, dn = 0;
+          if (p.taps[seg] == 9) {
+            if (p.s2_batch > 0 && seg == 0) {  // stride 2, pad 0: tap (kh, kw) -> parity plane, shift (kh>>1, kw>>1)
+              const int kh = tap / 3, kw = tap % 3;
+              dn = ((kh & 1) * 2 + (kw & 1)) * p.s2_batch;
+              dh = kh >> 1;
+              dw = kw >> 1;
+            } else {
+              dh = tap / 3 - 1;
+              dw = tap % 3 - 1;
+            }
+          }
+          tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0 + dn);
           tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
           if (++cbk == p.cb[seg]) {
             cbk = 0;
@@ -657,7 +675,10 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   const int H = x0.h, W = x0.w, HW = H * W;
-  const long long M = (long long)x0.n * HW;
+  if (a->s2_batch > 0 && (x0.n != 4 * a->s2_batch || a->taps[0] != 9 || nseg != 1))
+    return fail(IDF_ERR_ARG, "igemm: s2_batch needs one 9-tap segment holding 4*s2_batch parity planes");
+  const long long M = (long long)(a->s2_batch > 0 ? a->s2_batch : x0.n) * HW;
+  p.s2_batch = a->s2_batch;
   if (M <= 0 || M > 0x7fffffffLL) return fail(IDF_ERR_ARG, "igemm: bad M");
   // M-tile geometry: 128 consecutive NHWC pixels = tile_n images x tile_h rows x tile_w columns.
   const bool is_matrix = x0.n == 1 && x0.h == 1 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);

@@ -207,16 +207,23 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __r
                                                                 const float* __restrict__ w,
                                                                 const float* __restrict__ bias,
                                                                 __nv_bfloat16* __restrict__ y, long long ldy, int B,
-                                                                int H, int W, int Cout, long long dup_rows) {
+                                                                int H, int W, int Cout, long long dup_rows, int RB) {
+  // CTA = (row block of RB <= 8 rows, image). The fp32 input rows (+halo, zero padded) are staged once in shared
+  // memory; warp w walks output row h0 + w pixel by pixel with warp-wide broadcast reads of the 9*CIN patch.
+  extern __shared__ float s_x[];  // [CIN][RB + 2][W + 2]
   constexpr int K = CIN * 9;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int cgroups = Cout / 128;  // 128-channel slabs
-  const long long total = (long long)B * H * W * cgroups;
-  const long long warp_id = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * warps_per_block;
-  // consecutive warps of a block walk consecutive pixels of the same slab
-  for (int cg = 0; cg < cgroups; ++cg) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, h0 = blockIdx.x * RB;
+  const int pw = W + 2;
+  for (int i = threadIdx.x; i < CIN * (RB + 2) * pw; i += blockDim.x) {
+    const int c = i / ((RB + 2) * pw), rem = i % ((RB + 2) * pw);
+    const int hh = h0 + rem / pw - 1, ww = rem % pw - 1;
+    s_x[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((long long)b * CIN + c) * H + hh) * W + ww] : 0.f;
+  }
+  __syncthreads();
+  if (warp >= RB) return;
+  const int hq = h0 + warp;
+  for (int cg = 0; cg < Cout / 128; ++cg) {
     const int co = cg * 128 + lane * 4;
     float wr[4][K];
     float bs[4];
@@ -226,10 +233,9 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __r
 #pragma unroll
       for (int k = 0; k < K; ++k) wr[o][k] = w[(long long)(co + o) * K + k];
     }
-    for (long long pix = warp_id; pix < (long long)B * H * W; pix += nwarps) {
-      const int wq = (int)(pix % W);
-      const int hq = (int)((pix / W) % H);
-      const int b = (int)(pix / ((long long)W * H));
+    const long long row_pix = ((long long)b * H + hq) * W;
+#pragma unroll 2
+    for (int wq = 0; wq < W; ++wq) {
       float acc[4] = {bs[0], bs[1], bs[2], bs[3]};
 #pragma unroll
       for (int c = 0; c < CIN; ++c)
@@ -237,21 +243,17 @@ __global__ void __launch_bounds__(256) conv3x3_small_cin_kernel(const float* __r
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
-            const int hh = hq + kh - 1, ww = wq + kw - 1;
-            const float v = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                                ? __ldg(&x[(((long long)b * CIN + c) * H + hh) * W + ww])
-                                : 0.f;
+            const float v = s_x[(c * (RB + 2) + warp + kh) * pw + wq + kw];
 #pragma unroll
             for (int o = 0; o < 4; ++o) acc[o] = fmaf(v, wr[o][c * 9 + kh * 3 + kw], acc[o]);
           }
       uint2 o2;
       o2.x = pack_bf16x2(acc[0], acc[1]);
       o2.y = pack_bf16x2(acc[2], acc[3]);
-      *reinterpret_cast<uint2*>(y + pix * ldy + co) = o2;
-      if (dup_rows > 0) *reinterpret_cast<uint2*>(y + (pix + dup_rows) * ldy + co) = o2;
+      *reinterpret_cast<uint2*>(y + (row_pix + wq) * ldy + co) = o2;
+      if (dup_rows > 0) *reinterpret_cast<uint2*>(y + (row_pix + wq + dup_rows) * ldy + co) = o2;
     }
   }
-  (void)total;
 }
 
 // bf16 NHWC -> fp32 NCHW (Cout <= 8), 3x3 s1 p1. One warp = one pixel; lanes stride over (tap, 8-channel vector).
@@ -329,13 +331,25 @@ __global__ void __launch_bounds__(128) conv3x3_small_cout_tiled_kernel(const __n
   const int b = blockIdx.y;
   const int vec = Cin / 8;
   const int halo_w = TW + 2;
-  for (int i = threadIdx.x; i < (TH + 2) * halo_w * vec; i += blockDim.x) {
-    const int v = i % vec, pp = i / vec;
-    const int hh = h0 + pp / halo_w - 1, ww = w0 + pp % halo_w - 1;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-      val = *reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * ldx + v * 8);
-    *reinterpret_cast<uint4*>(s_in + pp * pix_bytes + v * 16) = val;
+  const int nvec = (TH + 2) * halo_w * vec;
+  for (int i0 = threadIdx.x; i0 < nvec; i0 += 8 * blockDim.x) {  // 8 independent 16-byte loads in flight per thread
+    uint4 val[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      val[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < nvec) {
+        const int v = i % vec, pp = i / vec;
+        const int hh = h0 + pp / halo_w - 1, ww = w0 + pp % halo_w - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+          val[u] = *reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * ldx + v * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < nvec) *reinterpret_cast<uint4*>(s_in + (i / vec) * pix_bytes + (i % vec) * 16) = val[u];
+    }
   }
   __syncthreads();
   const int r = threadIdx.x / TW, c = threadIdx.x % TW;
@@ -361,6 +375,84 @@ __global__ void __launch_bounds__(128) conv3x3_small_cout_tiled_kernel(const __n
 #pragma unroll
   for (int o = 0; o < COUT; ++o)
     y[(((long long)b * COUT + o) * H + (h0 + r)) * W + (w0 + c)] = acc[o] + (bias ? bias[o] : 0.f);
+}
+
+// Cin == 128 fast path: CTA = (TH x TW) pixel tile, warp w walks tile row w; lane l owns input channels 4l..4l+3
+// and keeps their 9 * 4 * COUT weights in registers. Per pixel: nine 8-byte shared-memory reads (one contiguous
+// 256-byte pixel per tap across the warp), 36 * COUT FMAs, and a 5-step shuffle reduction of the COUT partials.
+template <int COUT>
+__global__ void __launch_bounds__(128) conv3x3_small_cout_c128_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                      long long ldx, const float* __restrict__ w,
+                                                                      const float* __restrict__ bias,
+                                                                      float* __restrict__ y, int H, int W, int TH,
+                                                                      int TW) {
+  constexpr int CIN = 128;
+  extern __shared__ __align__(16) uint8_t s_in[];  // [(TH+2)*(TW+2)][CIN*2 + 16]
+  constexpr int pix_bytes = CIN * 2 + 16;
+  const int tiles_w = W / TW;
+  const int h0 = (blockIdx.x / tiles_w) * TH, w0 = (blockIdx.x % tiles_w) * TW;
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int vec = CIN / 8;
+  const int halo_w = TW + 2;
+  const int nvec = (TH + 2) * halo_w * vec;
+  for (int i0 = threadIdx.x; i0 < nvec; i0 += 8 * blockDim.x) {
+    uint4 val[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      val[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < nvec) {
+        const int v = i % vec, pp = i / vec;
+        const int hh = h0 + pp / halo_w - 1, ww = w0 + pp % halo_w - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+          val[u] = *reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * ldx + v * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < nvec) *reinterpret_cast<uint4*>(s_in + (i / vec) * pix_bytes + (i % vec) * 16) = val[u];
+    }
+  }
+  float wr[COUT][9][4];  // OIHW: w[(o*CIN + c)*9 + tap]
+#pragma unroll
+  for (int o = 0; o < COUT; ++o)
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wr[o][tap][e] = w[((long long)o * CIN + lane * 4 + e) * 9 + tap];
+  __syncthreads();
+  for (int r = warp; r < TH; r += 4) {
+    for (int c = 0; c < TW; ++c) {
+      float acc[COUT];
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(s_in + ((r + tap / 3) * halo_w + (c + tap % 3)) * pix_bytes +
+                                                          lane * 8);
+        const float f0 = bf16_lo(raw.x), f1 = bf16_hi(raw.x), f2 = bf16_lo(raw.y), f3 = bf16_hi(raw.y);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          acc[o] = fmaf(f0, wr[o][tap][0], acc[o]);
+          acc[o] = fmaf(f1, wr[o][tap][1], acc[o]);
+          acc[o] = fmaf(f2, wr[o][tap][2], acc[o]);
+          acc[o] = fmaf(f3, wr[o][tap][3], acc[o]);
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < COUT; ++o)
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
+      if (lane < COUT) {
+        float v = acc[0];
+#pragma unroll
+        for (int o = 1; o < COUT; ++o) v = (lane == o) ? acc[o] : v;
+        y[(((long long)b * COUT + lane) * H + (h0 + r)) * W + (w0 + c)] = v + (bias ? bias[lane] : 0.f);
+      }
+    }
+  }
 }
 
 // fp32 NCHW 1x1 convolution with tiny channel counts (decoder's first conv, encoder's last conv).
@@ -414,6 +506,33 @@ __global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, long long 
       val = *reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * ldx + v * 8);
     }
     *reinterpret_cast<uint4*>(y + opix * (9LL * C) + (long long)tap * C + v * 8) = val;
+  }
+}
+
+// y[(ph*2+pw)*B + b][h][w][:] = x[b][2h+ph][2w+pw][:]  (16-byte vectors, four independent copies per thread)
+__global__ void __launch_bounds__(256) space_to_depth2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                              __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                                                              int C) {
+  const int OH = H / 2, OW = W / 2, vec = C / 8;
+  const long long total = (long long)B * OH * OW * vec;  // one thread = one output pixel vector of all 4 planes
+  const long long plane = (long long)B * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    const long long opix = i / vec;
+    const int ow = (int)(opix % OW);
+    const int oh = (int)((opix / OW) % OH);
+    const int b = (int)(opix / ((long long)OW * OH));
+    const __nv_bfloat16* src = x + (((long long)b * H + 2 * oh) * W + 2 * ow) * ldx + v * 8;
+    const uint4 v00 = *reinterpret_cast<const uint4*>(src);
+    const uint4 v01 = *reinterpret_cast<const uint4*>(src + ldx);
+    const uint4 v10 = *reinterpret_cast<const uint4*>(src + (long long)W * ldx);
+    const uint4 v11 = *reinterpret_cast<const uint4*>(src + (long long)W * ldx + ldx);
+    __nv_bfloat16* dst = y + opix * C + v * 8;
+    *reinterpret_cast<uint4*>(dst) = v00;
+    *reinterpret_cast<uint4*>(dst + plane) = v01;
+    *reinterpret_cast<uint4*>(dst + 2 * plane) = v10;
+    *reinterpret_cast<uint4*>(dst + 3 * plane) = v11;
   }
 }
 
@@ -521,13 +640,17 @@ extern "C" int idf_conv3x3_small_cin(const float* x, const float* w, const float
   if (!x || !w || !y) return fail(IDF_ERR_ARG, "conv_small_cin: null pointer");
   if (Cout % 128 != 0 || ldy % 4 != 0) return fail(IDF_ERR_ARG, "conv_small_cin: Cout must be a multiple of 128");
   const long long pixels = (long long)B * H * W;
-  const unsigned grid = blocks_for(pixels, 8 * 4, 148 * 8);  // ~4 pixels per warp at least
+  int RB = 8;
+  while (RB > 1 && H % RB != 0) RB >>= 1;
+  const int smem = Cin * (RB + 2) * (W + 2) * 4;
+  if (smem > 48 * 1024) return fail(IDF_ERR_UNSUPPORTED, "conv_small_cin: image row block exceeds 48 KiB");
+  dim3 grid(H / RB, B);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   const long long dup_rows = dup ? pixels : 0;
   switch (Cin) {
-    case 3: conv3x3_small_cin_kernel<3><<<grid, 256, 0, s>>>(x, w, bias, yp, ldy, B, H, W, Cout, dup_rows); break;
-    case 4: conv3x3_small_cin_kernel<4><<<grid, 256, 0, s>>>(x, w, bias, yp, ldy, B, H, W, Cout, dup_rows); break;
+    case 3: conv3x3_small_cin_kernel<3><<<grid, 256, smem, s>>>(x, w, bias, yp, ldy, B, H, W, Cout, dup_rows, RB); break;
+    case 4: conv3x3_small_cin_kernel<4><<<grid, 256, smem, s>>>(x, w, bias, yp, ldy, B, H, W, Cout, dup_rows, RB); break;
     default: return fail(IDF_ERR_UNSUPPORTED, "conv_small_cin: Cin %d not in {3,4}", Cin);
   }
   return check_cuda(cudaGetLastError(), "conv_small_cin launch");
@@ -540,6 +663,20 @@ static int launch_small_cout(const __nv_bfloat16* x, long long ldx, const float*
     // tiled path whenever the image splits into 128-pixel tiles and the halo tile fits shared memory
     const int TW = W >= 32 ? 32 : W;
     const int TH = 128 / (TW > 0 ? TW : 1);
+    if (Cin == 128 && COUT <= 3 && TW * TH == 128 && W % TW == 0 && H % TH == 0) {
+      const int rsmem = (TH + 2) * (TW + 2) * (128 * 2 + 16);
+      static int rsmem_set = 0;
+      if (rsmem > 48 * 1024 && rsmem > rsmem_set) {
+        int rc = check_cuda(cudaFuncSetAttribute(conv3x3_small_cout_c128_kernel<COUT>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, rsmem),
+                            "conv_small_cout c128: cudaFuncSetAttribute");
+        if (rc != IDF_OK) return rc;
+        rsmem_set = rsmem;
+      }
+      dim3 grid((H / TH) * (W / TW), B);
+      conv3x3_small_cout_c128_kernel<COUT><<<grid, 128, rsmem, s>>>(x, ldx, w, bias, y, H, W, TH, TW);
+      return check_cuda(cudaGetLastError(), "conv_small_cout c128 launch");
+    }
     const int tsmem = ((9 * Cin * COUT * 4 + 15) & ~15) + (TH + 2) * (TW + 2) * (Cin * 2 + 16);
     if (TW * TH == 128 && W % TW == 0 && H % TH == 0 && tsmem <= 100 * 1024) {
       static int tsmem_set = 0;
@@ -611,6 +748,16 @@ extern "C" int idf_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int
   im2col_s2_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
   return check_cuda(cudaGetLastError(), "im2col_s2 launch");
+}
+
+extern "C" int idf_space_to_depth2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                                   idf_stream_t stream) {
+  if (!x || !y) return fail(IDF_ERR_ARG, "space_to_depth2: null pointer");
+  if (C % 8 != 0 || ldx % 8 != 0 || H % 2 != 0 || W % 2 != 0) return fail(IDF_ERR_ARG, "space_to_depth2: bad shape");
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  space_to_depth2_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
+  return check_cuda(cudaGetLastError(), "space_to_depth2 launch");
 }
 
 extern "C" int idf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t ldy, int32_t B, int32_t C, int32_t HW,

@@ -211,11 +211,11 @@ class UnetEngine:
             cat = ws.get(f"cat{i}", x.M, 2 * cout)
             cats.append(cat)
             x = self._block(p, x, cout, table, row_idx, final_dst=cat[:, cout:])
-            col = ws.get("col", x.M // 4, 9 * cout)
-            ops.im2col_s2(x.t, col, x.B, x.H, x.W, cout)
+            planes = ws.get("s2d", x.M, cout)  # four parity planes of the stride-2 conv input, stacked along n
+            ops.space_to_depth2(x.t, planes, x.B, x.H, x.W, cout)
             nxt = ws.get("dn", x.M // 4, cout)
-            ops.igemm([(col, (1, 1, x.M // 4), 9 * cout, 1)], w[f"down.{i}.w"], cout, nxt, bias=w[f"down.{i}.b"],
-                      zero_pad_last=True, epi_hw=(x.H // 2, x.W // 2))
+            ops.igemm([(planes, (4 * x.B, x.H // 2, x.W // 2), cout, 9)], w[f"down.{i}.w"], cout, nxt,
+                      bias=w[f"down.{i}.b"], zero_pad_last=True, s2_batch=x.B)
             self._tap(f"down.{i}", nxt)
             x = Act(nxt, x.B, x.H // 2, x.W // 2, cout)
         for p, cin, cout in self.mids:
@@ -372,11 +372,11 @@ class VaeEngine:
                 ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), x.C, 9)], w[p + ".w"], cout, dst, bias=w[p + ".b"])
                 x = Act(dst, x.B, 2 * x.H, 2 * x.W, cout)
             elif kind == "down":
-                col = ws.get("col", x.M // 4, 9 * x.C)
-                ops.im2col_s2(x.t, col, x.B, x.H, x.W, x.C)
+                planes = ws.get("s2d", x.M, x.C)
+                ops.space_to_depth2(x.t, planes, x.B, x.H, x.W, x.C)
                 dst = ws.get("xa", x.M // 4, cout)
-                ops.igemm([(col, (1, 1, x.M // 4), 9 * x.C, 1)], w[p + ".w"], cout, dst, bias=w[p + ".b"],
-                          zero_pad_last=True, epi_hw=(x.H // 2, x.W // 2))
+                ops.igemm([(planes, (4 * x.B, x.H // 2, x.W // 2), x.C, 9)], w[p + ".w"], cout, dst, bias=w[p + ".b"],
+                          zero_pad_last=True, s2_batch=x.B)
                 x = Act(dst, x.B, x.H // 2, x.W // 2, cout)
         return out_nchw
 

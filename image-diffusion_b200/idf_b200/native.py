@@ -30,7 +30,7 @@ class IgemmArgs(C.Structure):
         ("bias", _vp), ("rowbias", _vp), ("rowbias_idx", _vp), ("rowbias_ld", _i32),
         ("res", _vp), ("ldres", _i64),
         ("vt", _vp), ("vt_col0", _i32), ("vt_ld", _i64),
-        ("zero_pad_last", _i32), ("epi_h", _i32), ("epi_w", _i32),
+        ("zero_pad_last", _i32), ("epi_h", _i32), ("epi_w", _i32), ("s2_batch", _i32),
     ]
 
 
@@ -49,6 +49,7 @@ _SIGNATURES = {
     "idf_conv1x1_small_f32": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32],
     "idf_upsample_nearest2x": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32],
     "idf_im2col_s2": [_vp, _i64, _vp, _i32, _i32, _i32, _i32],
+    "idf_space_to_depth2": [_vp, _i64, _vp, _i32, _i32, _i32, _i32],
     "idf_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i64, _i32, _i32, _i32],
     "idf_nhwc_bf16_to_nchw_f32": [_vp, _i64, _vp, _i32, _i32, _i32],
 }

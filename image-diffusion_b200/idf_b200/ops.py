@@ -23,7 +23,7 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
-          res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None) -> torch.Tensor:
+          res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0) -> torch.Tensor:
     """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view."""
     a = IgemmArgs()
     if not 1 <= len(segs) <= 2:
@@ -50,6 +50,7 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
     a.vt_ld = vt.stride(0) if vt is not None else 0
     a.zero_pad_last = 1 if zero_pad_last else 0
     a.epi_h, a.epi_w = epi_hw if epi_hw is not None else (0, 0)
+    a.s2_batch = s2_batch
     call("idf_conv2d_igemm", a)
     return out
 
@@ -146,6 +147,11 @@ def upsample_nearest2x(x: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int,
 
 def im2col_s2(x: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, C: int):
     call("idf_im2col_s2", x.data_ptr(), x.stride(0), y.data_ptr(), B, H, W, C)
+    return y
+
+
+def space_to_depth2(x: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, C: int):
+    call("idf_space_to_depth2", x.data_ptr(), x.stride(0), y.data_ptr(), B, H, W, C)
     return y
 
 

@@ -84,6 +84,9 @@ typedef struct idf_igemm_args {
   int64_t vt_ld;
   int32_t zero_pad_last;
   int32_t epi_h, epi_w; /* output image geometry seen by the epilogue (sample = m / (epi_h*epi_w)); 0 = a[0].h/w */
+  int32_t s2_batch;     /* > 0: stride-2 pad-0 3x3 conv (Downsample, components.py:110): a[0] holds the four parity
+                           planes written by idf_space_to_depth2, stacked along n (n = 4*s2_batch); h/w are the
+                           OUTPUT grid. Tap (kh, kw) reads plane (kh&1, kw&1) shifted by (kh>>1, kw>>1). */
 } idf_igemm_args;
 
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);
@@ -199,6 +202,14 @@ int idf_upsample_nearest2x(const void* x, int64_t ldx, void* y, int64_t ldy, int
  */
 int idf_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
                   idf_stream_t stream);
+
+/*
+ * idf_space_to_depth2 — splits a channels-last bf16 image into its four (row parity, column parity) planes:
+ * y[(ph*2+pw)*B + b, h, w, :] = x[b, 2h+ph, 2w+pw, :]. Feeds the stride-2 tap addressing of idf_conv2d_igemm (the
+ * Downsample conv of components.py:110) without an im2col matrix. y is (4*B*(H/2)*(W/2), C) dense.
+ */
+int idf_space_to_depth2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                        idf_stream_t stream);
 
 /* idf_nchw_f32_to_nhwc_bf16 / idf_nhwc_bf16_to_nchw_f32 — layout + dtype conversion at the module boundary. */
 int idf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t ldy, int32_t B, int32_t C, int32_t HW,

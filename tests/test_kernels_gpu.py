@@ -244,6 +244,15 @@ def test_downsample_im2col_gemm(B, C, H):
     got = unrows(out, B, OH, OH)
     assert rel_err(got, ref) < 6e-3
     assert got[:, :, -1, :].abs().max().item() == 0.0 and got[:, :, :, -1].abs().max().item() == 0.0
+    # same convolution without the im2col matrix: parity planes + stride-2 tap addressing inside the GEMM
+    planes = torch.empty(4 * B * OH * OH, C, device=DEV, dtype=torch.bfloat16)
+    ops.space_to_depth2(rows(x), planes, B, H, H, C)
+    out2 = torch.empty(B * OH * OH, C, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(planes, (4 * B, OH, OH), C, 9)], ops.pack_conv_weight(w), C, out2, bias=b, zero_pad_last=True,
+              s2_batch=B)
+    got2 = unrows(out2, B, OH, OH)
+    assert rel_err(got2, ref) < 6e-3
+    assert got2[:, :, -1, :].abs().max().item() == 0.0 and got2[:, :, :, -1].abs().max().item() == 0.0
 
 
 def test_cfg_posterior_step():

@@ -22,7 +22,7 @@ with torch.no_grad():
         desc = ""
         if name == "idf_conv2d_igemm":
             g = a[0]
-            m = g.a[0].n * g.a[0].h * g.a[0].w
+            m = (g.s2_batch if g.s2_batch else g.a[0].n) * g.a[0].h * g.a[0].w
             k = g.taps[0] * g.a[0].c + (g.taps[1] * g.a[1].c if g.a[1].ptr else 0)
             desc = f"M={m} N={g.N} K={k} taps={g.taps[0]} res={bool(g.res)} vt={bool(g.vt)} f={2.0*m*g.N*k/1e9:.1f}GF"
         elif name == "idf_attention_fwd":
