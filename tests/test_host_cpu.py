@@ -1,0 +1,173 @@
+"""CPU-side checks: the C ABI (header <-> shared library <-> ctypes table), the drop-in modules' parameter trees and
+checkpoint formats, error behaviour without a GPU, and the batch-sharding logic (gloo, world_size 2)."""
+import os
+import re
+import tempfile
+
+import pytest
+import torch
+
+from oracle import ref_path as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_of_the_header():
+    from idf_b200 import native
+    header = open(os.path.join(ROOT, "include", "idf_b200.h")).read()
+    declared = set(re.findall(r"\b(idf_[a-z0-9_]+)\s*\(", header))
+    declared -= {"idf_nhwc", "idf_igemm_args"}
+    lib = native.load()
+    assert lib.idf_abi_version() == 1
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/idf_b200.h but not exported"
+    assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
+    assert lib.idf_last_error() is not None
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from idf_b200 import native
+    monkeypatch.setattr(native, "_lib", None)
+    monkeypatch.setattr(native, "LIB_PATH", "/nonexistent/libidf_b200.so")
+    with pytest.raises(native.NativeError, match="no fallback"):
+        native.load()
+
+
+def test_parameter_trees_match_reference_schema():
+    from modules.unet import Unet
+    from modules.vae import VAE
+    u = Unet(**O.UNET_ARCH)
+    assert {k: tuple(v.shape) for k, v in u.state_dict().items()} == \
+        {k: tuple(v) for k, v in O.unet_param_shapes(O.UNET_ARCH).items()}
+    assert sum(p.numel() for p in u.parameters()) == 60_475_523
+    assert u.time_dim == 512 and u.num_classes == 3 and set(u.architecture) == set(O.UNET_ARCH)
+    for arch, n in ((O.VAE_KL_ARCH, 36_319_935), (O.VAE_VQ_ARCH, 36_315_678)):
+        v = VAE(**arch)
+        assert {k: tuple(t.shape) for k, t in v.state_dict().items()} == \
+            {k: tuple(s) for k, s in O.vae_param_shapes(arch).items()}
+        assert sum(p.numel() for p in v.parameters()) == n
+        assert (v.codebook is None) == (arch["bottleneck"] == "kl")
+    # default init follows torch's Conv2d/Linear/GroupNorm/Embedding conventions
+    sd = u.state_dict()
+    assert torch.all(sd["out_conv.0.weight"] == 1) and torch.all(sd["out_conv.0.bias"] == 0)
+    w = sd["down_blocks.0.first_halfs.0.layers.2.weight"]
+    assert w.abs().max().item() <= 1 / (128 * 9) ** 0.5 + 1e-6
+    assert torch.allclose(sd["time_embedding.factor"], 10000 ** (torch.arange(0, 256, dtype=torch.float32) / 256))
+
+
+def test_checkpoint_round_trips():
+    from modules.components import Scheduler
+    from modules.diffusion import Diffusion
+    from modules.unet import Unet
+    from modules.vae import VAE
+    small_u = dict(O.UNET_ARCH, channels=[128, 256], mid_channels=[256, 256], time_dim=64)
+    small_v = dict(O.VAE_VQ_ARCH, channels=[128, 256], codebook_size=32)
+    with tempfile.TemporaryDirectory() as d:
+        u = Unet(**small_u)
+        path = os.path.join(d, "sub", "unet.pt")
+        u.to_checkpoint(path)
+        ck = torch.load(path, weights_only=False)
+        assert set(ck) == {"unet", "architecture"}
+        ck["unet"] = {"_orig_mod." + k: v for k, v in ck["unet"].items()}  # what torch.compile leaves behind
+        u2 = Unet.from_checkpoint(checkpoint=ck)
+        assert all(torch.equal(a, b) for a, b in zip(u.state_dict().values(), u2.state_dict().values()))
+        with pytest.raises(ValueError):
+            Unet.from_checkpoint()
+        v = VAE(**small_v)
+        dfn = Diffusion(v, u, Scheduler(1000), "cat,dog,bird", "cuda")
+        assert dfn.classes == ["cat", "dog", "bird"] and dfn.latent_shape == (3, 64, 64)
+        bundle = os.path.join(d, "bundle.pt")
+        dfn.to_checkpoint(bundle)
+        ck = torch.load(bundle, weights_only=False)
+        assert set(ck) == {"v", "u", "scheduler", "classes"} and ck["scheduler"]["type"] == "linear"
+        v2 = VAE.from_checkpoint(checkpoint=ck["v"])
+        assert all(torch.equal(a, b) for a, b in zip(v.state_dict().values(), v2.state_dict().values()))
+        with pytest.raises(ValueError):
+            VAE.from_checkpoint()
+
+
+def test_error_behaviour_without_gpu():
+    from modules.components import Codebook, Scheduler
+    from modules.diffusion import Diffusion
+    from modules.unet import Unet
+    from modules.vae import VAE
+    u = Unet(**dict(O.UNET_ARCH, channels=[128, 256], mid_channels=[256, 256], time_dim=64)).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        u(torch.zeros(1, 3, 8, 8), torch.zeros(1, dtype=torch.long))
+    vq = VAE(**dict(O.VAE_VQ_ARCH, channels=[128, 256], codebook_size=32)).eval()
+    kl = VAE(**dict(O.VAE_KL_ARCH, channels=[128, 256])).eval()
+    with pytest.raises(ValueError, match="Cannot sample"):
+        vq.encode(torch.zeros(1, 3, 16, 16), sample=True)
+    with pytest.raises(ValueError, match="Cannot quantize"):
+        kl.decode(torch.zeros(1, 3, 8, 8), quantize=True)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        kl.decode(torch.zeros(1, 3, 8, 8))
+    s = Scheduler(1000)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        s.add_noise(torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(ValueError):
+        Scheduler(10, type="quadratic")
+    if not torch.cuda.is_available():
+        with pytest.raises(AssertionError, match="GPU"):
+            Diffusion(kl, u, s, "a,b,c", "cuda").sample(3, num_images=1)
+    cb = Codebook(16, 3, 0.25, 0.99)
+    assert set(dict(cb.named_parameters())) == {"embeddings.weight", "ema_w"} and "ema_cluster_size" in dict(cb.named_buffers())
+
+
+def test_scheduler_tables_match_reference_golden():
+    from modules.components import Scheduler
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "scheduler.pt"), weights_only=False)
+    for typ in ("linear", "cosine"):
+        s = Scheduler(1000, 1e-4, 0.02, typ)
+        assert torch.equal(s.betas, g[typ]["betas"]) and torch.equal(s.alpha_cum_prod, g[typ]["alpha_cum_prod"])
+        assert torch.equal(s.sqrt_one_minus_alpha_cum_prod, torch.sqrt(1 - s.alpha_cum_prod))
+
+
+def test_layer_programs_match_oracle():
+    from idf_b200.spec import vae_program
+    for arch in (O.VAE_KL_ARCH, O.VAE_VQ_ARCH):
+        assert vae_program(arch, "decoder") == O.decoder_program(arch)
+        assert vae_program(arch, "encoder") == O.encoder_program(arch)
+
+
+def test_shard_bounds_cover_everything():
+    from idf_b200.dist import shard_bounds
+    for total, world, align in ((4096, 8, 48 * 0 + 64), (4096, 3, 64), (96, 2, 48), (48, 4, 48), (10, 4, 1)):
+        spans = [shard_bounds(total, world, r, align) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(lo % align == 0 and hi % align == 0 for lo, hi in spans)
+    with pytest.raises(ValueError):
+        shard_bounds(100, 2, 0, 48)
+
+
+def _gloo_worker(rank, world, port, total, out):
+    import torch.distributed as dist
+    from idf_b200.dist import gather_shards, shard_bounds
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_bounds(total, world, rank, 2)
+    local = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 3)
+    full = gather_shards(local, total, 2)
+    ok = torch.equal(full, torch.arange(total, dtype=torch.float32)[:, None].repeat(1, 3))
+    t = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(bool(t.item()))
+    dist.destroy_process_group()
+
+
+def test_gather_shards_gloo_world2():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 10, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
