@@ -46,6 +46,8 @@ struct IgemmParams {
   int tiles_per_img;  // HW / 128 when HW >= 128, else 0
   int matrix;         // 1: A is a plain (rows, cols) matrix walked 128 rows at a time along the w axis
   int s2_batch;       // > 0: segment 0 holds the 4 parity planes of a stride-2 conv input, stacked along n
+  int splits;         // split-K factor (persistent kernel): partial sums go to out_f32 + split * split_stride
+  long long split_stride;
   int M, N;
   int flags;
   const float* bias;
@@ -330,7 +332,8 @@ template <int BN, int NSTG>
 struct PgCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
-  static constexpr int STAGES = (NSTG == 3) ? 4 : ((BN == 128) ? 5 : 4);
+  // short-K (NSTG == 3) tiles only have 2..8 k-blocks: a shallow ring leaves room for the three staging buffers
+  static constexpr int STAGES = (NSTG == 3) ? (BN == 256 ? 2 : (BN == 192 ? 3 : 4)) : ((BN == 128) ? 5 : 4);
   static constexpr int TMEM_COLS = (BN == 128) ? 256 : 512;
   static constexpr int SMEM = STAGES * STAGE_BYTES + NSTG * PG_STG_BYTES + 1024 + 256;
 };
@@ -358,7 +361,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
   const int lane = threadIdx.x & 31;
   const int n_tiles = p.N / BN;
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int total_tiles = m_tiles * n_tiles;
+  // work unit = (output tile, K split); "total_tiles" counts units, the split index varies fastest
+  const int splits = p.splits;
+  const int total_tiles = m_tiles * n_tiles * splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
@@ -388,7 +393,8 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int kc = 0;  // running k-block counter across tiles (ring position)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int u = blockIdx.x; u < total_tiles; u += gridDim.x) {
+        const int t = u / splits, sp = u % splits;
         const int tile_m = t / n_tiles, n0 = (t % n_tiles) * BN;
         int img0, h0, w0 = 0;
         if (p.matrix) {
@@ -399,8 +405,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
         } else {
           img0 = tile_m * p.tile_n; h0 = 0;
         }
+        const int kb0 = (int)((long long)sp * p.kb_total / splits), kb1 = (int)((long long)(sp + 1) * p.kb_total / splits);
         int seg = 0, tap = 0, cbk = 0;
-        for (int kb = 0; kb < p.kb_total; ++kb, ++kc) {
+        if (kb0 < p.kb_seg0) { tap = kb0 / p.cb[0]; cbk = kb0 % p.cb[0]; }
+        else { seg = 1; tap = (kb0 - p.kb_seg0) / p.cb[1]; cbk = (kb0 - p.kb_seg0) % p.cb[1]; }
+        for (int kb = kb0; kb < kb1; ++kb, ++kc) {
           const int s = kc % STAGES;
           mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
@@ -430,19 +439,22 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
       int kc = 0, it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int u = blockIdx.x; u < total_tiles; u += gridDim.x, ++it) {
+        const int sp = u % splits;
+        const int kb0 = (int)((long long)sp * p.kb_total / splits), kb1 = (int)((long long)(sp + 1) * p.kb_total / splits);
         const int acc = it & 1;
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.kb_total; ++kb, ++kc) {
+        for (int kb = kb0; kb < kb1; ++kb, ++kc) {
           const int s = kc % STAGES;
           mbar_wait(&full_bar[s], (kc / STAGES) & 1);
           tc_fence_after_sync();
           const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + s * A_STAGE_BYTES), 128);
           const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + s * Cfg::B_BYTES), 128);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full[acc]);
@@ -471,7 +483,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
     };
     int it = 0, gc = 0;
     if (has_res && issuer && blockIdx.x < total_tiles && !((p.flags & F_VT) || to_f32)) load_res(blockIdx.x, 0, 0);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int u = blockIdx.x; u < total_tiles; u += gridDim.x, ++it) {
+      const int t = u / splits;  // (residual / staged paths are only used with splits == 1, where t == u)
+      const float* __restrict__ dummy = nullptr; (void)dummy;
+      float* out_f32 = p.out_f32 + (long long)(u % splits) * p.split_stride;
       const int tile_m = t / n_tiles, n0 = (t % n_tiles) * BN;
       const int acc = it & 1;
       const long long m = (long long)tile_m * BLOCK_M + r;
@@ -513,7 +528,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           if (NSTG >= 3) {
             if (issuer) {  // prefetch the next group's residual
               int nt = t, ncg = cg + 1;
-              if (ncg == GPT) { nt = t + gridDim.x; ncg = 0; }
+              if (ncg == GPT) { nt = t + gridDim.x; ncg = 0; }  // splits == 1 here
               if (nt < total_tiles) load_res(nt, ncg, gc + 1);
             }
           } else if (gc > 0) {
@@ -579,7 +594,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < 32; ++j) tcol[j * BLOCK_M] = __float2bfloat16_rn(a[j]);
           } else if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + m * p.out_f32_ld + nc0 + c * 32);
+            float4* dst = reinterpret_cast<float4*>(out_f32 + m * p.out_f32_ld + nc0 + c * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(a[4 * j + 0], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
           }
@@ -633,10 +648,61 @@ static int launch_persist(const IgemmParams& p, cudaStream_t stream) {
     if (rc != IDF_OK) return rc;
     attr_set = true;
   }
-  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BN);
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BN) * p.splits;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   igemm_persist_kernel<BN, NSTG><<<grid, PG_THREADS, Cfg::SMEM, stream>>>(p);
   return check_cuda(cudaGetLastError(), "igemm_persist launch");
+}
+
+// Split-K finish: out[m, n] = bf16( sum_s partial[s][m][n] + bias[n] + rowbias[row(sample(m))][n] ), partials summed in
+// split order (deterministic), padded rows written as exact zeros.
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ ws, long long split_stride,
+                                                            int splits, __nv_bfloat16* __restrict__ out, long long ldo,
+                                                            int M, int N, const float* __restrict__ bias,
+                                                            const float* __restrict__ rowbias,
+                                                            const int* __restrict__ rowbias_idx, int rowbias_ld,
+                                                            int H, int W, int zero_pad) {
+  const int vec = N / 8;
+  const long long total = (long long)M * vec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    const long long m = i / vec;
+    const int n = v * 8;
+    float acc[8];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(ws + m * N + n);
+      const float4 b = *reinterpret_cast<const float4*>(ws + m * N + n + 4);
+      acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w; acc[4] = b.x; acc[5] = b.y; acc[6] = b.z; acc[7] = b.w;
+    }
+    for (int s = 1; s < splits; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(ws + s * split_stride + m * N + n);
+      const float4 b = *reinterpret_cast<const float4*>(ws + s * split_stride + m * N + n + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    if (bias != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += bias[n + e];
+    }
+    const int HW = H * W;
+    if (rowbias != nullptr) {
+      const int sample = (int)(m / HW);
+      const float* rb = rowbias + (long long)(rowbias_idx ? rowbias_idx[sample] : sample) * rowbias_ld + n;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += rb[e];
+    }
+    uint4 o;
+    const int pix = (int)(m % HW);
+    if (zero_pad && ((pix / W == H - 1) || (pix % W == W - 1))) {
+      o = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+      o.x = pack_bf16x2(acc[0], acc[1]);
+      o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]);
+      o.w = pack_bf16x2(acc[6], acc[7]);
+    }
+    *reinterpret_cast<uint4*>(out + m * ldo + n) = o;
+  }
 }
 
 static int make_act_map(CUtensorMap* tm, const idf_nhwc_t& a, int tile_w, int tile_h, int tile_n) {
@@ -679,6 +745,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     return fail(IDF_ERR_ARG, "igemm: s2_batch needs one 9-tap segment holding 4*s2_batch parity planes");
   const long long M = (long long)(a->s2_batch > 0 ? a->s2_batch : x0.n) * HW;
   p.s2_batch = a->s2_batch;
+  p.splits = 1;
   if (M <= 0 || M > 0x7fffffffLL) return fail(IDF_ERR_ARG, "igemm: bad M");
   // M-tile geometry: 128 consecutive NHWC pixels = tile_n images x tile_h rows x tile_w columns.
   const bool is_matrix = x0.n == 1 && x0.h == 1 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
@@ -726,6 +793,24 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     }
     if (bn == 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d has no legal tile width", a->N);
   }
+  // split-K: when the tile list leaves a large part of the GPU idle (8x8 / 4x4 stages), split the K range of each
+  // tile over up to 4 work units; fp32 partials go to the caller's workspace and a finish kernel adds them in a
+  // fixed order (deterministic) together with the epilogue terms.
+  int splits = 1;
+  if (!legacy && !short_k && a->ws != nullptr && a->res == nullptr && a->vt == nullptr && !a->out_f32) {
+    const long long units = ((M + BLOCK_M - 1) / BLOCK_M) * (a->N / bn);
+    auto eff = [&](int sfac) {
+      const long long u = units * sfac;
+      return (double)u / (double)(((u + sm_count() - 1) / sm_count()) * sm_count());
+    };
+    double best = eff(1);
+    for (int sfac = 2; sfac <= 4; ++sfac) {
+      if (p.kb_total / sfac < 8) break;
+      if ((long long)sfac * M * a->N * 4 > a->ws_bytes) break;
+      if (eff(sfac) > best * 1.15) { best = eff(sfac); splits = sfac; }
+    }
+  }
+  p.splits = splits;
   if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, (uint32_t)bn)) != IDF_OK)
     return rc;
 
@@ -742,7 +827,15 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   if (a->bias != nullptr && (reinterpret_cast<uintptr_t>(a->bias) & 15))
     return fail(IDF_ERR_ARG, "igemm: bias must be 16-byte aligned");
   if (a->zero_pad_last) p.flags |= F_ZERO_PAD;
-  if (a->out_f32) {
+  if (splits > 1) {
+    // the GEMM writes raw fp32 partials; bias / time bias / padding mask move to the finish kernel
+    if ((reinterpret_cast<uintptr_t>(a->ws) & 15) || a->N % 8 != 0 || a->ldo % 8 != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15))
+      return fail(IDF_ERR_ARG, "igemm: split-K alignment");
+    p.bias = nullptr; p.rowbias = nullptr; p.flags = F_OUT_F32;
+    p.out_f32 = reinterpret_cast<float*>(a->ws);
+    p.out_f32_ld = a->N;
+    p.split_stride = M * a->N;
+  } else if (a->out_f32) {
     if (a->res != nullptr || a->vt != nullptr) return fail(IDF_ERR_UNSUPPORTED, "igemm: fp32 output excludes res/vt");
     if (a->ldo % 4 != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15)) return fail(IDF_ERR_ARG, "igemm: fp32 out alignment");
     p.flags |= F_OUT_F32;
@@ -779,12 +872,20 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   }
   if (!legacy) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (short_k) return launch_persist<128, 3>(p, st);
+    if (short_k) return launch_persist<128, 3>(p, st);  // (wider short-K tiles with a 2-stage ring measured slower)
     switch (bn) {
-      case 256: return launch_persist<256, 1>(p, st);
-      case 192: return launch_persist<192, 1>(p, st);
-      default: return launch_persist<128, 1>(p, st);
+      case 256: rc = launch_persist<256, 1>(p, st); break;
+      case 192: rc = launch_persist<192, 1>(p, st); break;
+      default: rc = launch_persist<128, 1>(p, st); break;
     }
+    if (rc != IDF_OK || splits == 1) return rc;
+    const long long vecs = M * (a->N / 8);
+    long long blocks = (vecs + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        reinterpret_cast<const float*>(a->ws), p.split_stride, splits, reinterpret_cast<__nv_bfloat16*>(a->out), a->ldo,
+        (int)M, a->N, a->bias, a->rowbias, a->rowbias_idx, a->rowbias_ld, p.H, p.W, a->zero_pad_last ? 1 : 0);
+    return check_cuda(cudaGetLastError(), "splitk_finish launch");
   }
   dim3 grid((unsigned)((M + BLOCK_M - 1) / BLOCK_M), (unsigned)(a->N / BLOCK_N));
   igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);

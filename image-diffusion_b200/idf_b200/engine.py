@@ -85,6 +85,9 @@ class UnetEngine:
         self.ws = Workspace(device)
         self.L, self.heads, self.G = arch["num_res_layers"], arch["num_heads"], arch["num_groups"]
         self.taps = None  # debugging aid: set to a dict to collect fp32 copies of intermediate activations
+        # split-K scratch: disabled by default — measured no gain at 8x8 and it would make the summation order (and so
+        # the bits) depend on the batch size; the kernel path stays available (tests/test_kernels_gpu.py)
+        self.splitk_ws = None
         self.downs, self.mids, self.ups = unet_blocks(arch)
         for _, cin, cout in self.downs + self.mids + self.ups:
             if cin % 64 or cout % 128:
@@ -157,11 +160,12 @@ class UnetEngine:
             y1 = ws.get("y1", M, cout)
             off = self.tp_off[(p, l)]
             ops.igemm([(h1, x.grid, cin, 9)], w[k + ".w1"], cout, y1, bias=w[k + ".b1"],
-                      rowbias=table[:, off:off + cout], rowbias_idx=idx)
+                      rowbias=table[:, off:off + cout], rowbias_idx=idx, ws=self.splitk_ws)
             h2 = ws.get("h2", M, cout)
             ops.groupnorm_silu(y1, h2, w[k + ".g2w"], w[k + ".g2b"], B, HW, cout, G, True)
             x2 = ws.get("x2", M, cout)
-            ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"])
+            ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"],
+                      ws=self.splitk_ws)
             h3 = ws.get("h3", M, cout)
             ops.groupnorm_silu(x2, h3, w[k + ".g3w"], w[k + ".g3b"], B, HW, cout, G, False)
             qk = ws.get("qk", M, 2 * cout)
@@ -215,7 +219,7 @@ class UnetEngine:
             ops.space_to_depth2(x.t, planes, x.B, x.H, x.W, cout)
             nxt = ws.get("dn", x.M // 4, cout)
             ops.igemm([(planes, (4 * x.B, x.H // 2, x.W // 2), cout, 9)], w[f"down.{i}.w"], cout, nxt,
-                      bias=w[f"down.{i}.b"], zero_pad_last=True, s2_batch=x.B)
+                      bias=w[f"down.{i}.b"], zero_pad_last=True, s2_batch=x.B, ws=self.splitk_ws)
             self._tap(f"down.{i}", nxt)
             x = Act(nxt, x.B, x.H // 2, x.W // 2, cout)
         for p, cin, cout in self.mids:
@@ -225,7 +229,8 @@ class UnetEngine:
             up = ws.get("up", 4 * x.M, c)
             ops.upsample_nearest2x(x.t, up, x.B, x.H, x.W, c)
             cat = cats.pop()
-            ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), c, 9)], w[f"up.{i}.w"], c, cat[:, :c], bias=w[f"up.{i}.b"])
+            ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), c, 9)], w[f"up.{i}.w"], c, cat[:, :c], bias=w[f"up.{i}.b"],
+                      ws=self.splitk_ws)
             self._tap(f"up.{i}", cat)
             x = self._block(p, Act(cat, x.B, 2 * x.H, 2 * x.W, 2 * c), cout, table, row_idx)
         h = ws.get("h1", x.M, x.C)

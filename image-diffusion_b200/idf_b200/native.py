@@ -31,6 +31,7 @@ class IgemmArgs(C.Structure):
         ("res", _vp), ("ldres", _i64),
         ("vt", _vp), ("vt_col0", _i32), ("vt_ld", _i64),
         ("zero_pad_last", _i32), ("epi_h", _i32), ("epi_w", _i32), ("s2_batch", _i32),
+        ("ws", _vp), ("ws_bytes", _i64),
     ]
 
 

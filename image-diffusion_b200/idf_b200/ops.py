@@ -23,7 +23,7 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
-          res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0) -> torch.Tensor:
+          res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0, ws=None) -> torch.Tensor:
     """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view."""
     a = IgemmArgs()
     if not 1 <= len(segs) <= 2:
@@ -51,6 +51,8 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
     a.zero_pad_last = 1 if zero_pad_last else 0
     a.epi_h, a.epi_w = epi_hw if epi_hw is not None else (0, 0)
     a.s2_batch = s2_batch
+    a.ws = ptr(ws)
+    a.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
     call("idf_conv2d_igemm", a)
     return out
 

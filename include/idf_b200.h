@@ -87,6 +87,9 @@ typedef struct idf_igemm_args {
   int32_t s2_batch;     /* > 0: stride-2 pad-0 3x3 conv (Downsample, components.py:110): a[0] holds the four parity
                            planes written by idf_space_to_depth2, stacked along n (n = 4*s2_batch); h/w are the
                            OUTPUT grid. Tap (kh, kw) reads plane (kh&1, kw&1) shifted by (kh>>1, kw>>1). */
+  void* ws;             /* optional caller-owned fp32 scratch (16-byte aligned) enabling split-K for GEMMs whose tile
+                           list underfills the GPU; NULL = never split */
+  int64_t ws_bytes;
 } idf_igemm_args;
 
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);

@@ -60,6 +60,31 @@ def test_conv3x3_igemm(B, Cin, Cout, H):
     assert (got - ref).abs().max().item() < 0.06
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H", [(9, 512, 512, 4), (24, 384, 512, 8), (96, 512, 512, 4)])
+def test_conv3x3_split_k(B, Cin, Cout, H):
+    """Small-M layers: K split over several work units, fp32 partials reduced by the finish kernel (with the time
+    bias and the fused 1x1 skip segment); deterministic from run to run."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(B + Cin)
+    h = torch.randn(B, Cin, H, H, device=DEV, generator=g)
+    x = torch.randn(B, 128, H, H, device=DEV, generator=g)
+    w3 = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cin)
+    w1 = torch.randn(Cout, 128, 1, 1, device=DEV, generator=g) / math.sqrt(128)
+    b = torch.randn(Cout, device=DEV, generator=g)
+    table = torch.randn(B, Cout, device=DEV, generator=g)
+    wcat = torch.cat([ops.pack_conv_weight(w3), ops.pack_conv_weight(w1)], dim=1).contiguous()
+    ws = torch.empty(16 * 1024 * 1024, device=DEV, dtype=torch.float32)
+    outs = []
+    for rep in range(2):
+        out = torch.empty(B * H * H, Cout, device=DEV, dtype=torch.bfloat16)
+        ops.igemm([(rows(h), (B, H, H), Cin, 9), (rows(x), (B, H, H), 128, 1)], wcat, Cout, out, bias=b, rowbias=table,
+                  ws=ws)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    ref = F.conv2d(bf(h), bf(w3), b, padding=1) + F.conv2d(bf(x), bf(w1)) + table[:, :, None, None]
+    assert rel_err(unrows(outs[0], B, H, H), ref) < 6e-3
+
+
 def test_conv3x3_rowbias_and_fused_skip():
     """second_half conv3x3 + 1x1 skip conv as one two-segment GEMM, plus a per-sample time bias."""
     ops = _ops()

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 rc_all=0
-for k in conv3x3_igemm rowbias linear_residual small_m qkv_attention groupnorm embed small_channel downsample cfg_posterior vq_argmin; do
+for k in conv3x3_igemm split_k rowbias linear_residual small_m qkv_attention groupnorm embed small_channel downsample cfg_posterior vq_argmin; do
   timeout 300 python -m pytest tests/test_kernels_gpu.py -q -x -k "$k" > gpurun_out/kt_$k.log 2>&1
   rc=$?
   echo "== $k rc=$rc"; tail -n 15 gpurun_out/kt_$k.log | cut -c1-300
