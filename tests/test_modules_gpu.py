@@ -257,3 +257,82 @@ def test_sharded_sampling_is_world_size_invariant(unet_pair, vae_kl_pair, monkey
     halves = torch.cat([run(2, 0), run(2, 1)], dim=0)
     assert torch.equal(full, halves)
     assert not torch.equal(full[:6], full[6:])  # different micro-batches draw different noise
+
+
+@pytest.mark.parametrize("res,B", [(16, 3), (64, 1), (8, 5)])
+def test_unet_other_latent_resolutions(unet_pair, res, B):
+    """The engine is not specialised to 32x32 latents: 64x64 (4096-token attention) is checked against the fp32
+    oracle on the same GPU; below 32x32 the bottleneck has fewer than 16 tokens per sample, which the attention
+    kernel rejects loudly (no silent fallback)."""
+    m, sd = unet_pair
+    x = gen(500 + res, B, 3, res, res).to(DEV)
+    t = torch.tensor(([17, 999, 0, 500, 250])[:B], device=DEV)
+    ctx = torch.tensor(([2, 1, 0, 1, 2])[:B], device=DEV)
+    if res < 32:
+        from idf_b200.native import NativeError
+        with pytest.raises(NativeError):
+            m(x, t, ctx)
+        return
+    out = m(x, t, ctx)
+    ref = O.unet_forward(sd, O.UNET_ARCH, x, t, ctx)
+    r = rel_rms(out, ref)
+    print(f"unet {res}x{res} B={B}: rel-RMS {r:.3e}")
+    assert r <= 3e-2, r
+
+
+def test_sampling_with_cosine_schedule_and_per_sample_scales(unet_pair):
+    """Scheduler(type='cosine') and a different guidance scale per sample (the reference's list-of-scales mode)."""
+    from idf_b200.sampler import CfgSampler
+    from modules.components import Scheduler
+    m, sd = unet_pair
+    N = 9
+    labels = torch.tensor([0, 1, 2] * 3, device=DEV)
+    cfg = torch.tensor([1, 2, 3, 4, 5, 6, 7, 8, 9], device=DEV)
+    sched = Scheduler(1000, type="cosine", device=DEV)
+    steps = [999, 800, 3, 0]
+    x_T = gen(31, N, 3, 32, 32).to(DEV)
+    noises = [gen(32 + k, N, 3, 32, 32).to(DEV) for k in range(len(steps))]
+    got = CfgSampler(m, sched, labels, cfg, (3, 32, 32)).run(x_T, steps=steps, noises=noises).clone()
+    ref = O.cfg_sample(sd, O.UNET_ARCH, O.SchedulerTables(1000, type="cosine", device=DEV), x_T, labels, cfg, noises,
+                       steps=steps)
+    r = rel_rms(got, ref)
+    print(f"cosine schedule, scales 1..9: rel-RMS {r:.3e}")
+    assert r <= 2e-2, r
+
+
+def test_vq_bundle_decode_requantizes(unet_pair):
+    """Diffusion over a VQ bundle re-runs the codebook on the sampled latent before decoding (diffusion.py:58-59)."""
+    from modules.components import Scheduler
+    from modules.diffusion import Diffusion
+    from modules.vae import VAE
+    unet, _ = unet_pair
+    sd = O.seeded_state_dict(O.vae_param_shapes(O.VAE_VQ_ARCH), 7)
+    sd["codebook.embeddings.weight"] = gen(8, 1024, 3) * 0.5
+    vae = VAE(**O.VAE_VQ_ARCH)
+    vae.load_state_dict(sd)
+    vae = vae.to(DEV).eval()
+    sdd = to_dev(sd)
+    z = gen(77, 2, 3, 32, 32).to(DEV)
+    out = vae.decode(z, quantize=True)
+    ref = O.vae_decode(sdd, O.VAE_VQ_ARCH, z, quantize=True)
+    assert rel_rms(out, ref) <= 3.5e-2
+    d = Diffusion(vae, unet, Scheduler(4, device=DEV), "a,b,c", DEV)
+    imgs = d.sample([2, 5], seed=1)   # list mode: len(classes) x len(cfg_scales) images
+    assert imgs.shape == (6, 3, 128, 128) and torch.isfinite(imgs).all()
+
+
+def test_vq_config5_batch256_indices():
+    """BASELINE config 5 at full size for the quantiser: 256 x 1024 latent vectors, indices bit-exact."""
+    from modules.components import Codebook
+    cb = Codebook(1024, 3, 0.25, 0.99).to(DEV).eval()
+    for tag, w in (("default", (torch.rand(1024, 3, generator=torch.Generator().manual_seed(65)) * 2 - 1) / 1024),
+                   ("normal", gen(66, 1024, 3))):
+        cb.embeddings.weight.data.copy_(w)
+        z = gen(90, 256, 3, 32, 32).to(DEV)
+        zq, idx = cb.quantize(z)
+        ref = torch.cdist(z.permute(0, 2, 3, 1).reshape(256, 1024, 3), w.to(DEV)[None].repeat(256, 1, 1)).argmin(-1).view(-1)
+        assert torch.equal(idx, ref), tag
+        q_out, loss, perp = cb(z)
+        _, loss_ref, perp_ref, _ = O.codebook_forward({"codebook.embeddings.weight": w.to(DEV)}, "codebook", z, 0.25)
+        assert abs(loss.item() - loss_ref.item()) <= 1e-5 * max(1.0, abs(loss_ref.item()))
+        assert abs(perp.item() - perp_ref.item()) <= 1e-2 * perp_ref.item()
