@@ -1,5 +1,7 @@
 // GroupNorm (+ SiLU) over channels-last bf16 activations, and the row softmax used by the VAE attention.
 // Both are memory-bound: 16-byte vector accesses, fp32 statistics, second pass served from L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 #include "../../include/idf_b200.h"
@@ -195,9 +197,16 @@ extern "C" int idf_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t l
   if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups != 0) return fail(IDF_ERR_ARG, "groupnorm: bad shape");
   const int cpg = C / groups;
   // groups per slab: as many as possible (<= 8) while a slab stays <= 8 sixteen-byte vectors wide
+  // ... and small enough that a CTA's slab (HW x V x 16 bytes) stays L1-resident between the two passes
+  static const int l1_kb = [] { const char* e = getenv("IDF_GN_SLAB_KB"); return e ? atoi(e) : 512; }();  // (64 KiB slabs measured no faster)
+  int vmax = 8;
+  while (vmax > 1 && (long long)HW * vmax * 16 > (long long)l1_kb * 1024) vmax >>= 1;
   int gps = 0;
   for (int d = 8; d >= 1; --d)
-    if (groups % d == 0 && (d * cpg) % 8 == 0 && d * cpg / 8 <= 8) { gps = d; break; }
+    if (groups % d == 0 && (d * cpg) % 8 == 0 && d * cpg / 8 <= vmax) { gps = d; break; }
+  if (gps == 0)
+    for (int d = 1; d <= 8; ++d)  // no slab that small: take the narrowest legal one
+      if (groups % d == 0 && (d * cpg) % 8 == 0 && d * cpg / 8 <= 8) { gps = d; break; }
   if (gps == 0) return fail(IDF_ERR_UNSUPPORTED, "groupnorm: %d channels in %d groups does not split into slabs", C, groups);
   const int V = gps * cpg / 8;
   if (ldx % 8 != 0 || ldy % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
