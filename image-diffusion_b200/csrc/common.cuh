@@ -144,11 +144,27 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t sw
   return d;
 }
 
-// Instruction descriptor for kind::f16, BF16 x BF16 -> FP32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
+// Shared-memory matrix descriptor for an MN-major operand (the M or N index is the contiguous one) stored as
+// K rows of 128 bytes (64 bf16 along M/N) with the 128-byte swizzle, e.g. a TMA box {64, rows}. Eight K rows form
+// one 1024-byte swizzle atom: SBO = distance between 8-row groups along K, LBO = distance between successive
+// 64-element chunks along M/N (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= 2ull << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for kind::f16, BF16 x BF16 -> FP32. a_mn / b_mn = 1 selects an MN-major operand.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
   return (1u << 4)            // D format: F32
          | (1u << 7)          // A format: BF16
          | (1u << 10)         // B format: BF16
+         | (a_mn << 15)       // A major: 0 = K, 1 = MN
+         | (b_mn << 16)       // B major
          | ((N >> 3) << 17)   // N / 8
          | ((M >> 4) << 24);  // M / 16
 }

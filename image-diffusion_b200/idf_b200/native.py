@@ -35,6 +35,11 @@ class IgemmArgs(C.Structure):
     ]
 
 
+class WgradArgs(C.Structure):
+    _fields_ = [("x", NHWC), ("taps", _i32), ("s2_batch", _i32), ("dy", _vp), ("ld_dy", _i64), ("cout", _i32),
+                ("grad", _vp), ("accumulate", _i32), ("ws", _vp), ("ws_bytes", _i64)]
+
+
 # name -> argtypes (the trailing stream argument is appended automatically)
 _SIGNATURES = {
     "idf_conv2d_igemm": [C.POINTER(IgemmArgs)],
@@ -53,6 +58,8 @@ _SIGNATURES = {
     "idf_space_to_depth2": [_vp, _i64, _vp, _i32, _i32, _i32, _i32],
     "idf_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i64, _i32, _i32, _i32],
     "idf_nhwc_bf16_to_nchw_f32": [_vp, _i64, _vp, _i32, _i32, _i32],
+    # training step
+    "idf_conv2d_wgrad": [C.POINTER(WgradArgs)],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["idf_last_error", "idf_abi_version"])
 

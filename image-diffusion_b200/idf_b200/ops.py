@@ -167,3 +167,24 @@ def rows_to_nchw(x: torch.Tensor, y_nchw: torch.Tensor):
     B, Cc, H, W = y_nchw.shape
     call("idf_nhwc_bf16_to_nchw_f32", x.data_ptr(), x.stride(0), y_nchw.data_ptr(), B, Cc, H * W)
     return y_nchw
+
+
+# =================================================================================================
+# training step (backward kernels)
+# =================================================================================================
+def conv_wgrad(x: torch.Tensor, grid, cin: int, taps: int, dy: torch.Tensor, cout: int, grad: torch.Tensor,
+               ws: torch.Tensor, *, accumulate: bool = False, s2_batch: int = 0) -> torch.Tensor:
+    """grad (cout, cin, kh, kw) fp32 (+)= sum_m dy[m, :]^T x[m + tap, :]. x / grid / cin / taps as passed to igemm."""
+    _check_bf16_rows(x, "wgrad x")
+    _check_bf16_rows(dy, "wgrad dy")
+    if grad.dtype != torch.float32 or not grad.is_contiguous() or grad.numel() != cout * cin * taps:
+        raise ValueError(f"wgrad: grad must be contiguous fp32 with {cout * cin * taps} elements")
+    a = native.WgradArgs()
+    n, h, w = grid
+    a.x = nhwc_view(x, n, h, w, cin)
+    a.taps, a.s2_batch = taps, s2_batch
+    a.dy, a.ld_dy, a.cout = dy.data_ptr(), dy.stride(0), cout
+    a.grad, a.accumulate = grad.data_ptr(), 1 if accumulate else 0
+    a.ws, a.ws_bytes = ws.data_ptr(), ws.numel() * ws.element_size()
+    call("idf_conv2d_wgrad", a)
+    return grad

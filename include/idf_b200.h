@@ -220,6 +220,37 @@ int idf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t ldy, int32_t B, i
 int idf_nhwc_bf16_to_nchw_f32(const void* x, int64_t ldx, float* y, int32_t B, int32_t C, int32_t HW,
                               idf_stream_t stream);
 
+/* =====================================================================================================
+ * Training step (trainers/diffusion_trainer.py:141-187): backward kernels of the UNet path. The data gradient of
+ * every convolution / linear layer is idf_conv2d_igemm itself, run on the output gradient with a re-packed weight
+ * (taps mirrored, channel roles swapped); everything else is below.
+ * ===================================================================================================== */
+
+/*
+ * idf_conv2d_wgrad — weight gradient of nn.Conv2d 3x3 (s1 p1, or the stride-2 Downsample conv) / 1x1 / nn.Linear:
+ *   grad[co, ci, kh, kw] (+)= sum over output pixels m of dy[m, co] * x[pixel(m) + (kh, kw), ci]
+ * (what autograd computes for components.py:455,501,110,125 and the Linear layers of components.py:81-83,97).
+ *   x        the layer's forward input, channels-last bf16 (the same view that was passed to idf_conv2d_igemm).
+ *   dy       bf16 (M, ld_dy) gradient of the layer output, M = n*h*w output pixels (s2_batch*h*w for stride 2).
+ *   grad     fp32, PyTorch parameter layout (cout, cin, kh, kw) contiguous; accumulate != 0 adds to it.
+ *   ws       caller-owned fp32 scratch for split-K partials, at least cout*taps*cin*4 bytes (more = more splits).
+ * Deterministic: partials are summed in a fixed order.
+ */
+typedef struct idf_wgrad_args {
+  idf_nhwc_t x;
+  int32_t taps;
+  int32_t s2_batch;
+  const void* dy;
+  int64_t ld_dy;
+  int32_t cout;
+  float* grad;
+  int32_t accumulate;
+  void* ws;
+  int64_t ws_bytes;
+} idf_wgrad_args;
+
+int idf_conv2d_wgrad(const idf_wgrad_args* args, idf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
