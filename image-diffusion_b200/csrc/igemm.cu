@@ -46,6 +46,8 @@ struct IgemmParams {
   int tiles_per_img;  // HW / 128 when HW >= 128, else 0
   int matrix;         // 1: A is a plain (rows, cols) matrix walked 128 rows at a time along the w axis
   int s2_batch;       // > 0: segment 0 holds the 4 parity planes of a stride-2 conv input, stacked along n
+  signed char tdh[2][9], tdw[2][9];  // per-segment tap offsets (rows, columns)
+  int tdn[9];                        // segment-0 image offset per tap (parity plane of a stride-2 conv)
   int splits;         // split-K factor (persistent kernel): partial sums go to out_f32 + split * split_stride
   long long split_stride;
   int M, N;
@@ -125,18 +127,7 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
-        int dh = 0, dw = 0, dn = 0;
-        if (p.taps[seg] == 9) {
-          if (p.s2_batch > 0 && seg == 0) {  // stride 2, pad 0: tap (kh, kw) -> parity plane, shift (kh>>1, kw>>1)
-            const int kh = tap / 3, kw = tap % 3;
-            dn = ((kh & 1) * 2 + (kw & 1)) * p.s2_batch;
-            dh = kh >> 1;
-            dw = kw >> 1;
-          } else {
-            dh = tap / 3 - 1;
-            dw = tap % 3 - 1;
-          }
-        }
+        const int dh = p.tdh[seg][tap], dw = p.tdw[seg][tap], dn = seg == 0 ? p.tdn[tap] : 0;
         tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0 + dn);
         tma_load_2d(smem_b + s * B_STAGE_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
         if (++cbk == p.cb[seg]) {
@@ -413,18 +404,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           const int s = kc % STAGES;
           mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          int dh = 0, dw = 0, dn = 0;
-          if (p.taps[seg] == 9) {
-            if (p.s2_batch > 0 && seg == 0) {  // stride 2, pad 0: tap (kh, kw) -> parity plane, shift (kh>>1, kw>>1)
-              const int kh = tap / 3, kw = tap % 3;
-              dn = ((kh & 1) * 2 + (kw & 1)) * p.s2_batch;
-              dh = kh >> 1;
-              dw = kw >> 1;
-            } else {
-              dh = tap / 3 - 1;
-              dw = tap % 3 - 1;
-            }
-          }
+          const int dh = p.tdh[seg][tap], dw = p.tdw[seg][tap], dn = seg == 0 ? p.tdn[tap] : 0;
           tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0 + dn);
           tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
           if (++cbk == p.cb[seg]) {
@@ -734,21 +714,23 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     const idf_nhwc_t& x = a->a[s];
     if (x.n != x0.n || x.h != x0.h || x.w != x0.w) return fail(IDF_ERR_ARG, "igemm: segments disagree on n/h/w");
     if (x.c <= 0 || x.c % BLOCK_K != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: channels %d not a multiple of 64", x.c);
-    if (a->taps[s] != 1 && a->taps[s] != 9) return fail(IDF_ERR_ARG, "igemm: taps must be 1 or 9");
+    const bool custom = s == 0 && a->custom_taps != 0;
+    if (custom ? (a->taps[s] < 1 || a->taps[s] > 9) : (a->taps[s] != 1 && a->taps[s] != 9))
+      return fail(IDF_ERR_ARG, "igemm: taps must be 1 or 9 (1..9 with custom_taps)");
   }
   if (a->N <= 0 || a->N % BLOCK_N != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d not a multiple of %d", a->N, BLOCK_N);
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   const int H = x0.h, W = x0.w, HW = H * W;
-  if (a->s2_batch > 0 && (x0.n != 4 * a->s2_batch || a->taps[0] != 9 || nseg != 1))
+  if (a->s2_batch > 0 && (x0.n != 4 * a->s2_batch || a->taps[0] != 9 || nseg != 1 || a->custom_taps))
     return fail(IDF_ERR_ARG, "igemm: s2_batch needs one 9-tap segment holding 4*s2_batch parity planes");
   const long long M = (long long)(a->s2_batch > 0 ? a->s2_batch : x0.n) * HW;
   p.s2_batch = a->s2_batch;
   p.splits = 1;
   if (M <= 0 || M > 0x7fffffffLL) return fail(IDF_ERR_ARG, "igemm: bad M");
   // M-tile geometry: 128 consecutive NHWC pixels = tile_n images x tile_h rows x tile_w columns.
-  const bool is_matrix = x0.n == 1 && x0.h == 1 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
+  const bool is_matrix = x0.n == 1 && x0.h == 1 && a->taps[0] == 1 && !a->custom_taps && (nseg == 1 || a->taps[1] == 1);
   if (is_matrix) {
     p.matrix = 1; p.tile_w = BLOCK_M; p.tile_h = 1; p.tile_n = 1; p.tiles_per_img = 0;
   } else if (W > BLOCK_M) {
@@ -760,6 +742,20 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     if (BLOCK_M % HW != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: %dx%d image does not tile", H, W);
     p.tile_w = W; p.tile_h = H; p.tile_n = BLOCK_M / HW; p.tiles_per_img = 0;
   }
+  // tap offsets: 3x3 stride 1 pad 1 -> (kh-1, kw-1); stride-2 pad-0 over parity planes -> plane (kh&1, kw&1)
+  // shifted by (kh>>1, kw>>1); custom_taps -> the caller's list (segment 0 only)
+  for (int s = 0; s < nseg; ++s)
+    for (int t = 0; t < a->taps[s]; ++t) {
+      if (s == 0 && a->custom_taps) {
+        p.tdh[s][t] = a->tap_dh[t]; p.tdw[s][t] = a->tap_dw[t];
+      } else if (a->taps[s] == 9 && a->s2_batch > 0 && s == 0) {
+        const int kh = t / 3, kw = t % 3;
+        p.tdn[t] = ((kh & 1) * 2 + (kw & 1)) * a->s2_batch;
+        p.tdh[s][t] = (signed char)(kh >> 1); p.tdw[s][t] = (signed char)(kw >> 1);
+      } else if (a->taps[s] == 9) {
+        p.tdh[s][t] = (signed char)(t / 3 - 1); p.tdw[s][t] = (signed char)(t % 3 - 1);
+      }
+    }
   int rc;
   int ktot = 0;
   for (int s = 0; s < nseg; ++s) {

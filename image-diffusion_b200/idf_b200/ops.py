@@ -23,7 +23,8 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
-          res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0, ws=None) -> torch.Tensor:
+          res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0, ws=None,
+          tap_offsets=None) -> torch.Tensor:
     """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view."""
     a = IgemmArgs()
     if not 1 <= len(segs) <= 2:
@@ -53,6 +54,10 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
     a.s2_batch = s2_batch
     a.ws = ptr(ws)
     a.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
+    if tap_offsets is not None:  # explicit (dh, dw) list for segment 0
+        a.custom_taps = 1
+        for i, (dh, dw) in enumerate(tap_offsets):
+            a.tap_dh[i], a.tap_dw[i] = dh, dw
     call("idf_conv2d_igemm", a)
     return out
 
@@ -188,3 +193,36 @@ def conv_wgrad(x: torch.Tensor, grid, cin: int, taps: int, dy: torch.Tensor, cou
     a.ws, a.ws_bytes = ws.data_ptr(), ws.numel() * ws.element_size()
     call("idf_conv2d_wgrad", a)
     return grad
+
+
+def pack_dgrad_weight(w: torch.Tensor) -> torch.Tensor:
+    """OIHW fp32 -> (I, KH*KW*O) bf16 such that igemm(dy, packed) is the data gradient of the stride-1 'same' conv:
+    dx[p] = sum_t dy[p + off(t)] W[:, :, mirrored t]^T (taps mirrored, channel roles swapped)."""
+    o, i, kh, kw = w.shape
+    return w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(i, kh * kw * o).to(torch.bfloat16).contiguous()
+
+
+_S2_PLANE_TAPS = {(p, q): [(kh, kw) for kh in ((0, 2) if p == 0 else (1,)) for kw in ((0, 2) if q == 0 else (1,))]
+                  for p in (0, 1) for q in (0, 1)}
+
+
+def pack_s2_dgrad_weights(w: torch.Tensor):
+    """Downsample conv (3x3, stride 2, pad 0): per input parity plane (p, q) the taps that reach it and the packed
+    (I, ntaps*O) bf16 weight; plane (p, q) position (a, b) receives dy[a - (kh>>1), b - (kw>>1)] W[:, :, kh, kw]^T."""
+    out = []
+    for p in (0, 1):
+        for q in (0, 1):
+            taps = _S2_PLANE_TAPS[(p, q)]
+            wp = torch.cat([w.detach()[:, :, kh, kw].t() for kh, kw in taps], dim=1).to(torch.bfloat16).contiguous()
+            out.append(([(-(kh >> 1), -(kw >> 1)) for kh, kw in taps], wp))
+    return out
+
+
+def conv_s2_dgrad(dy: torch.Tensor, B: int, OH: int, OW: int, cout: int, packed, planes_out: torch.Tensor, cin: int):
+    """Data gradient of the stride-2 conv into the four parity planes (the layout idf_space_to_depth2 produced in the
+    forward pass): four small igemm launches with 4 / 2 / 2 / 1 taps. dy must already have its padded last row /
+    column zeroed."""
+    rows = B * OH * OW
+    for k, (offs, wp) in enumerate(packed):
+        igemm([(dy, (B, OH, OW), cout, len(offs))], wp, cin, planes_out[k * rows:(k + 1) * rows], tap_offsets=offs)
+    return planes_out

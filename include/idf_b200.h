@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IDF_B200_ABI_VERSION 1
+#define IDF_B200_ABI_VERSION 2
 
 typedef struct CUstream_st* idf_stream_t;
 
@@ -90,6 +90,10 @@ typedef struct idf_igemm_args {
   void* ws;             /* optional caller-owned fp32 scratch (16-byte aligned) enabling split-K for GEMMs whose tile
                            list underfills the GPU; NULL = never split */
   int64_t ws_bytes;
+  int32_t custom_taps;  /* != 0: segment 0 has taps[0] in 1..9 taps at the explicit offsets below (rows, columns) instead
+                           of the 3x3 pattern; w's columns follow the list order. Used for the data gradient of the
+                           stride-2 Downsample conv, where each input parity plane sees 4, 2, 2 or 1 taps. */
+  int8_t tap_dh[9], tap_dw[9];
 } idf_igemm_args;
 
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);

@@ -74,3 +74,44 @@ def test_linear_wgrad_matrix_view():
     ops.conv_wgrad(x, (1, 1, M), K, 1, dy, N, grad, ws)
     ref = dy.float().t() @ x.float()
     assert rel_err(grad, ref) < 2e-5, rel_err(grad, ref)
+
+
+@pytest.mark.parametrize("B,C,H", [(3, 256, 32), (5, 384, 16), (7, 512, 8)])
+def test_downsample_conv_backward(B, C, H):
+    """Downsample (components.py:106-117): conv 3x3 stride 2 pad 0 then zero pad on the output. Weight gradient via
+    the parity-plane tap addressing, data gradient via four per-plane igemm launches with explicit tap lists."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(B + C + H)
+    x = bf(torch.randn(B, C, H, H, device=DEV, generator=g)).requires_grad_(True)
+    w = bf(torch.randn(C, C, 3, 3, device=DEV, generator=g) / math.sqrt(9 * C)).requires_grad_(True)
+    OH = H // 2
+    dy = bf(torch.randn(B, C, OH, OH, device=DEV, generator=g))
+    y = F.pad(F.conv2d(x, w, stride=2), (0, 1, 0, 1))
+    y.backward(dy)
+    dym = dy.clone()
+    dym[:, :, -1, :] = 0
+    dym[:, :, :, -1] = 0
+    planes = torch.empty(B * H * H, C, device=DEV, dtype=torch.bfloat16)
+    ops.space_to_depth2(rows(x.detach()), planes, B, H, H, C)
+    ws = torch.empty(16 * 1024 * 1024, device=DEV, dtype=torch.float32)
+    grad = torch.empty(C, C, 3, 3, device=DEV)
+    ops.conv_wgrad(planes, (4 * B, OH, OH), C, 9, rows(dym), C, grad, ws, s2_batch=B)
+    assert rel_err(grad, w.grad) < 2e-5, rel_err(grad, w.grad)
+    dplanes = torch.empty(B * H * H, C, device=DEV, dtype=torch.bfloat16)
+    ops.conv_s2_dgrad(rows(dym), B, OH, OH, C, ops.pack_s2_dgrad_weights(w), dplanes, C)
+    ref_planes = torch.empty_like(dplanes)
+    ops.space_to_depth2(rows(x.grad), ref_planes, B, H, H, C)
+    assert rel_err(dplanes.float(), ref_planes.float()) < 6e-3, rel_err(dplanes.float(), ref_planes.float())
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H", [(2, 128, 256, 32), (3, 1024, 384, 8)])
+def test_conv3x3_dgrad(B, Cin, Cout, H):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(B + Cin)
+    x = torch.zeros(B, Cin, H, H, device=DEV, requires_grad=True)
+    w = bf(torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cout))
+    dy = bf(torch.randn(B, Cout, H, H, device=DEV, generator=g))
+    F.conv2d(x, w, padding=1).backward(dy)
+    dx = torch.empty(B * H * H, Cin, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(rows(dy), (B, H, H), Cout, 9)], ops.pack_dgrad_weight(w), Cin, dx)
+    assert rel_err(unrows(dx, B, H, H), x.grad) < 6e-3
