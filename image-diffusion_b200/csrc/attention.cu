@@ -33,6 +33,7 @@ struct AttnParams {
   int kv_stages;   // 1 or 2
   float scale_log2e;
   int heads;
+  float* lse;  // optional (M, heads): log2-domain log-sum-exp of the scaled scores (training: consumed by the backward)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
 
     if (m < p.M) {
       const float inv = 1.f / l_run;
+      if (p.lse != nullptr) p.lse[m * p.heads + head] = fmaf(m_run, c, __log2f(l_run));
       __nv_bfloat16* dst = p.out + m * p.ld_out + head * HD;
 #pragma unroll
       for (int d0 = 0; d0 < HD; d0 += 8) {
@@ -600,6 +602,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
       const long long m = (long long)item_row0(item) + g * 128 + r;
       if (m < p.M) {
         const float inv = 1.f / l_run;
+        if (p.lse != nullptr) p.lse[m * p.heads + item_head(item)] = fmaf(m_run, c, __log2f(l_run));
         __nv_bfloat16* dst = p.out + m * p.ld_out + item_head(item) * HD;
 #pragma unroll
         for (int d0 = 0; d0 < HD; d0 += 8) {
@@ -660,9 +663,9 @@ static int launch_attention(const AttnParams& p, int tiles, int heads, cudaStrea
 
 using namespace idf;
 
-extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out,
-                                 int64_t ld_out, int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale,
-                                 idf_stream_t stream) {
+static int attention_fwd_impl(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out,
+                              int64_t ld_out, int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale,
+                              float* lse, idf_stream_t stream) {
   if (!qk || !vt || !out) return fail(IDF_ERR_ARG, "attention: null pointer");
   if (T < 16 || (T & (T - 1)) != 0) return fail(IDF_ERR_UNSUPPORTED, "attention: T = %d must be a power of two >= 16", T);
   if (M <= 0 || M % T != 0) return fail(IDF_ERR_ARG, "attention: M = %d not a multiple of T = %d", M, T);
@@ -680,6 +683,7 @@ extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, 
   p.kv_stages = p.nblk > 1 ? 2 : 1;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.heads = heads;
+  p.lse = lse;
 
   const int swz = head_dim <= 16 ? 32 : (head_dim <= 32 ? 64 : 128);
   const CUtensorMapSwizzle swz_enum = swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
@@ -722,4 +726,17 @@ extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, 
     case 64: return launch_attention<64>(p, tiles, heads, s);
     default: return fail(IDF_ERR_UNSUPPORTED, "attention: head_dim %d not in {16,32,48,64}", head_dim);
   }
+}
+
+extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out,
+                                 int64_t ld_out, int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale,
+                                 idf_stream_t stream) {
+  return attention_fwd_impl(qk, ld_qk, vt, ld_vt, out, ld_out, M, T, heads, head_dim, scale, nullptr, stream);
+}
+
+extern "C" int idf_attention_fwd_train(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out,
+                                       int64_t ld_out, int32_t M, int32_t T, int32_t heads, int32_t head_dim,
+                                       float scale, float* lse, idf_stream_t stream) {
+  if (!lse) return fail(IDF_ERR_ARG, "attention_fwd_train: lse is null");
+  return attention_fwd_impl(qk, ld_qk, vt, ld_vt, out, ld_out, M, T, heads, head_dim, scale, lse, stream);
 }

@@ -1,0 +1,386 @@
+// Fused multi-head self-attention backward on tcgen05 (sm_100a): dQ, dK, dV from Q, K, V^T, dO, the forward's
+// log-sum-exp and delta = rowsum(dO * O), with the probability tile recomputed on chip (never in HBM).
+//
+// One CTA owns one 128-key tile j of one head and walks over the query tiles i of the same sample(s). Everything is
+// computed TRANSPOSED (keys along TMEM lanes, one key row per thread) so that P^T and dS^T come out of the softmax
+// threads row-major in the layout the next three products need:
+//   S^T  = K_j Q_i^T                    (A = K_j  K-major,  B = Q_i  K-major)          128 x 128 x hd
+//   dP^T = V_j dO_i^T                   (A = V^T_j MN-major, B = dO_i K-major)         128 x 128 x hd
+//   P^T  = exp2(S^T * c - lse[q]),  dS^T = P^T * (dP^T - delta[q]) * scale             softmax threads -> bf16 smem
+//   dV_j += P^T  dO_i                   (A = P^T  K-major,  B = dO_i MN-major)         128 x hd x 128   (TMEM, all i)
+//   dK_j += dS^T Q_i                    (A = dS^T K-major,  B = Q_i  MN-major)         128 x hd x 128   (TMEM, all i)
+//   dQ_i  = dS   K_j                    (A = dS^T MN-major, B = K_j  MN-major)         128 x hd x 128   per i
+// The MN-major descriptors let Q_i, dO_i, K_j and V^T_j be used in both roles from ONE shared-memory copy as TMA
+// wrote it. dQ_i partials of different key tiles are added with vector fp32 reductions (red.global.add.v4.f32) when
+// a sample has more than one key tile, and stored directly otherwise.
+// Samples with fewer than 128 tokens share a tile under a block-diagonal mask, as in the forward kernel.
+//
+// Warp roles (192 threads): warps 0..3 = softmax / output rows, warp 4 = TMA producer, warp 5 = TMEM + MMA issuer.
+// TMEM columns: S^T [0,128) dP^T [128,256) dV [256,256+hd) dK [320,320+hd) dQ [384,384+hd).
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "host.h"
+#include "../../include/idf_b200.h"
+
+namespace idf {
+
+constexpr int ATB_THREADS = 192;
+constexpr int ATB_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16 columns
+constexpr int ATB_SMEM = 2 * ATB_TILE_BYTES /*K, V^T*/ + 4 * ATB_TILE_BYTES /*Q, dO x2 stages*/ +
+                         4 * ATB_TILE_BYTES /*P^T, dS^T (two 64-column halves each)*/ + 4 * 128 * 4 /*lse, delta x2*/ +
+                         1024 + 256;
+
+struct AttnBwdParams {
+  CUtensorMap tmQK;  // (M, 2C) bf16, box (64, 128)
+  CUtensorMap tmVT;  // (C, M)  bf16, box (64, HD)
+  CUtensorMap tmDO;  // (M, C)  bf16, box (64, 128)
+  const float* lse;
+  const float* delta;
+  __nv_bfloat16* dqkv;
+  long long ld_dqkv;
+  float* dq32;
+  int M, T, C, t_shift, nblk, heads;
+  float scale, scale_log2e;
+};
+
+__device__ __forceinline__ float atb_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_k = smem;
+  uint8_t* smem_vt = smem_k + ATB_TILE_BYTES;
+  uint8_t* smem_q = smem_vt + ATB_TILE_BYTES;       // [2]
+  uint8_t* smem_do = smem_q + 2 * ATB_TILE_BYTES;   // [2]
+  uint8_t* smem_p = smem_do + 2 * ATB_TILE_BYTES;   // two 64-column halves
+  uint8_t* smem_ds = smem_p + 2 * ATB_TILE_BYTES;
+  float* s_lse = reinterpret_cast<float*>(smem_ds + 2 * ATB_TILE_BYTES);  // [2][128]
+  float* s_delta = s_lse + 256;                                          // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* q_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint64_t* dq_empty = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int row0 = blockIdx.x * 128;  // first key row of this tile
+  const int q_base = (p.T >= 128) ? (row0 >> p.t_shift) << p.t_shift : row0;
+  const int n = p.nblk;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQK);
+    tma_prefetch_desc(&p.tmVT);
+    tma_prefetch_desc(&p.tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 4);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320,
+                 tmem_dq = tmem_base + 384;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, ATB_TILE_BYTES + 2 * HD * 128);
+      tma_load_2d(smem_k, &p.tmQK, kv_full, p.C + head * HD, row0);
+      tma_load_2d(smem_vt, &p.tmVT, kv_full, row0, head * HD);
+      tma_load_2d(smem_vt + HD * 128, &p.tmVT, kv_full, row0 + 64, head * HD);
+      for (int i = 0; i < n; ++i) {
+        const int st = i & 1;
+        mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[st], 2 * ATB_TILE_BYTES);
+        tma_load_2d(smem_q + st * ATB_TILE_BYTES, &p.tmQK, &q_full[st], head * HD, q_base + i * 128);
+        tma_load_2d(smem_do + st * ATB_TILE_BYTES, &p.tmDO, &q_full[st], head * HD, q_base + i * 128);
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);    // S^T  = K Q^T
+      constexpr uint32_t idesc_dp = umma_idesc_bf16(128, 128, 1, 0);   // dP^T = V dO^T, A = V^T tile (MN-major)
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(128, HD, 0, 1);   // dV / dK: A K-major, B MN-major
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, 1, 1);    // dQ: both MN-major
+      const uint64_t dk_k = umma_desc_kmajor(smem_u32(smem_k), 128);
+      const uint64_t dk_mn = umma_desc_mnmajor(smem_u32(smem_k), 8192, 1024);
+      const uint64_t dvt_mn = umma_desc_mnmajor(smem_u32(smem_vt), HD * 128, 1024);
+      const uint64_t dp0 = umma_desc_kmajor(smem_u32(smem_p), 128);
+      const uint64_t dp1 = umma_desc_kmajor(smem_u32(smem_p + ATB_TILE_BYTES), 128);
+      const uint64_t dds0 = umma_desc_kmajor(smem_u32(smem_ds), 128);
+      const uint64_t dds1 = umma_desc_kmajor(smem_u32(smem_ds + ATB_TILE_BYTES), 128);
+      const uint64_t dds_mn = umma_desc_mnmajor(smem_u32(smem_ds), ATB_TILE_BYTES, 1024);
+      mbar_wait(kv_full, 0);
+      auto issue_sdp = [&](int i) {
+        const int st = i & 1;
+        mbar_wait(&q_full[st], (i >> 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t dq_k = umma_desc_kmajor(smem_u32(smem_q + st * ATB_TILE_BYTES), 128);
+        const uint64_t ddo_k = umma_desc_kmajor(smem_u32(smem_do + st * ATB_TILE_BYTES), 128);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_s, dk_k + 2 * k, dq_k + 2 * k, idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_dp, dvt_mn + 128 * k, ddo_k + 2 * k, idesc_dp, k != 0);
+        umma_commit(sdp_full);
+      };
+      issue_sdp(0);
+      for (int i = 0; i < n; ++i) {
+        const int st = i & 1;
+        mbar_wait(pds_full, i & 1);
+        if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t dq_mn = umma_desc_mnmajor(smem_u32(smem_q + st * ATB_TILE_BYTES), 8192, 1024);
+        const uint64_t ddo_mn = umma_desc_mnmajor(smem_u32(smem_do + st * ATB_TILE_BYTES), 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (K = 128 queries, 16 per step)
+          umma_bf16(tmem_dv, (k < 4 ? dp0 : dp1) + 2 * (k & 3), ddo_mn + 128 * k, idesc_acc, (i > 0) || (k != 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK_j += dS^T Q_i
+          umma_bf16(tmem_dk, (k < 4 ? dds0 : dds1) + 2 * (k & 3), dq_mn + 128 * k, idesc_acc, (i > 0) || (k != 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ_i = dS K_j     (K = 128 keys)
+          umma_bf16(tmem_dq, dds_mn + 128 * k, dk_mn + 128 * k, idesc_dq, k != 0);
+        umma_commit(&q_empty[st]);
+        umma_commit(dq_full);
+        if (i + 1 < n) issue_sdp(i + 1);
+      }
+    }
+  } else {
+    const int r = warp * 32 + lane;  // key row of the tile == TMEM lane; also the query row when reading dQ
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const bool masked = p.T < 128;
+    const int row_seg = r >> p.t_shift;
+    const float c = p.scale_log2e;
+    auto fetch = [&](int i, float& l, float& d) {
+      const long long m = (long long)q_base + i * 128 + r;
+      l = 0.f; d = 0.f;
+      if (m < p.M) { l = p.lse[m * p.heads + head]; d = p.delta[m * p.heads + head]; }
+    };
+    {
+      float l, d;
+      fetch(0, l, d);
+      s_lse[r] = l;
+      s_delta[r] = d;
+    }
+    named_bar_sync(1, 128);
+    for (int i = 0; i < n; ++i) {
+      float l_next = 0.f, d_next = 0.f;
+      if (i + 1 < n) fetch(i + 1, l_next, d_next);
+      const float* lq = s_lse + (i & 1) * 128;
+      const float* dq = s_delta + (i & 1) * 128;
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tmem_s + lane_addr + ch * 32, sv);
+        tmem_ld_32x32(tmem_dp + lane_addr + ch * 32, dv);
+        tmem_ld_wait();
+        float pv[32], gv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int qc = ch * 32 + j;
+          float e = atb_exp2(fmaf(__uint_as_float(sv[j]), c, -lq[qc]));
+          if (masked && (qc >> p.t_shift) != row_seg) e = 0.f;
+          pv[j] = e;
+          gv[j] = e * (__uint_as_float(dv[j]) - dq[qc]) * p.scale;
+        }
+        uint8_t* prow = smem_p + (ch >> 1) * ATB_TILE_BYTES + r * 128;
+        uint8_t* grow = smem_ds + (ch >> 1) * ATB_TILE_BYTES + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((ch & 1) * 4 + q) ^ (r & 7);
+          uint4 o;
+          o.x = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
+          o.y = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
+          o.z = pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]);
+          o.w = pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
+          o.x = pack_bf16x2(gv[8 * q + 0], gv[8 * q + 1]);
+          o.y = pack_bf16x2(gv[8 * q + 2], gv[8 * q + 3]);
+          o.z = pack_bf16x2(gv[8 * q + 4], gv[8 * q + 5]);
+          o.w = pack_bf16x2(gv[8 * q + 6], gv[8 * q + 7]);
+          *reinterpret_cast<uint4*>(grow + chunk * 16) = o;
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      if (i + 1 < n) {
+        s_lse[((i + 1) & 1) * 128 + r] = l_next;
+        s_delta[((i + 1) & 1) * 128 + r] = d_next;
+      }
+      // dQ_i rows (lane = query row)
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after_sync();
+      float dqv[HD];
+#pragma unroll
+      for (int d0 = 0; d0 < HD; d0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_dq + lane_addr + d0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 16; ++d) dqv[d0 + d] = __uint_as_float(v[d]);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+      const long long m = (long long)q_base + i * 128 + r;
+      if (m < p.M) {
+        if (n == 1) {
+          __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + head * HD;
+#pragma unroll
+          for (int d0 = 0; d0 < HD; d0 += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(dqv[d0 + 0], dqv[d0 + 1]);
+            o.y = pack_bf16x2(dqv[d0 + 2], dqv[d0 + 3]);
+            o.z = pack_bf16x2(dqv[d0 + 4], dqv[d0 + 5]);
+            o.w = pack_bf16x2(dqv[d0 + 6], dqv[d0 + 7]);
+            *reinterpret_cast<uint4*>(dst + d0) = o;
+          }
+        } else {
+          float* dst = p.dq32 + m * p.C + head * HD;
+#pragma unroll
+          for (int d0 = 0; d0 < HD; d0 += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + d0), "f"(dqv[d0]), "f"(dqv[d0 + 1]),
+                         "f"(dqv[d0 + 2]), "f"(dqv[d0 + 3])
+                         : "memory");
+        }
+      }
+      named_bar_sync(1, 128);
+    }
+    // dV_j, dK_j rows (lane = key row); the last dq_full also covers the final accumulate
+    tc_fence_after_sync();
+    const long long m = (long long)row0 + r;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      float acc[HD];
+#pragma unroll
+      for (int d0 = 0; d0 < HD; d0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16((which == 0 ? tmem_dk : tmem_dv) + lane_addr + d0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[d0 + d] = __uint_as_float(v[d]);
+      }
+      if (m < p.M) {
+        __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + (which == 0 ? p.C : 2 * p.C) + head * HD;
+#pragma unroll
+        for (int d0 = 0; d0 < HD; d0 += 8) {
+          uint4 o;
+          o.x = pack_bf16x2(acc[d0 + 0], acc[d0 + 1]);
+          o.y = pack_bf16x2(acc[d0 + 2], acc[d0 + 3]);
+          o.z = pack_bf16x2(acc[d0 + 4], acc[d0 + 5]);
+          o.w = pack_bf16x2(acc[d0 + 6], acc[d0 + 7]);
+          *reinterpret_cast<uint4*>(dst + d0) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int HD>
+static int launch_attention_bwd(const AttnBwdParams& p, int tiles, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(attention_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM),
+                        "attention_bwd: cudaFuncSetAttribute");
+    if (rc != IDF_OK) return rc;
+    attr_set = true;
+  }
+  attention_bwd_kernel<HD><<<dim3(tiles, p.heads), ATB_THREADS, ATB_SMEM, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "attention_bwd launch");
+}
+
+}  // namespace idf
+
+using namespace idf;
+
+extern "C" int idf_attention_bwd(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, const void* d_out,
+                                 int64_t ld_do, const float* lse, const float* delta, void* dqkv, int64_t ld_dqkv,
+                                 float* dq32, int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale,
+                                 idf_stream_t stream) {
+  if (!qk || !vt || !d_out || !lse || !delta || !dqkv) return fail(IDF_ERR_ARG, "attention_bwd: null pointer");
+  if (T < 16 || (T & (T - 1)) != 0) return fail(IDF_ERR_UNSUPPORTED, "attention_bwd: T = %d must be a power of two >= 16", T);
+  if (M <= 0 || M % T != 0) return fail(IDF_ERR_ARG, "attention_bwd: M = %d not a multiple of T = %d", M, T);
+  const int C = heads * head_dim;
+  if ((reinterpret_cast<uintptr_t>(dqkv) & 15) || ld_dqkv % 8 != 0) return fail(IDF_ERR_ARG, "attention_bwd: output alignment");
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.lse = lse; p.delta = delta;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.ld_dqkv = ld_dqkv;
+  p.dq32 = dq32;
+  p.M = M; p.T = T; p.C = C; p.heads = heads;
+  while ((1 << p.t_shift) < T) ++p.t_shift;
+  p.nblk = T >= 128 ? T / 128 : 1;
+  if (p.nblk > 1 && (dq32 == nullptr || (reinterpret_cast<uintptr_t>(dq32) & 15)))
+    return fail(IDF_ERR_ARG, "attention_bwd: T > 128 needs a zeroed 16-byte aligned fp32 (M, C) dq32 accumulator");
+  p.scale = scale;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  int rc;
+  {
+    const uint64_t dims[2] = {(uint64_t)(2 * C), (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)ld_qk * 2};
+    const uint32_t box[2] = {64u, 128u};
+    if ((rc = encode_tmap(&p.tmQK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qk, 2, dims, strides, box,
+                          CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
+      return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)M, (uint64_t)C};
+    const uint64_t strides[1] = {(uint64_t)ld_vt * 2};
+    const uint32_t box[2] = {64u, (uint32_t)head_dim};
+    if ((rc = encode_tmap(&p.tmVT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, vt, 2, dims, strides, box,
+                          CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
+      return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)ld_do * 2};
+    const uint32_t box[2] = {64u, 128u};
+    if ((rc = encode_tmap(&p.tmDO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, d_out, 2, dims, strides, box,
+                          CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
+      return rc;
+  }
+  const int tiles = (M + 127) / 128;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (head_dim) {
+    case 16: return launch_attention_bwd<16>(p, tiles, s);
+    case 32: return launch_attention_bwd<32>(p, tiles, s);
+    case 48: return launch_attention_bwd<48>(p, tiles, s);
+    case 64: return launch_attention_bwd<64>(p, tiles, s);
+    default: return fail(IDF_ERR_UNSUPPORTED, "attention_bwd: head_dim %d not in {16,32,48,64}", head_dim);
+  }
+}

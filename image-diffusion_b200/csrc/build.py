@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
-SOURCES = ["host.cu", "igemm.cu", "attention.cu", "norm.cu", "pointwise.cu", "wgrad.cu"]
+SOURCES = ["host.cu", "igemm.cu", "attention.cu", "norm.cu", "pointwise.cu", "wgrad.cu", "train.cu", "attention_bwd.cu"]
 HEADERS = ["common.cuh", "host.h", os.path.join(ROOT, "include", "idf_b200.h")]
 LIB = os.path.join(PKG, "idf_b200", "libidf_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")

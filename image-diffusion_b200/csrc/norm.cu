@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv
                                                                       long long ldx, __nv_bfloat16* __restrict__ y,
                                                                       long long ldy, const float* __restrict__ gamma,
                                                                       const float* __restrict__ beta, int HW, int cpg,
-                                                                      int gps, int V, float eps) {
+                                                                      int gps, int V, float eps,
+                                                                      float* __restrict__ stats, int groups) {
   __shared__ float ch_s[GN_MAX_WARPS][VP * 8];
   __shared__ float ch_q[GN_MAX_WARPS][VP * 8];
   __shared__ float ct_s[VP * 8];
@@ -108,8 +109,14 @@ __global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv
     const float inv_cnt = 1.f / ((float)HW * (float)cpg);
     const float mean = a * inv_cnt;
     const float var = fmaxf(c * inv_cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
     g_mean[threadIdx.x] = mean;
-    g_rstd[threadIdx.x] = rsqrtf(var + eps);
+    g_rstd[threadIdx.x] = rstd;
+    if (stats != nullptr) {  // training: (mean, rstd) per (sample, group) for the backward pass
+      float* st = stats + ((long long)b * groups + blockIdx.y * gps + threadIdx.x) * 2;
+      st[0] = mean;
+      st[1] = rstd;
+    }
   }
   __syncthreads();
   if (!active) return;
@@ -190,9 +197,9 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 
 using namespace idf;
 
-extern "C" int idf_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
-                                  const float* beta, int32_t B, int32_t HW, int32_t C, int32_t groups, float eps,
-                                  int32_t apply_silu, idf_stream_t stream) {
+static int groupnorm_impl(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
+                          int32_t B, int32_t HW, int32_t C, int32_t groups, float eps, int32_t apply_silu,
+                          float* stats, idf_stream_t stream) {
   if (!x || !y || !gamma || !beta) return fail(IDF_ERR_ARG, "groupnorm: null pointer");
   if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups != 0) return fail(IDF_ERR_ARG, "groupnorm: bad shape");
   const int cpg = C / groups;
@@ -220,13 +227,26 @@ extern "C" int idf_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t l
   dim3 grid(B, groups / gps);
   const int threads = warps * 32;
   if (VP == 4) {
-    if (apply_silu) groupnorm_kernel<true, 4><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
-    else groupnorm_kernel<false, 4><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
+    if (apply_silu) groupnorm_kernel<true, 4><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
+    else groupnorm_kernel<false, 4><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
   } else {
-    if (apply_silu) groupnorm_kernel<true, 8><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
-    else groupnorm_kernel<false, 8><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps);
+    if (apply_silu) groupnorm_kernel<true, 8><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
+    else groupnorm_kernel<false, 8><<<grid, threads, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
   }
   return check_cuda(cudaGetLastError(), "groupnorm launch");
+}
+
+extern "C" int idf_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
+                                  const float* beta, int32_t B, int32_t HW, int32_t C, int32_t groups, float eps,
+                                  int32_t apply_silu, idf_stream_t stream) {
+  return groupnorm_impl(x, ldx, y, ldy, gamma, beta, B, HW, C, groups, eps, apply_silu, nullptr, stream);
+}
+
+extern "C" int idf_groupnorm_silu_train(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
+                                        const float* beta, int32_t B, int32_t HW, int32_t C, int32_t groups, float eps,
+                                        int32_t apply_silu, float* stats, idf_stream_t stream) {
+  if (!stats) return fail(IDF_ERR_ARG, "groupnorm_train: stats is null");
+  return groupnorm_impl(x, ldx, y, ldy, gamma, beta, B, HW, C, groups, eps, apply_silu, stats, stream);
 }
 
 extern "C" int idf_softmax_rows(const float* in, int64_t ld_in, void* out, int64_t ld_out, int32_t rows, int32_t cols,

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restric
                                                           float* __restrict__ Y, int ldy, int R, int K, int J,
                                                           const float* __restrict__ cls,
                                                           const int64_t* __restrict__ ctx,
-                                                          const float* __restrict__ mask) {
+                                                          const float* __restrict__ mask,
+                                                          float* __restrict__ Ypre = nullptr) {
   const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (j >= J) return;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restric
             const float mk = mask ? mask[r] : 1.f;
             v += mk * cls[(long long)ctx[r] * J + j];
           }
+          if (Ypre != nullptr) Ypre[(long long)r * ldy + j] = v;
           Y[(long long)r * ldy + j] = SILU_OUT ? silu_f(v) : v;
         }
       }
@@ -589,6 +591,33 @@ extern "C" int idf_embed_time_class(const int64_t* t, const int64_t* ctx, const 
   linear_rows_kernel<false><<<(P + wpb - 1) / wpb, 256, 0, s>>>(e, D, wp, bp, out, P, R, D, P, nullptr, nullptr,
                                                                 nullptr);
   return check_cuda(cudaGetLastError(), "embed launch");
+}
+
+// Training variant: same arithmetic, but every intermediate the backward pass needs is kept:
+// saved = e [R, D] | z1 [R, 4D] (pre-activation) | a1 = silu(z1) [R, 4D] | temb [R, D] (pre-activation) | s = silu(temb) [R, D]
+extern "C" int idf_embed_time_class_train(const int64_t* t, const int64_t* ctx, const float* ctx_mask, int32_t R,
+                                          int32_t D, const float* factor, const float* w1, const float* b1,
+                                          const float* w2, const float* b2, const float* class_w, const float* wp,
+                                          const float* bp, int32_t P, float* out, float* saved, idf_stream_t stream) {
+  if (!t || !factor || !w1 || !b1 || !w2 || !b2 || !wp || !bp || !out || !saved)
+    return fail(IDF_ERR_ARG, "embed_train: null pointer");
+  if (R <= 0 || D <= 0 || D % 8 != 0 || P <= 0) return fail(IDF_ERR_ARG, "embed_train: bad shape");
+  if (ctx != nullptr && class_w == nullptr) return fail(IDF_ERR_ARG, "embed_train: ctx without class_w");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* e = saved;
+  float* z1 = e + (long long)R * D;
+  float* a1 = z1 + (long long)R * 4 * D;
+  float* temb = a1 + (long long)R * 4 * D;
+  float* sv = temb + (long long)R * D;
+  sincos_kernel<<<(R * D + 255) / 256, 256, 0, s>>>(t, factor, e, R, D);
+  const int wpb = 8;
+  linear_rows_kernel<true><<<(4 * D + wpb - 1) / wpb, 256, 0, s>>>(e, D, w1, b1, a1, 4 * D, R, D, 4 * D, nullptr,
+                                                                   nullptr, nullptr, z1);
+  linear_rows_kernel<true><<<(D + wpb - 1) / wpb, 256, 0, s>>>(a1, 4 * D, w2, b2, sv, D, R, 4 * D, D, class_w, ctx,
+                                                               ctx_mask, temb);
+  linear_rows_kernel<false><<<(P + wpb - 1) / wpb, 256, 0, s>>>(sv, D, wp, bp, out, P, R, D, P, nullptr, nullptr,
+                                                                nullptr);
+  return check_cuda(cudaGetLastError(), "embed_train launch");
 }
 
 extern "C" int idf_cfg_posterior_step(const float* xt, const float* eps_cond, const float* eps_uncond,

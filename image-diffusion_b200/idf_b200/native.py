@@ -61,6 +61,26 @@ _SIGNATURES = {
     "idf_nhwc_bf16_to_nchw_f32": [_vp, _i64, _vp, _i32, _i32, _i32],
     # training step
     "idf_conv2d_wgrad": [C.POINTER(WgradArgs)],
+    "idf_groupnorm_silu_train": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp],
+    "idf_groupnorm_silu_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
+                               _i32, _i32],
+    "idf_reduce_rows_f32": [_vp, _i64, _i32, _i32, _vp, _i32],
+    "idf_colsum_bf16": [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32],
+    "idf_sum2x2_bf16": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32],
+    "idf_depth_to_space2": [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32],
+    "idf_zero_last_rowcol": [_vp, _i64, _i32, _i32, _i32, _i32],
+    "idf_conv3x3_small_cin_wgrad": [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32],
+    "idf_conv3x3_small_cout_bwd": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32],
+    "idf_embed_time_class_train": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    "idf_embed_time_class_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _i64],
+    "idf_mse_loss_grad": [_vp, _vp, _i64, _f32, _vp, _vp],
+    "idf_grad_norm_clip": [_vp, _i64, _f32, _f32, _vp, _vp, _i64],
+    "idf_adam_step": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
+    "idf_attention_fwd_train": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
+    "idf_attention_delta": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp],
+    "idf_attention_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _f32],
+    "idf_f32_to_bf16_rows": [_vp, _vp, _i64, _i64, _i32],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["idf_last_error", "idf_abi_version"])
 

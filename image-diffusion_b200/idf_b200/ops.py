@@ -226,3 +226,116 @@ def conv_s2_dgrad(dy: torch.Tensor, B: int, OH: int, OW: int, cout: int, packed,
     for k, (offs, wp) in enumerate(packed):
         igemm([(dy, (B, OH, OW), cout, len(offs))], wp, cin, planes_out[k * rows:(k + 1) * rows], tap_offsets=offs)
     return planes_out
+
+
+def groupnorm_silu_train(x, y, gamma, beta, B, HW, C, groups, silu, stats, eps: float = 1e-5):
+    _check_bf16_rows(x, "groupnorm x")
+    _check_bf16_rows(y, "groupnorm y")
+    call("idf_groupnorm_silu_train", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gamma.data_ptr(),
+         beta.data_ptr(), B, HW, C, groups, eps, 1 if silu else 0, stats.data_ptr())
+    return y
+
+
+def groupnorm_silu_bwd(x, dy, dx, gamma, beta, stats, dgamma_part, dbeta_part, B, HW, C, groups, silu, add=None):
+    for n, t in (("x", x), ("dy", dy), ("dx", dx)):
+        _check_bf16_rows(t, f"groupnorm_bwd {n}")
+    call("idf_groupnorm_silu_bwd", x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), ptr(add),
+         add.stride(0) if add is not None else 0, dx.data_ptr(), dx.stride(0), gamma.data_ptr(), beta.data_ptr(),
+         stats.data_ptr(), dgamma_part.data_ptr(), dbeta_part.data_ptr(), B, HW, C, groups, 1 if silu else 0)
+    return dx
+
+
+def reduce_rows(src: torch.Tensor, rows: int, cols: int, out: torch.Tensor, accumulate: bool = False, ld=None):
+    call("idf_reduce_rows_f32", src.data_ptr(), ld if ld is not None else src.stride(0), rows, cols, out.data_ptr(),
+         1 if accumulate else 0)
+    return out
+
+
+def colsum(x: torch.Tensor, B: int, HW: int, C: int, per_sample: torch.Tensor, total=None, accumulate=False):
+    _check_bf16_rows(x, "colsum x")
+    call("idf_colsum_bf16", x.data_ptr(), x.stride(0), B, HW, C, per_sample.data_ptr(), per_sample.stride(0),
+         ptr(total), 1 if accumulate else 0)
+    return per_sample
+
+
+def sum2x2(x, y, B, H, W, C):
+    call("idf_sum2x2_bf16", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), B, H, W, C)
+    return y
+
+
+def depth_to_space2(planes, y, B, H, W, C, add=None):
+    call("idf_depth_to_space2", planes.data_ptr(), y.data_ptr(), y.stride(0), ptr(add),
+         add.stride(0) if add is not None else 0, B, H, W, C)
+    return y
+
+
+def zero_last_rowcol(x, B, H, W, C):
+    call("idf_zero_last_rowcol", x.data_ptr(), x.stride(0), B, H, W, C)
+    return x
+
+
+def conv3x3_small_cin_wgrad(x_nchw, dy, grad_w, part):
+    B, Cin, H, W = x_nchw.shape
+    call("idf_conv3x3_small_cin_wgrad", x_nchw.data_ptr(), dy.data_ptr(), dy.stride(0), grad_w.data_ptr(),
+         part.data_ptr(), part.numel() * 4, B, Cin, H, W, grad_w.shape[0])
+    return grad_w
+
+
+def conv3x3_small_cout_bwd(h, dout_nchw, w, dh, grad_w, grad_b, part):
+    B, Cout, H, W = dout_nchw.shape
+    call("idf_conv3x3_small_cout_bwd", h.data_ptr(), h.stride(0), dout_nchw.data_ptr(), w.data_ptr(), dh.data_ptr(),
+         dh.stride(0), grad_w.data_ptr(), grad_b.data_ptr(), part.data_ptr(), part.numel() * 4, B, w.shape[1], H, W, Cout)
+    return dh
+
+
+def embed_time_class_train(t, ctx, ctx_mask, factor, w1, b1, w2, b2, class_w, wp, bp, out, saved):
+    R, D, P = t.shape[0], factor.shape[0] * 2, wp.shape[0]
+    call("idf_embed_time_class_train", t.data_ptr(), ptr(ctx), ptr(ctx_mask), R, D, factor.data_ptr(), w1.data_ptr(),
+         b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), ptr(class_w), wp.data_ptr(), bp.data_ptr(), P, out.data_ptr(),
+         saved.data_ptr())
+    return out
+
+
+def embed_time_class_bwd(dtable, ctx, ctx_mask, D, num_classes, w2, wp, saved, g_w1, g_b1, g_w2, g_b2, g_cls, g_wp,
+                         g_bp, scratch):
+    R, P = dtable.shape
+    call("idf_embed_time_class_bwd", dtable.data_ptr(), ptr(ctx), ptr(ctx_mask), R, D, P, num_classes, w2.data_ptr(),
+         wp.data_ptr(), saved.data_ptr(), g_w1.data_ptr(), g_b1.data_ptr(), g_w2.data_ptr(), g_b2.data_ptr(),
+         ptr(g_cls), g_wp.data_ptr(), g_bp.data_ptr(), scratch.data_ptr(), scratch.numel() * 4)
+
+
+def mse_loss_grad(pred, target, dpred, loss, grad_scale: float = 1.0):
+    call("idf_mse_loss_grad", pred.data_ptr(), target.data_ptr(), pred.numel(), grad_scale, ptr(dpred), ptr(loss))
+    return loss
+
+
+def grad_norm_clip(grad, out2, scratch, max_norm: float, grad_div: float = 1.0):
+    call("idf_grad_norm_clip", grad.data_ptr(), grad.numel(), grad_div, max_norm, out2.data_ptr(), scratch.data_ptr(),
+         scratch.numel() * 4)
+    return out2
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_div=1.0, clip2=None):
+    call("idf_adam_step", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+         lr, beta1, beta2, eps, step, grad_div, ptr(clip2))
+
+
+def attention_train(qk, vt, out, lse, M, T, heads, head_dim):
+    call("idf_attention_fwd_train", qk.data_ptr(), qk.stride(0), vt.data_ptr(), vt.stride(0), out.data_ptr(),
+         out.stride(0), M, T, heads, head_dim, 1.0 / math.sqrt(head_dim), lse.data_ptr())
+    return out
+
+
+def attention_bwd(qk, vt, o, d_out, lse, delta, dqkv, dq32, M, T, heads, head_dim):
+    """dqkv (M, 3C) bf16 <- [dQ | dK | dV]. dq32: fp32 (M, C) scratch, required (and zeroed here) when T > 128."""
+    C = heads * head_dim
+    call("idf_attention_delta", d_out.data_ptr(), d_out.stride(0), o.data_ptr(), o.stride(0), M, heads, head_dim,
+         delta.data_ptr())
+    if T > 128:
+        dq32.zero_()
+    call("idf_attention_bwd", qk.data_ptr(), qk.stride(0), vt.data_ptr(), vt.stride(0), d_out.data_ptr(),
+         d_out.stride(0), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), ptr(dq32), M, T, heads,
+         head_dim, 1.0 / math.sqrt(head_dim))
+    if T > 128:
+        call("idf_f32_to_bf16_rows", dq32.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), M, C)
+    return dqkv

@@ -255,6 +255,117 @@ typedef struct idf_wgrad_args {
 
 int idf_conv2d_wgrad(const idf_wgrad_args* args, idf_stream_t stream);
 
+
+/* idf_groupnorm_silu_train — idf_groupnorm_silu that also stores (mean, rstd) per (sample, group) into
+ * stats[(b*groups + g)*2 + {0,1}] for idf_groupnorm_silu_bwd. */
+int idf_groupnorm_silu_train(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
+                             int32_t B, int32_t HW, int32_t C, int32_t groups, float eps, int32_t apply_silu,
+                             float* stats, idf_stream_t stream);
+
+/*
+ * idf_groupnorm_silu_bwd — backward of GroupNorm (+SiLU) (components.py:453-454, 58; unet.py:98-99):
+ *   dx = rstd * (gamma*dz - mean_g(gamma*dz) - xhat * mean_g(gamma*dz*xhat)) (+ add),  dz = dy * silu'(gamma*xhat+beta)
+ * x is the forward INPUT, dy the gradient of the forward output; add (optional, bf16) is summed into dx (second
+ * gradient path into the same tensor: the residual / skip branch). dgamma_part / dbeta_part are fp32 (B, C)
+ * per-sample contributions; the caller reduces them over B with idf_reduce_rows_f32.
+ */
+int idf_groupnorm_silu_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* add, int64_t ldadd,
+                           void* dx, int64_t lddx, const float* gamma, const float* beta, const float* stats,
+                           float* dgamma_part, float* dbeta_part, int32_t B, int32_t HW, int32_t C, int32_t groups,
+                           int32_t apply_silu, idf_stream_t stream);
+
+/* idf_reduce_rows_f32 — out[c] (+)= sum_r in[r*ld + c], rows added in order (deterministic). */
+int idf_reduce_rows_f32(const float* in, int64_t ld, int32_t rows, int32_t cols, float* out, int32_t accumulate,
+                        idf_stream_t stream);
+
+/* idf_colsum_bf16 — per_sample[b*ld_ps + c] = sum over the HW pixel rows of sample b of x[., c] (bias gradient of a
+ * conv / linear layer, and the per-sample gradient of the time-projection bias, components.py:526-527); total
+ * (optional, fp32 [C]) (+)= the sum over samples. */
+int idf_colsum_bf16(const void* x, int64_t ldx, int32_t B, int32_t HW, int32_t C, float* per_sample, int64_t ld_ps,
+                    float* total, int32_t accumulate_total, idf_stream_t stream);
+
+/* idf_sum2x2_bf16 — adjoint of idf_upsample_nearest2x: y[b,h,w,:] = sum of the 2x2 block of x (B, 2H, 2W, C). */
+int idf_sum2x2_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t B, int32_t H, int32_t W, int32_t C,
+                    idf_stream_t stream);
+
+/* idf_depth_to_space2 — adjoint of idf_space_to_depth2 (H, W are the FULL resolution), plus an optional bf16 addend
+ * (the skip-connection gradient that meets the Downsample gradient at the same tensor). */
+int idf_depth_to_space2(const void* planes, void* y, int64_t ldy, const void* add, int64_t ldadd, int32_t B, int32_t H,
+                        int32_t W, int32_t C, idf_stream_t stream);
+
+/* idf_zero_last_rowcol — zeroes the last row and column of every image in place: the gradient that reaches the
+ * ConstantPad2d region of Downsample's output (components.py:113) is dropped. */
+int idf_zero_last_rowcol(void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, idf_stream_t stream);
+
+/* idf_conv3x3_small_cin_wgrad — weight gradient of in_conv (unet.py:45): x fp32 NCHW (B, 3, H, W), dy bf16 (M, lddy),
+ * grad_w fp32 (Cout, 3, 3, 3). part: fp32 scratch of B*(H/8)*Cout*27 floats. (Bias gradient: idf_colsum_bf16.) */
+int idf_conv3x3_small_cin_wgrad(const float* x, const void* dy, int64_t lddy, float* grad_w, float* part,
+                                int64_t part_bytes, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout,
+                                idf_stream_t stream);
+
+/* idf_conv3x3_small_cout_bwd — backward of out_conv's Conv2d (unet.py:100): h bf16 (M, ldh) is its (normalised,
+ * activated) input, dout fp32 NCHW (B, 3, H, W) the loss gradient, w fp32 (3, C, 3, 3). Writes dh bf16 (M, lddh),
+ * grad_w (3, C, 3, 3), grad_b (3). part: fp32 scratch of B*(H/8)*3*C*9 floats. */
+int idf_conv3x3_small_cout_bwd(const void* h, int64_t ldh, const float* dout, const float* w, void* dh, int64_t lddh,
+                               float* grad_w, float* grad_b, float* part, int64_t part_bytes, int32_t B, int32_t C,
+                               int32_t H, int32_t W, int32_t Cout, idf_stream_t stream);
+
+/* idf_embed_time_class_train — idf_embed_time_class keeping what the backward needs:
+ * saved = e [R,D] | z1 [R,4D] | silu(z1) [R,4D] | temb [R,D] | silu(temb) [R,D]  (11*R*D floats). */
+int idf_embed_time_class_train(const int64_t* t, const int64_t* ctx, const float* ctx_mask, int32_t R, int32_t time_dim,
+                               const float* factor, const float* w1, const float* b1, const float* w2, const float* b2,
+                               const float* class_w, const float* wp, const float* bp, int32_t P, float* out,
+                               float* saved, idf_stream_t stream);
+
+/* idf_embed_time_class_bwd — gradients of the time MLP, class embedding and all time projections
+ * (components.py:429-445, unet.py:42,109-114, components.py:486,526) from dtable (R, P) = the per-sample column
+ * sums of every first-half conv's output gradient. scratch: fp32, >= (ceil(P/256)*R*4D + 5*R*D) * 4 bytes. */
+int idf_embed_time_class_bwd(const float* dtable, const int64_t* ctx, const float* ctx_mask, int32_t R,
+                             int32_t time_dim, int32_t P, int32_t num_classes, const float* w2, const float* wp,
+                             const float* saved, float* g_w1, float* g_b1, float* g_w2, float* g_b2, float* g_cls,
+                             float* g_wp, float* g_bp, float* scratch, int64_t scratch_bytes, idf_stream_t stream);
+
+/* idf_mse_loss_grad — nn.MSELoss (diffusion_trainer.py:54,170): loss[0] = mean((pred-target)^2) and, when dpred is
+ * non-NULL, dpred = grad_scale * 2 (pred - target) / n. */
+int idf_mse_loss_grad(const float* pred, const float* target, int64_t n, float grad_scale, float* dpred, float* loss,
+                      idf_stream_t stream);
+
+/* idf_grad_norm_clip — nn.utils.clip_grad_norm_ (diffusion_trainer.py:178-181) over one flat fp32 gradient buffer:
+ * out2[0] = ||grad||_2 / grad_div, out2[1] = min(1, max_norm / (out2[0] + 1e-6)) (1 when max_norm <= 0).
+ * scratch: >= 1184 floats. */
+int idf_grad_norm_clip(const float* grad, int64_t n, float grad_div, float max_norm, float* out2, float* scratch,
+                       int64_t scratch_bytes, idf_stream_t stream);
+
+/* idf_adam_step — torch.optim.Adam defaults (diffusion_trainer.py:57-58,185) over flat fp32 buffers; the gradient is
+ * used as grad * clip2[1] / grad_div (clip2 from idf_grad_norm_clip, may be NULL). step counts from 1. */
+int idf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int32_t step, float grad_div, const float* clip2, idf_stream_t stream);
+
+/* idf_attention_fwd_train — idf_attention_fwd that also writes lse[m*heads + h] = log2(sum_j exp(s_mj)) + max (log2
+ * domain, scaled scores) for idf_attention_bwd. */
+int idf_attention_fwd_train(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out, int64_t ld_out,
+                            int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale, float* lse,
+                            idf_stream_t stream);
+
+/* idf_attention_delta — delta[m*heads + h] = sum_d dO[m, h*hd+d] * O[m, h*hd+d] (softmax backward row term). */
+int idf_attention_delta(const void* d_out, int64_t ld_do, const void* out, int64_t ld_o, int32_t M, int32_t heads,
+                        int32_t head_dim, float* delta, idf_stream_t stream);
+
+/*
+ * idf_attention_bwd — backward of components.py:86-94 on tcgen05, probabilities recomputed on chip.
+ *   qk, vt      as given to idf_attention_fwd;  d_out bf16 (M, ld_do) gradient of the attention output.
+ *   dqkv        bf16 (M, ld_dqkv): dQ -> columns [0,C), dK -> [C,2C), dV -> [2C,3C) (token-major: the operand layout
+ *               of the QKV Linear's data and weight gradients).
+ *   dq32        fp32 (M, C), ZEROED by the caller, required when T > 128: dQ partials of different key tiles are
+ *               accumulated there (fp32 reductions); convert with idf_f32_to_bf16_rows. Unused for T <= 128.
+ */
+int idf_attention_bwd(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, const void* d_out, int64_t ld_do,
+                      const float* lse, const float* delta, void* dqkv, int64_t ld_dqkv, float* dq32, int32_t M,
+                      int32_t T, int32_t heads, int32_t head_dim, float scale, idf_stream_t stream);
+
+/* idf_f32_to_bf16_rows — y[m*ldy + c] = bf16(x[m*C + c]). */
+int idf_f32_to_bf16_rows(const float* x, void* y, int64_t ldy, int64_t M, int32_t C, idf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

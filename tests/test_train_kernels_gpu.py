@@ -115,3 +115,193 @@ def test_conv3x3_dgrad(B, Cin, Cout, H):
     dx = torch.empty(B * H * H, Cin, device=DEV, dtype=torch.bfloat16)
     ops.igemm([(rows(dy), (B, H, H), Cout, 9)], ops.pack_dgrad_weight(w), Cin, dx)
     assert rel_err(unrows(dx, B, H, H), x.grad) < 6e-3
+
+
+@pytest.mark.parametrize("B,C,HW,silu,with_add", [(3, 128, 1024, True, False), (2, 384, 256, True, True),
+                                                  (5, 512, 64, False, True), (4, 1024, 64, True, False),
+                                                  (3, 512, 16, True, True), (2, 768, 256, True, False)])
+def test_groupnorm_silu_backward(B, C, HW, silu, with_add):
+    ops = _ops()
+    G = 32
+    g = torch.Generator(device=DEV).manual_seed(C + HW)
+    x = bf(torch.randn(B, HW, C, device=DEV, generator=g) * 1.5 + 0.3).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(C, device=DEV, generator=g)).requires_grad_(True)
+    beta = (0.2 * torch.randn(C, device=DEV, generator=g)).requires_grad_(True)
+    dy = bf(torch.randn(B, HW, C, device=DEV, generator=g))
+    add = bf(torch.randn(B, HW, C, device=DEV, generator=g)) if with_add else None
+    y = F.group_norm(x.transpose(1, 2), G, gamma, beta, 1e-5).transpose(1, 2)
+    if silu:
+        y = F.silu(y)
+    y.backward(dy)
+    xr = x.detach().reshape(B * HW, C).to(torch.bfloat16)
+    yk = torch.empty_like(xr)
+    stats = torch.empty(B, G, 2, device=DEV)
+    ops.groupnorm_silu_train(xr, yk, gamma.detach(), beta.detach(), B, HW, C, G, silu, stats)
+    assert rel_err(yk.float(), y.detach().reshape(B * HW, C)) < 6e-3
+    dx = torch.empty_like(xr)
+    dgp, dbp = torch.empty(B, C, device=DEV), torch.empty(B, C, device=DEV)
+    ops.groupnorm_silu_bwd(xr, dy.reshape(B * HW, C).to(torch.bfloat16), dx, gamma.detach(), beta.detach(), stats, dgp,
+                           dbp, B, HW, C, G, silu, add=None if add is None else add.reshape(B * HW, C).to(torch.bfloat16))
+    ref_dx = x.grad.reshape(B * HW, C) + (add.reshape(B * HW, C) if with_add else 0)
+    assert rel_err(dx.float(), ref_dx) < 8e-3, rel_err(dx.float(), ref_dx)
+    dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    ops.reduce_rows(dgp, B, C, dg)
+    ops.reduce_rows(dbp, B, C, db)
+    assert rel_err(dg, gamma.grad) < 2e-3, rel_err(dg, gamma.grad)
+    assert rel_err(db, beta.grad) < 2e-3, rel_err(db, beta.grad)
+
+
+def test_colsum_and_movers():
+    ops = _ops()
+    B, H, C = 5, 16, 384
+    g = torch.Generator(device=DEV).manual_seed(3)
+    wide = torch.randn(B * H * H, C + 64, device=DEV, generator=g).to(torch.bfloat16)
+    x = wide[:, 64:]
+    ps = torch.empty(B, 2 * C, device=DEV)
+    tot = torch.zeros(C, device=DEV)
+    ops.colsum(x, B, H * H, C, ps[:, C:], total=tot)
+    ref = x.float().reshape(B, H * H, C).sum(1)
+    assert rel_err(ps[:, C:], ref) < 1e-5
+    assert rel_err(tot, ref.sum(0)) < 1e-5
+    # nearest-2x adjoint
+    y = torch.empty(B * H * H // 4, C, device=DEV, dtype=torch.bfloat16)
+    ops.sum2x2(x, y, B, H // 2, H // 2, C)
+    refy = F.avg_pool2d(unrows(x, B, H, H), 2) * 4
+    assert rel_err(unrows(y, B, H // 2, H // 2), refy) < 4e-3
+    # space_to_depth2 round trip (+ addend)
+    planes = torch.empty(B * H * H, C, device=DEV, dtype=torch.bfloat16)
+    xc = x.contiguous()
+    ops.space_to_depth2(xc, planes, B, H, H, C)
+    back = torch.empty_like(xc)
+    ops.depth_to_space2(planes, back, B, H, H, C)
+    assert torch.equal(back, xc)
+    ops.depth_to_space2(planes, back, B, H, H, C, add=xc)
+    assert rel_err(back.float(), 2 * xc.float()) < 4e-3
+    z = xc.clone()
+    ops.zero_last_rowcol(z, B, H, H, C)
+    zr = unrows(xc, B, H, H)
+    zr[:, :, -1, :] = 0
+    zr[:, :, :, -1] = 0
+    assert torch.equal(unrows(z, B, H, H), zr)
+
+
+@pytest.mark.parametrize("B,T,heads,hd", [(3, 1024, 8, 32), (2, 1024, 8, 16), (5, 256, 8, 48), (6, 64, 8, 64),
+                                          (9, 16, 8, 64), (4, 256, 8, 32), (2, 128, 4, 64)])
+def test_attention_backward(B, T, heads, hd):
+    ops = _ops()
+    C, M = heads * hd, B * T
+    g = torch.Generator(device=DEV).manual_seed(T + hd)
+    q = bf(torch.randn(B, heads, T, hd, device=DEV, generator=g)).requires_grad_(True)
+    k = bf(torch.randn(B, heads, T, hd, device=DEV, generator=g)).requires_grad_(True)
+    v = bf(torch.randn(B, heads, T, hd, device=DEV, generator=g)).requires_grad_(True)
+    do = bf(torch.randn(B, heads, T, hd, device=DEV, generator=g))
+    o_ref = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), -1) @ v
+    o_ref.backward(do)
+    tok = lambda t: t.detach().transpose(1, 2).reshape(M, C)  # (B, heads, T, hd) -> (M, C) head-major channels
+    qk = torch.cat([tok(q), tok(k)], dim=1).to(torch.bfloat16).contiguous()
+    vt = tok(v).t().to(torch.bfloat16).contiguous()
+    o = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(M, heads, device=DEV)
+    ops.attention_train(qk, vt, o, lse, M, T, heads, hd)
+    assert rel_err(o.float(), tok(o_ref)) < 8e-3
+    s = (q @ k.transpose(-1, -2) / math.sqrt(hd)).detach()
+    lse_ref = (torch.logsumexp(s, -1) * 1.4426950408889634).transpose(1, 2).reshape(M, heads)
+    assert (lse - lse_ref).abs().max().item() < 2e-2
+    dqkv = torch.empty(M, 3 * C, device=DEV, dtype=torch.bfloat16)
+    delta = torch.empty(M, heads, device=DEV)
+    dq32 = torch.empty(M, C, device=DEV)
+    ops.attention_bwd(qk, vt, o, tok(do).to(torch.bfloat16).contiguous(), lse, delta, dqkv, dq32, M, T, heads, hd)
+    for name, got, ref in (("dq", dqkv[:, :C], tok(q.grad)), ("dk", dqkv[:, C:2 * C], tok(k.grad)),
+                           ("dv", dqkv[:, 2 * C:], tok(v.grad))):
+        e = rel_err(got.float(), ref)
+        assert e < 2e-2, (name, e)
+
+
+def test_edge_conv_backward():
+    ops = _ops()
+    B, H, C = 3, 32, 128
+    g = torch.Generator(device=DEV).manual_seed(9)
+    # in_conv weight gradient
+    x = torch.randn(B, 3, H, H, device=DEV, generator=g)
+    w = torch.zeros(C, 3, 3, 3, device=DEV, requires_grad=True)
+    dy = bf(torch.randn(B, C, H, H, device=DEV, generator=g))
+    F.conv2d(x, w, padding=1).backward(dy)
+    gw = torch.empty(C, 3, 3, 3, device=DEV)
+    part = torch.empty(B * (H // 8) * C * 27 * 4, device=DEV)
+    ops.conv3x3_small_cin_wgrad(x, rows(dy), gw, part)
+    assert rel_err(gw, w.grad) < 1e-4, rel_err(gw, w.grad)
+    # out_conv backward
+    h = bf(torch.randn(B, C, H, H, device=DEV, generator=g)).requires_grad_(True)
+    wo = (torch.randn(3, C, 3, 3, device=DEV, generator=g) / 30).requires_grad_(True)
+    bo = torch.zeros(3, device=DEV, requires_grad=True)
+    dout = torch.randn(B, 3, H, H, device=DEV, generator=g)
+    F.conv2d(h, wo, bo, padding=1).backward(dout)
+    dh = torch.empty(B * H * H, C, device=DEV, dtype=torch.bfloat16)
+    gwo, gbo = torch.empty(3, C, 3, 3, device=DEV), torch.empty(3, device=DEV)
+    ops.conv3x3_small_cout_bwd(rows(h.detach()), dout, wo.detach(), dh, gwo, gbo, part)
+    assert rel_err(unrows(dh, B, H, H), h.grad) < 6e-3
+    assert rel_err(gwo, wo.grad) < 1e-4
+    assert rel_err(gbo, bo.grad) < 1e-4
+
+
+def test_embedding_backward():
+    ops = _ops()
+    R, D, P, NC = 7, 128, 640, 3
+    g = torch.Generator(device=DEV).manual_seed(21)
+    rnd = lambda *s, sc=1.0: (torch.randn(*s, device=DEV, generator=g) * sc)
+    factor = 10000 ** (torch.arange(D // 2, device=DEV) / (D // 2))
+    w1, b1 = rnd(4 * D, D, sc=D ** -0.5).requires_grad_(True), rnd(4 * D, sc=0.1).requires_grad_(True)
+    w2, b2 = rnd(D, 4 * D, sc=(4 * D) ** -0.5).requires_grad_(True), rnd(D, sc=0.1).requires_grad_(True)
+    cls = rnd(NC, D).requires_grad_(True)
+    wp, bp = rnd(P, D, sc=D ** -0.5).requires_grad_(True), rnd(P, sc=0.1).requires_grad_(True)
+    t = torch.tensor([0, 5, 999, 250, 31, 700, 1], device=DEV)
+    ctx = torch.tensor([0, 1, 2, 2, 1, 0, 0], device=DEV)
+    mask = torch.tensor([1., 0, 1, 1, 0, 1, 1], device=DEV)
+    a = t[:, None] / factor
+    e = torch.cat([torch.sin(a), torch.cos(a)], -1)
+    temb = F.linear(F.silu(F.linear(e, w1, b1)), w2, b2) + (F.one_hot(ctx, NC).float() @ cls) * mask[:, None]
+    table_ref = F.linear(F.silu(temb), wp, bp)
+    dtable = rnd(R, P)
+    table_ref.backward(dtable)
+    table = torch.empty(R, P, device=DEV)
+    saved = torch.empty(R * 11 * D, device=DEV)
+    d = lambda x: x.detach().contiguous()
+    ops.embed_time_class_train(t, ctx, mask, factor.float().contiguous(), d(w1), d(b1), d(w2), d(b2), d(cls), d(wp),
+                               d(bp), table, saved)
+    assert rel_err(table, table_ref.detach()) < 1e-5
+    gs = {n: torch.empty_like(p) for n, p in (("w1", w1), ("b1", b1), ("w2", w2), ("b2", b2), ("cls", cls),
+                                               ("wp", wp), ("bp", bp))}
+    scratch = torch.empty(((P + 255) // 256) * R * 4 * D + 5 * R * D, device=DEV)
+    ops.embed_time_class_bwd(dtable, ctx, mask, D, NC, d(w2), d(wp), saved, gs["w1"], gs["b1"], gs["w2"], gs["b2"],
+                             gs["cls"], gs["wp"], gs["bp"], scratch)
+    for n, p in (("w1", w1), ("b1", b1), ("w2", w2), ("b2", b2), ("cls", cls), ("wp", wp), ("bp", bp)):
+        assert rel_err(gs[n], p.grad) < 1e-4, (n, rel_err(gs[n], p.grad))
+
+
+def test_loss_clip_adam():
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(2)
+    pred, tgt = torch.randn(48, 3, 32, 32, device=DEV, generator=g), torch.randn(48, 3, 32, 32, device=DEV, generator=g)
+    dp, loss = torch.empty_like(pred), torch.empty(1, device=DEV)
+    ops.mse_loss_grad(pred, tgt, dp, loss)
+    pr = pred.clone().requires_grad_(True)
+    lr_ = F.mse_loss(pr, tgt)
+    lr_.backward()
+    assert abs(loss.item() - lr_.item()) < 1e-6 * abs(lr_.item()) + 1e-7
+    assert rel_err(dp, pr.grad) < 1e-6
+    n = 1_000_003
+    p0 = torch.randn(n, device=DEV, generator=g)
+    grad = torch.randn(n, device=DEV, generator=g) * 0.01
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    out2, scratch = torch.empty(2, device=DEV), torch.empty(2048, device=DEV)
+    for step in (1, 2, 3):
+        ref_p.grad = grad.clone() * step
+        tn = torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        gk = grad * step
+        ops.grad_norm_clip(gk, out2, scratch, 1.0)
+        assert abs(out2[0].item() - tn.item()) < 1e-4 * tn.item()
+        ops.adam_step(p, gk, m, v, 1e-3, step, clip2=out2)
+        assert (p - ref_p.detach()).abs().max().item() < 2e-6
