@@ -554,14 +554,16 @@ __global__ void __launch_bounds__(256) sumsq_finish_kernel(const float* __restri
   }
 }
 
-// torch.optim.Adam (no weight decay, no amsgrad): g = grad * gscale[1] / grad_div; m, v updated in place;
-// p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+// torch.optim.Adam (no weight decay, no amsgrad): g = grad * clip2[1] / grad_div; m, v updated in place;
+// p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps). hyper = {lr, bc1 = 1 - beta1^step, sqrt(bc2)} lives in device memory
+// so that a captured CUDA graph can be replayed with a new learning rate / step count.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
-                                                   float lr, float beta1, float beta2, float eps, float bc1,
-                                                   float bc2_sqrt, float grad_div, const float* __restrict__ gscale) {
+                                                   const float* __restrict__ hyper, float beta1, float beta2, float eps,
+                                                   float grad_div, const float* __restrict__ gscale) {
   const float gs = (gscale ? gscale[1] : 1.f) / grad_div;
-  const float step = lr / bc1;
+  const float step = hyper[0] / hyper[1];
+  const float bc2_sqrt = hyper[2];
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float gi = g[i] * gs;
     const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
@@ -570,6 +572,28 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     v[i] = vi;
     p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
   }
+}
+
+// KL reparametrisation of the stored (mean || logvar) latents + forward diffusion (diffusion_trainer.py:149-164,
+// components.py:399-403): x0 = mean + rn * exp(0.5 * clamp(logvar, -30, 20)); x_t = sqrt(acp[t]) x0 + sqrt(1-acp[t]) noise.
+// lat is (N, 2*chw) fp32 when rn != nullptr, else (N, chw) and x0 = lat.
+__global__ void reparam_add_noise_kernel(const float* __restrict__ lat, const float* __restrict__ rn,
+                                         const float* __restrict__ noise, const int64_t* __restrict__ t,
+                                         const float* __restrict__ sa, const float* __restrict__ s1,
+                                         float* __restrict__ out, int N, int chw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * chw) return;
+  const int n = (int)(i / chw), k = (int)(i % chw);
+  float x0;
+  if (rn != nullptr) {
+    const float mean = lat[(long long)n * 2 * chw + k];
+    const float lv = fminf(fmaxf(lat[(long long)n * 2 * chw + chw + k], -30.f), 20.f);
+    x0 = fmaf(rn[i], expf(0.5f * lv), mean);
+  } else {
+    x0 = lat[i];
+  }
+  const int64_t tt = t[n];
+  out[i] = sa[tt] * x0 + s1[tt] * noise[i];
 }
 
 // row sums of dO * O per (token, head): D[m, h] = sum_d dO[m, h*hd + d] * O[m, h*hd + d]
@@ -781,15 +805,24 @@ extern "C" int idf_grad_norm_clip(const float* grad, int64_t n, float grad_div, 
   return check_cuda(cudaGetLastError(), "grad_norm_clip launch");
 }
 
-extern "C" int idf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                             float beta1, float beta2, float eps, int32_t step, float grad_div, const float* clip2,
-                             idf_stream_t stream) {
-  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return fail(IDF_ERR_ARG, "adam_step: bad argument");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, S(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                               (float)bc1, (float)sqrt(bc2), grad_div, clip2);
+extern "C" int idf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             const float* hyper, float beta1, float beta2, float eps, float grad_div,
+                             const float* clip2, idf_stream_t stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || n <= 0) return fail(IDF_ERR_ARG, "adam_step: bad argument");
+  adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, S(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, hyper, beta1, beta2,
+                                                               eps, grad_div, clip2);
   return check_cuda(cudaGetLastError(), "adam_step launch");
+}
+
+extern "C" int idf_reparam_add_noise(const float* latents, const float* reparam_noise, const float* noise,
+                                     const int64_t* t, const float* sqrt_alpha_cum_prod,
+                                     const float* sqrt_one_minus_alpha_cum_prod, float* out, int32_t N, int32_t chw,
+                                     idf_stream_t stream) {
+  if (!latents || !noise || !t || !sqrt_alpha_cum_prod || !sqrt_one_minus_alpha_cum_prod || !out)
+    return fail(IDF_ERR_ARG, "reparam_add_noise: null pointer");
+  reparam_add_noise_kernel<<<(unsigned)(((long long)N * chw + 255) / 256), 256, 0, S(stream)>>>(
+      latents, reparam_noise, noise, t, sqrt_alpha_cum_prod, sqrt_one_minus_alpha_cum_prod, out, N, chw);
+  return check_cuda(cudaGetLastError(), "reparam_add_noise launch");
 }
 
 extern "C" int idf_attention_delta(const void* d_out, int64_t ld_do, const void* out, int64_t ld_o, int32_t M,

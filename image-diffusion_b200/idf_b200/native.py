@@ -76,7 +76,8 @@ _SIGNATURES = {
                                  _vp, _vp, _i64],
     "idf_mse_loss_grad": [_vp, _vp, _i64, _f32, _vp, _vp],
     "idf_grad_norm_clip": [_vp, _i64, _f32, _f32, _vp, _vp, _i64],
-    "idf_adam_step": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
+    "idf_adam_step": [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _f32, _vp],
+    "idf_reparam_add_noise": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32],
     "idf_attention_fwd_train": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
     "idf_attention_delta": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp],
     "idf_attention_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _f32],

@@ -315,9 +315,22 @@ def grad_norm_clip(grad, out2, scratch, max_norm: float, grad_div: float = 1.0):
     return out2
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_div=1.0, clip2=None):
+def adam_hyper(lr: float, step: int, beta1=0.9, beta2=0.999):
+    """Host values of the device `hyper` array of idf_adam_step: {lr, 1 - beta1^step, sqrt(1 - beta2^step), 0}."""
+    return [lr, 1.0 - beta1 ** step, math.sqrt(1.0 - beta2 ** step), 0.0]
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, hyper, beta1=0.9, beta2=0.999, eps=1e-8, grad_div=1.0, clip2=None):
     call("idf_adam_step", param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
-         lr, beta1, beta2, eps, step, grad_div, ptr(clip2))
+         hyper.data_ptr(), beta1, beta2, eps, grad_div, ptr(clip2))
+
+
+def reparam_add_noise(latents, reparam_noise, noise, t, sched, out):
+    N = noise.shape[0]
+    call("idf_reparam_add_noise", latents.data_ptr(), ptr(reparam_noise), noise.data_ptr(), t.data_ptr(),
+         sched.sqrt_alpha_cum_prod.data_ptr(), sched.sqrt_one_minus_alpha_cum_prod.data_ptr(), out.data_ptr(), N,
+         noise.numel() // N)
+    return out
 
 
 def attention_train(qk, vt, out, lse, M, T, heads, head_dim):

@@ -9,6 +9,28 @@ import torch.nn as nn
 
 from idf_b200.engine import UnetEngine
 from idf_b200.spec import register_tree, unet_param_spec
+from idf_b200.train_engine import UnetTrainEngine
+
+
+class _UnetTrainFn(torch.autograd.Function):
+    """Autograd bridge for the reference trainer (trainers/diffusion_trainer.py:169-173): forward and backward both
+    run the C-ABI kernel sequences of UnetTrainEngine; parameter gradients come back as fp32 tensors in PyTorch layout
+    (copies of the engine's flat gradient buffer, so .grad accumulation semantics hold)."""
+
+    @staticmethod
+    def forward(ctx, module, x, t, context, mask, *params):
+        eng = module.train_engine()
+        out = torch.empty_like(x)
+        eng.forward(x, t, context, mask, out)
+        ctx.eng = eng
+        ctx.names = [n for n, _ in module.named_parameters()]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.eng
+        eng.backward(grad_out.to(torch.float32).contiguous())
+        return (None, None, None, None, None) + tuple(eng.gv[n].clone() for n in ctx.names)
 
 
 class Unet(nn.Module):
@@ -22,6 +44,13 @@ class Unet(nn.Module):
                                  num_classes=num_classes)
         register_tree(self, unet_param_spec(self.architecture))
         self._engines = {}
+        self._train_engine = None
+
+    def train_engine(self) -> UnetTrainEngine:
+        dev = self.in_conv.weight.device
+        if self._train_engine is None or self._train_engine.device != dev:
+            self._train_engine = UnetTrainEngine(self, self.architecture, dev)
+        return self._train_engine
 
     def engine(self, batch: int, height: int, width: int) -> UnetEngine:
         dev = self.in_conv.weight.device
@@ -36,9 +65,6 @@ class Unet(nn.Module):
         None (unconditional), context_mask (B, 1) multiplies the class embedding row (0 = dropped)."""
         if not x.is_cuda:
             raise RuntimeError("Unet.forward: CUDA (sm_100a) tensors required; there is no CPU path")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("Unet.forward under autograd: the backward kernels are not built yet "
-                                      "(inference / sampling only in this round); wrap the call in torch.no_grad()")
         B, _, H, W = x.shape
         xin = x.detach().to(torch.float32).contiguous()
         t = timestep.to(device=x.device, dtype=torch.int64).contiguous()
@@ -46,6 +72,8 @@ class Unet(nn.Module):
         mask = None
         if context is not None and context_mask is not None:
             mask = context_mask.to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return _UnetTrainFn.apply(self, xin, t, ctx, mask, *self.parameters())
         out = torch.empty_like(xin)
         self.engine(B, H, W).run(xin, t, ctx, mask, None, out)
         return out

@@ -337,9 +337,16 @@ int idf_grad_norm_clip(const float* grad, int64_t n, float grad_div, float max_n
                        int64_t scratch_bytes, idf_stream_t stream);
 
 /* idf_adam_step — torch.optim.Adam defaults (diffusion_trainer.py:57-58,185) over flat fp32 buffers; the gradient is
- * used as grad * clip2[1] / grad_div (clip2 from idf_grad_norm_clip, may be NULL). step counts from 1. */
-int idf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                  float beta2, float eps, int32_t step, float grad_div, const float* clip2, idf_stream_t stream);
+ * used as grad * clip2[1] / grad_div (clip2 from idf_grad_norm_clip, may be NULL). hyper is a DEVICE array
+ * {lr, 1 - beta1^step, sqrt(1 - beta2^step)} so a captured graph can be replayed with new values. */
+int idf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* hyper,
+                  float beta1, float beta2, float eps, float grad_div, const float* clip2, idf_stream_t stream);
+
+/* idf_reparam_add_noise — KL reparametrisation of stored (mean || logvar) latents (diffusion_trainer.py:149-155; skipped
+ * when reparam_noise is NULL, latents then being (N, chw)) followed by Scheduler.add_noise (components.py:399-403). */
+int idf_reparam_add_noise(const float* latents, const float* reparam_noise, const float* noise, const int64_t* t,
+                          const float* sqrt_alpha_cum_prod, const float* sqrt_one_minus_alpha_cum_prod, float* out,
+                          int32_t N, int32_t chw, idf_stream_t stream);
 
 /* idf_attention_fwd_train — idf_attention_fwd that also writes lse[m*heads + h] = log2(sum_j exp(s_mj)) + max (log2
  * domain, scaled scores) for idf_attention_bwd. */

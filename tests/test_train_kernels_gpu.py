@@ -303,5 +303,6 @@ def test_loss_clip_adam():
         gk = grad * step
         ops.grad_norm_clip(gk, out2, scratch, 1.0)
         assert abs(out2[0].item() - tn.item()) < 1e-4 * tn.item()
-        ops.adam_step(p, gk, m, v, 1e-3, step, clip2=out2)
+        hyper = torch.tensor(ops.adam_hyper(1e-3, step), device=DEV)
+        ops.adam_step(p, gk, m, v, hyper, clip2=out2)
         assert (p - ref_p.detach()).abs().max().item() < 2e-6
