@@ -188,8 +188,145 @@ def igemm_roofline(sampler, peak_tflops, peak_kind):
     return roof, breakdown
 
 
+TRAIN_GFLOP_PER_IMG = 3 * 22.755  # forward + data-gradient + weight-gradient GEMMs, SURVEY.md §8(d) config 4
+
+
+def kernel_breakdown(run_eager):
+    """CUDA-event time of every C-ABI call of one eager pass, summed per entry point."""
+    from idf_b200 import native, ops
+    records = []
+    orig_call = native.call
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        records.append((name, e0, e1))
+
+    try:
+        native.call = timed_call
+        ops.call = timed_call
+        torch.cuda._sleep(int(4e7))
+        run_eager()
+        torch.cuda.synchronize()
+    finally:
+        native.call = orig_call
+        ops.call = orig_call
+    by = {}
+    for name, e0, e1 in records:
+        d = by.setdefault(name, [0.0, 0])
+        d[0] += e0.elapsed_time(e1)
+        d[1] += 1
+    return {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])}
+
+
+def run_train(args):
+    """BASELINE configs[3]: UNet training step (epsilon-MSE forward + backward + clip + Adam), batch 48 per GPU, bf16
+    interior, NCCL gradient all-reduce across ranks. value = images/s over all ranks."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    warmup = max(args.warmup, 3)
+    peak_tflops, _, peak_kind = load_peaks()
+    from idf_b200.trainer import DiffusionTrainStep
+    unet, _, sched = build_models(dev)
+    unet.train()
+    ts = DiffusionTrainStep(unet, sched, BATCH, (3, 32, 32), clip_grad=1.0)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    lat = torch.randn(BATCH, 6, 32, 32, device=dev, generator=gen)
+    lab = torch.randint(0, 3, (BATCH,), device=dev, generator=gen)
+    for _ in range(warmup):
+        ts.step(lat, lab, 1e-4)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ts.step(lat, lab, 1e-4)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clock_info = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    # end to end: fp16 latents + labels from pinned host memory every step, loss read back every step
+    h_lat = torch.randn(BATCH, 6, 32, 32).half().pin_memory()
+    h_lab = torch.randint(0, 3, (BATCH,)).pin_memory()
+    d_lat, d_lab = torch.empty(BATCH, 6, 32, 32, device=dev, dtype=torch.float16), torch.empty(BATCH, device=dev, dtype=torch.int64)
+    h_loss = torch.empty(1).pin_memory()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        d_lat.copy_(h_lat, non_blocking=True)
+        d_lab.copy_(h_lab, non_blocking=True)
+        loss = ts.step(d_lat, d_lab, 1e-4)
+        h_loss.copy_(loss, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    breakdown = None
+    if rank == 0 and world == 1:
+        keep = (ts.flat_param.clone(), ts.exp_avg.clone(), ts.exp_avg_sq.clone())
+        breakdown = kernel_breakdown(ts._whole_step)
+        for dst, src in zip((ts.flat_param, ts.exp_avg, ts.exp_avg_sq), keep):
+            dst.copy_(src)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    value = world * BATCH * args.steps / (ms * 1e-3)
+    tfl = value / world * TRAIN_GFLOP_PER_IMG * 1e9 / 1e12
+    line = {
+        "metric": "UNet training step images/s (epsilon-MSE fwd+bwd+clip+Adam, diff-kl-lin-32x32 UNet, batch 48/GPU)",
+        "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[3]: UNet training step, batch 48 per GPU, 32x32x3 latents from stored (mean||logvar), "
+                               "random-init 60.5M-parameter UNet, fp32 master weights + Adam, bf16 interior; gradient "
+                               "all-reduce (NCCL) bucketed by backward stage when n_gpus > 1",
+                   "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                   "gflop_per_img": TRAIN_GFLOP_PER_IMG, "tflops_per_gpu": tfl,
+                   "pct_tensor_peak": tfl / peak_tflops, "loss": float(h_loss[0]), "graph": ts.graph is not None},
+        "clocks": clock_info,
+        "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "img/s",
+                "h2d_bytes_per_step": h_lat.numel() * 2 + h_lab.numel() * 8, "d2h_bytes_per_step": 4,
+                "how": "per step: fp16 latents + labels pinned host -> device, DiffusionTrainStep.step, loss -> host, sync"},
+        "gpu_launches": (ts.launches_per_step or 0) * args.steps,
+        "kernel_breakdown_ms_per_step": breakdown,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample: the headline CFG denoise metric (default); train: BASELINE configs[3] training step")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
@@ -199,6 +336,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")

@@ -171,3 +171,68 @@ def test_gather_shards_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+# ---------------------------------------------------------------------------------------------
+# training step: host-side logic (gradient layout, buckets, data-parallel averaging over gloo)
+# ---------------------------------------------------------------------------------------------
+def test_train_engine_gradient_layout_covers_every_parameter():
+    """The flat gradient buffer holds every reference parameter exactly once, in backward-completion order, with
+    q/k/v and the time projections stacked contiguously (they are written by one GEMM each)."""
+    from idf_b200.train_engine import UnetTrainEngine
+    from modules.unet import Unet
+    m = Unet(**O.UNET_ARCH)
+    e = UnetTrainEngine(m, m.architecture, "cpu")
+    names = dict(m.named_parameters())
+    assert set(e.grad_names) == set(names) and len(e.grad_names) == len(names) == 331
+    assert "time_embedding.factor" not in e.goff  # a buffer, not a parameter
+    spans = sorted((e.goff[n], e.goff[n] + names[n].numel()) for n in e.grad_names)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= e.flat_numel
+    assert e.flat_numel - sum(p.numel() for p in names.values()) < 4 * len(names)
+    a = "mid_blocks.0.self_attns.1"
+    assert e.goff[a + ".to_k.weight"] == e.goff[a + ".to_q.weight"] + 512 * 512
+    assert e.gspan(a + ".to_q.weight", a + ".to_v.weight").numel() == 3 * 512 * 512
+    assert e.grad_names[0] == "out_conv.2.weight" and e.grad_names[-1] == "class_embedding.weight"
+    ends = [end for _, end in e.bucket_ends]
+    assert ends == sorted(ends) and ends[-1] == e.flat_numel and len(ends) == 8
+    for n in e.grad_names:  # views alias the flat buffer
+        assert e.gv[n].data_ptr() == e.flat_grad.data_ptr() + 4 * e.goff[n] and e.gv[n].shape == names[n].shape
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from idf_b200.trainer import GradBuckets
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n = 1000
+    ends = [("a", 100), ("b", 450), ("c", 460), ("d", 1000)]
+    flat = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    gb = GradBuckets(flat, ends, min_bucket_elems=300)
+    plan = gb.plan()
+    ok = plan == [(0, 450), (450, 1000)]  # stages merged until a bucket holds >= 300 elements; the last closes the rest
+    for stage in range(len(ends)):
+        gb.on_stage_done(stage)
+    gb.works.clear()
+    expect = torch.arange(n, dtype=torch.float32) * sum(r + 1 for r in range(world))
+    ok = ok and torch.equal(flat, expect)
+    t = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(bool(t.item()))
+    dist.destroy_process_group()
+
+
+def test_grad_buckets_gloo_world2():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
