@@ -310,7 +310,8 @@ def run_train(args):
                                "all-reduce (NCCL) bucketed by backward stage when n_gpus > 1",
                    "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
                    "gflop_per_img": TRAIN_GFLOP_PER_IMG, "tflops_per_gpu": tfl,
-                   "pct_tensor_peak": tfl / peak_tflops, "loss": float(h_loss[0]), "graph": ts.graph is not None},
+                   "pct_tensor_peak": tfl / peak_tflops, "loss": float(h_loss[0]), "graph": ts.graph is not None,
+                   "graph_segments": len(ts.segments) if ts.segments else 0},
         "clocks": clock_info,
         "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "img/s",
                 "h2d_bytes_per_step": h_lat.numel() * 2 + h_lab.numel() * 8, "d2h_bytes_per_step": 4,

@@ -12,6 +12,8 @@ exactly where the reference draws them, or are injected for parity tests.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -100,8 +102,13 @@ class DiffusionTrainStep:
         self.hyper = z(4)
         self.hyper_host = torch.zeros(4, dtype=F32).pin_memory()
         self.sq_scratch = z(2048)
-        self.use_graph = use_graph and self.world == 1
+        # One rank: the whole step is ONE CUDA graph. Several ranks: the step is captured as a CHAIN of graphs cut at
+        # the gradient-bucket boundaries; the NCCL all-reduce of bucket k is issued eagerly on a side stream between
+        # the launches of segments k and k+1 and overlaps the remaining backward segments (collectives captured
+        # inside a graph with side-stream fork/join deadlocked under torch 2.11 + NCCL 2.28, measured on 2 x B200).
+        self.use_graph = use_graph
         self.graph = None
+        self.segments = None
         self.launches_per_step = None
 
     def _flatten_params(self):
@@ -147,8 +154,71 @@ class DiffusionTrainStep:
             self.buckets.finish()
         self._update()
 
+    def _capture_segments(self):
+        """world > 1: graphs [fwd + bwd stages up to bucket 0], [.. bucket 1], ..., [clip + Adam + re-pack]."""
+        stream = torch.cuda.Stream()
+        segs, state = [], {"g": None, "pool": torch.cuda.graph_pool_handle()}
+
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=state["pool"])
+            state["g"] = g
+
+        def cut(bucket):
+            state["g"].capture_end()
+            segs.append((state["g"], bucket))
+            begin()
+
+        def on_stage(stage):
+            if stage in self.buckets.ranges:
+                cut(self.buckets.ranges[stage])
+
+        torch.cuda.synchronize()
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            begin()
+            ops.reparam_add_noise(self.latents, self.reparam_noise, self.noise, self.t, self.sched, self.x_noise)
+            self.eng.forward(self.x_noise, self.t, self.labels, self.mask, self.pred)
+            ops.mse_loss_grad(self.pred, self.noise, self.dpred, self.loss)
+            self.eng.backward(self.dpred, on_stage_done=on_stage)
+            # the last backward stage always closes a bucket, so a fresh segment is open here: the update
+            self._update()
+            state["g"].capture_end()
+            segs.append((state["g"], None))
+        torch.cuda.current_stream().wait_stream(stream)
+        torch.cuda.synchronize()
+        self.segments = segs
+
+    def _replay_segments(self):
+        b = self.buckets
+        for g, bucket in self.segments:
+            if bucket is None:
+                b.finish()  # the update segment needs every bucket averaged
+            g.replay()
+            if bucket is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                with torch.cuda.stream(b.side):
+                    b.side.wait_event(ev)
+                    dist.all_reduce(b.flat[bucket[0]:bucket[1]], group=b.group)
+                    done = torch.cuda.Event()
+                    done.record(b.side)
+                b.works.append(done)
+
     def _ensure_graph(self):
-        if self.graph is not None or not self.use_graph:
+        if self.graph is not None or self.segments is not None or not self.use_graph:
+            return
+        if self.world > 1:
+            keep = (self.flat_param.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
+            self.hyper.copy_(torch.tensor(ops.adam_hyper(0.0, 1, *self.betas)))
+            self._whole_step()  # warm-up (eager): allocates workspaces, sets kernel attributes, initialises NCCL
+            torch.cuda.synchronize()
+            before = native.launch_count
+            self._capture_segments()
+            self.launches_per_step = native.launch_count - before
+            for dst, src in zip((self.flat_param, self.exp_avg, self.exp_avg_sq), keep):
+                dst.copy_(src)
+            self.eng.prepare(force=True)
             return
         keep = (self.flat_param.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
         self.hyper.copy_(torch.tensor(ops.adam_hyper(0.0, 1, *self.betas)))
@@ -181,6 +251,8 @@ class DiffusionTrainStep:
         self.hyper.copy_(self.hyper_host, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
+        elif self.segments is not None:
+            self._replay_segments()
         else:
             self._whole_step()
         return self.loss

@@ -31,7 +31,7 @@ sched = Scheduler(1000, device=dev)
 def make(batch):
     torch.manual_seed(2018)
     m = Unet(**UNET_ARCH).to(dev).train()
-    return m, DiffusionTrainStep(m, sched, batch, (3, 32, 32), clip_grad=1.0, use_graph=False)
+    return m, DiffusionTrainStep(m, sched, batch, (3, 32, 32), clip_grad=1.0, use_graph=(os.environ.get("DDP_CHECK_GRAPH", "1") == "1"))
 
 
 def load(ts, sl):
