@@ -34,6 +34,7 @@ struct AttnParams {
   float scale_log2e;
   int heads;
   float* lse;  // optional (M, heads): log2-domain log-sum-exp of the scaled scores (training: consumed by the backward)
+  int v_tok;   // 1: tmVT maps the token-major (M, 3C) QKV matrix, box (64, 128); V tiles are MN-major UMMA operands
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -48,7 +49,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   constexpr int QK_BYTES = 128 * SWZ;
   constexpr int V_BYTES = 2 * HD * 128;  // two boxes of (HD rows x 64 keys)
   constexpr int P_BYTES = 2 * 128 * 128; // two blocks of (128 rows x 64 keys)
-  constexpr int KV_BYTES = QK_BYTES + V_BYTES;
+  // V tile: two (HD rows x 64 keys) boxes of V^T (K-major operand), or - token-major V - one (128 keys x 64 columns)
+  // box of the QKV matrix used as an MN-major operand (no transposed copy of V exists then)
+  const int KV_BYTES = QK_BYTES + (p.v_tok ? 128 * 128 : V_BYTES);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -113,8 +116,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
         uint8_t* v_dst = k_dst + QK_BYTES;
         const int kv0 = kv_base + j * 128;
         tma_load_2d(k_dst, &p.tmQK, &kv_full[st], p.C + head * HD, kv0);
-        tma_load_2d(v_dst, &p.tmVT, &kv_full[st], kv0, head * HD);
-        tma_load_2d(v_dst + HD * 128, &p.tmVT, &kv_full[st], kv0 + 64, head * HD);
+        if (p.v_tok) {
+          tma_load_2d(v_dst, &p.tmVT, &kv_full[st], 2 * p.C + head * HD, kv0);
+        } else {
+          tma_load_2d(v_dst, &p.tmVT, &kv_full[st], kv0, head * HD);
+          tma_load_2d(v_dst + HD * 128, &p.tmVT, &kv_full[st], kv0 + 64, head * HD);
+        }
       }
     }
   } else if (warp == 5) {
@@ -122,6 +129,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
+      constexpr uint32_t idesc_o_mn = umma_idesc_bf16(128, HD, 0, 1);
       const uint64_t dq = umma_desc_kmajor(smem_u32(smem_q), SWZ);
       const uint64_t dp0 = umma_desc_kmajor(smem_u32(smem_p), 128);
       const uint64_t dp1 = umma_desc_kmajor(smem_u32(smem_p + 128 * 128), 128);
@@ -141,13 +149,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
 
         mbar_wait(p_full, j & 1);
         tc_fence_after_sync();
-        const uint64_t dv0 = umma_desc_kmajor(smem_u32(v_src), 128);
-        const uint64_t dv1 = umma_desc_kmajor(smem_u32(v_src + HD * 128), 128);
+        if (p.v_tok) {
+          const uint64_t dvm = umma_desc_mnmajor(smem_u32(v_src), 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t da = (k < 4 ? dp0 : dp1) + 2 * (k & 3);
-          const uint64_t db = (k < 4 ? dv0 : dv1) + 2 * (k & 3);
-          umma_bf16(tmem_o, da, db, idesc_o, k != 0);
+          for (int k = 0; k < 8; ++k)  // 16 keys per step = 16 rows of 128 bytes
+            umma_bf16(tmem_o, (k < 4 ? dp0 : dp1) + 2 * (k & 3), dvm + 128 * k, idesc_o_mn, k != 0);
+        } else {
+          const uint64_t dv0 = umma_desc_kmajor(smem_u32(v_src), 128);
+          const uint64_t dv1 = umma_desc_kmajor(smem_u32(v_src + HD * 128), 128);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t da = (k < 4 ? dp0 : dp1) + 2 * (k & 3);
+            const uint64_t db = (k < 4 ? dv0 : dv1) + 2 * (k & 3);
+            umma_bf16(tmem_o, da, db, idesc_o, k != 0);
+          }
         }
         umma_commit(&kv_empty[st]);
         umma_commit(o_full);
@@ -332,7 +347,7 @@ template <int HD>
 __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const __grid_constant__ AttnParams p) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
   constexpr int QK_BYTES = 128 * SWZ;
-  constexpr int V_BYTES = 2 * HD * 128;
+  const int V_BYTES = p.v_tok ? 128 * 128 : 2 * HD * 128;
   constexpr int P_BYTES = 2 * 128 * 128;
   constexpr int ATTP_KSTAGES = AttpK<HD>::STAGES;
 
@@ -423,8 +438,12 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
           mbar_wait(&v_empty[st], ((e / ATTP_VSTAGES) & 1) ^ 1);
           mbar_expect_tx(&v_full[st], V_BYTES);
           uint8_t* dst = smem_v + st * V_BYTES;
-          tma_load_2d(dst, &p.tmVT, &v_full[st], kv0, item_head(item) * HD);
-          tma_load_2d(dst + HD * 128, &p.tmVT, &v_full[st], kv0 + 64, item_head(item) * HD);
+          if (p.v_tok) {
+            tma_load_2d(dst, &p.tmVT, &v_full[st], 2 * p.C + item_head(item) * HD, kv0);
+          } else {
+            tma_load_2d(dst, &p.tmVT, &v_full[st], kv0, item_head(item) * HD);
+            tma_load_2d(dst + HD * 128, &p.tmVT, &v_full[st], kv0 + 64, item_head(item) * HD);
+          }
         };
         if (E > 0) load_k(0);
         if (E > 1) load_k(1);
@@ -438,6 +457,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
       if (elect_one()) {
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
+        constexpr uint32_t idesc_o_mn = umma_idesc_bf16(128, HD, 0, 1);
         auto issue_s = [&](int g, int e) {  // S_g = Q_g K_e^T
           const int item = e / n, j = e % n;
           const int st = e % ATTP_KSTAGES;
@@ -468,12 +488,20 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
           const uint8_t* vb = smem_v + vs * V_BYTES;
           const uint64_t dp0 = umma_desc_kmajor(smem_u32(pb), 128);
           const uint64_t dp1 = umma_desc_kmajor(smem_u32(pb + 128 * 128), 128);
-          const uint64_t dv0 = umma_desc_kmajor(smem_u32(vb), 128);
-          const uint64_t dv1 = umma_desc_kmajor(smem_u32(vb + HD * 128), 128);
+          if (p.v_tok) {
+            const uint64_t dvm = umma_desc_mnmajor(smem_u32(vb), 8192, 1024);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem_base + 256 + g * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), (k < 4 ? dv0 : dv1) + 2 * (k & 3),
-                      idesc_o, (j > 0) || (k != 0));  // accumulate over the item's key blocks
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem_base + 256 + g * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), dvm + 128 * k, idesc_o_mn,
+                        (j > 0) || (k != 0));
+          } else {
+            const uint64_t dv0 = umma_desc_kmajor(smem_u32(vb), 128);
+            const uint64_t dv1 = umma_desc_kmajor(smem_u32(vb + HD * 128), 128);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem_base + 256 + g * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), (k < 4 ? dv0 : dv1) + 2 * (k & 3),
+                        idesc_o, (j > 0) || (k != 0));  // accumulate over the item's key blocks
+          }
           umma_commit(&o_full[g]);
           if (g == 1) umma_commit(&v_empty[vs]);
         };
@@ -629,7 +657,8 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
 template <int HD>
 static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
-  const int smem = 4 * 128 * SWZ + 2 * (2 * 128 * 128) + AttpK<HD>::STAGES * 128 * SWZ + ATTP_VSTAGES * 2 * HD * 128 +
+  // (sized for the larger token-major V tile so that one attribute setting serves both operand layouts)
+  const int smem = 4 * 128 * SWZ + 2 * (2 * 128 * 128) + AttpK<HD>::STAGES * 128 * SWZ + ATTP_VSTAGES * 128 * 128 +
                    1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
@@ -647,7 +676,7 @@ static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cuda
 template <int HD>
 static int launch_attention(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
-  const int smem = 128 * SWZ + 2 * 128 * 128 + p.kv_stages * (128 * SWZ + 2 * HD * 128) + 1024 + 128;
+  const int smem = 128 * SWZ + 2 * 128 * 128 + p.kv_stages * (128 * SWZ + 128 * 128) + 1024 + 128;
   static int smem_set = 0;
   if (smem > smem_set) {
     int rc = check_cuda(cudaFuncSetAttribute(attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
@@ -665,7 +694,7 @@ using namespace idf;
 
 static int attention_fwd_impl(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out,
                               int64_t ld_out, int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale,
-                              float* lse, idf_stream_t stream) {
+                              float* lse, int v_tok, idf_stream_t stream) {
   if (!qk || !vt || !out) return fail(IDF_ERR_ARG, "attention: null pointer");
   if (T < 16 || (T & (T - 1)) != 0) return fail(IDF_ERR_UNSUPPORTED, "attention: T = %d must be a power of two >= 16", T);
   if (M <= 0 || M % T != 0) return fail(IDF_ERR_ARG, "attention: M = %d not a multiple of T = %d", M, T);
@@ -684,6 +713,7 @@ static int attention_fwd_impl(const void* qk, int64_t ld_qk, const void* vt, int
   p.scale_log2e = scale * 1.4426950408889634f;
   p.heads = heads;
   p.lse = lse;
+  p.v_tok = v_tok;
 
   const int swz = head_dim <= 16 ? 32 : (head_dim <= 32 ? 64 : 128);
   const CUtensorMapSwizzle swz_enum = swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
@@ -696,7 +726,14 @@ static int attention_fwd_impl(const void* qk, int64_t ld_qk, const void* vt, int
     if ((rc = encode_tmap(&p.tmQK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qk, 2, dims, strides, box, swz_enum)) != IDF_OK)
       return rc;
   }
-  {
+  if (v_tok) {  // vt == the (M, 3C) QKV matrix itself
+    const uint64_t dims[2] = {(uint64_t)(3 * C), (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)ld_vt * 2};
+    const uint32_t box[2] = {64u, 128u};
+    if ((rc = encode_tmap(&p.tmVT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, vt, 2, dims, strides, box,
+                          CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
+      return rc;
+  } else {
     const uint64_t dims[2] = {(uint64_t)M, (uint64_t)C};
     const uint64_t strides[1] = {(uint64_t)ld_vt * 2};
     const uint32_t box[2] = {64u, (uint32_t)head_dim};
@@ -731,12 +768,17 @@ static int attention_fwd_impl(const void* qk, int64_t ld_qk, const void* vt, int
 extern "C" int idf_attention_fwd(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out,
                                  int64_t ld_out, int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale,
                                  idf_stream_t stream) {
-  return attention_fwd_impl(qk, ld_qk, vt, ld_vt, out, ld_out, M, T, heads, head_dim, scale, nullptr, stream);
+  return attention_fwd_impl(qk, ld_qk, vt, ld_vt, out, ld_out, M, T, heads, head_dim, scale, nullptr, 0, stream);
 }
 
 extern "C" int idf_attention_fwd_train(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, void* out,
                                        int64_t ld_out, int32_t M, int32_t T, int32_t heads, int32_t head_dim,
                                        float scale, float* lse, idf_stream_t stream) {
   if (!lse) return fail(IDF_ERR_ARG, "attention_fwd_train: lse is null");
-  return attention_fwd_impl(qk, ld_qk, vt, ld_vt, out, ld_out, M, T, heads, head_dim, scale, lse, stream);
+  return attention_fwd_impl(qk, ld_qk, vt, ld_vt, out, ld_out, M, T, heads, head_dim, scale, lse, 0, stream);
+}
+
+extern "C" int idf_attention_fwd_qkv(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int32_t M, int32_t T,
+                                     int32_t heads, int32_t head_dim, float scale, float* lse, idf_stream_t stream) {
+  return attention_fwd_impl(qkv, ld_qkv, qkv, ld_qkv, out, ld_out, M, T, heads, head_dim, scale, lse, 1, stream);
 }

@@ -5,17 +5,19 @@
 // computed TRANSPOSED (keys along TMEM lanes, one key row per thread) so that P^T and dS^T come out of the softmax
 // threads row-major in the layout the next three products need:
 //   S^T  = K_j Q_i^T                    (A = K_j  K-major,  B = Q_i  K-major)          128 x 128 x hd
-//   dP^T = V_j dO_i^T                   (A = V^T_j MN-major, B = dO_i K-major)         128 x 128 x hd
+//   dP^T = V_j dO_i^T                   (A = V_j  K-major,  B = dO_i K-major)          128 x 128 x hd
 //   P^T  = exp2(S^T * c - lse[q]),  dS^T = P^T * (dP^T - delta[q]) * scale             softmax threads -> bf16 smem
 //   dV_j += P^T  dO_i                   (A = P^T  K-major,  B = dO_i MN-major)         128 x hd x 128   (TMEM, all i)
 //   dK_j += dS^T Q_i                    (A = dS^T K-major,  B = Q_i  MN-major)         128 x hd x 128   (TMEM, all i)
 //   dQ_i  = dS   K_j                    (A = dS^T MN-major, B = K_j  MN-major)         128 x hd x 128   per i
-// The MN-major descriptors let Q_i, dO_i, K_j and V^T_j be used in both roles from ONE shared-memory copy as TMA
-// wrote it. dQ_i partials of different key tiles are added with vector fp32 reductions (red.global.add.v4.f32) when
+// Q, K, V are read straight from the token-major (M, 3C) QKV matrix. The MN-major descriptors let Q_i, dO_i and K_j
+// be used in both operand roles from ONE shared-memory copy as TMA wrote it. dQ_i partials of different key tiles are added with vector fp32 reductions (red.global.add.v4.f32) when
 // a sample has more than one key tile, and stored directly otherwise.
 // Samples with fewer than 128 tokens share a tile under a block-diagonal mask, as in the forward kernel.
 //
-// Warp roles (192 threads): warps 0..3 = softmax / output rows, warp 4 = TMA producer, warp 5 = TMEM + MMA issuer.
+// Warp roles (320 threads): warps 0..7 = softmax / output rows (warp w owns TMEM lanes 32*(w%4).. and the query-column
+// half w/4 of every tile, so two warps per scheduler keep the MUFU pipe busy), warp 8 = TMA producer, warp 9 = TMEM +
+// MMA issuer.
 // TMEM columns: S^T [0,128) dP^T [128,256) dV [256,256+hd) dK [320,320+hd) dQ [384,384+hd).
 #include <stdlib.h>
 #include <string.h>
@@ -26,15 +28,14 @@
 
 namespace idf {
 
-constexpr int ATB_THREADS = 192;
+constexpr int ATB_THREADS = 320;
 constexpr int ATB_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16 columns
 constexpr int ATB_SMEM = 2 * ATB_TILE_BYTES /*K, V^T*/ + 4 * ATB_TILE_BYTES /*Q, dO x2 stages*/ +
                          4 * ATB_TILE_BYTES /*P^T, dS^T (two 64-column halves each)*/ + 4 * 128 * 4 /*lse, delta x2*/ +
                          1024 + 256;
 
 struct AttnBwdParams {
-  CUtensorMap tmQK;  // (M, 2C) bf16, box (64, 128)
-  CUtensorMap tmVT;  // (C, M)  bf16, box (64, HD)
+  CUtensorMap tmQK;  // (M, 3C) bf16 QKV matrix, box (64, 128)
   CUtensorMap tmDO;  // (M, C)  bf16, box (64, 128)
   const float* lse;
   const float* delta;
@@ -81,19 +82,18 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
   const int q_base = (p.T >= 128) ? (row0 >> p.t_shift) << p.t_shift : row0;
   const int n = p.nblk;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tmQK);
-    tma_prefetch_desc(&p.tmVT);
     tma_prefetch_desc(&p.tmDO);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, 8);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 4);
+    mbar_init(dq_empty, 8);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -104,12 +104,11 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320,
                  tmem_dq = tmem_base + 384;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
-      mbar_expect_tx(kv_full, ATB_TILE_BYTES + 2 * HD * 128);
+      mbar_expect_tx(kv_full, 2 * ATB_TILE_BYTES);
       tma_load_2d(smem_k, &p.tmQK, kv_full, p.C + head * HD, row0);
-      tma_load_2d(smem_vt, &p.tmVT, kv_full, row0, head * HD);
-      tma_load_2d(smem_vt + HD * 128, &p.tmVT, kv_full, row0 + 64, head * HD);
+      tma_load_2d(smem_vt, &p.tmQK, kv_full, 2 * p.C + head * HD, row0);
       for (int i = 0; i < n; ++i) {
         const int st = i & 1;
         mbar_wait(&q_empty[st], ((i >> 1) & 1) ^ 1);
@@ -118,15 +117,15 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
         tma_load_2d(smem_do + st * ATB_TILE_BYTES, &p.tmDO, &q_full[st], head * HD, q_base + i * 128);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);    // S^T  = K Q^T
-      constexpr uint32_t idesc_dp = umma_idesc_bf16(128, 128, 1, 0);   // dP^T = V dO^T, A = V^T tile (MN-major)
+      constexpr uint32_t idesc_dp = umma_idesc_bf16(128, 128, 0, 0);   // dP^T = V dO^T
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, HD, 0, 1);   // dV / dK: A K-major, B MN-major
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, 1, 1);    // dQ: both MN-major
       const uint64_t dk_k = umma_desc_kmajor(smem_u32(smem_k), 128);
       const uint64_t dk_mn = umma_desc_mnmajor(smem_u32(smem_k), 8192, 1024);
-      const uint64_t dvt_mn = umma_desc_mnmajor(smem_u32(smem_vt), HD * 128, 1024);
+      const uint64_t dv_k = umma_desc_kmajor(smem_u32(smem_vt), 128);
       const uint64_t dp0 = umma_desc_kmajor(smem_u32(smem_p), 128);
       const uint64_t dp1 = umma_desc_kmajor(smem_u32(smem_p + ATB_TILE_BYTES), 128);
       const uint64_t dds0 = umma_desc_kmajor(smem_u32(smem_ds), 128);
@@ -142,7 +141,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_s, dk_k + 2 * k, dq_k + 2 * k, idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_dp, dvt_mn + 128 * k, ddo_k + 2 * k, idesc_dp, k != 0);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_dp, dv_k + 2 * k, ddo_k + 2 * k, idesc_dp, k != 0);
         umma_commit(sdp_full);
       };
       issue_sdp(0);
@@ -168,32 +167,30 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
       }
     }
   } else {
-    const int r = warp * 32 + lane;  // key row of the tile == TMEM lane; also the query row when reading dQ
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;  // key row of the tile == TMEM lane; also the query row when reading dQ
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const bool masked = p.T < 128;
     const int row_seg = r >> p.t_shift;
     const float c = p.scale_log2e;
-    auto fetch = [&](int i, float& l, float& d) {
+    // per-query row terms of tile i: half 0 stages lse, half 1 stages delta (one value per thread)
+    auto fetch = [&](int i) {
       const long long m = (long long)q_base + i * 128 + r;
-      l = 0.f; d = 0.f;
-      if (m < p.M) { l = p.lse[m * p.heads + head]; d = p.delta[m * p.heads + head]; }
+      if (m >= p.M) return 0.f;
+      return half == 0 ? p.lse[m * p.heads + head] : p.delta[m * p.heads + head];
     };
-    {
-      float l, d;
-      fetch(0, l, d);
-      s_lse[r] = l;
-      s_delta[r] = d;
-    }
-    named_bar_sync(1, 128);
+    (half == 0 ? s_lse : s_delta)[r] = fetch(0);
+    named_bar_sync(1, 256);
     for (int i = 0; i < n; ++i) {
-      float l_next = 0.f, d_next = 0.f;
-      if (i + 1 < n) fetch(i + 1, l_next, d_next);
+      float next = 0.f;
+      if (i + 1 < n) next = fetch(i + 1);
       const float* lq = s_lse + (i & 1) * 128;
       const float* dq = s_delta + (i & 1) * 128;
       mbar_wait(sdp_full, i & 1);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int ch = half * 2 + cc;
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tmem_s + lane_addr + ch * 32, sv);
         tmem_ld_32x32(tmem_dp + lane_addr + ch * 32, dv);
@@ -207,11 +204,11 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
           pv[j] = e;
           gv[j] = e * (__uint_as_float(dv[j]) - dq[qc]) * p.scale;
         }
-        uint8_t* prow = smem_p + (ch >> 1) * ATB_TILE_BYTES + r * 128;
-        uint8_t* grow = smem_ds + (ch >> 1) * ATB_TILE_BYTES + r * 128;
+        uint8_t* prow = smem_p + half * ATB_TILE_BYTES + r * 128;
+        uint8_t* grow = smem_ds + half * ATB_TILE_BYTES + r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = ((ch & 1) * 4 + q) ^ (r & 7);
+          const int chunk = (cc * 4 + q) ^ (r & 7);
           uint4 o;
           o.x = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
           o.y = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
@@ -229,21 +226,22 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      if (i + 1 < n) {
-        s_lse[((i + 1) & 1) * 128 + r] = l_next;
-        s_delta[((i + 1) & 1) * 128 + r] = d_next;
-      }
-      // dQ_i rows (lane = query row)
+      if (i + 1 < n) (half == 0 ? s_lse : s_delta)[((i + 1) & 1) * 128 + r] = next;
+      // dQ_i rows (lane = query row); each half takes HD/2 of the columns
+      constexpr int HH = HD / 2;
       mbar_wait(dq_full, i & 1);
       tc_fence_after_sync();
-      float dqv[HD];
+      float dqv[HH];
 #pragma unroll
-      for (int d0 = 0; d0 < HD; d0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(tmem_dq + lane_addr + d0, v);
+      for (int d0 = 0; d0 < HH; d0 += 8) {
+        uint32_t v[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                     : "r"(tmem_dq + lane_addr + half * HH + d0)
+                     : "memory");
         tmem_ld_wait();
 #pragma unroll
-        for (int d = 0; d < 16; ++d) dqv[d0 + d] = __uint_as_float(v[d]);
+        for (int d = 0; d < 8; ++d) dqv[d0 + d] = __uint_as_float(v[d]);
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -251,9 +249,9 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
       const long long m = (long long)q_base + i * 128 + r;
       if (m < p.M) {
         if (n == 1) {
-          __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + head * HD;
+          __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + head * HD + half * HH;
 #pragma unroll
-          for (int d0 = 0; d0 < HD; d0 += 8) {
+          for (int d0 = 0; d0 < HH; d0 += 8) {
             uint4 o;
             o.x = pack_bf16x2(dqv[d0 + 0], dqv[d0 + 1]);
             o.y = pack_bf16x2(dqv[d0 + 2], dqv[d0 + 3]);
@@ -262,32 +260,31 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
             *reinterpret_cast<uint4*>(dst + d0) = o;
           }
         } else {
-          float* dst = p.dq32 + m * p.C + head * HD;
+          float* dst = p.dq32 + m * p.C + head * HD + half * HH;
 #pragma unroll
-          for (int d0 = 0; d0 < HD; d0 += 4)
+          for (int d0 = 0; d0 < HH; d0 += 4)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + d0), "f"(dqv[d0]), "f"(dqv[d0 + 1]),
                          "f"(dqv[d0 + 2]), "f"(dqv[d0 + 3])
                          : "memory");
         }
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
     }
-    // dV_j, dK_j rows (lane = key row); the last dq_full also covers the final accumulate
+    // dK_j rows (half 0) / dV_j rows (half 1), lane = key row; the last dq_full also covers the final accumulate
     tc_fence_after_sync();
     const long long m = (long long)row0 + r;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
+    {
       float acc[HD];
 #pragma unroll
       for (int d0 = 0; d0 < HD; d0 += 16) {
         uint32_t v[16];
-        tmem_ld_32x16((which == 0 ? tmem_dk : tmem_dv) + lane_addr + d0, v);
+        tmem_ld_32x16((half == 0 ? tmem_dk : tmem_dv) + lane_addr + d0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int d = 0; d < 16; ++d) acc[d0 + d] = __uint_as_float(v[d]);
       }
       if (m < p.M) {
-        __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + (which == 0 ? p.C : 2 * p.C) + head * HD;
+        __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + (half == 0 ? p.C : 2 * p.C) + head * HD;
 #pragma unroll
         for (int d0 = 0; d0 < HD; d0 += 8) {
           uint4 o;
@@ -303,7 +300,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     __syncwarp();
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
@@ -327,11 +324,10 @@ static int launch_attention_bwd(const AttnBwdParams& p, int tiles, cudaStream_t 
 
 using namespace idf;
 
-extern "C" int idf_attention_bwd(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, const void* d_out,
-                                 int64_t ld_do, const float* lse, const float* delta, void* dqkv, int64_t ld_dqkv,
-                                 float* dq32, int32_t M, int32_t T, int32_t heads, int32_t head_dim, float scale,
-                                 idf_stream_t stream) {
-  if (!qk || !vt || !d_out || !lse || !delta || !dqkv) return fail(IDF_ERR_ARG, "attention_bwd: null pointer");
+extern "C" int idf_attention_bwd(const void* qkv, int64_t ld_qkv, const void* d_out, int64_t ld_do, const float* lse,
+                                 const float* delta, void* dqkv, int64_t ld_dqkv, float* dq32, int32_t M, int32_t T,
+                                 int32_t heads, int32_t head_dim, float scale, idf_stream_t stream) {
+  if (!qkv || !d_out || !lse || !delta || !dqkv) return fail(IDF_ERR_ARG, "attention_bwd: null pointer");
   if (T < 16 || (T & (T - 1)) != 0) return fail(IDF_ERR_UNSUPPORTED, "attention_bwd: T = %d must be a power of two >= 16", T);
   if (M <= 0 || M % T != 0) return fail(IDF_ERR_ARG, "attention_bwd: M = %d not a multiple of T = %d", M, T);
   const int C = heads * head_dim;
@@ -351,18 +347,10 @@ extern "C" int idf_attention_bwd(const void* qk, int64_t ld_qk, const void* vt, 
   p.scale_log2e = scale * 1.4426950408889634f;
   int rc;
   {
-    const uint64_t dims[2] = {(uint64_t)(2 * C), (uint64_t)M};
-    const uint64_t strides[1] = {(uint64_t)ld_qk * 2};
+    const uint64_t dims[2] = {(uint64_t)(3 * C), (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)ld_qkv * 2};
     const uint32_t box[2] = {64u, 128u};
-    if ((rc = encode_tmap(&p.tmQK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qk, 2, dims, strides, box,
-                          CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
-      return rc;
-  }
-  {
-    const uint64_t dims[2] = {(uint64_t)M, (uint64_t)C};
-    const uint64_t strides[1] = {(uint64_t)ld_vt * 2};
-    const uint32_t box[2] = {64u, (uint32_t)head_dim};
-    if ((rc = encode_tmap(&p.tmVT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, vt, 2, dims, strides, box,
+    if ((rc = encode_tmap(&p.tmQK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, 2, dims, strides, box,
                           CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
       return rc;
   }

@@ -799,11 +799,17 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
       const long long u = units * sfac;
       return (double)u / (double)(((u + sm_count() - 1) / sm_count()) * sm_count());
     };
-    double best = eff(1);
-    for (int sfac = 2; sfac <= 4; ++sfac) {
-      if (p.kb_total / sfac < 8) break;
-      if ((long long)sfac * M * a->N * 4 > a->ws_bytes) break;
-      if (eff(sfac) > best * 1.15) { best = eff(sfac); splits = sfac; }
+    if (a->force_splits > 1) {
+      if ((long long)a->force_splits * M * a->N * 4 > a->ws_bytes || p.kb_total < a->force_splits)
+        return fail(IDF_ERR_ARG, "igemm: force_splits = %d does not fit the workspace / K", a->force_splits);
+      splits = a->force_splits;
+    } else {
+      double best = eff(1);
+      for (int sfac = 2; sfac <= 4; ++sfac) {
+        if (p.kb_total / sfac < 8) break;
+        if ((long long)sfac * M * a->N * 4 > a->ws_bytes) break;
+        if (eff(sfac) > best * 1.15) { best = eff(sfac); splits = sfac; }
+      }
     }
   }
   p.splits = splits;

@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restric
   const int lane = threadIdx.x & 31;
   if (j >= J) return;
   const float4* w4 = reinterpret_cast<const float4*>(W + (long long)j * K);
-  for (int r0 = 0; r0 < R; r0 += 8) {
+  // blockIdx.y walks the 8-row chunks in parallel (gridDim.y == 1: one CTA loops over all of them)
+  for (int r0 = blockIdx.y * 8; r0 < R; r0 += gridDim.y * 8) {
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -611,12 +612,13 @@ extern "C" int idf_embed_time_class_train(const int64_t* t, const int64_t* ctx, 
   float* sv = temb + (long long)R * D;
   sincos_kernel<<<(R * D + 255) / 256, 256, 0, s>>>(t, factor, e, R, D);
   const int wpb = 8;
-  linear_rows_kernel<true><<<(4 * D + wpb - 1) / wpb, 256, 0, s>>>(e, D, w1, b1, a1, 4 * D, R, D, 4 * D, nullptr,
-                                                                   nullptr, nullptr, z1);
-  linear_rows_kernel<true><<<(D + wpb - 1) / wpb, 256, 0, s>>>(a1, 4 * D, w2, b2, sv, D, R, 4 * D, D, class_w, ctx,
-                                                               ctx_mask, temb);
-  linear_rows_kernel<false><<<(P + wpb - 1) / wpb, 256, 0, s>>>(sv, D, wp, bp, out, P, R, D, P, nullptr, nullptr,
-                                                                nullptr);
+  const int rc = (R + 7) / 8;  // row chunks run as separate CTAs (R = batch size here, not a handful of rows)
+  linear_rows_kernel<true><<<dim3((4 * D + wpb - 1) / wpb, rc), 256, 0, s>>>(e, D, w1, b1, a1, 4 * D, R, D, 4 * D, nullptr,
+                                                                             nullptr, nullptr, z1);
+  linear_rows_kernel<true><<<dim3((D + wpb - 1) / wpb, rc), 256, 0, s>>>(a1, 4 * D, w2, b2, sv, D, R, 4 * D, D, class_w, ctx,
+                                                                         ctx_mask, temb);
+  linear_rows_kernel<false><<<dim3((P + wpb - 1) / wpb, rc), 256, 0, s>>>(sv, D, wp, bp, out, P, R, D, P, nullptr, nullptr,
+                                                                          nullptr);
   return check_cuda(cudaGetLastError(), "embed_train launch");
 }
 

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(GNB_MAX_WARPS * 32) groupnorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ dy, long long lddy,
     const __nv_bfloat16* __restrict__ add, long long ldadd, __nv_bfloat16* __restrict__ dx, long long lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
-    float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int HW, int C, int groups, int cpg, int gps, int V) {
+    float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, float* __restrict__ colsum_part, long long ld_cs,
+    int HW, int C, int groups, int cpg, int gps, int V) {
   __shared__ float ch_a[GNB_MAX_WARPS][VP * 8];
   __shared__ float ch_b[GNB_MAX_WARPS][VP * 8];
   __shared__ float ct_a[VP * 8];
@@ -133,38 +134,79 @@ __global__ void __launch_bounds__(GNB_MAX_WARPS * 32) groupnorm_bwd_kernel(
     g_b[threadIdx.x] = c * inv_cnt;
   }
   __syncthreads();
-  if (!active) return;
-  float ma[8], mb[8];
+  float ma[8], mb[8], cs[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int g = (v * 8 + e) / cpg;
+    const int g = active ? (v * 8 + e) / cpg : 0;
     ma[e] = g_a[g];
     mb[e] = g_b[g];
+    cs[e] = 0.f;
   }
-  __nv_bfloat16* dxb = dx + (long long)b * HW * lddx + c0 + v * 8;
-  const __nv_bfloat16* ab = add ? add + (long long)b * HW * ldadd + c0 + v * 8 : nullptr;
-  for (int pix = warp * RPW + prl; pix < HW; pix += rows_per_iter) {
-    const uint4 xr = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
-    const uint4 dr = *reinterpret_cast<const uint4*>(dyb + (long long)pix * lddy);
-    float xf[8], df[8], af[8];
-    unpack8t(xr, xf);
-    unpack8t(dr, df);
-    if (ab) {
-      const uint4 ar = *reinterpret_cast<const uint4*>(ab + (long long)pix * ldadd);
-      unpack8t(ar, af);
-    }
-    float o[8];
+  if (active) {
+    __nv_bfloat16* dxb = dx + (long long)b * HW * lddx + c0 + v * 8;
+    const __nv_bfloat16* ab = add ? add + (long long)b * HW * ldadd + c0 + v * 8 : nullptr;
+    for (int pix = warp * RPW + prl; pix < HW; pix += rows_per_iter) {
+      const uint4 xr = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
+      const uint4 dr = *reinterpret_cast<const uint4*>(dyb + (long long)pix * lddy);
+      float xf[8], df[8], af[8];
+      unpack8t(xr, xf);
+      unpack8t(dr, df);
+      if (ab) {
+        const uint4 ar = *reinterpret_cast<const uint4*>(ab + (long long)pix * ldadd);
+        unpack8t(ar, af);
+      }
+      float o[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xh = fmaf(xf[e], rs[e], -mr[e]);
-      float dz = df[e];
-      if (SILU) dz *= silu_grad(fmaf(ga[e], xh, be[e]));
-      float d = rs[e] * (fmaf(ga[e], dz, -ma[e]) - xh * mb[e]);
-      if (ab) d += af[e];
-      o[e] = d;
+      for (int e = 0; e < 8; ++e) {
+        const float xh = fmaf(xf[e], rs[e], -mr[e]);
+        float dz = df[e];
+        if (SILU) dz *= silu_grad(fmaf(ga[e], xh, be[e]));
+        float d = rs[e] * (fmaf(ga[e], dz, -ma[e]) - xh * mb[e]);
+        if (ab) d += af[e];
+        o[e] = d;
+        cs[e] += d;
+      }
+      *reinterpret_cast<uint4*>(dxb + (long long)pix * lddx) = pack8t(o);
     }
-    *reinterpret_cast<uint4*>(dxb + (long long)pix * lddx) = pack8t(o);
   }
+  if (colsum_part == nullptr) return;
+  // per-sample column sums of dx: the bias gradient of the layer that produced x (and, for a first-half conv, the
+  // per-sample gradient of its time-projection bias)
+#pragma unroll
+  for (int off = VP; off < 32; off <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], off);
+  }
+  if (prl == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ch_a[warp][v * 8 + e] = cs[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < V * 8) {
+    float a = 0.f;
+    for (int w = 0; w < nwarps; ++w) a += ch_a[w][threadIdx.x];
+    colsum_part[(long long)b * ld_cs + c0 + threadIdx.x] = a;
+  }
+}
+
+// Finalisation of one GroupNorm backward: dgamma / dbeta (and up to two copies of the fused bias gradient) as the
+// fixed-order sums over the batch of the per-sample partials.
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ dgamma_part, const float* __restrict__ dbeta_part,
+                                       const float* __restrict__ colsum_part, long long ld_cs, int B, int C,
+                                       float* __restrict__ g_gamma, float* __restrict__ g_beta,
+                                       float* __restrict__ g_bias1, float* __restrict__ g_bias2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, bb = 0.f, cc = 0.f;
+  for (int r = 0; r < B; ++r) {
+    a += dgamma_part[(long long)r * C + c];
+    bb += dbeta_part[(long long)r * C + c];
+    if (colsum_part != nullptr) cc += colsum_part[(long long)r * ld_cs + c];
+  }
+  g_gamma[c] = a;
+  g_beta[c] = bb;
+  if (g_bias1 != nullptr) g_bias1[c] = cc;
+  if (g_bias2 != nullptr) g_bias2[c] = cc;
 }
 
 // out[c] (+)= sum_r in[r, c]  (rows summed in order)
@@ -649,8 +691,9 @@ static inline __nv_bfloat16* BF(void* p) { return reinterpret_cast<__nv_bfloat16
 
 extern "C" int idf_groupnorm_silu_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* add,
                                       int64_t ldadd, void* dx, int64_t lddx, const float* gamma, const float* beta,
-                                      const float* stats, float* dgamma_part, float* dbeta_part, int32_t B, int32_t HW,
-                                      int32_t C, int32_t groups, int32_t apply_silu, idf_stream_t stream) {
+                                      const float* stats, float* dgamma_part, float* dbeta_part, float* colsum_part,
+                                      int64_t ld_cs, int32_t B, int32_t HW, int32_t C, int32_t groups,
+                                      int32_t apply_silu, idf_stream_t stream) {
   if (!x || !dy || !dx || !gamma || !beta || !stats || !dgamma_part || !dbeta_part)
     return fail(IDF_ERR_ARG, "groupnorm_bwd: null pointer");
   if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups != 0) return fail(IDF_ERR_ARG, "groupnorm_bwd: bad shape");
@@ -672,11 +715,22 @@ extern "C" int idf_groupnorm_silu_bwd(const void* x, int64_t ldx, const void* dy
 #define GNB_LAUNCH(SILU_, VP_)                                                                                        \
   groupnorm_bwd_kernel<SILU_, VP_><<<grid, threads, 0, S(stream)>>>(BF(x), ldx, BF(dy), lddy, BF(add), ldadd, BF(dx),  \
                                                                     lddx, gamma, beta, stats, dgamma_part, dbeta_part, \
-                                                                    HW, C, groups, cpg, gps, V)
+                                                                    colsum_part, ld_cs, HW, C, groups, cpg, gps, V)
   if (VP == 4) { if (apply_silu) GNB_LAUNCH(true, 4); else GNB_LAUNCH(false, 4); }
   else { if (apply_silu) GNB_LAUNCH(true, 8); else GNB_LAUNCH(false, 8); }
 #undef GNB_LAUNCH
   return check_cuda(cudaGetLastError(), "groupnorm_bwd launch");
+}
+
+extern "C" int idf_groupnorm_bwd_finalize(const float* dgamma_part, const float* dbeta_part, const float* colsum_part,
+                                          int64_t ld_cs, int32_t B, int32_t C, float* g_gamma, float* g_beta,
+                                          float* g_bias1, float* g_bias2, idf_stream_t stream) {
+  if (!dgamma_part || !dbeta_part || !g_gamma || !g_beta || B <= 0 || C <= 0)
+    return fail(IDF_ERR_ARG, "groupnorm_bwd_finalize: bad argument");
+  if ((g_bias1 || g_bias2) && !colsum_part) return fail(IDF_ERR_ARG, "groupnorm_bwd_finalize: bias without colsum");
+  gn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(dgamma_part, dbeta_part, colsum_part, ld_cs, B, C,
+                                                                 g_gamma, g_beta, g_bias1, g_bias2);
+  return check_cuda(cudaGetLastError(), "groupnorm_bwd_finalize launch");
 }
 
 extern "C" int idf_reduce_rows_f32(const float* in, int64_t ld, int32_t rows, int32_t cols, float* out,
@@ -718,7 +772,7 @@ extern "C" int idf_zero_last_rowcol(void* x, int64_t ldx, int32_t B, int32_t H, 
   return check_cuda(cudaGetLastError(), "zero_last_rowcol launch");
 }
 
-static int pick_band(int H) { return H % 8 == 0 ? 8 : 0; }
+static int pick_band(int H) { return H % 2 == 0 ? 2 : 0; }
 
 extern "C" int idf_conv3x3_small_cin_wgrad(const float* x, const void* dy, int64_t lddy, float* grad_w, float* part,
                                            int64_t part_bytes, int32_t B, int32_t Cin, int32_t H, int32_t W,
@@ -726,11 +780,11 @@ extern "C" int idf_conv3x3_small_cin_wgrad(const float* x, const void* dy, int64
   if (!x || !dy || !grad_w || !part) return fail(IDF_ERR_ARG, "small_cin_wgrad: null pointer");
   if (Cin != 3 || Cout % 128 != 0) return fail(IDF_ERR_UNSUPPORTED, "small_cin_wgrad: Cin must be 3, Cout %% 128 == 0");
   const int RB = pick_band(H);
-  if (RB == 0) return fail(IDF_ERR_UNSUPPORTED, "small_cin_wgrad: H %% 8 != 0");
+  if (RB == 0) return fail(IDF_ERR_UNSUPPORTED, "small_cin_wgrad: H %% 2 != 0");
   const int nparts = B * (H / RB);
   if ((long long)nparts * Cout * 27 * 4 > part_bytes) return fail(IDF_ERR_ARG, "small_cin_wgrad: scratch too small");
   const int smem = 3 * (RB + 2) * (W + 2) * 4;
-  small_cin_wgrad_kernel<3, 8><<<dim3(nparts, Cout / 128), 128, smem, S(stream)>>>(x, BF(dy), lddy, part, H, W, Cout);
+  small_cin_wgrad_kernel<3, 2><<<dim3(nparts, Cout / 128), 128, smem, S(stream)>>>(x, BF(dy), lddy, part, H, W, Cout);
   reduce_rows_kernel<<<(Cout * 27 + 127) / 128, 128, 0, S(stream)>>>(part, (long long)Cout * 27, nparts, Cout * 27, grad_w, 0);
   return check_cuda(cudaGetLastError(), "small_cin_wgrad launch");
 }
@@ -742,11 +796,11 @@ extern "C" int idf_conv3x3_small_cout_bwd(const void* h, int64_t ldh, const floa
   if (!h || !dout || !w || !dh || !grad_w || !grad_b || !part) return fail(IDF_ERR_ARG, "small_cout_bwd: null pointer");
   if (Cout != 3 || C % 128 != 0) return fail(IDF_ERR_UNSUPPORTED, "small_cout_bwd: Cout must be 3, C %% 128 == 0");
   const int RB = pick_band(H);
-  if (RB == 0) return fail(IDF_ERR_UNSUPPORTED, "small_cout_bwd: H %% 8 != 0");
+  if (RB == 0) return fail(IDF_ERR_UNSUPPORTED, "small_cout_bwd: H %% 2 != 0");
   const int nparts = B * (H / RB);
   if ((long long)nparts * Cout * C * 9 * 4 > part_bytes) return fail(IDF_ERR_ARG, "small_cout_bwd: scratch too small");
-  small_cout_dgrad_kernel<3, 8><<<dim3(nparts, C / 128), 128, 3 * (RB + 2) * (W + 2) * 4, S(stream)>>>(dout, w, BF(dh), lddh, H, W, C);
-  small_cout_wgrad_kernel<3, 8><<<dim3(nparts, C / 128), 128, 3 * RB * W * 4, S(stream)>>>(BF(h), ldh, dout, part, H, W, C);
+  small_cout_dgrad_kernel<3, 2><<<dim3(nparts, C / 128), 128, 3 * (RB + 2) * (W + 2) * 4, S(stream)>>>(dout, w, BF(dh), lddh, H, W, C);
+  small_cout_wgrad_kernel<3, 2><<<dim3(nparts, C / 128), 128, 3 * RB * W * 4, S(stream)>>>(BF(h), ldh, dout, part, H, W, C);
   reduce_rows_kernel<<<(Cout * C * 9 + 127) / 128, 128, 0, S(stream)>>>(part, (long long)Cout * C * 9, nparts, Cout * C * 9, grad_w, 0);
   nchw_channel_sum_kernel<<<Cout, 256, 0, S(stream)>>>(dout, B, Cout, H * W, grad_b);
   return check_cuda(cudaGetLastError(), "small_cout_bwd launch");

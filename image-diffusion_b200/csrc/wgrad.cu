@@ -304,7 +304,9 @@ extern "C" int idf_conv2d_wgrad(const idf_wgrad_args* a, idf_stream_t stream) {
   if (bn == 0) return fail(IDF_ERR_UNSUPPORTED, "wgrad: N = %d has no legal tile width", p.N);
   const long long per_split = (long long)a->cout * p.N * 4;
   const int units = p.m_tiles * (p.N / bn);
-  int splits = (sm_count() + units - 1) / units;
+  // one wave: the largest split count whose work units still fit the SM count (a second, partly filled wave would
+  // cost a full pass of the slowest unit)
+  int splits = units >= sm_count() ? 1 : sm_count() / units;
   if (splits > p.kb_total / 2) splits = p.kb_total / 2;
   if (splits > 64) splits = 64;
   if (splits < 1) splits = 1;

@@ -85,8 +85,10 @@ class UnetEngine:
         self.ws = Workspace(device)
         self.L, self.heads, self.G = arch["num_res_layers"], arch["num_heads"], arch["num_groups"]
         self.taps = None  # debugging aid: set to a dict to collect fp32 copies of intermediate activations
-        # split-K scratch: disabled by default — measured no gain at 8x8 and it would make the summation order (and so
-        # the bits) depend on the batch size; the kernel path stays available (tests/test_kernels_gpu.py)
+        # split-K: only the 4x4 stage (48 output tiles for 148 SMs at batch 96), with a FIXED split count so that the
+        # summation order - and the output bits - do not depend on the batch size. At 8x8 the fp32 partial traffic
+        # eats the gain (measured).
+        self.splitk = int(__import__("os").environ.get("IDF_SPLITK_4X4", "3"))
         self.splitk_ws = None
         self.downs, self.mids, self.ups = unet_blocks(arch)
         for _, cin, cout in self.downs + self.mids + self.ups:
@@ -152,6 +154,9 @@ class UnetEngine:
         B, H, W = x.grid
         M, HW = x.M, x.H * x.W
         hd = cout // self.heads
+        sk = {}
+        if self.splitk > 1 and HW <= 16:
+            sk = dict(ws=ws.get("splitk", 1, self.splitk * M * cout, torch.float32), splits=self.splitk)
         for l in range(self.L):
             cin = x.C
             k = f"{p}.{l}"
@@ -160,20 +165,19 @@ class UnetEngine:
             y1 = ws.get("y1", M, cout)
             off = self.tp_off[(p, l)]
             ops.igemm([(h1, x.grid, cin, 9)], w[k + ".w1"], cout, y1, bias=w[k + ".b1"],
-                      rowbias=table[:, off:off + cout], rowbias_idx=idx, ws=self.splitk_ws)
+                      rowbias=table[:, off:off + cout], rowbias_idx=idx, **sk)
             h2 = ws.get("h2", M, cout)
             ops.groupnorm_silu(y1, h2, w[k + ".g2w"], w[k + ".g2b"], B, HW, cout, G, True)
             x2 = ws.get("x2", M, cout)
-            ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"],
-                      ws=self.splitk_ws)
+            ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"], **sk)
             h3 = ws.get("h3", M, cout)
             ops.groupnorm_silu(x2, h3, w[k + ".g3w"], w[k + ".g3b"], B, HW, cout, G, False)
-            qk = ws.get("qk", M, 2 * cout)
-            vt = ws.get("vt", cout, M)
-            ops.igemm([(h3, (1, 1, M), cout, 1)], w[k + ".wqkv"], 3 * cout, qk, bias=w[k + ".bqkv"], vt=vt,
-                      vt_col0=2 * cout)
+            # Q | K | V token-major in one buffer: the attention kernel takes V tiles as MN-major tcgen05 operands, so
+            # the QKV GEMM has a plain TMA-store epilogue (no transposed V^T copy)
+            qk = ws.get("qkv", M, 3 * cout)
+            ops.igemm([(h3, (1, 1, M), cout, 1)], w[k + ".wqkv"], 3 * cout, qk, bias=w[k + ".bqkv"])
             o = ws.get("o", M, cout)
-            ops.attention(qk, vt, o, M, HW, self.heads, hd)
+            ops.attention_qkv(qk, o, M, HW, self.heads, hd)
             if l == self.L - 1 and final_dst is not None:
                 dst = final_dst
             else:
@@ -218,8 +222,11 @@ class UnetEngine:
             planes = ws.get("s2d", x.M, cout)  # four parity planes of the stride-2 conv input, stacked along n
             ops.space_to_depth2(x.t, planes, x.B, x.H, x.W, cout)
             nxt = ws.get("dn", x.M // 4, cout)
+            skd = {}
+            if self.splitk > 1 and (x.H // 2) * (x.W // 2) <= 16:
+                skd = dict(ws=ws.get("splitk", 1, self.splitk * (x.M // 4) * cout, torch.float32), splits=self.splitk)
             ops.igemm([(planes, (4 * x.B, x.H // 2, x.W // 2), cout, 9)], w[f"down.{i}.w"], cout, nxt,
-                      bias=w[f"down.{i}.b"], zero_pad_last=True, s2_batch=x.B, ws=self.splitk_ws)
+                      bias=w[f"down.{i}.b"], zero_pad_last=True, s2_batch=x.B, **skd)
             self._tap(f"down.{i}", nxt)
             x = Act(nxt, x.B, x.H // 2, x.W // 2, cout)
         for p, cin, cout in self.mids:
@@ -229,8 +236,7 @@ class UnetEngine:
             up = ws.get("up", 4 * x.M, c)
             ops.upsample_nearest2x(x.t, up, x.B, x.H, x.W, c)
             cat = cats.pop()
-            ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), c, 9)], w[f"up.{i}.w"], c, cat[:, :c], bias=w[f"up.{i}.b"],
-                      ws=self.splitk_ws)
+            ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), c, 9)], w[f"up.{i}.w"], c, cat[:, :c], bias=w[f"up.{i}.b"])
             self._tap(f"up.{i}", cat)
             x = self._block(p, Act(cat, x.B, 2 * x.H, 2 * x.W, 2 * c), cout, table, row_idx)
         h = ws.get("h1", x.M, x.C)

@@ -32,7 +32,7 @@ class IgemmArgs(C.Structure):
         ("vt", _vp), ("vt_col0", _i32), ("vt_ld", _i64),
         ("zero_pad_last", _i32), ("epi_h", _i32), ("epi_w", _i32), ("s2_batch", _i32),
         ("ws", _vp), ("ws_bytes", _i64),
-        ("custom_taps", _i32), ("tap_dh", C.c_int8 * 9), ("tap_dw", C.c_int8 * 9),
+        ("custom_taps", _i32), ("tap_dh", C.c_int8 * 9), ("tap_dw", C.c_int8 * 9), ("force_splits", _i32),
     ]
 
 
@@ -62,8 +62,9 @@ _SIGNATURES = {
     # training step
     "idf_conv2d_wgrad": [C.POINTER(WgradArgs)],
     "idf_groupnorm_silu_train": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp],
-    "idf_groupnorm_silu_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
-                               _i32, _i32],
+    "idf_groupnorm_silu_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32,
+                               _i32, _i32, _i32],
+    "idf_groupnorm_bwd_finalize": [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp],
     "idf_reduce_rows_f32": [_vp, _i64, _i32, _i32, _vp, _i32],
     "idf_colsum_bf16": [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32],
     "idf_sum2x2_bf16": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32],
@@ -80,7 +81,8 @@ _SIGNATURES = {
     "idf_reparam_add_noise": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32],
     "idf_attention_fwd_train": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
     "idf_attention_delta": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp],
-    "idf_attention_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _f32],
+    "idf_attention_fwd_qkv": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp],
+    "idf_attention_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _f32],
     "idf_f32_to_bf16_rows": [_vp, _vp, _i64, _i64, _i32],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["idf_last_error", "idf_abi_version"])

@@ -24,7 +24,7 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 
 def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
           res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0, ws=None,
-          tap_offsets=None) -> torch.Tensor:
+          tap_offsets=None, splits: int = 0) -> torch.Tensor:
     """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view."""
     a = IgemmArgs()
     if not 1 <= len(segs) <= 2:
@@ -54,6 +54,7 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
     a.s2_batch = s2_batch
     a.ws = ptr(ws)
     a.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
+    a.force_splits = splits
     if tap_offsets is not None:  # explicit (dh, dw) list for segment 0
         a.custom_taps = 1
         for i, (dh, dw) in enumerate(tap_offsets):
@@ -236,13 +237,21 @@ def groupnorm_silu_train(x, y, gamma, beta, B, HW, C, groups, silu, stats, eps: 
     return y
 
 
-def groupnorm_silu_bwd(x, dy, dx, gamma, beta, stats, dgamma_part, dbeta_part, B, HW, C, groups, silu, add=None):
+def groupnorm_silu_bwd(x, dy, dx, gamma, beta, stats, dgamma_part, dbeta_part, B, HW, C, groups, silu, add=None,
+                       colsum_part=None):
     for n, t in (("x", x), ("dy", dy), ("dx", dx)):
         _check_bf16_rows(t, f"groupnorm_bwd {n}")
     call("idf_groupnorm_silu_bwd", x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), ptr(add),
          add.stride(0) if add is not None else 0, dx.data_ptr(), dx.stride(0), gamma.data_ptr(), beta.data_ptr(),
-         stats.data_ptr(), dgamma_part.data_ptr(), dbeta_part.data_ptr(), B, HW, C, groups, 1 if silu else 0)
+         stats.data_ptr(), dgamma_part.data_ptr(), dbeta_part.data_ptr(), ptr(colsum_part),
+         colsum_part.stride(0) if colsum_part is not None else 0, B, HW, C, groups, 1 if silu else 0)
     return dx
+
+
+def groupnorm_bwd_finalize(dgamma_part, dbeta_part, B, C, g_gamma, g_beta, colsum_part=None, g_bias1=None, g_bias2=None):
+    call("idf_groupnorm_bwd_finalize", dgamma_part.data_ptr(), dbeta_part.data_ptr(), ptr(colsum_part),
+         colsum_part.stride(0) if colsum_part is not None else 0, B, C, g_gamma.data_ptr(), g_beta.data_ptr(),
+         ptr(g_bias1), ptr(g_bias2))
 
 
 def reduce_rows(src: torch.Tensor, rows: int, cols: int, out: torch.Tensor, accumulate: bool = False, ld=None):
@@ -339,16 +348,25 @@ def attention_train(qk, vt, out, lse, M, T, heads, head_dim):
     return out
 
 
-def attention_bwd(qk, vt, o, d_out, lse, delta, dqkv, dq32, M, T, heads, head_dim):
+def attention_qkv(qkv, out, M, T, heads, head_dim, lse=None):
+    """softmax(Q K^T / sqrt(hd)) V with Q | K | V read from the token-major (M, 3C) QKV GEMM output."""
+    _check_bf16_rows(qkv, "attention qkv")
+    _check_bf16_rows(out, "attention out")
+    call("idf_attention_fwd_qkv", qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), M, T, heads, head_dim,
+         1.0 / math.sqrt(head_dim), ptr(lse))
+    return out
+
+
+def attention_bwd(qkv, o, d_out, lse, delta, dqkv, dq32, M, T, heads, head_dim):
     """dqkv (M, 3C) bf16 <- [dQ | dK | dV]. dq32: fp32 (M, C) scratch, required (and zeroed here) when T > 128."""
     C = heads * head_dim
     call("idf_attention_delta", d_out.data_ptr(), d_out.stride(0), o.data_ptr(), o.stride(0), M, heads, head_dim,
          delta.data_ptr())
     if T > 128:
         dq32.zero_()
-    call("idf_attention_bwd", qk.data_ptr(), qk.stride(0), vt.data_ptr(), vt.stride(0), d_out.data_ptr(),
-         d_out.stride(0), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), ptr(dq32), M, T, heads,
-         head_dim, 1.0 / math.sqrt(head_dim))
+    call("idf_attention_bwd", qkv.data_ptr(), qkv.stride(0), d_out.data_ptr(), d_out.stride(0), lse.data_ptr(),
+         delta.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), ptr(dq32), M, T, heads, head_dim,
+         1.0 / math.sqrt(head_dim))
     if T > 128:
         call("idf_f32_to_bf16_rows", dq32.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), M, C)
     return dqkv

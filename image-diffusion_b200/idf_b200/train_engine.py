@@ -202,14 +202,13 @@ class UnetTrainEngine:
             ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"])
             h3, st3 = ws.get(k + ".h3", M, cout), ws.get(k + ".st3", B, 2 * G, F32)
             ops.groupnorm_silu_train(x2, h3, w[k + ".g3w"], w[k + ".g3b"], B, HW, cout, G, False, st3)
-            qk, vt = ws.get(k + ".qk", M, 2 * cout), ws.get(k + ".vt", cout, M)
-            ops.igemm([(h3, (1, 1, M), cout, 1)], w[k + ".wqkv"], 3 * cout, qk, bias=w[k + ".bqkv"], vt=vt,
-                      vt_col0=2 * cout)
+            qkv = ws.get(k + ".qkv", M, 3 * cout)
+            ops.igemm([(h3, (1, 1, M), cout, 1)], w[k + ".wqkv"], 3 * cout, qkv, bias=w[k + ".bqkv"])
             o, lse = ws.get(k + ".o", M, cout), ws.get(k + ".lse", M, self.heads, F32)
-            ops.attention_train(qk, vt, o, lse, M, HW, self.heads, hd)
+            ops.attention_qkv(qkv, o, M, HW, self.heads, hd, lse=lse)
             dst = final_dst if (l == self.L - 1 and final_dst is not None) else ws.get(k + ".out", M, cout)
             ops.igemm([(o, (1, 1, M), cout, 1)], w[k + ".wo"], cout, dst, bias=w[k + ".bo"], res=x2)
-            S.update(h1=h1, st1=st1, y1=y1, h2=h2, st2=st2, x2=x2, h3=h3, st3=st3, qk=qk, vt=vt, o=o, lse=lse)
+            S.update(h1=h1, st1=st1, y1=y1, h2=h2, st2=st2, x2=x2, h3=h3, st3=st3, qkv=qkv, o=o, lse=lse)
             x = Act(dst, B, H, W, cout)
         return x
 
@@ -264,12 +263,18 @@ class UnetTrainEngine:
         return dict(wg=ws.get("b.wgws", 1, 24 * 1024 * 1024, F32), ps=ws.get("b.ps", B, 4096, F32),
                     dgp=ws.get("b.dgp", B, 2048, F32), dbp=ws.get("b.dbp", B, 2048, F32))
 
-    def _gn_bwd(self, x2d, dy, dx, gw, gb, st, gname_w, gname_b, B, HW, C, silu, add=None):
+    def _gn_bwd(self, x2d, dy, dx, gw, gb, st, gname_w, gname_b, B, HW, C, silu, add=None, colsum=None, bias1=None,
+                bias2=None):
+        """GroupNorm(+SiLU) backward; `colsum` (B, C view, any row stride) additionally receives the per-sample column
+        sums of dx, whose batch sum goes to the bias gradients bias1 / bias2."""
         sc = self.sc
         dgp, dbp = sc["dgp"].view(-1)[:B * C].view(B, C), sc["dbp"].view(-1)[:B * C].view(B, C)
-        ops.groupnorm_silu_bwd(x2d, dy, dx, gw, gb, st, dgp, dbp, B, HW, C, self.G, silu, add=add)
-        ops.reduce_rows(dgp, B, C, self.g(gname_w))
-        ops.reduce_rows(dbp, B, C, self.g(gname_b))
+        if colsum is None and bias1 is not None:
+            colsum = sc["ps"][:, :C]
+        ops.groupnorm_silu_bwd(x2d, dy, dx, gw, gb, st, dgp, dbp, B, HW, C, self.G, silu, add=add, colsum_part=colsum)
+        ops.groupnorm_bwd_finalize(dgp, dbp, B, C, self.g(gname_w), self.g(gname_b), colsum_part=colsum,
+                                   g_bias1=None if bias1 is None else self.g(bias1),
+                                   g_bias2=None if bias2 is None else self.g(bias2))
 
     def _bwd_block(self, p, dout, cout, dtable, final_name=None):
         """dout: (M, cout) bf16 gradient of the block output. Returns the (M, cin_0) gradient of the block input."""
@@ -291,7 +296,7 @@ class UnetTrainEngine:
             dqkv = ws.get(f"b.dqkv.{M}", M, 3 * cout)
             delta = ws.get(f"b.delta.{M}", M, self.heads, F32)
             dq32 = ws.get(f"b.dq32.{M}.{cout}", M, cout, F32) if HW > 128 else None
-            ops.attention_bwd(S["qk"], S["vt"], S["o"], do, S["lse"], delta, dqkv, dq32, M, HW, self.heads, hd)
+            ops.attention_bwd(S["qkv"], S["o"], do, S["lse"], delta, dqkv, dq32, M, HW, self.heads, hd)
             # QKV Linear (weights stacked q | k | v: adjacent in the flat gradient buffer)
             ops.conv_wgrad(S["h3"], (1, 1, M), cout, 1, dqkv, 3 * cout,
                            self.gspan(a + ".to_q.weight", a + ".to_v.weight"), sc["wg"])
@@ -301,21 +306,20 @@ class UnetTrainEngine:
             # GN3 (no SiLU); the residual path adds dout
             dx2 = ws.get(f"b.dx2.{M}", M, cout)
             self._gn_bwd(S["x2"], dh3, dx2, w[k + ".g3w"], w[k + ".g3b"], S["st3"], a + ".groupnorm.weight",
-                         a + ".groupnorm.bias", B, HW, cout, False, add=dout)
-            # second conv3x3 (+) 1x1 skip conv
+                         a + ".groupnorm.bias", B, HW, cout, False, add=dout,
+                         bias1=f"{p}.second_halfs.{l}.layers.2.bias", bias2=f"{p}.residuals.{l}.bias")
+            # second conv3x3 (+) 1x1 skip conv (their shared bias gradient came out of the GN3 backward above)
             ops.conv_wgrad(S["h2"], grid, cout, 9, dx2, cout, self.g(f"{p}.second_halfs.{l}.layers.2.weight"), sc["wg"])
             ops.conv_wgrad(x.t, grid, cin, 1, dx2, cout, self.g(f"{p}.residuals.{l}.weight"), sc["wg"])
-            ops.colsum(dx2, B, HW, cout, sc["ps"], total=self.g(f"{p}.second_halfs.{l}.layers.2.bias"))
-            ops.reduce_rows(sc["ps"], B, cout, self.g(f"{p}.residuals.{l}.bias"))
             dh2 = ws.get(f"b.dh2.{M}", M, cout)
             ops.igemm([(dx2, grid, cout, 9)], w[k + ".w2d"], cout, dh2)
             dy1 = ws.get(f"b.dy1.{M}", M, cout)
-            self._gn_bwd(S["y1"], dh2, dy1, w[k + ".g2w"], w[k + ".g2b"], S["st2"],
-                         f"{p}.second_halfs.{l}.layers.0.weight", f"{p}.second_halfs.{l}.layers.0.bias", B, HW, cout, True)
-            # first conv3x3 (+ per-sample time bias)
-            ops.conv_wgrad(S["h1"], grid, cin, 9, dy1, cout, self.g(f"{p}.first_halfs.{l}.layers.2.weight"), sc["wg"])
             off = self.tp_off[(p, l)]
-            ops.colsum(dy1, B, HW, cout, dtable[:, off:off + cout], total=self.g(f"{p}.first_halfs.{l}.layers.2.bias"))
+            self._gn_bwd(S["y1"], dh2, dy1, w[k + ".g2w"], w[k + ".g2b"], S["st2"],
+                         f"{p}.second_halfs.{l}.layers.0.weight", f"{p}.second_halfs.{l}.layers.0.bias", B, HW, cout, True,
+                         colsum=dtable[:, off:off + cout], bias1=f"{p}.first_halfs.{l}.layers.2.bias")
+            # first conv3x3 (bias gradient + per-sample time-bias gradient came out of the GN2 backward above)
+            ops.conv_wgrad(S["h1"], grid, cin, 9, dy1, cout, self.g(f"{p}.first_halfs.{l}.layers.2.weight"), sc["wg"])
             dh1 = ws.get(f"b.dh1.{M}.{cin}", M, cin)
             ops.igemm([(dy1, grid, cout, 9)], w[k + ".w1d"], cin, dh1)
             dxa = ws.get(f"b.dxa.{M}.{cin}", M, cin)
@@ -347,7 +351,7 @@ class UnetTrainEngine:
         # out_conv: GN + SiLU + conv 128 -> z
         so = self.saved["out"]
         x = so["x"]
-        part = ws.get("b.edge_part", 1, max(B * (H // 8) * 3 * x.C * 9, B * (H // 8) * x.C * 27), F32)
+        part = ws.get("b.edge_part", 1, max(B * (H // 2) * 3 * x.C * 9, B * (H // 2) * x.C * 27), F32)
         dh = ws.get("b.out.dh", x.M, x.C)
         ops.conv3x3_small_cout_bwd(so["h"], dout_nchw, w["out.w"], dh, self.g("out_conv.2.weight"),
                                    self.g("out_conv.2.bias"), part)

@@ -94,6 +94,9 @@ typedef struct idf_igemm_args {
                            of the 3x3 pattern; w's columns follow the list order. Used for the data gradient of the
                            stride-2 Downsample conv, where each input parity plane sees 4, 2, 2 or 1 taps. */
   int8_t tap_dh[9], tap_dw[9];
+  int32_t force_splits; /* > 1 (needs ws): split K into exactly this many work units per tile instead of the occupancy
+                           heuristic. A fixed count keeps the summation order - and so the output bits - independent
+                           of the batch size. */
 } idf_igemm_args;
 
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);
@@ -267,12 +270,20 @@ int idf_groupnorm_silu_train(const void* x, int64_t ldx, void* y, int64_t ldy, c
  *   dx = rstd * (gamma*dz - mean_g(gamma*dz) - xhat * mean_g(gamma*dz*xhat)) (+ add),  dz = dy * silu'(gamma*xhat+beta)
  * x is the forward INPUT, dy the gradient of the forward output; add (optional, bf16) is summed into dx (second
  * gradient path into the same tensor: the residual / skip branch). dgamma_part / dbeta_part are fp32 (B, C)
- * per-sample contributions; the caller reduces them over B with idf_reduce_rows_f32.
+ * per-sample contributions. colsum_part (optional, fp32, row stride ld_cs) receives the per-sample column sums of dx:
+ * x is the output of a conv, so these are that conv's bias gradient per sample (and the per-sample gradient of its
+ * time-projection bias, components.py:526-527). idf_groupnorm_bwd_finalize sums all three over the batch.
  */
 int idf_groupnorm_silu_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const void* add, int64_t ldadd,
                            void* dx, int64_t lddx, const float* gamma, const float* beta, const float* stats,
-                           float* dgamma_part, float* dbeta_part, int32_t B, int32_t HW, int32_t C, int32_t groups,
-                           int32_t apply_silu, idf_stream_t stream);
+                           float* dgamma_part, float* dbeta_part, float* colsum_part, int64_t ld_cs, int32_t B,
+                           int32_t HW, int32_t C, int32_t groups, int32_t apply_silu, idf_stream_t stream);
+
+/* idf_groupnorm_bwd_finalize — g_gamma[c] = sum_b dgamma_part[b, c], g_beta likewise, and (optional) g_bias1 / g_bias2
+ * = sum_b colsum_part[b, c] (two destinations: the second-half conv and the 1x1 skip conv share their bias gradient). */
+int idf_groupnorm_bwd_finalize(const float* dgamma_part, const float* dbeta_part, const float* colsum_part,
+                               int64_t ld_cs, int32_t B, int32_t C, float* g_gamma, float* g_beta, float* g_bias1,
+                               float* g_bias2, idf_stream_t stream);
 
 /* idf_reduce_rows_f32 — out[c] (+)= sum_r in[r*ld + c], rows added in order (deterministic). */
 int idf_reduce_rows_f32(const float* in, int64_t ld, int32_t rows, int32_t cols, float* out, int32_t accumulate,
@@ -298,14 +309,14 @@ int idf_depth_to_space2(const void* planes, void* y, int64_t ldy, const void* ad
 int idf_zero_last_rowcol(void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C, idf_stream_t stream);
 
 /* idf_conv3x3_small_cin_wgrad — weight gradient of in_conv (unet.py:45): x fp32 NCHW (B, 3, H, W), dy bf16 (M, lddy),
- * grad_w fp32 (Cout, 3, 3, 3). part: fp32 scratch of B*(H/8)*Cout*27 floats. (Bias gradient: idf_colsum_bf16.) */
+ * grad_w fp32 (Cout, 3, 3, 3). part: fp32 scratch of B*(H/2)*Cout*27 floats. (Bias gradient: idf_colsum_bf16.) */
 int idf_conv3x3_small_cin_wgrad(const float* x, const void* dy, int64_t lddy, float* grad_w, float* part,
                                 int64_t part_bytes, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout,
                                 idf_stream_t stream);
 
 /* idf_conv3x3_small_cout_bwd — backward of out_conv's Conv2d (unet.py:100): h bf16 (M, ldh) is its (normalised,
  * activated) input, dout fp32 NCHW (B, 3, H, W) the loss gradient, w fp32 (3, C, 3, 3). Writes dh bf16 (M, lddh),
- * grad_w (3, C, 3, 3), grad_b (3). part: fp32 scratch of B*(H/8)*3*C*9 floats. */
+ * grad_w (3, C, 3, 3), grad_b (3). part: fp32 scratch of B*(H/2)*3*C*9 floats. */
 int idf_conv3x3_small_cout_bwd(const void* h, int64_t ldh, const float* dout, const float* w, void* dh, int64_t lddh,
                                float* grad_w, float* grad_b, float* part, int64_t part_bytes, int32_t B, int32_t C,
                                int32_t H, int32_t W, int32_t Cout, idf_stream_t stream);
@@ -358,17 +369,23 @@ int idf_attention_fwd_train(const void* qk, int64_t ld_qk, const void* vt, int64
 int idf_attention_delta(const void* d_out, int64_t ld_do, const void* out, int64_t ld_o, int32_t M, int32_t heads,
                         int32_t head_dim, float* delta, idf_stream_t stream);
 
+/* idf_attention_fwd_qkv — idf_attention_fwd reading Q, K AND V straight from the token-major (M, ld) QKV matrix
+ * (columns [0,C) Q, [C,2C) K, [2C,3C) V): V tiles are consumed as MN-major tcgen05 operands, so the QKV GEMM needs no
+ * transposing epilogue. lse (optional, fp32 (M, heads)) as in idf_attention_fwd_train. */
+int idf_attention_fwd_qkv(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int32_t M, int32_t T,
+                          int32_t heads, int32_t head_dim, float scale, float* lse, idf_stream_t stream);
+
 /*
  * idf_attention_bwd — backward of components.py:86-94 on tcgen05, probabilities recomputed on chip.
- *   qk, vt      as given to idf_attention_fwd;  d_out bf16 (M, ld_do) gradient of the attention output.
+ *   qkv         bf16 (M, ld_qkv) token-major [Q | K | V] as written by the QKV GEMM;  d_out bf16 (M, ld_do).
  *   dqkv        bf16 (M, ld_dqkv): dQ -> columns [0,C), dK -> [C,2C), dV -> [2C,3C) (token-major: the operand layout
  *               of the QKV Linear's data and weight gradients).
  *   dq32        fp32 (M, C), ZEROED by the caller, required when T > 128: dQ partials of different key tiles are
  *               accumulated there (fp32 reductions); convert with idf_f32_to_bf16_rows. Unused for T <= 128.
  */
-int idf_attention_bwd(const void* qk, int64_t ld_qk, const void* vt, int64_t ld_vt, const void* d_out, int64_t ld_do,
-                      const float* lse, const float* delta, void* dqkv, int64_t ld_dqkv, float* dq32, int32_t M,
-                      int32_t T, int32_t heads, int32_t head_dim, float scale, idf_stream_t stream);
+int idf_attention_bwd(const void* qkv, int64_t ld_qkv, const void* d_out, int64_t ld_do, const float* lse,
+                      const float* delta, void* dqkv, int64_t ld_dqkv, float* dq32, int32_t M, int32_t T,
+                      int32_t heads, int32_t head_dim, float scale, idf_stream_t stream);
 
 /* idf_f32_to_bf16_rows — y[m*ldy + c] = bf16(x[m*C + c]). */
 int idf_f32_to_bf16_rows(const float* x, void* y, int64_t ldy, int64_t M, int32_t C, idf_stream_t stream);

@@ -17,6 +17,13 @@ torch.backends.cuda.matmul.allow_tf32 = False
 
 DEV = "cuda"
 
+
+@pytest.fixture(autouse=True)
+def _grad_enabled():
+    """Other test modules switch autograd off globally; training needs it."""
+    with torch.enable_grad():
+        yield
+
 MID_ARCH = dict(z_dim=3, channels=[128, 256], mid_channels=[256, 256], time_dim=128, num_res_layers=2, num_heads=4,
                 num_groups=32, num_classes=3)
 
