@@ -1,6 +1,7 @@
 #include "host.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -64,6 +65,11 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* ptr, in
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(IDF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return IDF_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("IDF_PDL"); return e != nullptr && atoi(e) != 0; }();
+  return on;
 }
 
 int sm_count() {

@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
   using Cfg = PgCfg<BN, NSTG>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int GPT = (BN + 127) / 128;  // column groups per tile
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -379,6 +380,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -630,8 +632,8 @@ static int launch_persist(const IgemmParams& p, cudaStream_t stream) {
   }
   const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BN) * p.splits;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  igemm_persist_kernel<BN, NSTG><<<grid, PG_THREADS, Cfg::SMEM, stream>>>(p);
-  return check_cuda(cudaGetLastError(), "igemm_persist launch");
+  return check_cuda(launch_pdl(igemm_persist_kernel<BN, NSTG>, dim3(grid), dim3(PG_THREADS), Cfg::SMEM, stream, p),
+                    "igemm_persist launch");
 }
 
 // Split-K finish: out[m, n] = bf16( sum_s partial[s][m][n] + bias[n] + rowbias[row(sample(m))][n] ), partials summed in
@@ -642,6 +644,8 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
                                                             const float* __restrict__ rowbias,
                                                             const int* __restrict__ rowbias_idx, int rowbias_ld,
                                                             int H, int W, int zero_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vec = N / 8;
   const long long total = (long long)M * vec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -884,10 +888,11 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     const long long vecs = M * (a->N / 8);
     long long blocks = (vecs + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(
-        reinterpret_cast<const float*>(a->ws), p.split_stride, splits, reinterpret_cast<__nv_bfloat16*>(a->out), a->ldo,
-        (int)M, a->N, a->bias, a->rowbias, a->rowbias_idx, a->rowbias_ld, p.H, p.W, a->zero_pad_last ? 1 : 0);
-    return check_cuda(cudaGetLastError(), "splitk_finish launch");
+    return check_cuda(launch_pdl(splitk_finish_kernel, dim3((unsigned)blocks), dim3(256), 0, st,
+                                 reinterpret_cast<const float*>(a->ws), p.split_stride, splits,
+                                 reinterpret_cast<__nv_bfloat16*>(a->out), (long long)a->ldo, (int)M, a->N, a->bias,
+                                 a->rowbias, a->rowbias_idx, a->rowbias_ld, p.H, p.W, a->zero_pad_last ? 1 : 0),
+                      "splitk_finish launch");
   }
   dim3 grid((unsigned)((M + BLOCK_M - 1) / BLOCK_M), (unsigned)(a->N / BLOCK_N));
   igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);

@@ -87,9 +87,7 @@ __global__ void __launch_bounds__(GNB_MAX_WARPS * 32) groupnorm_bwd_kernel(
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s1[e] = 0.f; s2[e] = 0.f; }
   if (active) {
-    for (int pix = warp * RPW + prl; pix < HW; pix += rows_per_iter) {
-      const uint4 xr = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
-      const uint4 dr = *reinterpret_cast<const uint4*>(dyb + (long long)pix * lddy);
+    auto accum = [&](const uint4& xr, const uint4& dr) {
       float xf[8], df[8];
       unpack8t(xr, xf);
       unpack8t(dr, df);
@@ -101,7 +99,22 @@ __global__ void __launch_bounds__(GNB_MAX_WARPS * 32) groupnorm_bwd_kernel(
         s1[e] += dz;
         s2[e] = fmaf(dz, xh, s2[e]);
       }
+    };
+    // batches of two pixel rows: four independent 16-byte loads in flight per thread
+    int pix = warp * RPW + prl;
+    for (; pix + rows_per_iter < HW; pix += 2 * rows_per_iter) {
+      uint4 xr[2], dr[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        xr[i] = *reinterpret_cast<const uint4*>(xb + (long long)(pix + i * rows_per_iter) * ldx);
+        dr[i] = *reinterpret_cast<const uint4*>(dyb + (long long)(pix + i * rows_per_iter) * lddy);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) accum(xr[i], dr[i]);
     }
+    for (; pix < HW; pix += rows_per_iter)
+      accum(*reinterpret_cast<const uint4*>(xb + (long long)pix * ldx),
+            *reinterpret_cast<const uint4*>(dyb + (long long)pix * lddy));
   }
 #pragma unroll
   for (int off = VP; off < 32; off <<= 1) {
@@ -145,16 +158,11 @@ __global__ void __launch_bounds__(GNB_MAX_WARPS * 32) groupnorm_bwd_kernel(
   if (active) {
     __nv_bfloat16* dxb = dx + (long long)b * HW * lddx + c0 + v * 8;
     const __nv_bfloat16* ab = add ? add + (long long)b * HW * ldadd + c0 + v * 8 : nullptr;
-    for (int pix = warp * RPW + prl; pix < HW; pix += rows_per_iter) {
-      const uint4 xr = *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx);
-      const uint4 dr = *reinterpret_cast<const uint4*>(dyb + (long long)pix * lddy);
+    auto apply_store = [&](const uint4& xr, const uint4& dr, const uint4& ar, int pix) {
       float xf[8], df[8], af[8];
       unpack8t(xr, xf);
       unpack8t(dr, df);
-      if (ab) {
-        const uint4 ar = *reinterpret_cast<const uint4*>(ab + (long long)pix * ldadd);
-        unpack8t(ar, af);
-      }
+      if (ab) unpack8t(ar, af);
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -167,7 +175,25 @@ __global__ void __launch_bounds__(GNB_MAX_WARPS * 32) groupnorm_bwd_kernel(
         cs[e] += d;
       }
       *reinterpret_cast<uint4*>(dxb + (long long)pix * lddx) = pack8t(o);
+    };
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    int pix = warp * RPW + prl;
+    for (; pix + rows_per_iter < HW; pix += 2 * rows_per_iter) {
+      uint4 xr[2], dr[2], ar[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const long long pp = pix + i * rows_per_iter;
+        xr[i] = *reinterpret_cast<const uint4*>(xb + pp * ldx);
+        dr[i] = *reinterpret_cast<const uint4*>(dyb + pp * lddy);
+        ar[i] = ab ? *reinterpret_cast<const uint4*>(ab + pp * ldadd) : zero4;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) apply_store(xr[i], dr[i], ar[i], pix + i * rows_per_iter);
     }
+    for (; pix < HW; pix += rows_per_iter)
+      apply_store(*reinterpret_cast<const uint4*>(xb + (long long)pix * ldx),
+                  *reinterpret_cast<const uint4*>(dyb + (long long)pix * lddy),
+                  ab ? *reinterpret_cast<const uint4*>(ab + (long long)pix * ldadd) : zero4, pix);
   }
   if (colsum_part == nullptr) return;
   // per-sample column sums of dx: the bias gradient of the layer that produced x (and, for a first-half conv, the
