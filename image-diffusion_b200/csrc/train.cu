@@ -217,22 +217,36 @@ __global__ void __launch_bounds__(GNB_MAX_WARPS * 32) groupnorm_bwd_kernel(
 
 // Finalisation of one GroupNorm backward: dgamma / dbeta (and up to two copies of the fused bias gradient) as the
 // fixed-order sums over the batch of the per-sample partials.
-__global__ void gn_bwd_finalize_kernel(const float* __restrict__ dgamma_part, const float* __restrict__ dbeta_part,
-                                       const float* __restrict__ colsum_part, long long ld_cs, int B, int C,
-                                       float* __restrict__ g_gamma, float* __restrict__ g_beta,
-                                       float* __restrict__ g_bias1, float* __restrict__ g_bias2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(
+    const float* __restrict__ dgamma_part, const float* __restrict__ dbeta_part, const float* __restrict__ colsum_part,
+    long long ld_cs, int B, int C, float* __restrict__ g_gamma, float* __restrict__ g_beta, float* __restrict__ g_bias1,
+    float* __restrict__ g_bias2) {
+  // 32 channels x 8 row groups per CTA: row group k sums samples k, k+8, ...; the eight partials are then added in
+  // order (fixed summation order, independent loads in flight)
+  __shared__ float red[3][8][33];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float a = 0.f, bb = 0.f, cc = 0.f;
-  for (int r = 0; r < B; ++r) {
-    a += dgamma_part[(long long)r * C + c];
-    bb += dbeta_part[(long long)r * C + c];
-    if (colsum_part != nullptr) cc += colsum_part[(long long)r * ld_cs + c];
+  if (c < C) {
+    for (int r = rg; r < B; r += 8) {
+      a += dgamma_part[(long long)r * C + c];
+      bb += dbeta_part[(long long)r * C + c];
+      if (colsum_part != nullptr) cc += colsum_part[(long long)r * ld_cs + c];
+    }
   }
-  g_gamma[c] = a;
-  g_beta[c] = bb;
-  if (g_bias1 != nullptr) g_bias1[c] = cc;
-  if (g_bias2 != nullptr) g_bias2[c] = cc;
+  red[0][rg][cl] = a;
+  red[1][rg][cl] = bb;
+  red[2][rg][cl] = cc;
+  __syncthreads();
+  if (rg == 0 && c < C) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s0 += red[0][k][cl]; s1 += red[1][k][cl]; s2 += red[2][k][cl]; }
+    g_gamma[c] = s0;
+    g_beta[c] = s1;
+    if (g_bias1 != nullptr) g_bias1[c] = s2;
+    if (g_bias2 != nullptr) g_bias2[c] = s2;
+  }
 }
 
 // out[c] (+)= sum_r in[r, c]  (rows summed in order)
@@ -754,8 +768,8 @@ extern "C" int idf_groupnorm_bwd_finalize(const float* dgamma_part, const float*
   if (!dgamma_part || !dbeta_part || !g_gamma || !g_beta || B <= 0 || C <= 0)
     return fail(IDF_ERR_ARG, "groupnorm_bwd_finalize: bad argument");
   if ((g_bias1 || g_bias2) && !colsum_part) return fail(IDF_ERR_ARG, "groupnorm_bwd_finalize: bias without colsum");
-  gn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(dgamma_part, dbeta_part, colsum_part, ld_cs, B, C,
-                                                                 g_gamma, g_beta, g_bias1, g_bias2);
+  gn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, S(stream)>>>(dgamma_part, dbeta_part, colsum_part, ld_cs, B, C, g_gamma,
+                                                               g_beta, g_bias1, g_bias2);
   return check_cuda(cudaGetLastError(), "groupnorm_bwd_finalize launch");
 }
 

@@ -13,7 +13,9 @@
 // ~10..100 output tiles of a layer fill 148 SMs. Partials go to an fp32 workspace; wgrad_finish_kernel adds them
 // in split order (deterministic) and scatters into PyTorch's OIHW parameter layout.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Warp roles (224 threads): warp 0 = TMA producer (dY chunks + first half of the X chunks), warp 6 = second TMA
+// producer (the other X chunks: six small boxes per k-block are too many for one issuing thread), warp 1 = TMEM
+// allocator + MMA issuer, warps 2..5 = epilogue.
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,7 +28,7 @@ namespace idf {
 constexpr int WG_BM = 128;
 constexpr int WG_BK = 64;                 // pixels per k-block
 constexpr int WG_CHUNK_BYTES = 64 * 128;  // one {64 channels x 64 pixels} box
-constexpr int WG_THREADS = 192;
+constexpr int WG_THREADS = 224;
 
 struct WgradParams {
   CUtensorMap tmDY;  // 2-D (M, Cout), box {64, 64}
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     tma_prefetch_desc(&p.tmDY);
     tma_prefetch_desc(&p.tmX);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);  // one arrive.expect_tx per producer warp
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -95,28 +97,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 0 || warp == 6) {
     if (elect_one()) {
+      constexpr int NCH = BN / 64;        // X chunks per stage
+      constexpr int C_SPLIT = NCH / 2;    // warp 0 loads dY + chunks [0, C_SPLIT), warp 6 chunks [C_SPLIT, NCH)
+      const bool first = warp == 0;
+      const int c_lo = first ? 0 : C_SPLIT, c_hi = first ? C_SPLIT : NCH;
+      const uint32_t my_bytes = (uint32_t)(c_hi - c_lo) * WG_CHUNK_BYTES + (first ? Cfg::A_BYTES : 0);
       int kc = 0;
       for (int u = blockIdx.x; u < total; u += gridDim.x) {
         const int t = u / splits, sp = u % splits;
         const int co0 = (t / n_tiles) * WG_BM;
-        const int g0 = (t % n_tiles) * (BN / 64);  // first 64-column chunk of this tile
+        const int g0 = (t % n_tiles) * NCH;  // first 64-column chunk of this tile
         const int kb0 = (int)((long long)sp * p.kb_total / splits), kb1 = (int)((long long)(sp + 1) * p.kb_total / splits);
         for (int kb = kb0; kb < kb1; ++kb, ++kc) {
           const int s = kc % STAGES;
           mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          mbar_expect_tx(&full_bar[s], my_bytes);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          tma_load_2d(sa, &p.tmDY, &full_bar[s], co0, kb * WG_BK);
-          tma_load_2d(sa + WG_CHUNK_BYTES, &p.tmDY, &full_bar[s], co0 + 64, kb * WG_BK);
+          if (first) {
+            tma_load_2d(sa, &p.tmDY, &full_bar[s], co0, kb * WG_BK);
+            tma_load_2d(sa + WG_CHUNK_BYTES, &p.tmDY, &full_bar[s], co0 + 64, kb * WG_BK);
+          }
           int img0, h0, w0 = 0;
           if (p.matrix) { img0 = 0; h0 = 0; w0 = kb * WG_BK; }
           else if (p.tiles_per_img > 0) { img0 = kb / p.tiles_per_img; h0 = (kb % p.tiles_per_img) * p.tile_h; }
           else { img0 = kb * p.tile_n; h0 = 0; }
-#pragma unroll
-          for (int c = 0; c < BN / 64; ++c) {
+          for (int c = c_lo; c < c_hi; ++c) {
             const int g = g0 + c;
             const int tap = g / p.cb, ci0 = (g % p.cb) * 64;
             tma_load_4d(sb + c * WG_CHUNK_BYTES, &p.tmX, &full_bar[s], ci0, w0 + p.dw[tap], h0 + p.dh[tap],
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         umma_commit(&tmem_full[acc]);
       }
     }
-  } else {
+  } else if (warp < 6) {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;

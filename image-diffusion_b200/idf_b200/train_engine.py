@@ -118,67 +118,92 @@ class UnetTrainEngine:
     # ---------------------------------------------------------------------------------------------
     # packed weights (forward + data-gradient layouts), refreshed in place so that addresses stay fixed
     # ---------------------------------------------------------------------------------------------
-    def _pk(self, name, value):
+    def _buf(self, name, rows, cols, dtype=BF16):
         buf = self.pw.get(name)
         if buf is None:
-            self.pw[name] = value.contiguous().clone()
-        else:
-            buf.copy_(value)
+            buf = self.pw[name] = torch.empty(rows, cols, device=self.device, dtype=dtype)
+        return buf
+
+    # tap offsets of the data gradient of a 3x3 stride-1 'same' conv when the weight keeps its (kh, kw) order:
+    # dx[p] = sum_t dy[p - off(t)] W_t^T with off(t) = (kh - 1, kw - 1)
+    DGRAD_TAPS = [(1 - kh, 1 - kw) for kh in range(3) for kw in range(3)]
 
     def prepare(self, force=False):
+        """Refreshes the bf16 operand copies of the weights IN PLACE (fixed addresses: safe inside a captured graph).
+        Every copy is one strided copy kernel that fuses the fp32 -> bf16 cast with the layout permutation; fp32
+        parameters (biases, norm gains, embedding MLP) are used where they live, without a copy."""
         key = tuple((p.data_ptr(), p._version) for p in self.params.values())
         if not force and key == self.pkey:
             return
         self.pkey = key
         sd = {k: v.detach() for k, v in self.params.items()}
-        pk, pd, f = ops.pack_conv_weight, ops.pack_dgrad_weight, lambda t: t.to(F32)
-        for p, cin, cout in self.downs + self.mids + self.ups:
+        pw = self.pw
+
+        def conv_fwd(dst2d, w):      # (O, I, kh, kw) -> (O, kh*kw*I) rows = output channel, columns (tap, ci)
+            o, i, kh, kw = w.shape
+            dst2d.view(o, kh, kw, i).copy_(w.permute(0, 2, 3, 1))
+
+        def conv_dgrad(dst2d, w):    # (O, I, kh, kw) -> (I, kh*kw*O) rows = input channel, columns (tap, co)
+            o, i, kh, kw = w.shape
+            dst2d.view(i, kh, kw, o).copy_(w.permute(1, 2, 3, 0))
+
+        for p, cin0, cout in self.downs + self.mids + self.ups:
             for l in range(self.L):
+                cin = cin0 if l == 0 else cout
                 k, a = f"{p}.{l}", f"{p}.self_attns.{l}"
                 w1, w2 = sd[f"{p}.first_halfs.{l}.layers.2.weight"], sd[f"{p}.second_halfs.{l}.layers.2.weight"]
                 wr = sd[f"{p}.residuals.{l}.weight"]
-                self._pk(k + ".w1", pk(w1))
-                self._pk(k + ".b1", f(sd[f"{p}.first_halfs.{l}.layers.2.bias"]))
-                self._pk(k + ".w2", torch.cat([pk(w2), pk(wr)], dim=1))
-                self._pk(k + ".b2", f(sd[f"{p}.second_halfs.{l}.layers.2.bias"] + sd[f"{p}.residuals.{l}.bias"]))
-                wqkv = torch.cat([sd[a + ".to_q.weight"], sd[a + ".to_k.weight"], sd[a + ".to_v.weight"]], dim=0)
-                self._pk(k + ".wqkv", wqkv.to(BF16))
-                self._pk(k + ".bqkv", f(torch.cat([sd[a + ".to_q.bias"], sd[a + ".to_k.bias"], sd[a + ".to_v.bias"]])))
-                self._pk(k + ".wo", sd[a + ".out_proj.weight"].to(BF16))
-                self._pk(k + ".bo", f(sd[a + ".out_proj.bias"]))
+                conv_fwd(self._buf(k + ".w1", cout, 9 * cin), w1)
+                w2b = self._buf(k + ".w2", cout, 9 * cout + cin)
+                conv_fwd(w2b[:, :9 * cout], w2)
+                w2b[:, 9 * cout:].copy_(wr.view(cout, cin))
+                torch.add(sd[f"{p}.second_halfs.{l}.layers.2.bias"], sd[f"{p}.residuals.{l}.bias"],
+                          out=self._buf(k + ".b2", 1, cout, F32).view(-1))
+                wqkv, wqkvd = self._buf(k + ".wqkv", 3 * cout, cout), self._buf(k + ".wqkvd", cout, 3 * cout)
+                for j, n in enumerate(("to_q", "to_k", "to_v")):
+                    wj = sd[f"{a}.{n}.weight"]
+                    wqkv[j * cout:(j + 1) * cout].copy_(wj)
+                    wqkvd[:, j * cout:(j + 1) * cout].copy_(wj.t())
+                torch.cat([sd[a + ".to_q.bias"], sd[a + ".to_k.bias"], sd[a + ".to_v.bias"]],
+                          out=self._buf(k + ".bqkv", 1, 3 * cout, F32).view(-1))
+                self._buf(k + ".wo", cout, cout).copy_(sd[a + ".out_proj.weight"])
+                self._buf(k + ".wod", cout, cout).copy_(sd[a + ".out_proj.weight"].t())
+                conv_dgrad(self._buf(k + ".w1d", cin, 9 * cout), w1)
+                conv_dgrad(self._buf(k + ".w2d", cout, 9 * cout), w2)
+                self._buf(k + ".wrd", cin, cout).copy_(wr.view(cout, cin).t())
+                pw[k + ".b1"], pw[k + ".bo"] = sd[f"{p}.first_halfs.{l}.layers.2.bias"], sd[a + ".out_proj.bias"]
+                pw[k + ".b2"], pw[k + ".bqkv"] = pw[k + ".b2"].view(-1), pw[k + ".bqkv"].view(-1)
                 for n, key_ in (("g1", f"{p}.first_halfs.{l}.layers.0"), ("g2", f"{p}.second_halfs.{l}.layers.0"),
                                 ("g3", a + ".groupnorm")):
-                    self._pk(f"{k}.{n}w", f(sd[key_ + ".weight"]))
-                    self._pk(f"{k}.{n}b", f(sd[key_ + ".bias"]))
-                # data-gradient layouts
-                self._pk(k + ".w1d", pd(w1))
-                self._pk(k + ".w2d", pd(w2))
-                self._pk(k + ".wrd", pd(wr))
-                self._pk(k + ".wqkvd", wqkv.t().to(BF16))
-                self._pk(k + ".wod", sd[a + ".out_proj.weight"].t().to(BF16))
+                    pw[f"{k}.{n}w"], pw[f"{k}.{n}b"] = sd[key_ + ".weight"], sd[key_ + ".bias"]
         for i in range(len(self.downs)):
             wd, wu = sd[f"downsamples.{i}.down.weight"], sd[f"upsamples.{i}.conv.weight"]
-            self._pk(f"down.{i}.w", pk(wd))
-            self._pk(f"down.{i}.b", f(sd[f"downsamples.{i}.down.bias"]))
-            for j, (offs, wp) in enumerate(ops.pack_s2_dgrad_weights(wd)):
-                self._pk(f"down.{i}.wd{j}", wp)
-                self.pw[f"down.{i}.offs{j}"] = offs
-            self._pk(f"up.{i}.w", pk(wu))
-            self._pk(f"up.{i}.b", f(sd[f"upsamples.{i}.conv.bias"]))
-            self._pk(f"up.{i}.wd", pd(wu))
-        self._pk("in.w", f(sd["in_conv.weight"]))
-        self._pk("in.b", f(sd["in_conv.bias"]))
-        self._pk("out.gw", f(sd["out_conv.0.weight"]))
-        self._pk("out.gb", f(sd["out_conv.0.bias"]))
-        self._pk("out.w", f(sd["out_conv.2.weight"]))
-        self._pk("out.b", f(sd["out_conv.2.bias"]))
-        self._pk("t.factor", f(self.m.time_embedding.factor.detach()))
-        for n, key_ in (("t.w1", "time_embedding.embeddings.0.weight"), ("t.b1", "time_embedding.embeddings.0.bias"),
-                        ("t.w2", "time_embedding.embeddings.2.weight"), ("t.b2", "time_embedding.embeddings.2.bias"),
-                        ("t.cls", "class_embedding.weight")):
-            self._pk(n, f(sd[key_]))
-        self._pk("t.wp", f(torch.cat([sd[f"{p}.time_projs.{l}.1.weight"] for p, l in self.order], dim=0)))
-        self._pk("t.bp", f(torch.cat([sd[f"{p}.time_projs.{l}.1.bias"] for p, l in self.order], dim=0)))
+            c = wd.shape[0]
+            conv_fwd(self._buf(f"down.{i}.w", c, 9 * c), wd)
+            pw[f"down.{i}.b"] = sd[f"downsamples.{i}.down.bias"]
+            for j, (pq, taps) in enumerate(sorted(ops._S2_PLANE_TAPS.items())):
+                dst = self._buf(f"down.{i}.wd{j}", c, len(taps) * c)
+                for t, (kh, kw) in enumerate(taps):
+                    dst[:, t * c:(t + 1) * c].copy_(wd[:, :, kh, kw].t())
+                pw[f"down.{i}.offs{j}"] = [(-(kh >> 1), -(kw >> 1)) for kh, kw in taps]
+            cu = wu.shape[0]
+            conv_fwd(self._buf(f"up.{i}.w", cu, 9 * cu), wu)
+            conv_dgrad(self._buf(f"up.{i}.wd", cu, 9 * cu), wu)
+            pw[f"up.{i}.b"] = sd[f"upsamples.{i}.conv.bias"]
+        pw["in.w"], pw["in.b"] = sd["in_conv.weight"], sd["in_conv.bias"]
+        pw["out.gw"], pw["out.gb"] = sd["out_conv.0.weight"], sd["out_conv.0.bias"]
+        pw["out.w"], pw["out.b"] = sd["out_conv.2.weight"], sd["out_conv.2.bias"]
+        pw["t.factor"] = self.m.time_embedding.factor.detach().to(F32)
+        pw["t.w1"], pw["t.b1"] = sd["time_embedding.embeddings.0.weight"], sd["time_embedding.embeddings.0.bias"]
+        pw["t.w2"], pw["t.b2"] = sd["time_embedding.embeddings.2.weight"], sd["time_embedding.embeddings.2.bias"]
+        pw["t.cls"] = sd["class_embedding.weight"]
+        torch.cat([sd[f"{p}.time_projs.{l}.1.weight"] for p, l in self.order], dim=0, out=self._buf("t.wp", self.P, self.D, F32))
+        torch.cat([sd[f"{p}.time_projs.{l}.1.bias"] for p, l in self.order], dim=0,
+                  out=self._buf("t.bp", 1, self.P, F32).view(-1))
+        pw["t.bp"] = pw["t.bp"].view(-1)
+        for name, t in pw.items():  # the kernels take fp32 parameters as they are stored
+            if isinstance(t, torch.Tensor) and (t.dtype not in (BF16, F32) or not t.is_contiguous()):
+                raise RuntimeError(f"UnetTrainEngine: parameter {name} must be contiguous fp32")
 
     # ---------------------------------------------------------------------------------------------
     # forward (activations kept per layer)
@@ -312,7 +337,7 @@ class UnetTrainEngine:
             ops.conv_wgrad(S["h2"], grid, cout, 9, dx2, cout, self.g(f"{p}.second_halfs.{l}.layers.2.weight"), sc["wg"])
             ops.conv_wgrad(x.t, grid, cin, 1, dx2, cout, self.g(f"{p}.residuals.{l}.weight"), sc["wg"])
             dh2 = ws.get(f"b.dh2.{M}", M, cout)
-            ops.igemm([(dx2, grid, cout, 9)], w[k + ".w2d"], cout, dh2)
+            ops.igemm([(dx2, grid, cout, 9)], w[k + ".w2d"], cout, dh2, tap_offsets=self.DGRAD_TAPS)
             dy1 = ws.get(f"b.dy1.{M}", M, cout)
             off = self.tp_off[(p, l)]
             self._gn_bwd(S["y1"], dh2, dy1, w[k + ".g2w"], w[k + ".g2b"], S["st2"],
@@ -321,7 +346,7 @@ class UnetTrainEngine:
             # first conv3x3 (bias gradient + per-sample time-bias gradient came out of the GN2 backward above)
             ops.conv_wgrad(S["h1"], grid, cin, 9, dy1, cout, self.g(f"{p}.first_halfs.{l}.layers.2.weight"), sc["wg"])
             dh1 = ws.get(f"b.dh1.{M}.{cin}", M, cin)
-            ops.igemm([(dy1, grid, cout, 9)], w[k + ".w1d"], cin, dh1)
+            ops.igemm([(dy1, grid, cout, 9)], w[k + ".w1d"], cin, dh1, tap_offsets=self.DGRAD_TAPS)
             dxa = ws.get(f"b.dxa.{M}.{cin}", M, cin)
             self._gn_bwd(x.t, dh1, dxa, w[k + ".g1w"], w[k + ".g1b"], S["st1"], f"{p}.first_halfs.{l}.layers.0.weight",
                          f"{p}.first_halfs.{l}.layers.0.bias", B, HW, cin, True)
@@ -369,7 +394,7 @@ class UnetTrainEngine:
             ops.conv_wgrad(su["up"], su["grid"], c, 9, dleft, c, self.g(f"upsamples.{i}.conv.weight"), sc["wg"])
             ops.colsum(dleft, b_, h_ * w_, c, sc["ps"], total=self.g(f"upsamples.{i}.conv.bias"))
             dup = ws.get(f"b.dup{i}", b_ * h_ * w_, c)
-            ops.igemm([(dleft, su["grid"], c, 9)], w[f"up.{i}.wd"], c, dup)
+            ops.igemm([(dleft, su["grid"], c, 9)], w[f"up.{i}.wd"], c, dup, tap_offsets=self.DGRAD_TAPS)
             d = ws.get(f"b.dlow{i}", b_ * h_ * w_ // 4, c)
             ops.sum2x2(dup, d, b_, h_ // 2, w_ // 2, c)
             done()
