@@ -791,6 +791,30 @@ extern "C" int idf_space_to_depth2(const void* x, int64_t ldx, void* y, int32_t 
   return check_cuda(cudaGetLastError(), "space_to_depth2 launch");
 }
 
+// uint8 NHWC image batch -> fp32 NCHW, y = x * scale + shift (prepare_dataset.py:104-105: / 127.5 - 1.0 and permute)
+__global__ void u8_nhwc_to_f32_nchw_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, int B, int H, int W,
+                                           int C, float scale, float shift) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % C);
+    const long long b = r / C;
+    y[i] = fmaf((float)x[((b * H + h) * W + w) * C + c], scale, shift);
+  }
+}
+
+extern "C" int idf_u8_nhwc_to_f32_nchw(const uint8_t* x, float* y, int32_t B, int32_t H, int32_t W, int32_t C,
+                                       float scale, float shift, idf_stream_t stream) {
+  if (!x || !y || B <= 0) return fail(IDF_ERR_ARG, "u8_nhwc_to_f32_nchw: bad argument");
+  const long long total = (long long)B * C * H * W;
+  u8_nhwc_to_f32_nchw_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, B, H, W, C,
+                                                                                                        scale, shift);
+  return check_cuda(cudaGetLastError(), "u8_nhwc_to_f32_nchw launch");
+}
+
 extern "C" int idf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t ldy, int32_t B, int32_t C, int32_t HW,
                                          idf_stream_t stream) {
   if (!x || !y) return fail(IDF_ERR_ARG, "nchw_to_nhwc: null pointer");

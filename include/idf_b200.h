@@ -387,6 +387,11 @@ int idf_attention_bwd(const void* qkv, int64_t ld_qkv, const void* d_out, int64_
                       const float* delta, void* dqkv, int64_t ld_dqkv, float* dq32, int32_t M, int32_t T,
                       int32_t heads, int32_t head_dim, float scale, idf_stream_t stream);
 
+/* idf_u8_nhwc_to_f32_nchw — dataset-scale latent extraction front end (scripts/prepare_dataset.py:103-106): uint8
+ * (B, H, W, C) images -> fp32 (B, C, H, W) with y = x * scale + shift (1/127.5, -1). */
+int idf_u8_nhwc_to_f32_nchw(const uint8_t* x, float* y, int32_t B, int32_t H, int32_t W, int32_t C, float scale,
+                            float shift, idf_stream_t stream);
+
 /* idf_f32_to_bf16_rows — y[m*ldy + c] = bf16(x[m*C + c]). */
 int idf_f32_to_bf16_rows(const float* x, void* y, int64_t ldy, int64_t M, int32_t C, idf_stream_t stream);
 

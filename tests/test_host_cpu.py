@@ -236,3 +236,27 @@ def test_grad_buckets_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side pieces either side of the hot path
+# ---------------------------------------------------------------------------------------------
+def test_warmup_lr_matches_reference_formula():
+    """trainers/diffusion_trainer.py:133-138."""
+    from idf_b200.pipeline import warmup_lr
+    lr, ws = 2e-4, 100
+    assert warmup_lr(0, lr, ws) == pytest.approx(lr / 100)
+    assert warmup_lr(50, lr, ws) == pytest.approx(lr / 100 + (lr - lr / 100) * 0.5)
+    assert warmup_lr(100, lr, ws) == lr and warmup_lr(10**6, lr, ws) == lr
+    assert warmup_lr(0, lr, 0) == lr
+
+
+def test_image_grid_matches_make_grid():
+    """scripts/sample_grid.py:44-45: make_grid(images, nrow) then clamp(-1, 1), (x + 1) / 2."""
+    from idf_b200.pipeline import image_grid
+    from torchvision.utils import make_grid
+    imgs = torch.randn(7, 3, 16, 12, generator=torch.Generator().manual_seed(3)) * 1.5
+    ref = (make_grid(imgs, nrow=3).permute(1, 2, 0).clamp(-1.0, 1.0).numpy() + 1) / 2
+    got = image_grid(imgs, nrow=3)
+    assert got.dtype.name == "uint8" and got.shape == ref.shape
+    assert abs(got.astype("float32") / 255.0 - ref).max() <= 0.5 / 255 + 1e-6

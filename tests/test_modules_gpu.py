@@ -336,3 +336,25 @@ def test_vq_config5_batch256_indices():
         _, loss_ref, perp_ref, _ = O.codebook_forward({"codebook.embeddings.weight": w.to(DEV)}, "codebook", z, 0.25)
         assert abs(loss.item() - loss_ref.item()) <= 1e-5 * max(1.0, abs(loss_ref.item()))
         assert abs(perp.item() - perp_ref.item()) <= 1e-2 * perp_ref.item()
+
+
+def test_extract_latents_dataset_wire_format():
+    """SURVEY §8f-1 (scripts/prepare_dataset.py:95-109): uint8 NHWC images -> fp16 [M, 6, 32, 32] latents, batched with
+    a ragged last batch; values against the fp32 oracle encoder."""
+    import numpy as np
+    from idf_b200.pipeline import extract_latents
+    from modules.vae import VAE
+    vsd = O.seeded_state_dict(O.vae_param_shapes(O.VAE_KL_ARCH), 2018)
+    vae = VAE(**O.VAE_KL_ARCH)
+    vae.load_state_dict(vsd)
+    vae = vae.to(DEV).eval()
+    rng = np.random.default_rng(0)
+    images = rng.integers(0, 256, size=(5, 128, 128, 3), dtype=np.uint8)
+    lat = extract_latents(vae, images, batch_size=2)
+    assert lat.dtype == np.float16 and lat.shape == (5, 6, 32, 32)
+    x = torch.from_numpy(images).to(DEV).float() / 127.5 - 1.0
+    ref = O.vae_encode({k: v.to(DEV) for k, v in vsd.items()}, O.VAE_KL_ARCH, x.permute(0, 3, 1, 2))
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    got = torch.from_numpy(lat.astype(np.float32)).to(DEV)
+    err = ((got - ref).norm() / ref.norm()).item()
+    assert err < 3.5e-2, err

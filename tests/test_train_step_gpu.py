@@ -171,3 +171,36 @@ def test_fused_train_step_matches_reference_semantics():
         for _ in range(2):
             l2 = ts.step(lat, c, lr=1e-3).item()
             assert l2 == l2 and l2 < 10
+
+
+def test_trainer_loop_and_reference_format_checkpoints(tmp_path):
+    """LR warm-up + epoch loop + checkpoints in the reference's save_checkpoint layout; the optimizer
+    state loads into a stock torch.optim.Adam over the same parameter order and resumes bit-identically here."""
+    from idf_b200.pipeline import DiffusionTrainer, load_train_checkpoint
+    from modules.components import Scheduler
+    from modules.unet import Unet
+    O, m, sd, *_ = _setup(MID_ARCH, 4, 16, 31)
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(12, 6, 16, 16, generator=g).half().numpy()
+    lab = torch.randint(0, 3, (12,), generator=g).numpy().astype("uint8")
+    tr = DiffusionTrainer(m, Scheduler(1000, device=DEV), 4, 1e-3, warmup_steps=4, epochs=2, checkpoints_dir=str(tmp_path),
+                          log_interval=1, latent_shape=(3, 16, 16))
+    hist = tr.fit(lat, lab, generator=g)
+    assert len(hist) == 6 and all(h[1] == h[1] for h in hist)
+    assert hist[0][3] == pytest.approx(1e-5) and hist[-1][3] == 1e-3  # warm-up from lr/100, then constant
+    ck = torch.load(tmp_path / "unet-epoch-01.pt", weights_only=False)
+    assert set(ck) == {"unet", "optim", "epoch", "architecture"} and ck["epoch"] == 1
+    assert ck["architecture"] == MID_ARCH and set(ck["unet"]) == set(sd)
+    # the optimizer state is what torch.optim.Adam itself would have written
+    ref_m = Unet(**MID_ARCH).to(DEV)
+    ref_m.load_state_dict(ck["unet"])
+    opt = torch.optim.Adam(ref_m.parameters())
+    opt.load_state_dict(ck["optim"])
+    st = opt.state[next(iter(ref_m.parameters()))]
+    assert float(st["step"]) == 6 and st["exp_avg"].shape == next(iter(ref_m.parameters())).shape
+    # resume
+    m2 = Unet(**MID_ARCH).to(DEV).train()
+    tr2 = DiffusionTrainer(m2, Scheduler(1000, device=DEV), 4, 1e-3, 4, 3, checkpoint=str(tmp_path / "unet-epoch-01.pt"),
+                           latent_shape=(3, 16, 16))
+    assert tr2.curr_epoch == 2 and tr2.step_fn.step_count == 6
+    assert torch.equal(tr2.step_fn.exp_avg, tr.step_fn.exp_avg) and torch.equal(tr2.step_fn.flat_param, tr.step_fn.flat_param)
