@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
               ev[i] = fast_exp2(fmaf(__uint_as_float(sv[ch][8 * q + i]), c, -mc));
               ps[i & 3] += ev[i];
             }
-            uint4 o;
+            uint4 o;  // (an ALU-only bf16 pack instead of F2FP on the XU pipe measured no faster: 317 vs 316 us)
             o.x = pack_bf16x2(ev[0], ev[1]);
             o.y = pack_bf16x2(ev[2], ev[3]);
             o.z = pack_bf16x2(ev[4], ev[5]);

@@ -30,7 +30,7 @@ constexpr int TMEM_COLS = 128;
 constexpr int IGEMM_THREADS = 192;
 constexpr int IGEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 
-enum : int { F_RES = 1, F_ZERO_PAD = 2, F_VT = 4, F_OUT_F32 = 8 };
+enum : int { F_RES = 1, F_ZERO_PAD = 2, F_VT = 4, F_OUT_F32 = 8, F_OUT_UP2 = 16 };
 
 struct IgemmParams {
   CUtensorMap tmA[2];
@@ -598,8 +598,18 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
           if (issuer) {
-            for (int bx = 0; bx < gcols / 64; ++bx)
-              tma_store_2d(&p.tmC, stage_c + bx * (BLOCK_M * 128), nc0 + bx * 64, tile_m * BLOCK_M);
+            if (p.flags & F_OUT_UP2) {
+              // tile rows = low-resolution pixels (img, h, w); tmC is a 4-D map over the 2x-resolution output whose
+              // (w, h) strides are doubled and whose base sits at this launch's (row, column) parity
+              int img0, h0;
+              if (p.tiles_per_img > 0) { img0 = tile_m / p.tiles_per_img; h0 = (tile_m % p.tiles_per_img) * p.tile_h; }
+              else { img0 = tile_m * p.tile_n; h0 = 0; }
+              for (int bx = 0; bx < gcols / 64; ++bx)
+                tma_store_4d(&p.tmC, stage_c + bx * (BLOCK_M * 128), nc0 + bx * 64, 0, h0, img0);
+            } else {
+              for (int bx = 0; bx < gcols / 64; ++bx)
+                tma_store_2d(&p.tmC, stage_c + bx * (BLOCK_M * 128), nc0 + bx * 64, tile_m * BLOCK_M);
+            }
             tma_store_commit();
           }
         } else if (issuer) {
@@ -778,7 +788,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   int bn = BLOCK_N;
   // short-K GEMMs (K <= 1024: QKV / out_proj / skip projections) are epilogue- and memory-bound: narrow tiles with
   // triple-buffered staging keep loads, residual prefetch and stores in flight together
-  const bool short_k = !legacy && ktot <= 1024;
+  const bool short_k = !legacy && ktot <= 1024 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
   if (!legacy && !short_k) {
     const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     const int cands[3] = {256, 192, 128};
@@ -797,7 +807,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   // tile over up to 4 work units; fp32 partials go to the caller's workspace and a finish kernel adds them in a
   // fixed order (deterministic) together with the epilogue terms.
   int splits = 1;
-  if (!legacy && !short_k && a->ws != nullptr && a->res == nullptr && a->vt == nullptr && !a->out_f32) {
+  if (!legacy && !short_k && a->ws != nullptr && a->res == nullptr && a->vt == nullptr && !a->out_f32 && !a->out_up2) {
     const long long units = ((M + BLOCK_M - 1) / BLOCK_M) * (a->N / bn);
     auto eff = [&](int sfac) {
       const long long u = units * sfac;
@@ -860,7 +870,21 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
       p.vt_ld = a->vt_ld;
       out_cols = a->vt_col0;
     }
-    if ((rc = make_mat_map(&p.tmC, a->out, (uint64_t)M, (uint64_t)out_cols, (uint64_t)a->ldo, 64, BLOCK_M)) != IDF_OK)
+    if (a->out_up2) {
+      // sub-pixel store: row (img, h, w) of this GEMM lands at pixel (img, 2h + ph, 2w + pw) of the (n, 2h, 2w) output
+      if (a->res != nullptr || a->vt != nullptr || is_matrix || legacy || a->s2_batch > 0)
+        return fail(IDF_ERR_UNSUPPORTED, "igemm: out_up2 excludes res / vt / matrix / stride-2 inputs");
+      if (a->out_ph < 0 || a->out_ph > 1 || a->out_pw < 0 || a->out_pw > 1) return fail(IDF_ERR_ARG, "igemm: bad output parity");
+      p.flags |= F_OUT_UP2;
+      const long long ldo = a->ldo;
+      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a->out) + ((long long)a->out_ph * 2 * W + a->out_pw) * ldo;
+      const uint64_t dims[4] = {(uint64_t)out_cols, (uint64_t)W, (uint64_t)H, (uint64_t)x0.n};
+      const uint64_t strides[3] = {(uint64_t)(2 * ldo) * 2, (uint64_t)(4 * W * ldo) * 2, (uint64_t)(4LL * HW * ldo) * 2};
+      const uint32_t box[4] = {64u, (uint32_t)p.tile_w, (uint32_t)p.tile_h, (uint32_t)p.tile_n};
+      if ((rc = encode_tmap(&p.tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 4, dims, strides, box,
+                            CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
+        return rc;
+    } else if ((rc = make_mat_map(&p.tmC, a->out, (uint64_t)M, (uint64_t)out_cols, (uint64_t)a->ldo, 64, BLOCK_M)) != IDF_OK)
       return rc;
     if (a->res != nullptr) {
       p.flags |= F_RES;

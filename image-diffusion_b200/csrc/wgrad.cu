@@ -304,10 +304,10 @@ extern "C" int idf_conv2d_wgrad(const idf_wgrad_args* a, idf_stream_t stream) {
   p.N = a->taps * x.c;
   int bn = 0;
   {
+    static const int force_bn = [] { const char* e = getenv("IDF_WGRAD_BN"); return e ? atoi(e) : 0; }();
     const int cands[3] = {256, 192, 128};
     for (int i = 0; i < 3 && bn == 0; ++i)
-      if (p.N % cands[i] == 0) bn = cands[i];
-    if (bn == 0) bn = 64 * 0;
+      if (p.N % cands[i] == 0 && (force_bn == 0 || cands[i] <= force_bn)) bn = cands[i];
   }
   if (bn == 0) return fail(IDF_ERR_UNSUPPORTED, "wgrad: N = %d has no legal tile width", p.N);
   const long long per_split = (long long)a->cout * p.N * 4;
@@ -317,6 +317,10 @@ extern "C" int idf_conv2d_wgrad(const idf_wgrad_args* a, idf_stream_t stream) {
   int splits = units >= sm_count() ? 1 : sm_count() / units;
   if (splits > p.kb_total / 2) splits = p.kb_total / 2;
   if (splits > 64) splits = 64;
+  {
+    static const int force_splits = [] { const char* e = getenv("IDF_WGRAD_SPLITS"); return e ? atoi(e) : 0; }();
+    if (force_splits > 0) splits = force_splits;
+  }
   if (splits < 1) splits = 1;
   if (per_split * splits > a->ws_bytes) splits = (int)(a->ws_bytes / per_split);
   if (splits < 1) return fail(IDF_ERR_ARG, "wgrad: workspace of %lld bytes is smaller than one partial (%lld)",

@@ -130,7 +130,7 @@ class UnetEngine:
         for i in range(len(self.downs)):
             w[f"down.{i}.w"] = pk(sd[f"downsamples.{i}.down.weight"])
             w[f"down.{i}.b"] = _f32(sd[f"downsamples.{i}.down.bias"])
-            w[f"up.{i}.w"] = pk(sd[f"upsamples.{i}.conv.weight"])
+            w[f"up.{i}.w"] = ops.pack_upsample_conv_weights(sd[f"upsamples.{i}.conv.weight"])
             w[f"up.{i}.b"] = _f32(sd[f"upsamples.{i}.conv.bias"])
         w["in.w"], w["in.b"] = _f32(sd["in_conv.weight"]), _f32(sd["in_conv.bias"])
         w["out.gw"], w["out.gb"] = _f32(sd["out_conv.0.weight"]), _f32(sd["out_conv.0.bias"])
@@ -233,10 +233,10 @@ class UnetEngine:
             x = self._block(p, x, cout, table, row_idx)
         for i, (p, cin, cout) in enumerate(self.ups):
             c = x.C
-            up = ws.get("up", 4 * x.M, c)
-            ops.upsample_nearest2x(x.t, up, x.B, x.H, x.W, c)
             cat = cats.pop()
-            ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), c, 9)], w[f"up.{i}.w"], c, cat[:, :c], bias=w[f"up.{i}.b"])
+            # nearest-2x + conv3x3 as four sub-pixel convolutions on the low-resolution tensor (4/9 of the FLOPs, no
+            # upsampled copy), stored straight into the left half of the concat buffer
+            ops.upsample_conv3x3(x.t, x.grid, c, w[f"up.{i}.w"], c, cat[:, :c], bias=w[f"up.{i}.b"])
             self._tap(f"up.{i}", cat)
             x = self._block(p, Act(cat, x.B, 2 * x.H, 2 * x.W, 2 * c), cout, table, row_idx)
         h = ws.get("h1", x.M, x.C)

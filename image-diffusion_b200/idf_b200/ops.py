@@ -24,7 +24,7 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 
 def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
           res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0, ws=None,
-          tap_offsets=None, splits: int = 0) -> torch.Tensor:
+          tap_offsets=None, splits: int = 0, out_up2=None) -> torch.Tensor:
     """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view."""
     a = IgemmArgs()
     if not 1 <= len(segs) <= 2:
@@ -55,6 +55,8 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
     a.ws = ptr(ws)
     a.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
     a.force_splits = splits
+    if out_up2 is not None:  # (row parity, column parity) of the 2x-resolution output this launch fills
+        a.out_up2, (a.out_ph, a.out_pw) = 1, out_up2
     if tap_offsets is not None:  # explicit (dh, dw) list for segment 0
         a.custom_taps = 1
         for i, (dh, dw) in enumerate(tap_offsets):
@@ -370,3 +372,30 @@ def attention_bwd(qkv, o, d_out, lse, delta, dqkv, dq32, M, T, heads, head_dim):
     if T > 128:
         call("idf_f32_to_bf16_rows", dq32.data_ptr(), dqkv.data_ptr(), dqkv.stride(0), M, C)
     return dqkv
+
+
+# Nearest-2x upsampling followed by a 3x3 'same' conv (Upsample, components.py:124-130) as four sub-pixel convolutions
+# on the LOW-resolution input: output pixel (2h+p, 2w+q) only sees 2x2 source pixels, with the 3x3 taps that fall on
+# the same source pixel summed. Row parity p: source row offsets and the kernel rows that map onto each of them.
+_UP2_ROWS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}
+
+
+def pack_upsample_conv_weights(w: torch.Tensor):
+    """OIHW fp32 3x3 -> [((p, q), tap offsets [(dh, dw)] * 4, (O, 4*I) bf16)] for the four output parities."""
+    out = []
+    for p in (0, 1):
+        for q in (0, 1):
+            offs, mats = [], []
+            for dh, khs in _UP2_ROWS[p]:
+                for dw, kws in _UP2_ROWS[q]:
+                    offs.append((dh, dw))
+                    mats.append(sum(w.detach()[:, :, kh, kw] for kh in khs for kw in kws))
+            out.append(((p, q), offs, torch.cat(mats, dim=1).to(torch.bfloat16).contiguous()))
+    return out
+
+
+def upsample_conv3x3(x: torch.Tensor, grid, c: int, packed, n_out: int, out: torch.Tensor, bias=None):
+    """out (B*2H*2W, ld) <- conv3x3(nearest2x(x)) + bias, x (B*H*W, c) at the low resolution `grid` = (B, H, W)."""
+    for (p, q), offs, wp in packed:
+        igemm([(x, grid, c, 4)], wp, n_out, out, bias=bias, tap_offsets=offs, out_up2=(p, q))
+    return out

@@ -97,6 +97,12 @@ typedef struct idf_igemm_args {
   int32_t force_splits; /* > 1 (needs ws): split K into exactly this many work units per tile instead of the occupancy
                            heuristic. A fixed count keeps the summation order - and so the output bits - independent
                            of the batch size. */
+  int32_t out_up2;      /* != 0: sub-pixel output. Row (img, h, w) of the GEMM is stored at pixel (img, 2h + out_ph,
+                           2w + out_pw) of an (n, 2h, 2w) image in `out` (row stride ldo). Four such launches, one per
+                           parity, with 2x2 custom taps and pre-summed weights, ARE nearest-2x upsampling followed by a
+                           3x3 conv (Upsample, components.py:124-130) at 4/9 of the FLOPs and without the upsampled
+                           tensor ever existing. */
+  int32_t out_ph, out_pw;
 } idf_igemm_args;
 
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);

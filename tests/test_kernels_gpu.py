@@ -327,3 +327,20 @@ def test_vq_argmin_bit_exact(spread):
     mism = (idx != ref).sum().item()
     assert mism == 0, f"{mism} / {idx.numel()} indices differ"
     assert torch.equal(zq, cb[ref])
+
+
+@pytest.mark.parametrize("B,C,H", [(3, 512, 4), (2, 384, 8), (5, 256, 16), (96, 256, 16)])
+def test_upsample_conv_as_subpixel_convs(B, C, H):
+    """Upsample (components.py:124-130) = nearest 2x + conv3x3, computed as four sub-pixel 2x2 convolutions on the
+    low-resolution input that store straight into the (strided) left half of the concat buffer."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(B + C + H)
+    x = torch.randn(B, C, H, H, device=DEV, generator=g)
+    w = torch.randn(C, C, 3, 3, device=DEV, generator=g) / math.sqrt(9 * C)
+    b = torch.randn(C, device=DEV, generator=g)
+    cat = torch.zeros(B * 4 * H * H, 2 * C, device=DEV, dtype=torch.bfloat16)
+    ops.upsample_conv3x3(rows(x), (B, H, H), C, ops.pack_upsample_conv_weights(w), C, cat[:, :C], bias=b)
+    ref = F.conv2d(F.interpolate(bf(x), scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    got = unrows(cat[:, :C], B, 2 * H, 2 * H)
+    assert rel_err(got, ref) < 8e-3, rel_err(got, ref)
+    assert cat[:, C:].abs().max().item() == 0.0  # the other half of the buffer is untouched
