@@ -15,10 +15,15 @@
 // a sample has more than one key tile, and stored directly otherwise.
 // Samples with fewer than 128 tokens share a tile under a block-diagonal mask, as in the forward kernel.
 //
-// Warp roles (320 threads): warps 0..7 = softmax / output rows (warp w owns TMEM lanes 32*(w%4).. and the query-column
-// half w/4 of every tile, so two warps per scheduler keep the MUFU pipe busy), warp 8 = TMA producer, warp 9 = TMEM +
-// MMA issuer.
-// TMEM columns: S^T [0,128) dP^T [128,256) dV [256,256+hd) dK [320,320+hd) dQ [384,384+hd).
+// Pipelining: every 128-query tile is processed as two 64-column halves ("mini-iterations"). S^T / dP^T live in two
+// TMEM buffers and dS^T in four shared-memory blocks (tile parity x half), so the MMA thread issues the score products
+// of mini-iteration m+1 BEFORE it waits for the softmax threads of m, and the accumulate products of m run while the
+// softmax threads already work on m+1. dQ_i needs all 128 queries and is issued after the second half; its rows are
+// read back one mini-iteration later.
+//
+// Warp roles (320 threads): warps 0..7 = softmax / output rows (warp w owns TMEM lanes 32*(w%4).. and the 32-column
+// group w/4 of every 64-column half), warp 8 = TMA producer, warp 9 = TMEM + MMA issuer.
+// TMEM columns: [S^T | dP^T] x 2 buffers [0,256), dV [256,256+hd), dK [320,320+hd), dQ [384,384+hd).
 #include <stdlib.h>
 #include <string.h>
 
@@ -30,9 +35,9 @@ namespace idf {
 
 constexpr int ATB_THREADS = 320;
 constexpr int ATB_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16 columns
-constexpr int ATB_SMEM = 2 * ATB_TILE_BYTES /*K, V^T*/ + 4 * ATB_TILE_BYTES /*Q, dO x2 stages*/ +
-                         4 * ATB_TILE_BYTES /*P^T, dS^T (two 64-column halves each)*/ + 4 * 128 * 4 /*lse, delta x2*/ +
-                         1024 + 256;
+constexpr int ATB_SMEM = 2 * ATB_TILE_BYTES /*K, V*/ + 4 * ATB_TILE_BYTES /*Q, dO x2 stages*/ +
+                         2 * ATB_TILE_BYTES /*P^T halves*/ + 4 * ATB_TILE_BYTES /*dS^T: tile parity x half*/ +
+                         4 * 128 * 4 /*lse, delta x2*/ + 1024 + 256;
 
 struct AttnBwdParams {
   CUtensorMap tmQK;  // (M, 3C) bf16 QKV matrix, box (64, 128)
@@ -59,21 +64,24 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_k = smem;
   uint8_t* smem_vt = smem_k + ATB_TILE_BYTES;
-  uint8_t* smem_q = smem_vt + ATB_TILE_BYTES;       // [2]
-  uint8_t* smem_do = smem_q + 2 * ATB_TILE_BYTES;   // [2]
-  uint8_t* smem_p = smem_do + 2 * ATB_TILE_BYTES;   // two 64-column halves
-  uint8_t* smem_ds = smem_p + 2 * ATB_TILE_BYTES;
-  float* s_lse = reinterpret_cast<float*>(smem_ds + 2 * ATB_TILE_BYTES);  // [2][128]
+  uint8_t* smem_q = smem_vt + ATB_TILE_BYTES;       // [2 stages]
+  uint8_t* smem_do = smem_q + 2 * ATB_TILE_BYTES;   // [2 stages]
+  uint8_t* smem_p = smem_do + 2 * ATB_TILE_BYTES;   // [2 halves]
+  uint8_t* smem_ds = smem_p + 2 * ATB_TILE_BYTES;   // [2 tile parities][2 halves]
+  float* s_lse = reinterpret_cast<float*>(smem_ds + 4 * ATB_TILE_BYTES);  // [2][128]
   float* s_delta = s_lse + 256;                                          // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
   uint64_t* kv_full = bars;
-  uint64_t* q_full = bars + 1;    // [2]
-  uint64_t* q_empty = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* pds_full = bars + 6;
-  uint64_t* dq_full = bars + 7;
-  uint64_t* dq_empty = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* q_full = bars + 1;      // [2] per Q / dO stage
+  uint64_t* q_empty = bars + 3;     // [2]
+  uint64_t* sdp_full = bars + 5;    // [2] per S / dP TMEM buffer
+  uint64_t* sdp_empty = bars + 7;   // [2]
+  uint64_t* pds_full = bars + 9;    // [2] per half
+  uint64_t* p_empty = bars + 11;    // [2] per half: P block read by the dV products
+  uint64_t* ds_empty = bars + 13;   // [2] per tile parity: dS blocks read by the dK / dQ products
+  uint64_t* dq_full = bars + 15;
+  uint64_t* dq_empty = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -81,14 +89,21 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
   const int row0 = blockIdx.x * 128;  // first key row of this tile
   const int q_base = (p.T >= 128) ? (row0 >> p.t_shift) << p.t_shift : row0;
   const int n = p.nblk;
+  const int nm = 2 * n;  // mini-iterations
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tmQK);
     tma_prefetch_desc(&p.tmDO);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-    mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 8);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+      mbar_init(&sdp_full[s], 1);
+      mbar_init(&sdp_empty[s], 8);
+      mbar_init(&pds_full[s], 8);
+      mbar_init(&p_empty[s], 1);
+      mbar_init(&ds_empty[s], 1);
+    }
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 8);
     fence_mbar_init();
@@ -101,8 +116,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320,
-                 tmem_dq = tmem_base + 384;
+  const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320, tmem_dq = tmem_base + 384;
 
   if (warp == 8) {
     if (elect_one()) {
@@ -119,117 +133,73 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
     }
   } else if (warp == 9) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);    // S^T  = K Q^T
-      constexpr uint32_t idesc_dp = umma_idesc_bf16(128, 128, 0, 0);   // dP^T = V dO^T
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);     // S^T / dP^T halves: 128 keys x 64 queries
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, HD, 0, 1);   // dV / dK: A K-major, B MN-major
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, 1, 1);    // dQ: both MN-major
       const uint64_t dk_k = umma_desc_kmajor(smem_u32(smem_k), 128);
       const uint64_t dk_mn = umma_desc_mnmajor(smem_u32(smem_k), 8192, 1024);
       const uint64_t dv_k = umma_desc_kmajor(smem_u32(smem_vt), 128);
-      const uint64_t dp0 = umma_desc_kmajor(smem_u32(smem_p), 128);
-      const uint64_t dp1 = umma_desc_kmajor(smem_u32(smem_p + ATB_TILE_BYTES), 128);
-      const uint64_t dds0 = umma_desc_kmajor(smem_u32(smem_ds), 128);
-      const uint64_t dds1 = umma_desc_kmajor(smem_u32(smem_ds + ATB_TILE_BYTES), 128);
-      const uint64_t dds_mn = umma_desc_mnmajor(smem_u32(smem_ds), ATB_TILE_BYTES, 1024);
       mbar_wait(kv_full, 0);
-      auto issue_sdp = [&](int i) {
-        const int st = i & 1;
-        mbar_wait(&q_full[st], (i >> 1) & 1);
+      auto issue_sdp = [&](int m) {
+        const int i = m >> 1, h = m & 1, st = i & 1, buf = m & 1;
+        if (h == 0) mbar_wait(&q_full[st], (i >> 1) & 1);
+        mbar_wait(&sdp_empty[buf], ((m >> 1) & 1) ^ 1);  // softmax threads have pulled the buffer's previous contents
         tc_fence_after_sync();
-        const uint64_t dq_k = umma_desc_kmajor(smem_u32(smem_q + st * ATB_TILE_BYTES), 128);
-        const uint64_t ddo_k = umma_desc_kmajor(smem_u32(smem_do + st * ATB_TILE_BYTES), 128);
+        const uint64_t dq_k = umma_desc_kmajor(smem_u32(smem_q + st * ATB_TILE_BYTES + h * 8192), 128);
+        const uint64_t ddo_k = umma_desc_kmajor(smem_u32(smem_do + st * ATB_TILE_BYTES + h * 8192), 128);
+        const uint32_t ts = tmem_base + buf * 128;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_s, dk_k + 2 * k, dq_k + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(ts, dk_k + 2 * k, dq_k + 2 * k, idesc_s, k != 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16(tmem_dp, dv_k + 2 * k, ddo_k + 2 * k, idesc_dp, k != 0);
-        umma_commit(sdp_full);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(ts + 64, dv_k + 2 * k, ddo_k + 2 * k, idesc_s, k != 0);
+        umma_commit(&sdp_full[buf]);
       };
       issue_sdp(0);
-      for (int i = 0; i < n; ++i) {
-        const int st = i & 1;
-        mbar_wait(pds_full, i & 1);
-        if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);
+      for (int m = 0; m < nm; ++m) {
+        const int i = m >> 1, h = m & 1, st = i & 1;
+        if (m + 1 < nm) issue_sdp(m + 1);  // scores of the next half run under the softmax of this one
+        mbar_wait(&pds_full[h], i & 1);
         tc_fence_after_sync();
-        const uint64_t dq_mn = umma_desc_mnmajor(smem_u32(smem_q + st * ATB_TILE_BYTES), 8192, 1024);
+        const uint64_t dp_h = umma_desc_kmajor(smem_u32(smem_p + h * ATB_TILE_BYTES), 128);
+        const uint64_t dds_h = umma_desc_kmajor(smem_u32(smem_ds + ((i & 1) * 2 + h) * ATB_TILE_BYTES), 128);
         const uint64_t ddo_mn = umma_desc_mnmajor(smem_u32(smem_do + st * ATB_TILE_BYTES), 8192, 1024);
+        const uint64_t dq_mn = umma_desc_mnmajor(smem_u32(smem_q + st * ATB_TILE_BYTES), 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dV_j += P^T dO_i   (K = 128 queries, 16 per step)
-          umma_bf16(tmem_dv, (k < 4 ? dp0 : dp1) + 2 * (k & 3), ddo_mn + 128 * k, idesc_acc, (i > 0) || (k != 0));
+        for (int k = 0; k < 4; ++k)  // dV_j += P^T[:, half] dO_i[half]   (K = 64 queries)
+          umma_bf16(tmem_dv, dp_h + 2 * k, ddo_mn + 128 * (4 * h + k), idesc_acc, (m > 0) || (k != 0));
+        umma_commit(&p_empty[h]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dK_j += dS^T Q_i
-          umma_bf16(tmem_dk, (k < 4 ? dds0 : dds1) + 2 * (k & 3), dq_mn + 128 * k, idesc_acc, (i > 0) || (k != 0));
+        for (int k = 0; k < 4; ++k)  // dK_j += dS^T[:, half] Q_i[half]
+          umma_bf16(tmem_dk, dds_h + 2 * k, dq_mn + 128 * (4 * h + k), idesc_acc, (m > 0) || (k != 0));
+        if (h == 1) {
+          mbar_wait(dq_empty, (i & 1) ^ 1);  // rows of dQ_{i-1} have been read back
+          tc_fence_after_sync();
+          const uint64_t dds_mn = umma_desc_mnmajor(smem_u32(smem_ds + (i & 1) * 2 * ATB_TILE_BYTES), ATB_TILE_BYTES, 1024);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dQ_i = dS K_j     (K = 128 keys)
-          umma_bf16(tmem_dq, dds_mn + 128 * k, dk_mn + 128 * k, idesc_dq, k != 0);
-        umma_commit(&q_empty[st]);
-        umma_commit(dq_full);
-        if (i + 1 < n) issue_sdp(i + 1);
+          for (int k = 0; k < 8; ++k)  // dQ_i = dS K_j     (K = 128 keys)
+            umma_bf16(tmem_dq, dds_mn + 128 * k, dk_mn + 128 * k, idesc_dq, k != 0);
+          umma_commit(&ds_empty[i & 1]);
+          umma_commit(&q_empty[st]);
+          umma_commit(dq_full);
+        }
       }
     }
   } else {
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, cg = warp >> 2;
     const int r = quad * 32 + lane;  // key row of the tile == TMEM lane; also the query row when reading dQ
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const bool masked = p.T < 128;
     const int row_seg = r >> p.t_shift;
     const float c = p.scale_log2e;
-    // per-query row terms of tile i: half 0 stages lse, half 1 stages delta (one value per thread)
+    constexpr int HH = HD / 2;
+    // per-query row terms of tile i: column group 0 stages lse, group 1 stages delta (one value per thread)
     auto fetch = [&](int i) {
       const long long m = (long long)q_base + i * 128 + r;
       if (m >= p.M) return 0.f;
-      return half == 0 ? p.lse[m * p.heads + head] : p.delta[m * p.heads + head];
+      return cg == 0 ? p.lse[m * p.heads + head] : p.delta[m * p.heads + head];
     };
-    (half == 0 ? s_lse : s_delta)[r] = fetch(0);
-    named_bar_sync(1, 256);
-    for (int i = 0; i < n; ++i) {
-      float next = 0.f;
-      if (i + 1 < n) next = fetch(i + 1);
-      const float* lq = s_lse + (i & 1) * 128;
-      const float* dq = s_delta + (i & 1) * 128;
-      mbar_wait(sdp_full, i & 1);
-      tc_fence_after_sync();
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int ch = half * 2 + cc;
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tmem_s + lane_addr + ch * 32, sv);
-        tmem_ld_32x32(tmem_dp + lane_addr + ch * 32, dv);
-        tmem_ld_wait();
-        float pv[32], gv[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int qc = ch * 32 + j;
-          float e = atb_exp2(fmaf(__uint_as_float(sv[j]), c, -lq[qc]));
-          if (masked && (qc >> p.t_shift) != row_seg) e = 0.f;
-          pv[j] = e;
-          gv[j] = e * (__uint_as_float(dv[j]) - dq[qc]) * p.scale;
-        }
-        uint8_t* prow = smem_p + half * ATB_TILE_BYTES + r * 128;
-        uint8_t* grow = smem_ds + half * ATB_TILE_BYTES + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (cc * 4 + q) ^ (r & 7);
-          uint4 o;
-          o.x = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
-          o.y = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
-          o.z = pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]);
-          o.w = pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
-          o.x = pack_bf16x2(gv[8 * q + 0], gv[8 * q + 1]);
-          o.y = pack_bf16x2(gv[8 * q + 2], gv[8 * q + 3]);
-          o.z = pack_bf16x2(gv[8 * q + 4], gv[8 * q + 5]);
-          o.w = pack_bf16x2(gv[8 * q + 6], gv[8 * q + 7]);
-          *reinterpret_cast<uint4*>(grow + chunk * 16) = o;
-        }
-      }
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-      if (i + 1 < n) (half == 0 ? s_lse : s_delta)[((i + 1) & 1) * 128 + r] = next;
-      // dQ_i rows (lane = query row); each half takes HD/2 of the columns
-      constexpr int HH = HD / 2;
-      mbar_wait(dq_full, i & 1);
+    auto dq_readout = [&](int t) {  // rows of dQ_t (lane = query row); each column group takes HD/2 columns
+      mbar_wait(dq_full, t & 1);
       tc_fence_after_sync();
       float dqv[HH];
 #pragma unroll
@@ -237,7 +207,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
         uint32_t v[8];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                     : "r"(tmem_dq + lane_addr + half * HH + d0)
+                     : "r"(tmem_dq + lane_addr + cg * HH + d0)
                      : "memory");
         tmem_ld_wait();
 #pragma unroll
@@ -246,10 +216,10 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
-      const long long m = (long long)q_base + i * 128 + r;
+      const long long m = (long long)q_base + t * 128 + r;
       if (m < p.M) {
         if (n == 1) {
-          __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + head * HD + half * HH;
+          __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + head * HD + cg * HH;
 #pragma unroll
           for (int d0 = 0; d0 < HH; d0 += 8) {
             uint4 o;
@@ -260,7 +230,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
             *reinterpret_cast<uint4*>(dst + d0) = o;
           }
         } else {
-          float* dst = p.dq32 + m * p.C + head * HD + half * HH;
+          float* dst = p.dq32 + m * p.C + head * HD + cg * HH;
 #pragma unroll
           for (int d0 = 0; d0 < HH; d0 += 4)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + d0), "f"(dqv[d0]), "f"(dqv[d0 + 1]),
@@ -268,9 +238,65 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
                          : "memory");
         }
       }
-      named_bar_sync(1, 256);
+    };
+    (cg == 0 ? s_lse : s_delta)[r] = fetch(0);
+    named_bar_sync(1, 256);
+    float next = 0.f;
+    for (int m = 0; m < nm; ++m) {
+      const int i = m >> 1, h = m & 1, buf = m & 1;
+      if (h == 0 && i + 1 < n) next = fetch(i + 1);
+      const float* lq = s_lse + (i & 1) * 128 + h * 64 + cg * 32;
+      const float* dq = s_delta + (i & 1) * 128 + h * 64 + cg * 32;
+      mbar_wait(&sdp_full[buf], (m >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32(tmem_base + buf * 128 + lane_addr + cg * 32, sv);
+      tmem_ld_32x32(tmem_base + buf * 128 + 64 + lane_addr + cg * 32, dv);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sdp_empty[buf]);
+      float pv[32], gv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float e = atb_exp2(fmaf(__uint_as_float(sv[j]), c, -lq[j]));
+        if (masked && ((h * 64 + cg * 32 + j) >> p.t_shift) != row_seg) e = 0.f;
+        pv[j] = e;
+        gv[j] = e * (__uint_as_float(dv[j]) - dq[j]) * p.scale;
+      }
+      // the blocks about to be overwritten must have been consumed: P block h by the dV products of m-2, the dS
+      // blocks of this tile parity by the dK / dQ products of tile i-2
+      mbar_wait(&p_empty[h], ((m >> 1) & 1) ^ 1);
+      mbar_wait(&ds_empty[i & 1], ((i >> 1) & 1) ^ 1);
+      uint8_t* prow = smem_p + h * ATB_TILE_BYTES + r * 128;
+      uint8_t* grow = smem_ds + ((i & 1) * 2 + h) * ATB_TILE_BYTES + r * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = (cg * 4 + q) ^ (r & 7);
+        uint4 o;
+        o.x = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
+        o.y = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
+        o.z = pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]);
+        o.w = pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]);
+        *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
+        o.x = pack_bf16x2(gv[8 * q + 0], gv[8 * q + 1]);
+        o.y = pack_bf16x2(gv[8 * q + 2], gv[8 * q + 3]);
+        o.z = pack_bf16x2(gv[8 * q + 4], gv[8 * q + 5]);
+        o.w = pack_bf16x2(gv[8 * q + 6], gv[8 * q + 7]);
+        *reinterpret_cast<uint4*>(grow + chunk * 16) = o;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full[h]);
+      if (h == 0) {
+        if (i > 0) dq_readout(i - 1);  // one half-tile late: the dQ products have had time to finish
+      } else {
+        if (i + 1 < n) (cg == 0 ? s_lse : s_delta)[((i + 1) & 1) * 128 + r] = next;
+        named_bar_sync(1, 256);
+      }
     }
-    // dK_j rows (half 0) / dV_j rows (half 1), lane = key row; the last dq_full also covers the final accumulate
+    dq_readout(n - 1);
+    // dK_j rows (column group 0) / dV_j rows (group 1), lane = key row; the last dq_full covers every product
     tc_fence_after_sync();
     const long long m = (long long)row0 + r;
     {
@@ -278,13 +304,13 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
 #pragma unroll
       for (int d0 = 0; d0 < HD; d0 += 16) {
         uint32_t v[16];
-        tmem_ld_32x16((half == 0 ? tmem_dk : tmem_dv) + lane_addr + d0, v);
+        tmem_ld_32x16((cg == 0 ? tmem_dk : tmem_dv) + lane_addr + d0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int d = 0; d < 16; ++d) acc[d0 + d] = __uint_as_float(v[d]);
       }
       if (m < p.M) {
-        __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + (half == 0 ? p.C : 2 * p.C) + head * HD;
+        __nv_bfloat16* dst = p.dqkv + m * p.ld_dqkv + (cg == 0 ? p.C : 2 * p.C) + head * HD;
 #pragma unroll
         for (int d0 = 0; d0 < HD; d0 += 8) {
           uint4 o;
