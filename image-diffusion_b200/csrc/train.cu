@@ -714,6 +714,50 @@ __global__ void f32_to_bf16_rows_kernel(const float* __restrict__ x, __nv_bfloat
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight re-pack after an optimizer step: every bf16 operand copy (forward and data-gradient layouts of all conv /
+// linear weights) and the few fused fp32 vectors, in ONE launch driven by a job table. CTA = (job, outer index): the
+// source elements of one output row are gathered into shared memory (contiguous for forward layouts, 36-byte runs for
+// data-gradient layouts) and written out as coalesced bf16 rows  dst[outer*dldo + t*dldt + inner].
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PACK_CHUNK = 1024;  // inner elements staged per pass (x taps <= 9 -> 36 KiB of shared memory)
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const idf_pack_job* __restrict__ jobs,
+                                                           const int32_t* __restrict__ prefix, int njobs) {
+  extern __shared__ float pk_sm[];
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (prefix[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const idf_pack_job jb = jobs[lo];
+  const long long outer = (int)blockIdx.x - prefix[lo];
+  const float* src = jb.src + outer * jb.so;
+  if (jb.out_f32) {
+    float* dst = reinterpret_cast<float*>(jb.dst) + outer * jb.dldo;
+    const float* src2 = jb.src2 ? jb.src2 + outer * jb.so : nullptr;
+    for (int k = threadIdx.x; k < jb.n_inner; k += blockDim.x)
+      dst[k] = src[(long long)k * jb.si] + (src2 ? src2[(long long)k * jb.si] : 0.f);
+    return;
+  }
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(jb.dst) + outer * jb.dldo;
+  const int T = jb.n_taps;
+  for (int i0 = 0; i0 < jb.n_inner; i0 += PACK_CHUNK) {
+    const int ni = jb.n_inner - i0 < PACK_CHUNK ? jb.n_inner - i0 : PACK_CHUNK;
+    const int n = ni * T;
+    for (int f = threadIdx.x; f < n; f += blockDim.x) {
+      const int inner = f / T, t = f - inner * T;
+      pk_sm[f] = src[(long long)(i0 + inner) * jb.si + (long long)t * jb.st];
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < n; g += blockDim.x) {
+      const int t = g / ni, inner = g - t * ni;
+      dst[(long long)t * jb.dldt + i0 + inner] = __float2bfloat16_rn(pk_sm[inner * T + t]);
+    }
+    __syncthreads();
+  }
+}
+
 static inline unsigned grid_for(long long work, int block, int cap = 148 * 16) {
   long long g = (work + block - 1) / block;
   if (g > cap) g = cap;
@@ -917,6 +961,13 @@ extern "C" int idf_reparam_add_noise(const float* latents, const float* reparam_
   reparam_add_noise_kernel<<<(unsigned)(((long long)N * chw + 255) / 256), 256, 0, S(stream)>>>(
       latents, reparam_noise, noise, t, sqrt_alpha_cum_prod, sqrt_one_minus_alpha_cum_prod, out, N, chw);
   return check_cuda(cudaGetLastError(), "reparam_add_noise launch");
+}
+
+extern "C" int idf_pack_weights(const idf_pack_job* jobs_dev, const int32_t* cta_prefix_dev, int32_t njobs,
+                                int32_t total_ctas, idf_stream_t stream) {
+  if (!jobs_dev || !cta_prefix_dev || njobs <= 0 || total_ctas <= 0) return fail(IDF_ERR_ARG, "pack_weights: bad argument");
+  pack_weights_kernel<<<total_ctas, 256, PACK_CHUNK * 9 * sizeof(float), S(stream)>>>(jobs_dev, cta_prefix_dev, njobs);
+  return check_cuda(cudaGetLastError(), "pack_weights launch");
 }
 
 extern "C" int idf_attention_delta(const void* d_out, int64_t ld_do, const void* out, int64_t ld_o, int32_t M,

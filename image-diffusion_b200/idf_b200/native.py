@@ -42,6 +42,11 @@ class WgradArgs(C.Structure):
                 ("grad", _vp), ("accumulate", _i32), ("ws", _vp), ("ws_bytes", _i64)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("src", _vp), ("src2", _vp), ("dst", _vp), ("n_outer", _i32), ("n_taps", _i32), ("n_inner", _i32),
+                ("out_f32", _i32), ("so", _i64), ("si", _i64), ("st", _i64), ("dldo", _i64), ("dldt", _i64)]
+
+
 # name -> argtypes (the trailing stream argument is appended automatically)
 _SIGNATURES = {
     "idf_conv2d_igemm": [C.POINTER(IgemmArgs)],
@@ -86,6 +91,7 @@ _SIGNATURES = {
     "idf_attention_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _f32],
     "idf_f32_to_bf16_rows": [_vp, _vp, _i64, _i64, _i32],
     "idf_u8_nhwc_to_f32_nchw": [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32],
+    "idf_pack_weights": [_vp, _vp, _i32, _i32],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["idf_last_error", "idf_abi_version"])
 

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import native, ops
 from .engine import BF16, Act, Workspace
 from .spec import unet_blocks
 
@@ -129,50 +129,81 @@ class UnetTrainEngine:
     DGRAD_TAPS = [(1 - kh, 1 - kw) for kh in range(3) for kw in range(3)]
 
     def prepare(self, force=False):
-        """Refreshes the bf16 operand copies of the weights IN PLACE (fixed addresses: safe inside a captured graph).
-        Every copy is one strided copy kernel that fuses the fp32 -> bf16 cast with the layout permutation; fp32
-        parameters (biases, norm gains, embedding MLP) are used where they live, without a copy."""
+        """Refreshes the bf16 operand copies of the weights IN PLACE (fixed addresses: safe inside a captured graph)
+        with ONE launch of idf_pack_weights over a job table; fp32 parameters (biases, norm gains, embedding MLP) are
+        used where they live, without a copy. The table is rebuilt only when a parameter's storage moves."""
         key = tuple((p.data_ptr(), p._version) for p in self.params.values())
         if not force and key == self.pkey:
             return
         self.pkey = key
+        ptrs = tuple(k[0] for k in key)
+        if ptrs != getattr(self, "_job_ptrs", None):
+            self._build_pack_jobs()
+            self._job_ptrs = ptrs
+        native.call("idf_pack_weights", self._jobs_dev.data_ptr(), self._job_prefix.data_ptr(), self._njobs,
+                    self._pack_ctas)
+
+    def _build_pack_jobs(self):
         sd = {k: v.detach() for k, v in self.params.items()}
+        for k, v in sd.items():
+            if v.dtype != F32 or not v.is_contiguous():
+                raise RuntimeError(f"UnetTrainEngine: parameter {k} must be contiguous fp32")
         pw = self.pw
+        jobs = []
 
-        def conv_fwd(dst2d, w):      # (O, I, kh, kw) -> (O, kh*kw*I) rows = output channel, columns (tap, ci)
-            o, i, kh, kw = w.shape
-            dst2d.view(o, kh, kw, i).copy_(w.permute(0, 2, 3, 1))
+        def job(src, dst, n_outer, n_taps, n_inner, so, si, st, dldo, dldt, out_f32=0, src2=None, src_off=0):
+            j = native.PackJob()
+            j.src, j.src2 = src.data_ptr() + 4 * src_off, (src2.data_ptr() if src2 is not None else None)
+            j.dst = dst.data_ptr()
+            j.n_outer, j.n_taps, j.n_inner, j.out_f32 = n_outer, n_taps, n_inner, out_f32
+            j.so, j.si, j.st, j.dldo, j.dldt = so, si, st, dldo, dldt
+            jobs.append(j)
 
-        def conv_dgrad(dst2d, w):    # (O, I, kh, kw) -> (I, kh*kw*O) rows = input channel, columns (tap, co)
+        def conv_fwd(dst2d, w):      # (O, I, kh, kw) -> rows = output channel, columns (tap, ci)
             o, i, kh, kw = w.shape
-            dst2d.view(i, kh, kw, o).copy_(w.permute(1, 2, 3, 0))
+            job(w, dst2d, o, kh * kw, i, i * kh * kw, kh * kw, 1, dst2d.stride(0), i)
+
+        def conv_dgrad(dst2d, w):    # (O, I, kh, kw) -> rows = input channel, columns (tap, co), taps in (kh, kw) order
+            o, i, kh, kw = w.shape
+            job(w, dst2d, i, kh * kw, o, kh * kw, i * kh * kw, 1, dst2d.stride(0), o)
+
+        def lin(dst2d, w2d):         # (O, I) row-major copy
+            o, i = w2d.shape
+            job(w2d, dst2d, o, 1, i, i, 1, 0, dst2d.stride(0), 0)
+
+        def lin_t(dst2d, w2d):       # (O, I) -> (I, O)
+            o, i = w2d.shape
+            job(w2d, dst2d, i, 1, o, 1, i, 0, dst2d.stride(0), 0)
+
+        def vec(dst1d, a, b=None):   # fp32 vector copy / sum
+            job(a, dst1d, 1, 1, a.numel(), 0, 1, 0, 0, 0, out_f32=1, src2=b)
 
         for p, cin0, cout in self.downs + self.mids + self.ups:
             for l in range(self.L):
                 cin = cin0 if l == 0 else cout
                 k, a = f"{p}.{l}", f"{p}.self_attns.{l}"
                 w1, w2 = sd[f"{p}.first_halfs.{l}.layers.2.weight"], sd[f"{p}.second_halfs.{l}.layers.2.weight"]
-                wr = sd[f"{p}.residuals.{l}.weight"]
+                wr = sd[f"{p}.residuals.{l}.weight"].view(cout, cin)
                 conv_fwd(self._buf(k + ".w1", cout, 9 * cin), w1)
                 w2b = self._buf(k + ".w2", cout, 9 * cout + cin)
                 conv_fwd(w2b[:, :9 * cout], w2)
-                w2b[:, 9 * cout:].copy_(wr.view(cout, cin))
-                torch.add(sd[f"{p}.second_halfs.{l}.layers.2.bias"], sd[f"{p}.residuals.{l}.bias"],
-                          out=self._buf(k + ".b2", 1, cout, F32).view(-1))
+                lin(w2b[:, 9 * cout:], wr)
+                vec(self._buf(k + ".b2", 1, cout, F32).view(-1), sd[f"{p}.second_halfs.{l}.layers.2.bias"],
+                    sd[f"{p}.residuals.{l}.bias"])
                 wqkv, wqkvd = self._buf(k + ".wqkv", 3 * cout, cout), self._buf(k + ".wqkvd", cout, 3 * cout)
+                bqkv = self._buf(k + ".bqkv", 1, 3 * cout, F32).view(-1)
                 for j, n in enumerate(("to_q", "to_k", "to_v")):
                     wj = sd[f"{a}.{n}.weight"]
-                    wqkv[j * cout:(j + 1) * cout].copy_(wj)
-                    wqkvd[:, j * cout:(j + 1) * cout].copy_(wj.t())
-                torch.cat([sd[a + ".to_q.bias"], sd[a + ".to_k.bias"], sd[a + ".to_v.bias"]],
-                          out=self._buf(k + ".bqkv", 1, 3 * cout, F32).view(-1))
-                self._buf(k + ".wo", cout, cout).copy_(sd[a + ".out_proj.weight"])
-                self._buf(k + ".wod", cout, cout).copy_(sd[a + ".out_proj.weight"].t())
+                    lin(wqkv[j * cout:(j + 1) * cout], wj)
+                    lin_t(wqkvd[:, j * cout:(j + 1) * cout], wj)
+                    vec(bqkv[j * cout:(j + 1) * cout], sd[f"{a}.{n}.bias"])
+                lin(self._buf(k + ".wo", cout, cout), sd[a + ".out_proj.weight"])
+                lin_t(self._buf(k + ".wod", cout, cout), sd[a + ".out_proj.weight"])
                 conv_dgrad(self._buf(k + ".w1d", cin, 9 * cout), w1)
                 conv_dgrad(self._buf(k + ".w2d", cout, 9 * cout), w2)
-                self._buf(k + ".wrd", cin, cout).copy_(wr.view(cout, cin).t())
+                lin_t(self._buf(k + ".wrd", cin, cout), wr)
                 pw[k + ".b1"], pw[k + ".bo"] = sd[f"{p}.first_halfs.{l}.layers.2.bias"], sd[a + ".out_proj.bias"]
-                pw[k + ".b2"], pw[k + ".bqkv"] = pw[k + ".b2"].view(-1), pw[k + ".bqkv"].view(-1)
+                pw[k + ".b2"], pw[k + ".bqkv"] = pw[k + ".b2"].view(-1), bqkv
                 for n, key_ in (("g1", f"{p}.first_halfs.{l}.layers.0"), ("g2", f"{p}.second_halfs.{l}.layers.0"),
                                 ("g3", a + ".groupnorm")):
                     pw[f"{k}.{n}w"], pw[f"{k}.{n}b"] = sd[key_ + ".weight"], sd[key_ + ".bias"]
@@ -183,8 +214,8 @@ class UnetTrainEngine:
             pw[f"down.{i}.b"] = sd[f"downsamples.{i}.down.bias"]
             for j, (pq, taps) in enumerate(sorted(ops._S2_PLANE_TAPS.items())):
                 dst = self._buf(f"down.{i}.wd{j}", c, len(taps) * c)
-                for t, (kh, kw) in enumerate(taps):
-                    dst[:, t * c:(t + 1) * c].copy_(wd[:, :, kh, kw].t())
+                for t, (kh, kw) in enumerate(taps):  # dst[ci, t*c + co] = wd[co, ci, kh, kw]
+                    job(wd, dst[:, t * c:(t + 1) * c], c, 1, c, 9, c * 9, 0, dst.stride(0), 0, src_off=kh * 3 + kw)
                 pw[f"down.{i}.offs{j}"] = [(-(kh >> 1), -(kw >> 1)) for kh, kw in taps]
             cu = wu.shape[0]
             conv_fwd(self._buf(f"up.{i}.w", cu, 9 * cu), wu)
@@ -197,13 +228,24 @@ class UnetTrainEngine:
         pw["t.w1"], pw["t.b1"] = sd["time_embedding.embeddings.0.weight"], sd["time_embedding.embeddings.0.bias"]
         pw["t.w2"], pw["t.b2"] = sd["time_embedding.embeddings.2.weight"], sd["time_embedding.embeddings.2.bias"]
         pw["t.cls"] = sd["class_embedding.weight"]
-        torch.cat([sd[f"{p}.time_projs.{l}.1.weight"] for p, l in self.order], dim=0, out=self._buf("t.wp", self.P, self.D, F32))
-        torch.cat([sd[f"{p}.time_projs.{l}.1.bias"] for p, l in self.order], dim=0,
-                  out=self._buf("t.bp", 1, self.P, F32).view(-1))
-        pw["t.bp"] = pw["t.bp"].view(-1)
-        for name, t in pw.items():  # the kernels take fp32 parameters as they are stored
-            if isinstance(t, torch.Tensor) and (t.dtype not in (BF16, F32) or not t.is_contiguous()):
-                raise RuntimeError(f"UnetTrainEngine: parameter {name} must be contiguous fp32")
+        twp, tbp = self._buf("t.wp", self.P, self.D, F32), self._buf("t.bp", 1, self.P, F32).view(-1)
+        pw["t.bp"] = tbp
+        for p, l in self.order:
+            off, wproj = self.tp_off[(p, l)], sd[f"{p}.time_projs.{l}.1.weight"]
+            cout = wproj.shape[0]
+            job(wproj, twp[off:off + cout], cout, 1, self.D, self.D, 1, 0, self.D, 0, out_f32=1)
+            vec(tbp[off:off + cout], sd[f"{p}.time_projs.{l}.1.bias"])
+        # device job table + first-CTA prefix
+        import ctypes
+        arr = (native.PackJob * len(jobs))(*jobs)
+        raw = torch.frombuffer(bytearray(ctypes.string_at(ctypes.addressof(arr), ctypes.sizeof(arr))), dtype=torch.uint8)
+        prefix, tot = [], 0
+        for j in jobs:
+            prefix.append(tot)
+            tot += j.n_outer
+        self._jobs_dev = raw.to(self.device)
+        self._job_prefix = torch.tensor(prefix, dtype=torch.int32, device=self.device)
+        self._njobs, self._pack_ctas = len(jobs), tot
 
     # ---------------------------------------------------------------------------------------------
     # forward (activations kept per layer)

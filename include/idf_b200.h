@@ -393,6 +393,26 @@ int idf_attention_bwd(const void* qkv, int64_t ld_qkv, const void* d_out, int64_
                       const float* delta, void* dqkv, int64_t ld_dqkv, float* dq32, int32_t M, int32_t T,
                       int32_t heads, int32_t head_dim, float scale, idf_stream_t stream);
 
+/*
+ * idf_pack_weights — refreshes the kernels' operand copies of the parameters after an optimizer step, all in one launch.
+ * Job j copies an fp32 source tensor into its destination layout: for outer index o (one CTA each), tap t, inner index i
+ *     dst[o*dldo + t*dldt + i] = src[o*so + i*si + t*st]        (bf16 destination; fp32 and "+ src2[...]" if out_f32)
+ * which covers (O,I,kh,kw) -> (O, taps*I) forward layouts, (I, taps*O) data-gradient layouts, transposes and the fused
+ * bias / stacked vectors. jobs_dev and cta_prefix_dev (first CTA of each job, ascending) are DEVICE arrays built by the
+ * caller once; total_ctas = sum of n_outer. n_taps <= 9; for out_f32 jobs n_taps must be 1.
+ */
+typedef struct idf_pack_job {
+  const float* src;
+  const float* src2; /* optional second addend (out_f32 only) */
+  void* dst;
+  int32_t n_outer, n_taps, n_inner, out_f32;
+  int64_t so, si, st;
+  int64_t dldo, dldt;
+} idf_pack_job;
+
+int idf_pack_weights(const idf_pack_job* jobs_dev, const int32_t* cta_prefix_dev, int32_t njobs, int32_t total_ctas,
+                     idf_stream_t stream);
+
 /* idf_u8_nhwc_to_f32_nchw — dataset-scale latent extraction front end (scripts/prepare_dataset.py:103-106): uint8
  * (B, H, W, C) images -> fp32 (B, C, H, W) with y = x * scale + shift (1/127.5, -1). */
 int idf_u8_nhwc_to_f32_nchw(const uint8_t* x, float* y, int32_t B, int32_t H, int32_t W, int32_t C, float scale,
