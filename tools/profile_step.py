@@ -12,8 +12,12 @@ with torch.no_grad():
     s = CfgSampler(unet, sched, labels, torch.full((BATCH,), 3, device="cuda"), (3, 32, 32), use_graph=False)
     s.set_latent(torch.randn(BATCH, 3, 32, 32, device="cuda"))
     for k in range(steps):
+        if k == steps - 1:  # ncu --profile-from-start off: exactly ONE step is profiled
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         s.step(999 - k)
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     if len(sys.argv) > 2:
         vae.decode(s.latent.clone())
         torch.cuda.synchronize()

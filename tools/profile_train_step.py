@@ -10,7 +10,11 @@ unet, _, sched = build_models("cuda")
 unet.train()
 ts = DiffusionTrainStep(unet, sched, BATCH, (3, 32, 32), use_graph=False)
 lat = torch.randn(BATCH, 6, 32, 32, device="cuda"); lab = torch.randint(0, 3, (BATCH,), device="cuda")
-for _ in range(steps):
+for k in range(steps):
+    if k == steps - 1:  # ncu --profile-from-start off: exactly ONE step is profiled
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     ts.step(lat, lab, 1e-4)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", float(ts.loss))
