@@ -791,6 +791,20 @@ extern "C" int idf_space_to_depth2(const void* x, int64_t ldx, void* y, int32_t 
   return check_cuda(cudaGetLastError(), "space_to_depth2 launch");
 }
 
+// out[i] = base[i] + t[0] * rows_per_t: row of sample i in a per-timestep embedding table (timestep read on the device)
+__global__ void rowidx_from_timestep_kernel(const int32_t* __restrict__ base, const int64_t* __restrict__ t,
+                                            int rows_per_t, int32_t* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = base[i] + (int32_t)t[0] * rows_per_t;
+}
+
+extern "C" int idf_rowidx_from_timestep(const int32_t* base, const int64_t* t, int32_t rows_per_t, int32_t* out,
+                                        int32_t n, idf_stream_t stream) {
+  if (!base || !t || !out || n <= 0) return fail(IDF_ERR_ARG, "rowidx_from_timestep: bad argument");
+  rowidx_from_timestep_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(base, t, rows_per_t, out, n);
+  return check_cuda(cudaGetLastError(), "rowidx_from_timestep launch");
+}
+
 // uint8 NHWC image batch -> fp32 NCHW, y = x * scale + shift (prepare_dataset.py:104-105: / 127.5 - 1.0 and permute)
 __global__ void u8_nhwc_to_f32_nchw_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, int B, int H, int W,
                                            int C, float scale, float shift) {

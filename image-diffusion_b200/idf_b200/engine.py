@@ -190,24 +190,33 @@ class UnetEngine:
             x = Act(dst, B, H, W, cout)
         return x
 
-    def run(self, x_nchw, t_rows, ctx_rows, mask_rows, row_idx, out_nchw, dup_input=False):
+    def embedding_table(self, t_rows, ctx_rows, mask_rows, out=None):
+        """(R, P) fp32 table of every layer's time-projection bias for R (timestep, class, mask) rows
+        (TimeEmbedding + class embedding + all time_projs, unet.py:106-114 and components.py:526)."""
+        self.prepare()
+        w, ws = self.packed.w, self.ws
+        R, D = t_rows.shape[0], self.arch["time_dim"]
+        table = out if out is not None else ws.get("tp_table", R, self.P, torch.float32)
+        scratch = ws.get("tp_scratch", R, 5 * D, torch.float32)
+        ops.embed_time_class(t_rows, ctx_rows, mask_rows, w["t.factor"], w["t.w1"], w["t.b1"], w["t.w2"], w["t.b2"],
+                             w["t.cls"], w["t.wp"], w["t.bp"], table, scratch)
+        return table
+
+    def run(self, x_nchw, t_rows, ctx_rows, mask_rows, row_idx, out_nchw, dup_input=False, table=None):
         """x_nchw fp32 (B, z, H, W) -> out_nchw fp32 (B, z, H, W). With dup_input the network runs at batch 2*B on
         [x ; x] (CFG batch doubling; out_nchw then has 2*B samples) without materialising the doubled input.
 
         t_rows int64 (R,), ctx_rows int64 (R,) or None, mask_rows fp32 (R,) or None describe R distinct
         (timestep, class) embedding rows; row_idx int32 (B,) maps each sample to its row (None: R == B, identity).
+        With `table` (from embedding_table) the embedding kernels are skipped and row_idx indexes that table.
         """
         self.prepare()
         w, ws = self.packed.w, self.ws
         B, _, H, W = x_nchw.shape
         if dup_input:
             B *= 2
-        R = t_rows.shape[0]
-        D = self.arch["time_dim"]
-        table = ws.get("tp_table", R, self.P, torch.float32)
-        scratch = ws.get("tp_scratch", R, 5 * D, torch.float32)
-        ops.embed_time_class(t_rows, ctx_rows, mask_rows, w["t.factor"], w["t.w1"], w["t.b1"], w["t.w2"], w["t.b2"],
-                             w["t.cls"], w["t.wp"], w["t.bp"], table, scratch)
+        if table is None:  # `table`: precomputed rows (e.g. every timestep of a sampling run), indexed by row_idx
+            table = self.embedding_table(t_rows, ctx_rows, mask_rows)
         ch = list(self.arch["channels"])
         a0 = ws.get("in", B * H * W, ch[0])
         ops.conv3x3_small_cin(x_nchw, w["in.w"], w["in.b"], a0, dup=dup_input)

@@ -92,6 +92,7 @@ _SIGNATURES = {
     "idf_f32_to_bf16_rows": [_vp, _vp, _i64, _i64, _i32],
     "idf_u8_nhwc_to_f32_nchw": [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32],
     "idf_pack_weights": [_vp, _vp, _i32, _i32],
+    "idf_rowidx_from_timestep": [_vp, _vp, _i32, _vp, _i32],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["idf_last_error", "idf_abi_version"])
 

@@ -25,6 +25,12 @@ class CfgSampler:
         self.ctx_rows = torch.cat([torch.arange(K, device=dev), torch.zeros(1, device=dev, dtype=torch.int64)])
         self.mask_rows = torch.cat([torch.ones(K, device=dev), torch.zeros(1, device=dev)]).to(torch.float32)
         self.row_idx = torch.cat([labels.to(torch.int32), torch.full((N,), K, device=dev, dtype=torch.int32)])
+        # The embedding path depends only on (timestep, class row): its output for EVERY timestep of the schedule is
+        # computed once per weight version ((T*(K+1), P) fp32, 78 MB for T = 1000) and the step indexes into it, so no
+        # embedding kernel runs inside the step.
+        self.rows_per_t = K + 1
+        self.base_idx = self.row_idx.clone()
+        self.table_all = None
         self.cfg = cfg_scales.to(device=dev, dtype=torch.float32).contiguous()
         self.xx = torch.zeros(N, *latent_shape, device=dev, dtype=torch.float32)        # x_t (fp32 state)
         self.eps = torch.empty(2 * N, *latent_shape, device=dev, dtype=torch.float32)  # [eps_cond ; eps_uncond]
@@ -33,9 +39,29 @@ class CfgSampler:
         self.graph = None
         self.launches_per_step = None
 
+    def _ensure_table(self):
+        """Cached on the engine (shared by every sampler of the same batch size), refreshed when the weights change."""
+        eng = self.engine
+        eng.prepare()
+        T, R = self.sched.num_steps, self.rows_per_t
+        cache = eng.__dict__.setdefault("cfg_tables", {})
+        entry = cache.get((T, R))
+        if entry is not None and entry[0] == eng.packed.key:
+            self.table_all = entry[1]
+            return
+        dev = self.row_idx.device
+        table = entry[1] if entry is not None else torch.empty(T * R, eng.P, device=dev, dtype=torch.float32)
+        t_all = torch.arange(T, device=dev, dtype=torch.int64).repeat_interleave(R)
+        eng.embedding_table(t_all, self.ctx_rows.repeat(T), self.mask_rows.repeat(T), out=table)
+        cache[(T, R)] = (eng.packed.key, table)
+        self.table_all = table
+
     def _step(self):
         N = self.N
-        self.engine.run(self.xx, self.t_rows, self.ctx_rows, self.mask_rows, self.row_idx, self.eps, dup_input=True)
+        native.call("idf_rowidx_from_timestep", self.base_idx.data_ptr(), self.t_rows.data_ptr(), self.rows_per_t,
+                    self.row_idx.data_ptr(), 2 * N)
+        self.engine.run(self.xx, self.t_rows, self.ctx_rows, self.mask_rows, self.row_idx, self.eps, dup_input=True,
+                        table=self.table_all)
         ops.cfg_posterior_step(self.xx, self.eps[:N], self.eps[N:], self.z, self.cfg, self.t_rows[:1], self.sched,
                                self.xx)
 
@@ -67,6 +93,8 @@ class CfgSampler:
     def step(self, i: int, noise: torch.Tensor | None = None):
         """Advance x_i -> x_{i-1}. `noise` injects the step's N(0,1) draw; None draws it from the global CUDA
         generator exactly where the reference does (components.py:423: randn_like(xt), skipped at i == 0)."""
+        if self.table_all is None:  # (weights are frozen for the lifetime of a sampler)
+            self._ensure_table()
         self._ensure_graph()
         self.t_rows.fill_(i)
         if i > 0:

@@ -393,6 +393,12 @@ int idf_attention_bwd(const void* qkv, int64_t ld_qkv, const void* d_out, int64_
                       const float* delta, void* dqkv, int64_t ld_dqkv, float* dq32, int32_t M, int32_t T,
                       int32_t heads, int32_t head_dim, float scale, idf_stream_t stream);
 
+/* idf_rowidx_from_timestep — out[i] = base[i] + t[0] * rows_per_t: per-sample row into a table of idf_embed_time_class
+ * outputs precomputed for every timestep of a sampling run (the timestep is read on the device, so a captured step
+ * needs no host-side index update). */
+int idf_rowidx_from_timestep(const int32_t* base, const int64_t* t, int32_t rows_per_t, int32_t* out, int32_t n,
+                             idf_stream_t stream);
+
 /*
  * idf_pack_weights — refreshes the kernels' operand copies of the parameters after an optimizer step, all in one launch.
  * Job j copies an fp32 source tensor into its destination layout: for outer index o (one CTA each), tap t, inner index i
