@@ -41,7 +41,8 @@ static void resolve_encode() {
 }
 
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* ptr, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                const uint32_t* elem_strides) {
   std::call_once(g_encode_once, resolve_encode);
   if (!g_encode) return fail(IDF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(IDF_ERR_ARG, "TMA base pointer not 16-byte aligned");
@@ -52,7 +53,7 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* ptr, in
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     gbox[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (box[i] == 0 || box[i] > 256) return fail(IDF_ERR_ARG, "TMA box dim %d = %u out of range", i, box[i]);
   }
   for (int i = 0; i + 1 < rank; ++i) {

@@ -20,7 +20,8 @@ int check_cuda(cudaError_t e, const char* what);
 // Encode a tiled bf16/f32 tensor map. dims[0] is the contiguous dimension. strides_bytes has rank-1 entries
 // (dimension 0 is dense). Returns IDF_OK or an error code with the message set.
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* ptr, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                const uint32_t* elem_strides = nullptr);
 
 int sm_count();
 

@@ -46,6 +46,8 @@ struct IgemmParams {
   int tiles_per_img;  // HW / 128 when HW >= 128, else 0
   int matrix;         // 1: A is a plain (rows, cols) matrix walked 128 rows at a time along the w axis
   int s2_batch;       // > 0: segment 0 holds the 4 parity planes of a stride-2 conv input, stacked along n
+  int s2_direct;      // 1: segment 0 is the FULL-resolution input read with TMA element strides (2, 2): tap (kh, kw)
+                      //    of output tile origin (h0, w0) starts at source pixel (2*h0 + kh, 2*w0 + kw)
   signed char tdh[2][9], tdw[2][9];  // per-segment tap offsets (rows, columns)
   int tdn[9];                        // segment-0 image offset per tap (parity plane of a stride-2 conv)
   int splits;         // split-K factor (persistent kernel): partial sums go to out_f32 + split * split_stride
@@ -407,7 +409,9 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           const int dh = p.tdh[seg][tap], dw = p.tdw[seg][tap], dn = seg == 0 ? p.tdn[tap] : 0;
-          tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0 + dn);
+          const int sc = (p.s2_direct && seg == 0) ? 2 : 1;
+          tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, sc * w0 + dw, sc * h0 + dh,
+                      img0 + dn);
           tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
           if (++cbk == p.cb[seg]) {
             cbk = 0;
@@ -699,12 +703,14 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
   }
 }
 
-static int make_act_map(CUtensorMap* tm, const idf_nhwc_t& a, int tile_w, int tile_h, int tile_n) {
+static int make_act_map(CUtensorMap* tm, const idf_nhwc_t& a, int tile_w, int tile_h, int tile_n, int stride = 1) {
   const uint64_t dims[4] = {(uint64_t)a.c, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.n};
   const uint64_t strides[3] = {(uint64_t)a.sw * 2, (uint64_t)a.sh * 2, (uint64_t)a.sn * 2};
-  const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)tile_w, (uint32_t)tile_h, (uint32_t)tile_n};
+  // with element strides the box is the SOURCE span: tile_w * stride pixels of which every stride-th is fetched
+  const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)(tile_w * stride), (uint32_t)(tile_h * stride), (uint32_t)tile_n};
+  const uint32_t estr[4] = {1u, (uint32_t)stride, (uint32_t)stride, 1u};
   return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.ptr, 4, dims, strides, box,
-                     CU_TENSOR_MAP_SWIZZLE_128B);
+                     CU_TENSOR_MAP_SWIZZLE_128B, estr);
 }
 
 static int make_mat_map(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
@@ -736,11 +742,15 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  const int H = x0.h, W = x0.w, HW = H * W;
+  const int s2d = a->s2_direct ? 1 : 0;
+  if (s2d && (a->s2_batch > 0 || a->taps[0] != 9 || nseg != 1 || a->custom_taps || (x0.h & 1) || (x0.w & 1)))
+    return fail(IDF_ERR_ARG, "igemm: s2_direct needs one 9-tap segment over an even-sized full-resolution input");
+  const int H = s2d ? x0.h / 2 : x0.h, W = s2d ? x0.w / 2 : x0.w, HW = H * W;  // OUTPUT grid
   if (a->s2_batch > 0 && (x0.n != 4 * a->s2_batch || a->taps[0] != 9 || nseg != 1 || a->custom_taps))
     return fail(IDF_ERR_ARG, "igemm: s2_batch needs one 9-tap segment holding 4*s2_batch parity planes");
   const long long M = (long long)(a->s2_batch > 0 ? a->s2_batch : x0.n) * HW;
   p.s2_batch = a->s2_batch;
+  p.s2_direct = s2d;
   p.splits = 1;
   if (M <= 0 || M > 0x7fffffffLL) return fail(IDF_ERR_ARG, "igemm: bad M");
   // M-tile geometry: 128 consecutive NHWC pixels = tile_n images x tile_h rows x tile_w columns.
@@ -762,6 +772,8 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     for (int t = 0; t < a->taps[s]; ++t) {
       if (s == 0 && a->custom_taps) {
         p.tdh[s][t] = a->tap_dh[t]; p.tdw[s][t] = a->tap_dw[t];
+      } else if (a->taps[s] == 9 && s2d && s == 0) {
+        p.tdh[s][t] = (signed char)(t / 3); p.tdw[s][t] = (signed char)(t % 3);
       } else if (a->taps[s] == 9 && a->s2_batch > 0 && s == 0) {
         const int kh = t / 3, kw = t % 3;
         p.tdn[t] = ((kh & 1) * 2 + (kw & 1)) * a->s2_batch;
@@ -773,7 +785,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   int rc;
   int ktot = 0;
   for (int s = 0; s < nseg; ++s) {
-    if ((rc = make_act_map(&p.tmA[s], a->a[s], p.tile_w, p.tile_h, p.tile_n)) != IDF_OK) return rc;
+    if ((rc = make_act_map(&p.tmA[s], a->a[s], p.tile_w, p.tile_h, p.tile_n, (s2d && s == 0) ? 2 : 1)) != IDF_OK) return rc;
     p.cb[s] = a->a[s].c / BLOCK_K;
     p.taps[s] = a->taps[s];
     ktot += a->taps[s] * a->a[s].c;
@@ -872,7 +884,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     }
     if (a->out_up2) {
       // sub-pixel store: row (img, h, w) of this GEMM lands at pixel (img, 2h + ph, 2w + pw) of the (n, 2h, 2w) output
-      if (a->res != nullptr || a->vt != nullptr || is_matrix || legacy || a->s2_batch > 0)
+      if (a->res != nullptr || a->vt != nullptr || is_matrix || legacy || a->s2_batch > 0 || s2d)
         return fail(IDF_ERR_UNSUPPORTED, "igemm: out_up2 excludes res / vt / matrix / stride-2 inputs");
       if (a->out_ph < 0 || a->out_ph > 1 || a->out_pw < 0 || a->out_pw > 1) return fail(IDF_ERR_ARG, "igemm: bad output parity");
       p.flags |= F_OUT_UP2;

@@ -228,14 +228,13 @@ class UnetEngine:
             cat = ws.get(f"cat{i}", x.M, 2 * cout)
             cats.append(cat)
             x = self._block(p, x, cout, table, row_idx, final_dst=cat[:, cout:])
-            planes = ws.get("s2d", x.M, cout)  # four parity planes of the stride-2 conv input, stacked along n
-            ops.space_to_depth2(x.t, planes, x.B, x.H, x.W, cout)
             nxt = ws.get("dn", x.M // 4, cout)
             skd = {}
             if self.splitk > 1 and (x.H // 2) * (x.W // 2) <= 16:
                 skd = dict(ws=ws.get("splitk", 1, self.splitk * (x.M // 4) * cout, torch.float32), splits=self.splitk)
-            ops.igemm([(planes, (4 * x.B, x.H // 2, x.W // 2), cout, 9)], w[f"down.{i}.w"], cout, nxt,
-                      bias=w[f"down.{i}.b"], zero_pad_last=True, s2_batch=x.B, **skd)
+            # stride-2 pad-0 conv read straight from the block output (TMA element strides): no parity-plane copy
+            ops.igemm([(x.t, x.grid, cout, 9)], w[f"down.{i}.w"], cout, nxt, bias=w[f"down.{i}.b"], zero_pad_last=True,
+                      s2_direct=True, **skd)
             self._tap(f"down.{i}", nxt)
             x = Act(nxt, x.B, x.H // 2, x.W // 2, cout)
         for p, cin, cout in self.mids:

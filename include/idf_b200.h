@@ -103,6 +103,9 @@ typedef struct idf_igemm_args {
                            3x3 conv (Upsample, components.py:124-130) at 4/9 of the FLOPs and without the upsampled
                            tensor ever existing. */
   int32_t out_ph, out_pw;
+  int32_t s2_direct;    /* != 0: stride-2 pad-0 3x3 conv (Downsample, components.py:110) read straight from the
+                           FULL-resolution input a[0] (n, 2h, 2w) through a TMA map with element strides (2, 2): no
+                           parity-plane copy. The output grid is (n, h, w); use with zero_pad_last. */
 } idf_igemm_args;
 
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);

@@ -344,3 +344,22 @@ def test_upsample_conv_as_subpixel_convs(B, C, H):
     got = unrows(cat[:, :C], B, 2 * H, 2 * H)
     assert rel_err(got, ref) < 8e-3, rel_err(got, ref)
     assert cat[:, C:].abs().max().item() == 0.0  # the other half of the buffer is untouched
+
+
+@pytest.mark.parametrize("B,C,H", [(3, 256, 32), (5, 384, 16), (7, 512, 8), (96, 512, 8)])
+def test_downsample_conv_strided_tma(B, C, H):
+    """Downsample (components.py:106-117) read from the full-resolution input through a TMA map with element strides
+    (2, 2); the input may be a column slice of the concat buffer."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(B + C + H)
+    x = torch.randn(B, C, H, H, device=DEV, generator=g)
+    w = torch.randn(C, C, 3, 3, device=DEV, generator=g) / math.sqrt(9 * C)
+    b = torch.randn(C, device=DEV, generator=g)
+    cat = torch.zeros(B * H * H, 2 * C, device=DEV, dtype=torch.bfloat16)
+    cat[:, C:] = rows(x)
+    out = torch.empty(B * H * H // 4, C, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(cat[:, C:], (B, H, H), C, 9)], ops.pack_conv_weight(w), C, out, bias=b, zero_pad_last=True, s2_direct=True)
+    ref = F.pad(F.conv2d(bf(x), bf(w), b, stride=2), (0, 1, 0, 1))
+    got = unrows(out, B, H // 2, H // 2)
+    assert rel_err(got, ref) < 6e-3, rel_err(got, ref)
+    assert got[:, :, -1, :].abs().max().item() == 0.0 and got[:, :, :, -1].abs().max().item() == 0.0
