@@ -351,15 +351,13 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
   constexpr int QK_BYTES = 128 * SWZ;
   const int V_BYTES = p.v_tok ? 128 * 128 : 2 * HD * 128;
-  constexpr int P_BYTES = 2 * 128 * 128;
   constexpr int ATTP_KSTAGES = AttpK<HD>::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* smem_q = smem;                                 // [2 items][2 tiles][QK_BYTES]
-  uint8_t* smem_p = smem_q + 4 * QK_BYTES;                // [2 groups][P_BYTES]
-  uint8_t* smem_k = smem_p + 2 * P_BYTES;                 // [ATTP_KSTAGES][QK_BYTES]
+  uint8_t* smem_k = smem_q + 4 * QK_BYTES;                // [ATTP_KSTAGES][QK_BYTES]
   uint8_t* smem_v = smem_k + ATTP_KSTAGES * QK_BYTES;     // [ATTP_VSTAGES][V_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + ATTP_VSTAGES * V_BYTES);
   uint64_t* q_full = bars;                           // [2]
@@ -488,23 +486,22 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
           if (g == 0) mbar_wait(&v_full[vs], (e / ATTP_VSTAGES) & 1);
           if (j == 0 && item > 0) mbar_wait(&o_empty[g], (item - 1) & 1);  // previous item's output rows were read
           tc_fence_after_sync();
-          const uint8_t* pb = smem_p + g * P_BYTES;
+          // A = P_g from tensor memory (packed bf16 pairs, 64 columns for 128 keys): the probabilities never touch
+          // shared memory, whose port is left to TMA writes and the K / V / Q operand reads
           const uint8_t* vb = smem_v + vs * V_BYTES;
-          const uint64_t dp0 = umma_desc_kmajor(smem_u32(pb), 128);
-          const uint64_t dp1 = umma_desc_kmajor(smem_u32(pb + 128 * 128), 128);
+          const uint32_t tp = tmem_base + 384 + g * 64;
           if (p.v_tok) {
             const uint64_t dvm = umma_desc_mnmajor(smem_u32(vb), 8192, 1024);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem_base + 256 + g * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), dvm + 128 * k, idesc_o_mn,
-                        (j > 0) || (k != 0));
+              umma_bf16_ts(tmem_base + 256 + g * 64, tp + 8 * k, dvm + 128 * k, idesc_o_mn, (j > 0) || (k != 0));
           } else {
             const uint64_t dv0 = umma_desc_kmajor(smem_u32(vb), 128);
             const uint64_t dv1 = umma_desc_kmajor(smem_u32(vb + HD * 128), 128);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              umma_bf16(tmem_base + 256 + g * 64, (k < 4 ? dp0 : dp1) + 2 * (k & 3), (k < 4 ? dv0 : dv1) + 2 * (k & 3),
-                        idesc_o, (j > 0) || (k != 0));  // accumulate over the item's key blocks
+              umma_bf16_ts(tmem_base + 256 + g * 64, tp + 8 * k, (k < 4 ? dv0 : dv1) + 2 * (k & 3), idesc_o,
+                           (j > 0) || (k != 0));  // accumulate over the item's key blocks
           }
           umma_commit(&o_full[g]);
           if (g == 1) umma_commit(&v_empty[vs]);
@@ -539,8 +536,8 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
     const int r = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float c = p.scale_log2e;
-    uint8_t* pbuf = smem_p + g * P_BYTES;
     const uint32_t tmem_o = tmem_base + 256 + g * 64 + lane_addr;
+    const uint32_t tmem_p = tmem_base + 384 + g * 64 + lane_addr;
 
     int e = 0;
     for (int item = 0; item < my_items; ++item) {
@@ -593,7 +590,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
         float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          uint8_t* prow = pbuf + (ch >> 1) * (128 * 128) + r * 128;
+          uint32_t pk[16];  // 32 probabilities of this row as 16 packed bf16 pairs -> 16 TMEM columns
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float ev[8];
@@ -602,16 +599,15 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
               ev[i] = fast_exp2(fmaf(__uint_as_float(sv[ch][8 * q + i]), c, -mc));
               ps[i & 3] += ev[i];
             }
-            uint4 o;  // (an ALU-only bf16 pack instead of F2FP on the XU pipe measured no faster: 317 vs 316 us)
-            o.x = pack_bf16x2(ev[0], ev[1]);
-            o.y = pack_bf16x2(ev[2], ev[3]);
-            o.z = pack_bf16x2(ev[4], ev[5]);
-            o.w = pack_bf16x2(ev[6], ev[7]);
-            const int chunk = ((ch & 1) * 4 + q) ^ (r & 7);
-            *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
+            pk[4 * q + 0] = pack_bf16x2(ev[0], ev[1]);
+            pk[4 * q + 1] = pack_bf16x2(ev[2], ev[3]);
+            pk[4 * q + 2] = pack_bf16x2(ev[4], ev[5]);
+            pk[4 * q + 3] = pack_bf16x2(ev[6], ev[7]);
           }
+          tmem_st_32x16(tmem_p + ch * 16, pk);
         }
-        fence_proxy_async_smem();
+        tmem_st_wait();
+        tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
         l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
@@ -662,8 +658,7 @@ template <int HD>
 static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
   // (sized for the larger token-major V tile so that one attribute setting serves both operand layouts)
-  const int smem = 4 * 128 * SWZ + 2 * (2 * 128 * 128) + AttpK<HD>::STAGES * 128 * SWZ + ATTP_VSTAGES * 128 * 128 +
-                   1024 + 512;
+  const int smem = 4 * 128 * SWZ + AttpK<HD>::STAGES * 128 * SWZ + ATTP_VSTAGES * 128 * 128 + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(attention_pipe_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
