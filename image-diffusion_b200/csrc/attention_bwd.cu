@@ -7,7 +7,7 @@
 //   S^T  = K_j Q_i^T                    (A = K_j  K-major,  B = Q_i  K-major)          128 x 128 x hd
 //   dP^T = V_j dO_i^T                   (A = V_j  K-major,  B = dO_i K-major)          128 x 128 x hd
 //   P^T  = exp2(S^T * c - lse[q]),  dS^T = P^T * (dP^T - delta[q]) * scale             softmax threads -> bf16 smem
-//   dV_j += P^T  dO_i                   (A = P^T  K-major,  B = dO_i MN-major)         128 x hd x 128   (TMEM, all i)
+//   dV_j += P^T  dO_i                   (A = P^T  in TMEM,  B = dO_i MN-major)         128 x hd x 128   (TMEM, all i)
 //   dK_j += dS^T Q_i                    (A = dS^T K-major,  B = Q_i  MN-major)         128 x hd x 128   (TMEM, all i)
 //   dQ_i  = dS   K_j                    (A = dS^T MN-major, B = K_j  MN-major)         128 x hd x 128   per i
 // Q, K, V are read straight from the token-major (M, 3C) QKV matrix. The MN-major descriptors let Q_i, dO_i and K_j
@@ -23,7 +23,9 @@
 //
 // Warp roles (320 threads): warps 0..7 = softmax / output rows (warp w owns TMEM lanes 32*(w%4).. and the 32-column
 // group w/4 of every 64-column half), warp 8 = TMA producer, warp 9 = TMEM + MMA issuer.
-// TMEM columns: [S^T | dP^T] x 2 buffers [0,256), dV [256,256+hd), dK [320,320+hd), dQ [384,384+hd).
+// TMEM columns: [S^T | dP^T] x 2 buffers [0,256), dV [256,256+hd), dK [320,320+hd), dQ [384,384+hd), P^T as packed bf16
+// pairs [448,512) (32 columns per 64-query half): P^T never touches shared memory, it is the A operand of the dV
+// product straight from tensor memory. dS^T has to live in shared memory because dQ needs it transposed (MN-major).
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,8 +38,7 @@ namespace idf {
 constexpr int ATB_THREADS = 320;
 constexpr int ATB_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16 columns
 constexpr int ATB_SMEM = 2 * ATB_TILE_BYTES /*K, V*/ + 4 * ATB_TILE_BYTES /*Q, dO x2 stages*/ +
-                         2 * ATB_TILE_BYTES /*P^T halves*/ + 4 * ATB_TILE_BYTES /*dS^T: tile parity x half*/ +
-                         4 * 128 * 4 /*lse, delta x2*/ + 1024 + 256;
+                         4 * ATB_TILE_BYTES /*dS^T: tile parity x half*/ + 4 * 128 * 4 /*lse, delta x2*/ + 1024 + 256;
 
 struct AttnBwdParams {
   CUtensorMap tmQK;  // (M, 3C) bf16 QKV matrix, box (64, 128)
@@ -66,8 +67,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
   uint8_t* smem_vt = smem_k + ATB_TILE_BYTES;
   uint8_t* smem_q = smem_vt + ATB_TILE_BYTES;       // [2 stages]
   uint8_t* smem_do = smem_q + 2 * ATB_TILE_BYTES;   // [2 stages]
-  uint8_t* smem_p = smem_do + 2 * ATB_TILE_BYTES;   // [2 halves]
-  uint8_t* smem_ds = smem_p + 2 * ATB_TILE_BYTES;   // [2 tile parities][2 halves]
+  uint8_t* smem_ds = smem_do + 2 * ATB_TILE_BYTES;  // [2 tile parities][2 halves]
   float* s_lse = reinterpret_cast<float*>(smem_ds + 4 * ATB_TILE_BYTES);  // [2][128]
   float* s_delta = s_lse + 256;                                          // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320, tmem_dq = tmem_base + 384;
+  const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 320, tmem_dq = tmem_base + 384,
+                 tmem_p = tmem_base + 448;
 
   if (warp == 8) {
     if (elect_one()) {
@@ -160,13 +161,12 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
         if (m + 1 < nm) issue_sdp(m + 1);  // scores of the next half run under the softmax of this one
         mbar_wait(&pds_full[h], i & 1);
         tc_fence_after_sync();
-        const uint64_t dp_h = umma_desc_kmajor(smem_u32(smem_p + h * ATB_TILE_BYTES), 128);
         const uint64_t dds_h = umma_desc_kmajor(smem_u32(smem_ds + ((i & 1) * 2 + h) * ATB_TILE_BYTES), 128);
         const uint64_t ddo_mn = umma_desc_mnmajor(smem_u32(smem_do + st * ATB_TILE_BYTES), 8192, 1024);
         const uint64_t dq_mn = umma_desc_mnmajor(smem_u32(smem_q + st * ATB_TILE_BYTES), 8192, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // dV_j += P^T[:, half] dO_i[half]   (K = 64 queries)
-          umma_bf16(tmem_dv, dp_h + 2 * k, ddo_mn + 128 * (4 * h + k), idesc_acc, (m > 0) || (k != 0));
+          umma_bf16_ts(tmem_dv, tmem_p + h * 32 + 8 * k, ddo_mn + 128 * (4 * h + k), idesc_acc, (m > 0) || (k != 0));
         umma_commit(&p_empty[h]);
 #pragma unroll
         for (int k = 0; k < 4; ++k)  // dK_j += dS^T[:, half] Q_i[half]
@@ -268,23 +268,25 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) attention_bwd_kernel(const __g
       // blocks of this tile parity by the dK / dQ products of tile i-2
       mbar_wait(&p_empty[h], ((m >> 1) & 1) ^ 1);
       mbar_wait(&ds_empty[i & 1], ((i >> 1) & 1) ^ 1);
-      uint8_t* prow = smem_p + h * ATB_TILE_BYTES + r * 128;
       uint8_t* grow = smem_ds + ((i & 1) * 2 + h) * ATB_TILE_BYTES + r * 128;
+      uint32_t pk[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
+        pk[4 * q + 0] = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
+        pk[4 * q + 1] = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
+        pk[4 * q + 2] = pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]);
+        pk[4 * q + 3] = pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]);
         const int chunk = (cg * 4 + q) ^ (r & 7);
         uint4 o;
-        o.x = pack_bf16x2(pv[8 * q + 0], pv[8 * q + 1]);
-        o.y = pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]);
-        o.z = pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]);
-        o.w = pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]);
-        *reinterpret_cast<uint4*>(prow + chunk * 16) = o;
         o.x = pack_bf16x2(gv[8 * q + 0], gv[8 * q + 1]);
         o.y = pack_bf16x2(gv[8 * q + 2], gv[8 * q + 3]);
         o.z = pack_bf16x2(gv[8 * q + 4], gv[8 * q + 5]);
         o.w = pack_bf16x2(gv[8 * q + 6], gv[8 * q + 7]);
         *reinterpret_cast<uint4*>(grow + chunk * 16) = o;
       }
+      tmem_st_32x16(tmem_p + lane_addr + h * 32 + cg * 16, pk);  // P^T[key r][32 queries] as 16 packed columns
+      tmem_st_wait();
+      tc_fence_before_sync();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[h]);
