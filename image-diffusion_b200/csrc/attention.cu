@@ -352,6 +352,11 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
   constexpr int QK_BYTES = 128 * SWZ;
   const int V_BYTES = p.v_tok ? 128 * 128 : 2 * HD * 128;
   constexpr int ATTP_KSTAGES = AttpK<HD>::STAGES;
+  // Row sums on the tensor core: for head_dim <= 48 the 64-column output accumulator has 16 spare columns, which
+  // receive P x ones (a second, tiny product per key block). The softmax threads then do no additions at all (128
+  // FADD per row and key block saved; the loop is issue-bound, not MUFU-bound), and the denominator is the sum of
+  // the SAME bf16-rounded probabilities that multiply V.
+  constexpr bool LSUM = HD <= 48;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -359,7 +364,8 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
   uint8_t* smem_q = smem;                                 // [2 items][2 tiles][QK_BYTES]
   uint8_t* smem_k = smem_q + 4 * QK_BYTES;                // [ATTP_KSTAGES][QK_BYTES]
   uint8_t* smem_v = smem_k + ATTP_KSTAGES * QK_BYTES;     // [ATTP_VSTAGES][V_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + ATTP_VSTAGES * V_BYTES);
+  uint8_t* smem_ones = smem_v + ATTP_VSTAGES * V_BYTES;   // 16 rows x 128 bytes of bf16 1.0 (any layout: all ones)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + 2048);
   uint64_t* q_full = bars;                           // [2]
   uint64_t* q_empty = q_full + 2;                    // [2]
   uint64_t* k_full = q_empty + 2;                    // [4]
@@ -403,6 +409,8 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
     tmem_alloc(tmem_slot, ATTP_TMEM_COLS);
     tmem_relinquish();
   }
+  if (threadIdx.x < 128) reinterpret_cast<uint4*>(smem_ones)[threadIdx.x] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -503,6 +511,13 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
               umma_bf16_ts(tmem_base + 256 + g * 64, tp + 8 * k, (k < 4 ? dv0 : dv1) + 2 * (k & 3), idesc_o,
                            (j > 0) || (k != 0));  // accumulate over the item's key blocks
           }
+          if constexpr (LSUM) {
+            constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16);
+            const uint64_t d1 = umma_desc_kmajor(smem_u32(smem_ones), 128);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)  // l_g (+)= P_g x 1 into the accumulator's spare columns [48, 64)
+              umma_bf16_ts(tmem_base + 256 + g * 64 + 48, tp + 8 * k, d1, idesc_l, (j > 0) || (k != 0));
+          }
           umma_commit(&o_full[g]);
           if (g == 1) umma_commit(&v_empty[vs]);
         };
@@ -581,6 +596,14 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
               for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
               tmem_st_32x16(tmem_o + d0, v);
             }
+            if constexpr (LSUM) {
+              uint32_t v[16];
+              tmem_ld_32x16(tmem_o + 48, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
+              tmem_st_32x16(tmem_o + 48, v);
+            }
             tmem_st_wait();
             tc_fence_before_sync();
           }
@@ -597,7 +620,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               ev[i] = fast_exp2(fmaf(__uint_as_float(sv[ch][8 * q + i]), c, -mc));
-              ps[i & 3] += ev[i];
+              if constexpr (!LSUM) ps[i & 3] += ev[i];
             }
             pk[4 * q + 0] = pack_bf16x2(ev[0], ev[1]);
             pk[4 * q + 1] = pack_bf16x2(ev[2], ev[3]);
@@ -623,6 +646,12 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
         tmem_ld_wait();
 #pragma unroll
         for (int d = 0; d < 16; ++d) o_acc[d0 + d] = __uint_as_float(v[d]);
+      }
+      if constexpr (LSUM) {
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_o + 48, v);
+        tmem_ld_wait();
+        l_run = __uint_as_float(v[0]);
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -658,7 +687,7 @@ template <int HD>
 static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cudaStream_t stream) {
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
   // (sized for the larger token-major V tile so that one attribute setting serves both operand layouts)
-  const int smem = 4 * 128 * SWZ + AttpK<HD>::STAGES * 128 * SWZ + ATTP_VSTAGES * 128 * 128 + 1024 + 512;
+  const int smem = 4 * 128 * SWZ + AttpK<HD>::STAGES * 128 * SWZ + ATTP_VSTAGES * 128 * 128 + 2048 + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = check_cuda(cudaFuncSetAttribute(attention_pipe_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
