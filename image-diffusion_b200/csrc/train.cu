@@ -499,21 +499,38 @@ __global__ void __launch_bounds__(256) nchw_channel_sum_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------------------------
 // small fp32 GEMMs of the embedding MLP backward (R <= a few hundred rows)
 // ---------------------------------------------------------------------------------------------------------------
-// out[j, k] = sum_r A[r, j] * Bm[r, k]   (dW = dY^T X); optional bias_out[j] = sum_r A[r, j]
+// out[j, k] = sum_r A[r, j] * Bm[r, k]   (dW = dY^T X); optional bias_out[j] = sum_r A[r, j].
+// CTA = (32 rows j, 256 columns k): the (R x 32) slice of A is staged in shared memory once, every thread keeps 32
+// accumulators for its column, so Bm is read once per 32 output rows instead of once per output row.
+constexpr int OR_JT = 32;
 __global__ void __launch_bounds__(256) outer_rows_kernel(const float* __restrict__ A, int lda,
                                                          const float* __restrict__ Bm, int ldb, int R, int J, int K,
                                                          float* __restrict__ out, float* __restrict__ bias_out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y;
-  float a = 0.f, bs = 0.f;
+  extern __shared__ float or_sm[];  // [R][OR_JT]
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int j0 = blockIdx.y * OR_JT;
+  for (int i = threadIdx.x; i < R * OR_JT; i += 256) {
+    const int r = i / OR_JT, jj = i % OR_JT;
+    or_sm[i] = (j0 + jj < J) ? A[(long long)r * lda + j0 + jj] : 0.f;
+  }
+  __syncthreads();
+  float acc[OR_JT];
+#pragma unroll
+  for (int jj = 0; jj < OR_JT; ++jj) acc[jj] = 0.f;
   if (k < K) {
     for (int r = 0; r < R; ++r) {
-      const float av = A[(long long)r * lda + j];
-      a = fmaf(av, Bm[(long long)r * ldb + k], a);
-      bs += av;
+      const float b = Bm[(long long)r * ldb + k];
+#pragma unroll
+      for (int jj = 0; jj < OR_JT; ++jj) acc[jj] = fmaf(or_sm[r * OR_JT + jj], b, acc[jj]);
     }
-    out[(long long)j * K + k] = a;
-    if (bias_out != nullptr && k == 0) bias_out[j] = bs;
+#pragma unroll
+    for (int jj = 0; jj < OR_JT; ++jj)
+      if (j0 + jj < J) out[(long long)(j0 + jj) * K + k] = acc[jj];
+  }
+  if (bias_out != nullptr && blockIdx.x == 0 && threadIdx.x < OR_JT && j0 + threadIdx.x < J) {
+    float bs = 0.f;
+    for (int r = 0; r < R; ++r) bs += or_sm[r * OR_JT + threadIdx.x];
+    bias_out[j0 + threadIdx.x] = bs;
   }
 }
 
@@ -646,14 +663,30 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   const float gs = (gscale ? gscale[1] : 1.f) / grad_div;
   const float step = hyper[0] / hyper[1];
   const float bc2_sqrt = hyper[2];
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const float gi = g[i] * gs;
-    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
-    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
-    m[i] = mi;
-    v[i] = vi;
-    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= gs;
+    mi = fmaf(beta1, mi, (1.f - beta1) * gi);
+    vi = fmaf(beta2, vi, (1.f - beta2) * gi * gi);
+    pi -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  };
+  const long long n4 = n / 4;  // (the flat buffers are 16-byte aligned)
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    upd(pp.x, gg.x, mm.x, vv.x);
+    upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z);
+    upd(pp.w, gg.w, mm.w, vv.w);
+    p4[i] = pp;
+    m4[i] = mm;
+    v4[i] = vv;
   }
+  if (blockIdx.x == 0)
+    for (long long i = n4 * 4 + threadIdx.x; i < n; i += 256) upd(p[i], g[i], m[i], v[i]);
 }
 
 // KL reparametrisation of the stored (mean || logvar) latents + forward diffusion (diffusion_trainer.py:149-164,
@@ -912,17 +945,19 @@ extern "C" int idf_embed_time_class_bwd(const float* dtable, const int64_t* ctx,
   float* dz1 = dtemb + (long long)R * D;
   cudaStream_t s = S(stream);
   // time projections: g_wp = dtable^T s, g_bp = colsum(dtable); ds = dtable wp; dtemb = ds * silu'(temb)
-  outer_rows_kernel<<<dim3((D + 255) / 256, P), 256, 0, s>>>(dtable, P, sv, D, R, P, D, g_wp, g_bp);
+  const int or_smem = R * OR_JT * (int)sizeof(float);
+  if (or_smem > 48 * 1024) return fail(IDF_ERR_UNSUPPORTED, "embed_bwd: batch %d too large for the staged outer product", R);
+  outer_rows_kernel<<<dim3((D + 255) / 256, (P + OR_JT - 1) / OR_JT), 256, or_smem, s>>>(dtable, P, sv, D, R, P, D, g_wp, g_bp);
   xw_slice_kernel<<<dim3((D + 127) / 128, (R + 7) / 8, slices_p), 128, 0, s>>>(dtable, P, wp, R, P, D, part);
   xw_finish_kernel<<<(R * D + 255) / 256, 256, 0, s>>>(part, slices_p, R, D, temb, dtemb);
   if (ctx != nullptr && g_cls != nullptr)
     class_grad_kernel<<<dim3((D + 127) / 128, num_classes), 128, 0, s>>>(dtemb, ctx, ctx_mask, R, D, num_classes, g_cls);
   // second Linear: g_w2 = dtemb^T a1, g_b2 = colsum(dtemb); da1 = dtemb w2; dz1 = da1 * silu'(z1)
-  outer_rows_kernel<<<dim3((4 * D + 255) / 256, D), 256, 0, s>>>(dtemb, D, a1, 4 * D, R, D, 4 * D, g_w2, g_b2);
+  outer_rows_kernel<<<dim3((4 * D + 255) / 256, (D + OR_JT - 1) / OR_JT), 256, or_smem, s>>>(dtemb, D, a1, 4 * D, R, D, 4 * D, g_w2, g_b2);
   xw_slice_kernel<<<dim3((4 * D + 127) / 128, (R + 7) / 8, slices_d), 128, 0, s>>>(dtemb, D, w2, R, D, 4 * D, part);
   xw_finish_kernel<<<(R * 4 * D + 255) / 256, 256, 0, s>>>(part, slices_d, R, 4 * D, z1, dz1);
   // first Linear: g_w1 = dz1^T e, g_b1 = colsum(dz1)
-  outer_rows_kernel<<<dim3((D + 255) / 256, 4 * D), 256, 0, s>>>(dz1, 4 * D, e, D, R, 4 * D, D, g_w1, g_b1);
+  outer_rows_kernel<<<dim3((D + 255) / 256, (4 * D + OR_JT - 1) / OR_JT), 256, or_smem, s>>>(dz1, 4 * D, e, D, R, 4 * D, D, g_w1, g_b1);
   return check_cuda(cudaGetLastError(), "embed_bwd launch");
 }
 
@@ -947,6 +982,9 @@ extern "C" int idf_adam_step(float* param, const float* grad, float* exp_avg, fl
                              const float* hyper, float beta1, float beta2, float eps, float grad_div,
                              const float* clip2, idf_stream_t stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || n <= 0) return fail(IDF_ERR_ARG, "adam_step: bad argument");
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+       reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+    return fail(IDF_ERR_ARG, "adam_step: buffers must be 16-byte aligned");
   adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, S(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, hyper, beta1, beta2,
                                                                eps, grad_div, clip2);
   return check_cuda(cudaGetLastError(), "adam_step launch");
