@@ -46,6 +46,9 @@ struct IgemmParams {
   int tiles_per_img;  // HW / 128 when HW >= 128, else 0
   int matrix;         // 1: A is a plain (rows, cols) matrix walked 128 rows at a time along the w axis
   int s2_batch;       // > 0: segment 0 holds the 4 parity planes of a stride-2 conv input, stacked along n
+  int w_mn;           // 1: W is stored (K rows, N columns) per tap - a FORWARD-packed weight used for the data gradient:
+                      //    B tiles are fetched as 64x64 boxes and consumed as MN-major operands (no transposed copy)
+  signed char wtap[9];  // tap column block of W for the i-th A tap (identity unless a tap subset is used)
   int s2_direct;      // 1: segment 0 is the FULL-resolution input read with TMA element strides (2, 2): tap (kh, kw)
                       //    of output tile origin (h0, w0) starts at source pixel (2*h0 + kh, 2*w0 + kw)
   signed char tdh[2][9], tdw[2][9];  // per-segment tap offsets (rows, columns)
@@ -412,7 +415,14 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           const int sc = (p.s2_direct && seg == 0) ? 2 : 1;
           tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, sc * w0 + dw, sc * h0 + dh,
                       img0 + dn);
-          tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+          if (p.w_mn) {
+            const int col0 = p.wtap[tap] * p.N + n0;
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(smem_b + s * Cfg::B_BYTES + c * 8192, &p.tmB, &full_bar[s], col0 + c * 64, cbk * BLOCK_K);
+          } else {
+            tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+          }
           if (++cbk == p.cb[seg]) {
             cbk = 0;
             if (++tap == p.taps[seg]) { tap = 0; ++seg; }
@@ -437,10 +447,18 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           mbar_wait(&full_bar[s], (kc / STAGES) & 1);
           tc_fence_after_sync();
           const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + s * A_STAGE_BYTES), 128);
-          const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + s * Cfg::B_BYTES), 128);
+          if (p.w_mn) {
+            constexpr uint32_t idesc_mn = umma_idesc_bf16(BLOCK_M, BN, 0, 1);
+            const uint64_t db = umma_desc_mnmajor(smem_u32(smem_b + s * Cfg::B_BYTES), 8192, 1024);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma_bf16(tmem_d, da + 2 * k, db + 128 * k, idesc_mn, (kb > kb0) || (k != 0));
+          } else {
+            const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + s * Cfg::B_BYTES), 128);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+          }
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full[acc]);
@@ -793,7 +811,17 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   if (nseg == 1) { p.cb[1] = 1; p.taps[1] = 1; }
   p.kb_seg0 = a->taps[0] * p.cb[0];
   p.kb_total = ktot / BLOCK_K;
-  if (a->ldw < ktot) return fail(IDF_ERR_ARG, "igemm: ldw %lld < K %d", (long long)a->ldw, ktot);
+  if (a->w_mn) {
+    if (nseg != 1) return fail(IDF_ERR_UNSUPPORTED, "igemm: w_mn takes one input segment");
+    int maxt = 0;
+    for (int t = 0; t < a->taps[0]; ++t) {
+      p.wtap[t] = a->custom_taps ? a->w_tap_ids[t] : (signed char)t;
+      if (p.wtap[t] < 0 || p.wtap[t] > 8) return fail(IDF_ERR_ARG, "igemm: bad w_tap_ids");
+      if (p.wtap[t] > maxt) maxt = p.wtap[t];
+    }
+    if (a->ldw < (long long)(maxt + 1) * a->N) return fail(IDF_ERR_ARG, "igemm: ldw %lld too small for w_mn", (long long)a->ldw);
+    p.w_mn = 1;
+  } else if (a->ldw < ktot) return fail(IDF_ERR_ARG, "igemm: ldw %lld < K %d", (long long)a->ldw, ktot);
   // tile width: the persistent kernel takes 256 / 192 / 128 columns per tile; pick the widest that divides N (and
   // the V^T split point) unless that would leave SMs without a tile
   static const int legacy = [] { const char* e = getenv("IDF_IGEMM_LEGACY"); return e ? atoi(e) : 0; }();
@@ -839,7 +867,12 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     }
   }
   p.splits = splits;
-  if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, (uint32_t)bn)) != IDF_OK)
+  if (a->w_mn) {  // rows = the A operand's channels (K per tap), columns = (weight tap, output column)
+    int maxt = 0;
+    for (int t = 0; t < a->taps[0]; ++t) maxt = p.wtap[t] > maxt ? p.wtap[t] : maxt;
+    if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)x0.c, (uint64_t)(maxt + 1) * a->N, (uint64_t)a->ldw, 64, 64)) != IDF_OK)
+      return rc;
+  } else if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, (uint32_t)bn)) != IDF_OK)
     return rc;
 
   p.H = a->epi_h > 0 ? a->epi_h : H;
@@ -930,6 +963,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
                                  a->rowbias, a->rowbias_idx, a->rowbias_ld, p.H, p.W, a->zero_pad_last ? 1 : 0),
                       "splitk_finish launch");
   }
+  if (a->w_mn || a->out_up2 || a->s2_direct) return fail(IDF_ERR_UNSUPPORTED, "igemm: legacy kernel lacks this mode");
   dim3 grid((unsigned)((M + BLOCK_M - 1) / BLOCK_M), (unsigned)(a->N / BLOCK_N));
   igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_cuda(cudaGetLastError(), "igemm launch");

@@ -33,7 +33,8 @@ class IgemmArgs(C.Structure):
         ("zero_pad_last", _i32), ("epi_h", _i32), ("epi_w", _i32), ("s2_batch", _i32),
         ("ws", _vp), ("ws_bytes", _i64),
         ("custom_taps", _i32), ("tap_dh", C.c_int8 * 9), ("tap_dw", C.c_int8 * 9), ("force_splits", _i32),
-        ("out_up2", _i32), ("out_ph", _i32), ("out_pw", _i32), ("s2_direct", _i32),
+        ("out_up2", _i32), ("out_ph", _i32), ("out_pw", _i32),
+        ("w_mn", _i32), ("w_tap_ids", C.c_int8 * 9), ("s2_direct", _i32),
     ]
 
 

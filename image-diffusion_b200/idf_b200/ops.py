@@ -24,7 +24,8 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 
 def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
           res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0, ws=None,
-          tap_offsets=None, splits: int = 0, out_up2=None, s2_direct: bool = False) -> torch.Tensor:
+          tap_offsets=None, splits: int = 0, out_up2=None, s2_direct: bool = False, w_mn: bool = False,
+          w_tap_ids=None) -> torch.Tensor:
     """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view."""
     a = IgemmArgs()
     if not 1 <= len(segs) <= 2:
@@ -56,6 +57,10 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
     a.ws_bytes = ws.numel() * ws.element_size() if ws is not None else 0
     a.force_splits = splits
     a.s2_direct = 1 if s2_direct else 0
+    a.w_mn = 1 if w_mn else 0
+    if w_tap_ids is not None:
+        for i, t in enumerate(w_tap_ids):
+            a.w_tap_ids[i] = t
     if out_up2 is not None:  # (row parity, column parity) of the 2x-resolution output this launch fills
         a.out_up2, (a.out_ph, a.out_pw) = 1, out_up2
     if tap_offsets is not None:  # explicit (dh, dw) list for segment 0

@@ -9,8 +9,9 @@ Per DiffusionBlock layer (components.py:518-536), backward of
 is: wgrad/colsum/dgrad of out_proj -> attention backward -> wgrad/colsum/dgrad of QKV -> GN3 backward (+ dout) ->
 wgrad x2 / colsum / dgrad of the second conv -> GN2+SiLU backward -> wgrad/colsum (bias + per-sample time-bias
 gradient)/dgrad of the first conv -> GN1+SiLU backward -> 1x1 skip dgrad with the GN1 result as epilogue addend.
-Data gradients of all convolutions run on the SAME tcgen05 implicit-GEMM kernel as the forward pass (mirrored taps,
-swapped channel roles); weight gradients on the MN-major tcgen05 kernel (csrc/wgrad.cu).
+Data gradients of all convolutions run on the SAME tcgen05 implicit-GEMM kernel as the forward pass, reading the SAME
+forward-packed weights as MN-major operands (mirrored tap offsets, no transposed weight copies); weight gradients on
+the MN-major tcgen05 kernel (csrc/wgrad.cu).
 """
 from __future__ import annotations
 
@@ -163,17 +164,9 @@ class UnetTrainEngine:
             o, i, kh, kw = w.shape
             job(w, dst2d, o, kh * kw, i, i * kh * kw, kh * kw, 1, dst2d.stride(0), i)
 
-        def conv_dgrad(dst2d, w):    # (O, I, kh, kw) -> rows = input channel, columns (tap, co), taps in (kh, kw) order
-            o, i, kh, kw = w.shape
-            job(w, dst2d, i, kh * kw, o, kh * kw, i * kh * kw, 1, dst2d.stride(0), o)
-
         def lin(dst2d, w2d):         # (O, I) row-major copy
             o, i = w2d.shape
             job(w2d, dst2d, o, 1, i, i, 1, 0, dst2d.stride(0), 0)
-
-        def lin_t(dst2d, w2d):       # (O, I) -> (I, O)
-            o, i = w2d.shape
-            job(w2d, dst2d, i, 1, o, 1, i, 0, dst2d.stride(0), 0)
 
         def vec(dst1d, a, b=None):   # fp32 vector copy / sum
             job(a, dst1d, 1, 1, a.numel(), 0, 1, 0, 0, 0, out_f32=1, src2=b)
@@ -190,18 +183,13 @@ class UnetTrainEngine:
                 lin(w2b[:, 9 * cout:], wr)
                 vec(self._buf(k + ".b2", 1, cout, F32).view(-1), sd[f"{p}.second_halfs.{l}.layers.2.bias"],
                     sd[f"{p}.residuals.{l}.bias"])
-                wqkv, wqkvd = self._buf(k + ".wqkv", 3 * cout, cout), self._buf(k + ".wqkvd", cout, 3 * cout)
+                wqkv = self._buf(k + ".wqkv", 3 * cout, cout)
                 bqkv = self._buf(k + ".bqkv", 1, 3 * cout, F32).view(-1)
                 for j, n in enumerate(("to_q", "to_k", "to_v")):
                     wj = sd[f"{a}.{n}.weight"]
                     lin(wqkv[j * cout:(j + 1) * cout], wj)
-                    lin_t(wqkvd[:, j * cout:(j + 1) * cout], wj)
                     vec(bqkv[j * cout:(j + 1) * cout], sd[f"{a}.{n}.bias"])
                 lin(self._buf(k + ".wo", cout, cout), sd[a + ".out_proj.weight"])
-                lin_t(self._buf(k + ".wod", cout, cout), sd[a + ".out_proj.weight"])
-                conv_dgrad(self._buf(k + ".w1d", cin, 9 * cout), w1)
-                conv_dgrad(self._buf(k + ".w2d", cout, 9 * cout), w2)
-                lin_t(self._buf(k + ".wrd", cin, cout), wr)
                 pw[k + ".b1"], pw[k + ".bo"] = sd[f"{p}.first_halfs.{l}.layers.2.bias"], sd[a + ".out_proj.bias"]
                 pw[k + ".b2"], pw[k + ".bqkv"] = pw[k + ".b2"].view(-1), bqkv
                 for n, key_ in (("g1", f"{p}.first_halfs.{l}.layers.0"), ("g2", f"{p}.second_halfs.{l}.layers.0"),
@@ -212,14 +200,8 @@ class UnetTrainEngine:
             c = wd.shape[0]
             conv_fwd(self._buf(f"down.{i}.w", c, 9 * c), wd)
             pw[f"down.{i}.b"] = sd[f"downsamples.{i}.down.bias"]
-            for j, (pq, taps) in enumerate(sorted(ops._S2_PLANE_TAPS.items())):
-                dst = self._buf(f"down.{i}.wd{j}", c, len(taps) * c)
-                for t, (kh, kw) in enumerate(taps):  # dst[ci, t*c + co] = wd[co, ci, kh, kw]
-                    job(wd, dst[:, t * c:(t + 1) * c], c, 1, c, 9, c * 9, 0, dst.stride(0), 0, src_off=kh * 3 + kw)
-                pw[f"down.{i}.offs{j}"] = [(-(kh >> 1), -(kw >> 1)) for kh, kw in taps]
             cu = wu.shape[0]
             conv_fwd(self._buf(f"up.{i}.w", cu, 9 * cu), wu)
-            conv_dgrad(self._buf(f"up.{i}.wd", cu, 9 * cu), wu)
             pw[f"up.{i}.b"] = sd[f"upsamples.{i}.conv.bias"]
         pw["in.w"], pw["in.b"] = sd["in_conv.weight"], sd["in_conv.bias"]
         pw["out.gw"], pw["out.gb"] = sd["out_conv.0.weight"], sd["out_conv.0.bias"]
@@ -358,7 +340,7 @@ class UnetTrainEngine:
             ops.conv_wgrad(S["o"], (1, 1, M), cout, 1, dout, cout, self.g(a + ".out_proj.weight"), sc["wg"])
             ops.colsum(dout, B, HW, cout, sc["ps"], total=self.g(a + ".out_proj.bias"))
             do = ws.get(f"b.do.{M}", M, cout)
-            ops.igemm([(dout, (1, 1, M), cout, 1)], w[k + ".wod"], cout, do)
+            ops.igemm([(dout, (1, 1, M), cout, 1)], w[k + ".wo"], cout, do, w_mn=True)
             # attention
             dqkv = ws.get(f"b.dqkv.{M}", M, 3 * cout)
             delta = ws.get(f"b.delta.{M}", M, self.heads, F32)
@@ -369,7 +351,7 @@ class UnetTrainEngine:
                            self.gspan(a + ".to_q.weight", a + ".to_v.weight"), sc["wg"])
             ops.colsum(dqkv, B, HW, 3 * cout, sc["ps"], total=self.gspan(a + ".to_q.bias", a + ".to_v.bias"))
             dh3 = ws.get(f"b.dh3.{M}", M, cout)
-            ops.igemm([(dqkv, (1, 1, M), 3 * cout, 1)], w[k + ".wqkvd"], cout, dh3)
+            ops.igemm([(dqkv, (1, 1, M), 3 * cout, 1)], w[k + ".wqkv"], cout, dh3, w_mn=True)
             # GN3 (no SiLU); the residual path adds dout
             dx2 = ws.get(f"b.dx2.{M}", M, cout)
             self._gn_bwd(S["x2"], dh3, dx2, w[k + ".g3w"], w[k + ".g3b"], S["st3"], a + ".groupnorm.weight",
@@ -379,7 +361,8 @@ class UnetTrainEngine:
             ops.conv_wgrad(S["h2"], grid, cout, 9, dx2, cout, self.g(f"{p}.second_halfs.{l}.layers.2.weight"), sc["wg"])
             ops.conv_wgrad(x.t, grid, cin, 1, dx2, cout, self.g(f"{p}.residuals.{l}.weight"), sc["wg"])
             dh2 = ws.get(f"b.dh2.{M}", M, cout)
-            ops.igemm([(dx2, grid, cout, 9)], w[k + ".w2d"], cout, dh2, tap_offsets=self.DGRAD_TAPS)
+            ops.igemm([(dx2, grid, cout, 9)], w[k + ".w2"][:, :9 * cout], cout, dh2, tap_offsets=self.DGRAD_TAPS, w_mn=True,
+                      w_tap_ids=range(9))
             dy1 = ws.get(f"b.dy1.{M}", M, cout)
             off = self.tp_off[(p, l)]
             self._gn_bwd(S["y1"], dh2, dy1, w[k + ".g2w"], w[k + ".g2b"], S["st2"],
@@ -388,12 +371,12 @@ class UnetTrainEngine:
             # first conv3x3 (bias gradient + per-sample time-bias gradient came out of the GN2 backward above)
             ops.conv_wgrad(S["h1"], grid, cin, 9, dy1, cout, self.g(f"{p}.first_halfs.{l}.layers.2.weight"), sc["wg"])
             dh1 = ws.get(f"b.dh1.{M}.{cin}", M, cin)
-            ops.igemm([(dy1, grid, cout, 9)], w[k + ".w1d"], cin, dh1, tap_offsets=self.DGRAD_TAPS)
+            ops.igemm([(dy1, grid, cout, 9)], w[k + ".w1"], cin, dh1, tap_offsets=self.DGRAD_TAPS, w_mn=True, w_tap_ids=range(9))
             dxa = ws.get(f"b.dxa.{M}.{cin}", M, cin)
             self._gn_bwd(x.t, dh1, dxa, w[k + ".g1w"], w[k + ".g1b"], S["st1"], f"{p}.first_halfs.{l}.layers.0.weight",
                          f"{p}.first_halfs.{l}.layers.0.bias", B, HW, cin, True)
             dx = ws.get(final_name if (l == 0 and final_name) else f"b.dx{l % 2}.{M}.{cin}", M, cin)
-            ops.igemm([(dx2, grid, cout, 1)], w[k + ".wrd"], cin, dx, res=dxa)
+            ops.igemm([(dx2, grid, cout, 1)], w[k + ".w2"][:, 9 * cout:], cin, dx, res=dxa, w_mn=True)
             dout = dx
         return dout
 
@@ -436,7 +419,8 @@ class UnetTrainEngine:
             ops.conv_wgrad(su["up"], su["grid"], c, 9, dleft, c, self.g(f"upsamples.{i}.conv.weight"), sc["wg"])
             ops.colsum(dleft, b_, h_ * w_, c, sc["ps"], total=self.g(f"upsamples.{i}.conv.bias"))
             dup = ws.get(f"b.dup{i}", b_ * h_ * w_, c)
-            ops.igemm([(dleft, su["grid"], c, 9)], w[f"up.{i}.wd"], c, dup, tap_offsets=self.DGRAD_TAPS)
+            ops.igemm([(dleft, su["grid"], c, 9)], w[f"up.{i}.w"], c, dup, tap_offsets=self.DGRAD_TAPS, w_mn=True,
+                      w_tap_ids=range(9))
             d = ws.get(f"b.dlow{i}", b_ * h_ * w_ // 4, c)
             ops.sum2x2(dup, d, b_, h_ // 2, w_ // 2, c)
             done()
@@ -453,8 +437,11 @@ class UnetTrainEngine:
                            sc["wg"], s2_batch=b_)
             ops.colsum(d, b_, oh * ow, cout, sc["ps"], total=self.g(f"downsamples.{i}.down.bias"))
             dplanes = ws.get(f"b.dplanes{i}", b_ * h_ * w_, cout)
-            packed = [(w[f"down.{i}.offs{j}"], w[f"down.{i}.wd{j}"]) for j in range(4)]
-            ops.conv_s2_dgrad(d, b_, oh, ow, cout, packed, dplanes, cout)
+            rows_ = b_ * oh * ow
+            for j, (pq, taps) in enumerate(sorted(ops._S2_PLANE_TAPS.items())):  # one launch per input parity plane
+                ops.igemm([(d, (b_, oh, ow), cout, len(taps))], w[f"down.{i}.w"], cout, dplanes[j * rows_:(j + 1) * rows_],
+                          tap_offsets=[(-(kh >> 1), -(kw >> 1)) for kh, kw in taps], w_mn=True,
+                          w_tap_ids=[kh * 3 + kw for kh, kw in taps])
             dfull = ws.get(f"b.dfull{i}", b_ * h_ * w_, cout)
             ops.depth_to_space2(dplanes, dfull, b_, h_, w_, cout, add=dskips[i])
             d = self._bwd_block(p, dfull, cout, dtable)

@@ -103,6 +103,11 @@ typedef struct idf_igemm_args {
                            3x3 conv (Upsample, components.py:124-130) at 4/9 of the FLOPs and without the upsampled
                            tensor ever existing. */
   int32_t out_ph, out_pw;
+  int32_t w_mn;         /* != 0: data-gradient mode. `w` is the FORWARD weight matrix of the layer, (a[0].c rows, ldw), whose
+                           column block [t*N, (t+1)*N) holds tap t: out[m, n] = sum_t sum_k A[pixel(m)+tap_t, k] w[k, t*N+n].
+                           The tensor core reads it as an MN-major operand, so no transposed weight copy is needed.
+                           With custom_taps, w_tap_ids[i] names the column block of the i-th tap. One segment only. */
+  int8_t w_tap_ids[9];
   int32_t s2_direct;    /* != 0: stride-2 pad-0 3x3 conv (Downsample, components.py:110) read straight from the
                            FULL-resolution input a[0] (n, 2h, 2w) through a TMA map with element strides (2, 2): no
                            parity-plane copy. The output grid is (n, h, w); use with zero_pad_last. */

@@ -122,6 +122,28 @@ def test_conv3x3_dgrad(B, Cin, Cout, H):
     dx = torch.empty(B * H * H, Cin, device=DEV, dtype=torch.bfloat16)
     ops.igemm([(rows(dy), (B, H, H), Cout, 9)], ops.pack_dgrad_weight(w), Cin, dx)
     assert rel_err(unrows(dx, B, H, H), x.grad) < 6e-3
+    # same result from the FORWARD-packed weight read as an MN-major operand (what the training engine does)
+    dx2 = torch.empty_like(dx)
+    taps = [(1 - kh, 1 - kw) for kh in range(3) for kw in range(3)]
+    ops.igemm([(rows(dy), (B, H, H), Cout, 9)], ops.pack_conv_weight(w), Cin, dx2, tap_offsets=taps, w_mn=True,
+              w_tap_ids=range(9))
+    assert rel_err(unrows(dx2, B, H, H), x.grad) < 6e-3
+    assert rel_err(dx2.float(), dx.float()) < 2e-3
+
+
+def test_linear_dgrad_from_forward_weight():
+    """dX = dY W for nn.Linear (W stored (out, in) as in the forward pass), column-sliced weight, residual epilogue."""
+    ops = _ops()
+    M, O, I = 3 * 256, 768, 256
+    g = torch.Generator(device=DEV).manual_seed(2)
+    dy = torch.randn(M, O, device=DEV, generator=g).to(torch.bfloat16)
+    wide = (torch.randn(O, I + 128, device=DEV, generator=g) / math.sqrt(O)).to(torch.bfloat16)
+    w = wide[:, 128:]
+    res = torch.randn(M, I, device=DEV, generator=g).to(torch.bfloat16)
+    dx = torch.empty(M, I, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(dy, (1, 1, M), O, 1)], w, I, dx, res=res, w_mn=True)
+    ref = dy.float() @ w.float() + res.float()
+    assert rel_err(dx.float(), ref) < 6e-3
 
 
 @pytest.mark.parametrize("B,C,HW,silu,with_add", [(3, 128, 1024, True, False), (2, 384, 256, True, True),
