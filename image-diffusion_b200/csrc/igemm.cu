@@ -319,7 +319,6 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
 // i + 1, and the smem ring keeps streaming across tile boundaries. BN = 256 halves the A re-reads and takes the
 // per-MMA shared-memory traffic below the 128 B/clk limit that bounds 128 x 128 tiles.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PG_THREADS = 192;
 constexpr int PG_STG_BYTES = 2 * BLOCK_M * 128;  // one staging buffer: two (128 rows x 64 cols) swizzled boxes
 
 // BN: tile width; NSTG: epilogue staging buffers (1: long-K tiles whose epilogue hides under the next mainloop;
@@ -334,9 +333,14 @@ struct PgCfg {
   static constexpr int SMEM = STAGES * STAGE_BYTES + NSTG * PG_STG_BYTES + 1024 + 256;
 };
 
-template <int BN, int NSTG>
-__global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
+// EW: epilogue warpgroups (warps 2 .. 2 + 4 EW - 1). Warp w reads TMEM lanes 32 (w % 4) .. +31, so every warpgroup
+// covers all 128 rows; the warpgroups split the 32-column chunks of each column group between them. With one warp
+// per scheduler (EW = 1) nothing hides the TMEM / L1 / shared-memory latencies of the epilogue, which is what bounds
+// the short-K GEMMs and the single-tile-per-CTA launches of the 8x8 / 4x4 stages.
+template <int BN, int NSTG, int EW>
+__global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = PgCfg<BN, NSTG>;
+  constexpr int EPI_THREADS = 128 * EW;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int GPT = (BN + 127) / 128;  // column groups per tile
   pdl_launch_dependents();
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 4 * EW);
     }
     for (int i = 0; i < NSTG; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
@@ -465,10 +469,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2 .. 2 + 4 EW - 1)
     // Work unit = "column group": up to 128 output columns of a tile = one staging buffer. Groups are numbered gc
     // across tiles; group gc owns staging buffer gc % NSTG.
     const int quad = warp & 3;
+    const int wg = (warp - 2) >> 2;  // which share of each column group's chunks this warp takes
     const int r = quad * 32 + lane;
     const int et = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           if (NSTG >= 3 && has_res) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSTG >= 3 ? NSTG - 2 : 0) : "memory");
           else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSTG - 1) : "memory");
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, EPI_THREADS);
         if (has_res && staged) {
           if (NSTG >= 3) {
             if (issuer) {  // prefetch the next group's residual
@@ -540,35 +545,11 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           }
           mbar_wait(&res_bar[gc % NSTG], (gc / NSTG) & 1);
         }
-#pragma unroll 1
-        for (int c = 0; c < gcols / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_d + cg * 128 + c * 32, v);
-          tmem_ld_wait();
-          if (cg * 128 + (c + 1) * 32 == BN) {  // last TMEM read of this tile: release the accumulator buffer
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
+        // one 32-column chunk: + bias terms, + residual, mask, convert, store (staging / transposed staging / fp32)
+        auto finish_chunk = [&](const int c, const uint32_t (&v)[32], const float (&bb)[32]) {
           float a[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc0 + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              a[4 * j + 0] += b.x; a[4 * j + 1] += b.y; a[4 * j + 2] += b.z; a[4 * j + 3] += b.w;
-            }
-          }
-          if (rb != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(rb + cg * 128 + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              a[4 * j + 0] += b.x; a[4 * j + 1] += b.y; a[4 * j + 2] += b.z; a[4 * j + 3] += b.w;
-            }
-          }
+          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]) + bb[j];
           if (staged) {
             uint8_t* box = stage_c + (c >> 1) * (BLOCK_M * 128) + r * 128;
 #pragma unroll
@@ -602,13 +583,56 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(a[4 * j + 0], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
           }
+        };
+        // bias + per-sample time bias of one chunk, fetched while the TMEM loads are in flight
+        auto load_bias = [&](const int c, float (&bb)[32]) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bb[j] = 0.f;
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nc0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              bb[4 * j + 0] = b.x; bb[4 * j + 1] = b.y; bb[4 * j + 2] = b.z; bb[4 * j + 3] = b.w;
+            }
+          }
+          if (rb != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(rb + cg * 128 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              bb[4 * j + 0] += b.x; bb[4 * j + 1] += b.y; bb[4 * j + 2] += b.z; bb[4 * j + 3] += b.w;
+            }
+          }
+        };
+        // this warpgroup's chunks of the group, two at a time: both TMEM loads and the bias loads are issued before
+        // the single wait
+        const int my_nch = (gcols / 32) / EW;
+        const int cbase = wg * my_nch;
+#pragma unroll 1
+        for (int i0 = 0; i0 < my_nch; i0 += 2) {
+          const int c0 = cbase + i0;
+          const bool two = i0 + 1 < my_nch;
+          uint32_t v0[32], v1[32];
+          float bb0[32], bb1[32];
+          tmem_ld_32x32(tmem_d + cg * 128 + c0 * 32, v0);
+          if (two) tmem_ld_32x32(tmem_d + cg * 128 + (c0 + 1) * 32, v1);
+          load_bias(c0, bb0);
+          if (two) load_bias(c0 + 1, bb1);
+          tmem_ld_wait();
+          if (cg == GPT - 1 && i0 + 2 >= my_nch) {  // this warp's last TMEM read of the tile: release the accumulator
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          finish_chunk(c0, v0, bb0);
+          if (two) finish_chunk(c0 + 1, v1, bb1);
         }
         if (to_vt) {
-          named_bar_sync(1, 128);
+          named_bar_sync(1, EPI_THREADS);
           const long long m0 = (long long)tile_m * BLOCK_M;
           __nv_bfloat16* gbase = p.vt + (long long)(nc0 - p.vt_col0) * p.vt_ld + m0;
-          for (int i = 0; i < gcols / 8; ++i) {
-            const int q = i * 128 + et;
+          for (int q = et; q < gcols * 16; q += EPI_THREADS) {
             const int col = q >> 4, part = q & 15;
             if (m0 + part * 8 < p.M) {
               const uint4 vv = *reinterpret_cast<const uint4*>(stage_c + col * (BLOCK_M * 2) + part * 16);
@@ -618,7 +642,7 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
           if (issuer) tma_store_commit();  // empty bulk group: keeps "groups pending" == "staging buffers in use"
         } else if (staged) {
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, EPI_THREADS);
           if (issuer) {
             if (p.flags & F_OUT_UP2) {
               // tile rows = low-resolution pixels (img, h, w); tmC is a 4-D map over the 2x-resolution output whose
@@ -651,12 +675,12 @@ __global__ void __launch_bounds__(PG_THREADS, 1) igemm_persist_kernel(const __gr
   }
 }
 
-template <int BN, int NSTG>
-static int launch_persist(const IgemmParams& p, cudaStream_t stream) {
+template <int BN, int NSTG, int EW>
+static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
   using Cfg = PgCfg<BN, NSTG>;
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(igemm_persist_kernel<BN, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int rc = check_cuda(cudaFuncSetAttribute(igemm_persist_kernel<BN, NSTG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM),
                         "igemm_persist: cudaFuncSetAttribute");
     if (rc != IDF_OK) return rc;
@@ -664,8 +688,15 @@ static int launch_persist(const IgemmParams& p, cudaStream_t stream) {
   }
   const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BN) * p.splits;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  return check_cuda(launch_pdl(igemm_persist_kernel<BN, NSTG>, dim3(grid), dim3(PG_THREADS), Cfg::SMEM, stream, p),
+  return check_cuda(launch_pdl(igemm_persist_kernel<BN, NSTG, EW>, dim3(grid), dim3(64 + 128 * EW), Cfg::SMEM, stream, p),
                     "igemm_persist launch");
+}
+
+template <int BN, int NSTG>
+static int launch_persist(const IgemmParams& p, cudaStream_t stream) {
+  // IDF_EPI_WG=1 selects the single-warpgroup epilogue (kept for A/B measurements)
+  static const int ew = [] { const char* e = getenv("IDF_EPI_WG"); return e ? atoi(e) : 2; }();
+  return ew == 1 ? launch_persist_ew<BN, NSTG, 1>(p, stream) : launch_persist_ew<BN, NSTG, 2>(p, stream);
 }
 
 // Split-K finish: out[m, n] = bf16( sum_s partial[s][m][n] + bias[n] + rowbias[row(sample(m))][n] ), partials summed in
