@@ -44,6 +44,9 @@ struct IgemmParams {
   int H, W, HW;
   int tile_w, tile_h, tile_n;
   int tiles_per_img;  // HW / 128 when HW >= 128, else 0
+  int tpi_shift;      // log2(tiles_per_img) when it is a power of two, else -1 (the per-tile divisions sit on the
+  int hw_shift;       // single-thread TMA producer's critical path: shifts where possible); same for HW and W
+  int w_shift;
   int matrix;         // 1: A is a plain (rows, cols) matrix walked 128 rows at a time along the w axis
   int s2_batch;       // > 0: segment 0 holds the 4 parity planes of a stride-2 conv input, stacked along n
   int w_mn;           // 1: W is stored (K rows, N columns) per tap - a FORWARD-packed weight used for the data gradient:
@@ -321,14 +324,39 @@ __global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_co
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PG_STG_BYTES = 2 * BLOCK_M * 128;  // one staging buffer: two (128 rows x 64 cols) swizzled boxes
 
+// Work-unit walk shared by the three roles of the persistent kernel: unit u = (tile_m * n_tiles + n_idx) * splits + sp
+// advances by gridDim.x per iteration. The stride is decomposed once, so a step costs three compare-and-carry adds
+// instead of four integer divisions (the producer is ONE thread: with 2-8 k-blocks per tile its per-tile scalar
+// work, not the tensor pipe or the loads in flight, bounded the short-K GEMMs).
+struct TileWalk {
+  int sp, n_idx, tile_m;
+  int dsp, dn, dm, splits, n_tiles;
+  __device__ __forceinline__ void init(int u0, int stride, int splits_, int n_tiles_) {
+    splits = splits_; n_tiles = n_tiles_;
+    int t = u0, g1 = stride;
+    sp = 0; dsp = 0;
+    if (splits > 1) { sp = u0 % splits; t = u0 / splits; dsp = stride % splits; g1 = stride / splits; }
+    n_idx = t % n_tiles; tile_m = t / n_tiles;
+    dn = g1 % n_tiles; dm = g1 / n_tiles;
+  }
+  __device__ __forceinline__ void next() {
+    int c = 0;
+    sp += dsp;
+    if (sp >= splits) { sp -= splits; c = 1; }
+    n_idx += dn + c;
+    if (n_idx >= n_tiles) { n_idx -= n_tiles; tile_m += 1; }
+    tile_m += dm;
+  }
+};
+
 // BN: tile width; NSTG: epilogue staging buffers (1: long-K tiles whose epilogue hides under the next mainloop;
 // 3: short-K, epilogue-bound tiles - store of group g-1, fill of group g and residual prefetch of group g+1 overlap)
 template <int BN, int NSTG>
 struct PgCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
-  // short-K (NSTG == 3) tiles only have 2..8 k-blocks: a shallow ring leaves room for the three staging buffers
-  static constexpr int STAGES = (NSTG == 3) ? (BN == 256 ? 2 : (BN == 192 ? 3 : 4)) : ((BN == 128) ? 5 : 4);
+  // as many ring stages as fit beside the staging buffers in the 227 KiB of shared memory
+  static constexpr int STAGES = (232448 - 1024 - 256 - NSTG * PG_STG_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (BN == 128) ? 256 : 512;
   static constexpr int SMEM = STAGES * STAGE_BYTES + NSTG * PG_STG_BYTES + 1024 + 256;
 };
@@ -394,42 +422,61 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      int kc = 0;  // running k-block counter across tiles (ring position)
-      for (int u = blockIdx.x; u < total_tiles; u += gridDim.x) {
-        const int t = u / splits, sp = u % splits;
-        const int tile_m = t / n_tiles, n0 = (t % n_tiles) * BN;
+      TileWalk tw;
+      tw.init(blockIdx.x, gridDim.x, splits, n_tiles);
+      int stage = 0;
+      uint32_t phase = 0;  // ring position, carried across tiles
+      const bool wmn = p.w_mn != 0;
+      for (int u = blockIdx.x; u < total_tiles; u += gridDim.x, tw.next()) {
+        const int tile_m = tw.tile_m, n0 = tw.n_idx * BN;
         int img0, h0, w0 = 0;
         if (p.matrix) {
           img0 = 0; h0 = 0; w0 = tile_m * BLOCK_M;
         } else if (p.tiles_per_img > 0) {
-          img0 = tile_m / p.tiles_per_img;
-          h0 = (tile_m % p.tiles_per_img) * p.tile_h;
+          if (p.tpi_shift >= 0) {
+            img0 = tile_m >> p.tpi_shift;
+            h0 = (tile_m & (p.tiles_per_img - 1)) * p.tile_h;
+          } else {
+            img0 = tile_m / p.tiles_per_img;
+            h0 = (tile_m % p.tiles_per_img) * p.tile_h;
+          }
         } else {
           img0 = tile_m * p.tile_n; h0 = 0;
         }
-        const int kb0 = (int)((long long)sp * p.kb_total / splits), kb1 = (int)((long long)(sp + 1) * p.kb_total / splits);
+        int kb0 = 0, kb1 = p.kb_total;
         int seg = 0, tap = 0, cbk = 0;
-        if (kb0 < p.kb_seg0) { tap = kb0 / p.cb[0]; cbk = kb0 % p.cb[0]; }
-        else { seg = 1; tap = (kb0 - p.kb_seg0) / p.cb[1]; cbk = (kb0 - p.kb_seg0) % p.cb[1]; }
-        for (int kb = kb0; kb < kb1; ++kb, ++kc) {
-          const int s = kc % STAGES;
-          mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          const int dh = p.tdh[seg][tap], dw = p.tdw[seg][tap], dn = seg == 0 ? p.tdn[tap] : 0;
+        if (splits > 1) {
+          kb0 = tw.sp * p.kb_total / splits; kb1 = (tw.sp + 1) * p.kb_total / splits;
+          if (kb0 < p.kb_seg0) { tap = kb0 / p.cb[0]; cbk = kb0 % p.cb[0]; }
+          else { seg = 1; tap = (kb0 - p.kb_seg0) / p.cb[1]; cbk = (kb0 - p.kb_seg0) % p.cb[1]; }
+        }
+        // per-tap values live in registers and are refreshed only when the tap changes
+        int cb_cur = p.cb[seg], taps_cur = p.taps[seg];
+        int ax = 0, ay = 0, an = 0, bcol = 0;
+        auto load_tap = [&]() {
           const int sc = (p.s2_direct && seg == 0) ? 2 : 1;
-          tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, sc * w0 + dw, sc * h0 + dh,
-                      img0 + dn);
-          if (p.w_mn) {
-            const int col0 = p.wtap[tap] * p.N + n0;
+          ax = sc * w0 + p.tdw[seg][tap];
+          ay = sc * h0 + p.tdh[seg][tap];
+          an = img0 + (seg == 0 ? p.tdn[tap] : 0);
+          if (wmn) bcol = p.wtap[tap] * p.N + n0;
+        };
+        load_tap();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(smem_a + stage * A_STAGE_BYTES, &p.tmA[seg], &full_bar[stage], cbk * BLOCK_K, ax, ay, an);
+          if (wmn) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(smem_b + s * Cfg::B_BYTES + c * 8192, &p.tmB, &full_bar[s], col0 + c * 64, cbk * BLOCK_K);
+              tma_load_2d(smem_b + stage * Cfg::B_BYTES + c * 8192, &p.tmB, &full_bar[stage], bcol + c * 64, cbk * BLOCK_K);
           } else {
-            tma_load_2d(smem_b + s * Cfg::B_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
           }
-          if (++cbk == p.cb[seg]) {
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++cbk == cb_cur) {
             cbk = 0;
-            if (++tap == p.taps[seg]) { tap = 0; ++seg; }
+            if (++tap == taps_cur) { tap = 0; seg = 1; cb_cur = p.cb[1]; taps_cur = p.taps[1]; }
+            if (kb + 1 < kb1) load_tap();
           }
         }
       }
@@ -438,32 +485,38 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
-      int kc = 0, it = 0;
+      int it = 0, stage = 0, sp = blockIdx.x % splits;
+      const int dsp = gridDim.x % splits;
+      uint32_t phase = 0;
       for (int u = blockIdx.x; u < total_tiles; u += gridDim.x, ++it) {
-        const int sp = u % splits;
-        const int kb0 = (int)((long long)sp * p.kb_total / splits), kb1 = (int)((long long)(sp + 1) * p.kb_total / splits);
+        int kb0 = 0, kb1 = p.kb_total;
+        if (splits > 1) {
+          kb0 = sp * p.kb_total / splits; kb1 = (sp + 1) * p.kb_total / splits;
+          sp += dsp;
+          if (sp >= splits) sp -= splits;
+        }
         const int acc = it & 1;
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb, ++kc) {
-          const int s = kc % STAGES;
-          mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + s * A_STAGE_BYTES), 128);
+          const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + stage * A_STAGE_BYTES), 128);
           if (p.w_mn) {
             constexpr uint32_t idesc_mn = umma_idesc_bf16(BLOCK_M, BN, 0, 1);
-            const uint64_t db = umma_desc_mnmajor(smem_u32(smem_b + s * Cfg::B_BYTES), 8192, 1024);
+            const uint64_t db = umma_desc_mnmajor(smem_u32(smem_b + stage * Cfg::B_BYTES), 8192, 1024);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k)
               umma_bf16(tmem_d, da + 2 * k, db + 128 * k, idesc_mn, (kb > kb0) || (k != 0));
           } else {
-            const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + s * Cfg::B_BYTES), 128);
+            const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + stage * Cfg::B_BYTES), 128);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k)
               umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
           }
-          umma_commit(&empty_bar[s]);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);
       }
@@ -481,22 +534,25 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
     const bool to_f32 = (p.flags & F_OUT_F32) != 0;
     const bool issuer = (warp == 2) && elect_one();
     auto group_cols = [&](int cg) { return (BN - cg * 128) < 128 ? (BN - cg * 128) : 128; };
-    auto load_res = [&](int t, int cg, int gc) {  // residual boxes of group (t, cg) -> staging buffer gc % NSTG
+    // residual boxes of group (tile (tm, ni), cg) -> staging buffer gc % NSTG
+    auto load_res = [&](int tm, int ni, int cg, int gc) {
       const int bufi = gc % NSTG;
       const int gcols = group_cols(cg);
-      const int nc0 = (t % n_tiles) * BN + cg * 128;
+      const int nc0 = ni * BN + cg * 128;
       uint8_t* dst = stage_base + bufi * PG_STG_BYTES;
       mbar_expect_tx(&res_bar[bufi], (gcols / 64) * BLOCK_M * 128);
       for (int bx = 0; bx < gcols / 64; ++bx)
-        tma_load_2d(dst + bx * (BLOCK_M * 128), &p.tmR, &res_bar[bufi], nc0 + bx * 64, (t / n_tiles) * BLOCK_M);
+        tma_load_2d(dst + bx * (BLOCK_M * 128), &p.tmR, &res_bar[bufi], nc0 + bx * 64, tm * BLOCK_M);
     };
     int it = 0, gc = 0;
-    if (has_res && issuer && blockIdx.x < total_tiles && !((p.flags & F_VT) || to_f32)) load_res(blockIdx.x, 0, 0);
-    for (int u = blockIdx.x; u < total_tiles; u += gridDim.x, ++it) {
-      const int t = u / splits;  // (residual / staged paths are only used with splits == 1, where t == u)
-      const float* __restrict__ dummy = nullptr; (void)dummy;
-      float* out_f32 = p.out_f32 + (long long)(u % splits) * p.split_stride;
-      const int tile_m = t / n_tiles, n0 = (t % n_tiles) * BN;
+    if (has_res && issuer && blockIdx.x < total_tiles && !((p.flags & F_VT) || to_f32))
+      load_res((int)blockIdx.x / n_tiles, (int)blockIdx.x % n_tiles, 0, 0);  // (residual path: splits == 1)
+    TileWalk tw;
+    tw.init(blockIdx.x, gridDim.x, splits, n_tiles);
+    for (int u = blockIdx.x; u < total_tiles; u += gridDim.x, ++it, tw.next()) {
+      const int t = tw.tile_m * n_tiles + tw.n_idx;  // (residual / staged paths are only used with splits == 1, where t == u)
+      float* out_f32 = p.out_f32 + (long long)tw.sp * p.split_stride;
+      const int tile_m = tw.tile_m, n0 = tw.n_idx * BN;
       const int acc = it & 1;
       const long long m = (long long)tile_m * BLOCK_M + r;
       const bool row_ok = m < p.M;
@@ -506,10 +562,16 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
       int sample = 0;
       bool zero_row = false;
       if (p.rowbias != nullptr || (p.flags & F_ZERO_PAD)) {
-        const long long mm = row_ok ? m : 0;
-        sample = (int)(mm / p.HW);
-        const int pix = (int)(mm % p.HW);
-        if (p.flags & F_ZERO_PAD) zero_row = (pix / p.W == p.H - 1) || (pix % p.W == p.W - 1);
+        const int mm = row_ok ? (int)m : 0;
+        int pix;
+        if (p.hw_shift >= 0) { sample = mm >> p.hw_shift; pix = mm & (p.HW - 1); }
+        else { sample = mm / p.HW; pix = mm % p.HW; }
+        if (p.flags & F_ZERO_PAD) {
+          int ph, pw;
+          if (p.w_shift >= 0) { ph = pix >> p.w_shift; pw = pix & (p.W - 1); }
+          else { ph = pix / p.W; pw = pix % p.W; }
+          zero_row = (ph == p.H - 1) || (pw == p.W - 1);
+        }
       }
       const float* rb = nullptr;
       if (p.rowbias != nullptr) {
@@ -537,11 +599,12 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           if (NSTG >= 3) {
             if (issuer) {  // prefetch the next group's residual
               int nt = t, ncg = cg + 1;
-              if (ncg == GPT) { nt = t + gridDim.x; ncg = 0; }  // splits == 1 here
-              if (nt < total_tiles) load_res(nt, ncg, gc + 1);
+              TileWalk nx = tw;
+              if (ncg == GPT) { nt = t + gridDim.x; ncg = 0; nx.next(); }  // splits == 1 here
+              if (nt < total_tiles) load_res(nx.tile_m, nx.n_idx, ncg, gc + 1);
             }
           } else if (gc > 0) {
-            if (issuer) load_res(t, cg, gc);
+            if (issuer) load_res(tile_m, tw.n_idx, cg, gc);
           }
           mbar_wait(&res_bar[gc % NSTG], (gc / NSTG) & 1);
         }
@@ -909,6 +972,15 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   p.H = a->epi_h > 0 ? a->epi_h : H;
   p.W = a->epi_w > 0 ? a->epi_w : W;
   p.HW = p.H * p.W;
+  auto log2_or_neg = [](int v) {
+    if (v <= 0 || (v & (v - 1)) != 0) return -1;
+    int sh = 0;
+    while ((1 << sh) < v) ++sh;
+    return sh;
+  };
+  p.tpi_shift = log2_or_neg(p.tiles_per_img);
+  p.hw_shift = log2_or_neg(p.HW);
+  p.w_shift = log2_or_neg(p.W);
   p.M = (int)M; p.N = a->N;
   p.bias = a->bias;
   p.rowbias = a->rowbias;
