@@ -104,39 +104,56 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       const bool first = warp == 0;
       const int c_lo = first ? 0 : C_SPLIT, c_hi = first ? C_SPLIT : NCH;
       const uint32_t my_bytes = (uint32_t)(c_hi - c_lo) * WG_CHUNK_BYTES + (first ? Cfg::A_BYTES : 0);
-      int kc = 0;
+      // The issuing thread is the kernel's critical path (six small boxes per 512-clock k-block): everything that
+      // does not change from one k-block to the next - the chunks' tap offsets and channel origins - is computed once
+      // per tile, and the pixel origin / ring position advance incrementally (no divisions inside the K loop).
+      int stage = 0;
+      uint32_t phase = 0;
       for (int u = blockIdx.x; u < total; u += gridDim.x) {
         const int t = u / splits, sp = u % splits;
         const int co0 = (t / n_tiles) * WG_BM;
         const int g0 = (t % n_tiles) * NCH;  // first 64-column chunk of this tile
         const int kb0 = (int)((long long)sp * p.kb_total / splits), kb1 = (int)((long long)(sp + 1) * p.kb_total / splits);
-        for (int kb = kb0; kb < kb1; ++kb, ++kc) {
-          const int s = kc % STAGES;
-          mbar_wait(&empty_bar[s], ((kc / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[s], my_bytes);
-          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+        int c_ci[NCH], c_dw[NCH], c_dh[NCH], c_dn[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int g = g0 + c;
+          const int tap = g / p.cb;
+          c_ci[c] = (g - tap * p.cb) * 64;
+          c_dw[c] = p.dw[tap]; c_dh[c] = p.dh[tap]; c_dn[c] = p.dn[tap];
+        }
+        int img0 = 0, h0 = 0, w0 = 0, tin = 0;
+        if (p.matrix) w0 = kb0 * WG_BK;
+        else if (p.tiles_per_img > 0) { img0 = kb0 / p.tiles_per_img; tin = kb0 - img0 * p.tiles_per_img; h0 = tin * p.tile_h; }
+        else img0 = kb0 * p.tile_n;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], my_bytes);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           if (first) {
-            tma_load_2d(sa, &p.tmDY, &full_bar[s], co0, kb * WG_BK);
-            tma_load_2d(sa + WG_CHUNK_BYTES, &p.tmDY, &full_bar[s], co0 + 64, kb * WG_BK);
+            tma_load_2d(sa, &p.tmDY, &full_bar[stage], co0, kb * WG_BK);
+            tma_load_2d(sa + WG_CHUNK_BYTES, &p.tmDY, &full_bar[stage], co0 + 64, kb * WG_BK);
           }
-          int img0, h0, w0 = 0;
-          if (p.matrix) { img0 = 0; h0 = 0; w0 = kb * WG_BK; }
-          else if (p.tiles_per_img > 0) { img0 = kb / p.tiles_per_img; h0 = (kb % p.tiles_per_img) * p.tile_h; }
-          else { img0 = kb * p.tile_n; h0 = 0; }
-          for (int c = c_lo; c < c_hi; ++c) {
-            const int g = g0 + c;
-            const int tap = g / p.cb, ci0 = (g % p.cb) * 64;
-            tma_load_4d(sb + c * WG_CHUNK_BYTES, &p.tmX, &full_bar[s], ci0, w0 + p.dw[tap], h0 + p.dh[tap],
-                        img0 + p.dn[tap]);
-          }
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+            if (c >= c_lo && c < c_hi)
+              tma_load_4d(sb + c * WG_CHUNK_BYTES, &p.tmX, &full_bar[stage], c_ci[c], w0 + c_dw[c], h0 + c_dh[c],
+                          img0 + c_dn[c]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (p.matrix) w0 += WG_BK;
+          else if (p.tiles_per_img > 0) {
+            h0 += p.tile_h;
+            if (++tin == p.tiles_per_img) { tin = 0; h0 = 0; ++img0; }
+          } else img0 += p.tile_n;
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(WG_BM, BN, 1, 1);
-      int kc = 0, it = 0;
+      int it = 0, stage = 0;
+      uint32_t phase = 0;
       for (int u = blockIdx.x; u < total; u += gridDim.x, ++it) {
         const int sp = u % splits;
         const int kb0 = (int)((long long)sp * p.kb_total / splits), kb1 = (int)((long long)(sp + 1) * p.kb_total / splits);
@@ -144,9 +161,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb, ++kc) {
-          const int s = kc % STAGES;
-          mbar_wait(&full_bar[s], (kc / STAGES) & 1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int s = stage;
+          mbar_wait(&full_bar[s], phase);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint64_t da = umma_desc_mnmajor(sa, WG_CHUNK_BYTES, 1024);
