@@ -351,9 +351,10 @@ struct TileWalk {
 
 // BN: tile width; NSTG: epilogue staging buffers (1: long-K tiles whose epilogue hides under the next mainloop;
 // 3: short-K, epilogue-bound tiles - store of group g-1, fill of group g and residual prefetch of group g+1 overlap)
-template <int BN, int NSTG>
+// PAIR: two CTAs of a cluster share one 256-row MMA (cta_group::2); each stages half of the B tile
+template <int BN, int NSTG, bool PAIR = false>
 struct PgCfg {
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
   // as many ring stages as fit beside the staging buffers in the 227 KiB of shared memory
   static constexpr int STAGES = (232448 - 1024 - 256 - NSTG * PG_STG_BYTES) / STAGE_BYTES;
@@ -365,9 +366,9 @@ struct PgCfg {
 // covers all 128 rows; the warpgroups split the 32-column chunks of each column group between them. With one warp
 // per scheduler (EW = 1) nothing hides the TMEM / L1 / shared-memory latencies of the epilogue, which is what bounds
 // the short-K GEMMs and the single-tile-per-CTA launches of the 8x8 / 4x4 stages.
-template <int BN, int NSTG, int EW>
+template <int BN, int NSTG, int EW, bool PAIR>
 __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
-  using Cfg = PgCfg<BN, NSTG>;
+  using Cfg = PgCfg<BN, NSTG, PAIR>;
   constexpr int EPI_THREADS = 128 * EW;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int GPT = (BN + 127) / 128;  // column groups per tile
@@ -389,7 +390,11 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = p.N / BN;
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  // PAIR: a work unit covers the two consecutive M tiles 2 * tile_mp + rank; the cluster (not the CTA) walks the list
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int walker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int walkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_tiles = PAIR ? ((p.M + BLOCK_M - 1) / BLOCK_M + 1) / 2 : (p.M + BLOCK_M - 1) / BLOCK_M;
   // work unit = (output tile, K split); "total_tiles" counts units, the split index varies fastest
   const int splits = p.splits;
   const int total_tiles = m_tiles * n_tiles * splits;
@@ -404,17 +409,18 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4 * EW);
+      mbar_init(&tmem_empty[i], (PAIR ? 2 : 1) * 4 * EW);  // PAIR: the epilogue warps of both CTAs arrive on the even CTA's
     }
     for (int i = 0; i < NSTG; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
@@ -423,12 +429,12 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       TileWalk tw;
-      tw.init(blockIdx.x, gridDim.x, splits, n_tiles);
+      tw.init(walker, walkers, splits, n_tiles);
       int stage = 0;
       uint32_t phase = 0;  // ring position, carried across tiles
       const bool wmn = p.w_mn != 0;
-      for (int u = blockIdx.x; u < total_tiles; u += gridDim.x, tw.next()) {
-        const int tile_m = tw.tile_m, n0 = tw.n_idx * BN;
+      for (int u = walker; u < total_tiles; u += walkers, tw.next()) {
+        const int tile_m = PAIR ? 2 * tw.tile_m + rank : tw.tile_m, n0 = tw.n_idx * BN;
         int img0, h0, w0 = 0;
         if (p.matrix) {
           img0 = 0; h0 = 0; w0 = tile_m * BLOCK_M;
@@ -458,19 +464,34 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           ax = sc * w0 + p.tdw[seg][tap];
           ay = sc * h0 + p.tdh[seg][tap];
           an = img0 + (seg == 0 ? p.tdn[tap] : 0);
-          if (wmn) bcol = p.wtap[tap] * p.N + n0;
+          if (wmn) bcol = p.wtap[tap] * p.N + n0 + (PAIR ? rank * (BN / 2) : 0);
         };
         load_tap();
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_4d(smem_a + stage * A_STAGE_BYTES, &p.tmA[seg], &full_bar[stage], cbk * BLOCK_K, ax, ay, an);
-          if (wmn) {
+          if constexpr (PAIR) {
+            // the even CTA's barrier counts the bytes of both CTAs' loads (its own arrival keeps the phase open)
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_4d_pair(smem_a + stage * A_STAGE_BYTES, &p.tmA[seg], &full_bar[stage], cbk * BLOCK_K, ax, ay, an);
+            if (wmn) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(smem_b + stage * Cfg::B_BYTES + c * 8192, &p.tmB, &full_bar[stage], bcol + c * 64, cbk * BLOCK_K);
+              for (int c = 0; c < BN / 128; ++c)
+                tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES + c * 8192, &p.tmB, &full_bar[stage], bcol + c * 64,
+                                 cbk * BLOCK_K);
+            } else {
+              tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], kb * BLOCK_K,
+                               n0 + rank * (BN / 2));
+            }
           } else {
-            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &p.tmA[seg], &full_bar[stage], cbk * BLOCK_K, ax, ay, an);
+            if (wmn) {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_2d(smem_b + stage * Cfg::B_BYTES + c * 8192, &p.tmB, &full_bar[stage], bcol + c * 64, cbk * BLOCK_K);
+            } else {
+              tma_load_2d(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (++cbk == cb_cur) {
@@ -483,12 +504,12 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
-      int it = 0, stage = 0, sp = blockIdx.x % splits;
-      const int dsp = gridDim.x % splits;
+    if (rank == 0 && elect_one()) {  // PAIR: the even CTA issues for both
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BN);
+      int it = 0, stage = 0, sp = walker % splits;
+      const int dsp = walkers % splits;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_tiles; u += gridDim.x, ++it) {
+      for (int u = walker; u < total_tiles; u += walkers, ++it) {
         int kb0 = 0, kb1 = p.kb_total;
         if (splits > 1) {
           kb0 = sp * p.kb_total / splits; kb1 = (sp + 1) * p.kb_total / splits;
@@ -504,21 +525,27 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           tc_fence_after_sync();
           const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + stage * A_STAGE_BYTES), 128);
           if (p.w_mn) {
-            constexpr uint32_t idesc_mn = umma_idesc_bf16(BLOCK_M, BN, 0, 1);
+            constexpr uint32_t idesc_mn = umma_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BN, 0, 1);
             const uint64_t db = umma_desc_mnmajor(smem_u32(smem_b + stage * Cfg::B_BYTES), 8192, 1024);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k)
-              umma_bf16(tmem_d, da + 2 * k, db + 128 * k, idesc_mn, (kb > kb0) || (k != 0));
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              if constexpr (PAIR) umma_bf16_pair(tmem_d, da + 2 * k, db + 128 * k, idesc_mn, (kb > kb0) || (k != 0));
+              else umma_bf16(tmem_d, da + 2 * k, db + 128 * k, idesc_mn, (kb > kb0) || (k != 0));
+            }
           } else {
             const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + stage * Cfg::B_BYTES), 128);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k)
-              umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              if constexpr (PAIR) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+              else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0) || (k != 0));
+            }
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);
       }
     }
   } else {
@@ -545,14 +572,14 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         tma_load_2d(dst + bx * (BLOCK_M * 128), &p.tmR, &res_bar[bufi], nc0 + bx * 64, tm * BLOCK_M);
     };
     int it = 0, gc = 0;
-    if (has_res && issuer && blockIdx.x < total_tiles && !((p.flags & F_VT) || to_f32))
-      load_res((int)blockIdx.x / n_tiles, (int)blockIdx.x % n_tiles, 0, 0);  // (residual path: splits == 1)
+    if (has_res && issuer && walker < total_tiles && !((p.flags & F_VT) || to_f32))
+      load_res((PAIR ? 2 : 1) * (walker / n_tiles) + rank, walker % n_tiles, 0, 0);  // (residual path: splits == 1)
     TileWalk tw;
-    tw.init(blockIdx.x, gridDim.x, splits, n_tiles);
-    for (int u = blockIdx.x; u < total_tiles; u += gridDim.x, ++it, tw.next()) {
-      const int t = tw.tile_m * n_tiles + tw.n_idx;  // (residual / staged paths are only used with splits == 1, where t == u)
+    tw.init(walker, walkers, splits, n_tiles);
+    for (int u = walker; u < total_tiles; u += walkers, ++it, tw.next()) {
+      const int t = u;  // (the residual prefetch below is only used with splits == 1, where the unit is the tile)
       float* out_f32 = p.out_f32 + (long long)tw.sp * p.split_stride;
-      const int tile_m = tw.tile_m, n0 = tw.n_idx * BN;
+      const int tile_m = PAIR ? 2 * tw.tile_m + rank : tw.tile_m, n0 = tw.n_idx * BN;
       const int acc = it & 1;
       const long long m = (long long)tile_m * BLOCK_M + r;
       const bool row_ok = m < p.M;
@@ -600,8 +627,8 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
             if (issuer) {  // prefetch the next group's residual
               int nt = t, ncg = cg + 1;
               TileWalk nx = tw;
-              if (ncg == GPT) { nt = t + gridDim.x; ncg = 0; nx.next(); }  // splits == 1 here
-              if (nt < total_tiles) load_res(nx.tile_m, nx.n_idx, ncg, gc + 1);
+              if (ncg == GPT) { nt = t + walkers; ncg = 0; nx.next(); }  // splits == 1 here
+              if (nt < total_tiles) load_res(PAIR ? 2 * nx.tile_m + rank : nx.tile_m, nx.n_idx, ncg, gc + 1);
             }
           } else if (gc > 0) {
             if (issuer) load_res(tile_m, tw.n_idx, cg, gc);
@@ -686,7 +713,10 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           if (cg == GPT - 1 && i0 + 2 >= my_nch) {  // this warp's last TMEM read of the tile: release the accumulator
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_even_cta(&tmem_empty[acc]);
+              else mbar_arrive(&tmem_empty[acc]);
+            }
           }
           finish_chunk(c0, v0, bb0);
           if (two) finish_chunk(c0 + 1, v1, bb1);
@@ -730,36 +760,60 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may leave while the pair's MMAs / remote arrivals can touch it
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <int BN, int NSTG, int EW>
+template <int BN, int NSTG, int EW, bool PAIR>
 static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
-  using Cfg = PgCfg<BN, NSTG>;
+  using Cfg = PgCfg<BN, NSTG, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(igemm_persist_kernel<BN, NSTG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM),
+    int rc = check_cuda(cudaFuncSetAttribute(igemm_persist_kernel<BN, NSTG, EW, PAIR>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM),
                         "igemm_persist: cudaFuncSetAttribute");
     if (rc != IDF_OK) return rc;
     attr_set = true;
   }
-  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BN) * p.splits;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  return check_cuda(launch_pdl(igemm_persist_kernel<BN, NSTG, EW>, dim3(grid), dim3(64 + 128 * EW), Cfg::SMEM, stream, p),
-                    "igemm_persist launch");
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  if constexpr (PAIR) {
+    // one cluster of two CTAs per TPC; the cluster walks the list of (M-tile pair, N tile, K split) units
+    const int units = ((m_tiles + 1) / 2) * (p.N / BN) * p.splits;
+    const int clusters = units < sm_count() / 2 ? units : sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(64 + 128 * EW);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return check_cuda(cudaLaunchKernelEx(&cfg, igemm_persist_kernel<BN, NSTG, EW, PAIR>, p), "igemm_persist pair launch");
+  } else {
+    const int tiles = m_tiles * (p.N / BN) * p.splits;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    return check_cuda(launch_pdl(igemm_persist_kernel<BN, NSTG, EW, PAIR>, dim3(grid), dim3(64 + 128 * EW), Cfg::SMEM,
+                                 stream, p),
+                      "igemm_persist launch");
+  }
 }
 
 template <int BN, int NSTG>
-static int launch_persist(const IgemmParams& p, cudaStream_t stream) {
-  // IDF_EPI_WG=1 selects the single-warpgroup epilogue (kept for A/B measurements)
+static int launch_persist(const IgemmParams& p, cudaStream_t stream, bool pair) {
+  // IDF_EPI_WG=1 selects the single-warpgroup epilogue (kept for A/B measurements; single-CTA kernels only)
   static const int ew = [] { const char* e = getenv("IDF_EPI_WG"); return e ? atoi(e) : 2; }();
-  return ew == 1 ? launch_persist_ew<BN, NSTG, 1>(p, stream) : launch_persist_ew<BN, NSTG, 2>(p, stream);
+  if (pair) return launch_persist_ew<BN, NSTG, 2, true>(p, stream);
+  return ew == 1 ? launch_persist_ew<BN, NSTG, 1, false>(p, stream) : launch_persist_ew<BN, NSTG, 2, false>(p, stream);
 }
 
 // Split-K finish: out[m, n] = bf16( sum_s partial[s][m][n] + bias[n] + rowbias[row(sample(m))][n] ), partials summed in
@@ -961,12 +1015,20 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     }
   }
   p.splits = splits;
+  // CTA pairs (cta_group::2). Measured on B200 (profiles/r01_igemm_pair_vs_single.txt): 256-wide tiles of the
+  // 32x32 / 16x16 stages gain 5-9 %, 192-wide tiles lose 13-17 %, everything else is neutral or pays for the
+  // cluster start-up: IDF_IGEMM_PAIR = 1 (default) pairs only the former, 2 = wherever legal, 0 = never.
+  static const int pair_mode = [] { const char* e = getenv("IDF_IGEMM_PAIR"); return e ? atoi(e) : 1; }();
+  const bool pair_legal = !legacy && M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2;
+  const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && bn == 256 && !short_k &&
+                                                      (M + BLOCK_M - 1) / BLOCK_M >= sm_count()));
   if (a->w_mn) {  // rows = the A operand's channels (K per tap), columns = (weight tap, output column)
     int maxt = 0;
     for (int t = 0; t < a->taps[0]; ++t) maxt = p.wtap[t] > maxt ? p.wtap[t] : maxt;
     if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)x0.c, (uint64_t)(maxt + 1) * a->N, (uint64_t)a->ldw, 64, 64)) != IDF_OK)
       return rc;
-  } else if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, (uint32_t)bn)) != IDF_OK)
+  } else if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K,
+                                (uint32_t)(pair ? bn / 2 : bn))) != IDF_OK)
     return rc;
 
   p.H = a->epi_h > 0 ? a->epi_h : H;
@@ -1050,11 +1112,11 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   }
   if (!legacy) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (short_k) return launch_persist<128, 3>(p, st);  // (wider short-K tiles with a 2-stage ring measured slower)
+    if (short_k) return launch_persist<128, 3>(p, st, pair);  // (wider short-K tiles with a 2-stage ring measured slower)
     switch (bn) {
-      case 256: rc = launch_persist<256, 1>(p, st); break;
-      case 192: rc = launch_persist<192, 1>(p, st); break;
-      default: rc = launch_persist<128, 1>(p, st); break;
+      case 256: rc = launch_persist<256, 1>(p, st, pair); break;
+      case 192: rc = launch_persist<192, 1>(p, st, pair); break;
+      default: rc = launch_persist<128, 1>(p, st, pair); break;
     }
     if (rc != IDF_OK || splits == 1) return rc;
     const long long vecs = M * (a->N / 8);
