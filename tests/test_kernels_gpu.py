@@ -60,6 +60,28 @@ def test_conv3x3_igemm(B, Cin, Cout, H):
     assert (got - ref).abs().max().item() < 0.06
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H", [(20, 128, 256, 32), (80, 64, 512, 16), (297, 64, 256, 8)])
+def test_conv3x3_igemm_cta_pair(B, Cin, Cout, H):
+    """Layers with >= 148 M tiles and 256-wide N tiles run on CTA pairs (cta_group::2: one 256-row MMA per two CTAs,
+    each staging half of the weight tile). The last shape has an odd number of M tiles, the last one partial: the
+    odd CTA of the final pair works on a tile that lies entirely outside the matrix."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + Cin + Cout + H)
+    x = torch.randn(B, Cin, H, H, device=DEV, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, device=DEV, generator=g)
+    table = torch.randn(B, Cout, device=DEV, generator=g)
+    out = torch.empty(B * H * H, Cout, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(rows(x), (B, H, H), Cin, 9)], ops.pack_conv_weight(w), Cout, out, bias=b, rowbias=table)
+    ref = F.conv2d(bf(x), bf(w), b, padding=1) + table[:, :, None, None]
+    got = unrows(out, B, H, H)
+    assert rel_err(got, ref) < 6e-3, rel_err(got, ref)
+    assert (got - ref).abs().max().item() < 0.08
+    out2 = torch.empty_like(out)
+    ops.igemm([(rows(x), (B, H, H), Cin, 9)], ops.pack_conv_weight(w), Cout, out2, bias=b, rowbias=table)
+    assert torch.equal(out, out2)  # deterministic
+
+
 @pytest.mark.parametrize("B,Cin,Cout,H", [(9, 512, 512, 4), (24, 384, 512, 8), (96, 512, 512, 4)])
 def test_conv3x3_split_k(B, Cin, Cout, H):
     """Small-M layers: K split over several work units, fp32 partials reduced by the finish kernel (with the time
