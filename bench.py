@@ -177,8 +177,11 @@ def igemm_flops(name, a):
         return 0.0
     g = a[0]
     m = (g.s2_batch if g.s2_batch else g.a[0].n) * g.a[0].h * g.a[0].w
+    if g.s2_direct:  # stride-2 conv read from the full-resolution input: a quarter as many output pixels
+        m //= 4
     k = g.taps[0] * g.a[0].c + (g.taps[1] * g.a[1].c if g.a[1].ptr else 0)
-    return 2.0 * m * g.N * k
+    n = g.N * (4 if g.out_up2 == 2 else 1)  # fused Upsample conv: four sub-pixel convolutions in one launch
+    return 2.0 * m * n * k
 
 
 def igemm_roofline(sampler, peak_tflops, peak_kind):

@@ -36,6 +36,7 @@ struct IgemmParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
   CUtensorMap tmC;
+  CUtensorMap tmCx[3];  // up2_all: output maps of parities 1..3 (tmC is parity 0)
   CUtensorMap tmR;
   int kb_seg0;   // k-blocks (of 64) in segment 0
   int kb_total;  // k-blocks in both segments
@@ -56,6 +57,11 @@ struct IgemmParams {
                       //    of output tile origin (h0, w0) starts at source pixel (2*h0 + kh, 2*w0 + kw)
   signed char tdh[2][9], tdw[2][9];  // per-segment tap offsets (rows, columns)
   int tdn[9];                        // segment-0 image offset per tap (parity plane of a stride-2 conv)
+  int up2_all;        // 1: ONE launch covers the four sub-pixel convolutions of an Upsample layer: the N-tile index
+                      //    carries the output parity (row parity * 2 + column parity) in its two low bits; parity
+                      //    selects the weight block (rows parity * N .. of the stacked weight matrix), the tap
+                      //    offsets (dh, dw) = ((tap >> 1) - 1 + row parity, (tap & 1) - 1 + column parity) and
+                      //    the output map
   int splits;         // split-K factor (persistent kernel): partial sums go to out_f32 + split * split_stride
   long long split_stride;
   int M, N;
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int n_tiles = p.N / BN;
+  const int n_tiles = (p.N / BN) * (p.up2_all ? 4 : 1);
   // PAIR: a work unit covers the two consecutive M tiles 2 * tile_mp + rank; the cluster (not the CTA) walks the list
   const int rank = PAIR ? (int)cluster_ctarank() : 0;
   const int walker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -434,7 +440,9 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
       uint32_t phase = 0;  // ring position, carried across tiles
       const bool wmn = p.w_mn != 0;
       for (int u = walker; u < total_tiles; u += walkers, tw.next()) {
-        const int tile_m = PAIR ? 2 * tw.tile_m + rank : tw.tile_m, n0 = tw.n_idx * BN;
+        const int par = p.up2_all ? (tw.n_idx & 3) : 0;
+        const int tile_m = PAIR ? 2 * tw.tile_m + rank : tw.tile_m, n0 = (p.up2_all ? (tw.n_idx >> 2) : tw.n_idx) * BN;
+        const int brow0 = par * p.N + n0;  // row of the (stacked) weight matrix
         int img0, h0, w0 = 0;
         if (p.matrix) {
           img0 = 0; h0 = 0; w0 = tile_m * BLOCK_M;
@@ -461,8 +469,13 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         int ax = 0, ay = 0, an = 0, bcol = 0;
         auto load_tap = [&]() {
           const int sc = (p.s2_direct && seg == 0) ? 2 : 1;
-          ax = sc * w0 + p.tdw[seg][tap];
-          ay = sc * h0 + p.tdh[seg][tap];
+          if (p.up2_all) {
+            ax = w0 + (tap & 1) - 1 + (par & 1);
+            ay = h0 + (tap >> 1) - 1 + (par >> 1);
+          } else {
+            ax = sc * w0 + p.tdw[seg][tap];
+            ay = sc * h0 + p.tdh[seg][tap];
+          }
           an = img0 + (seg == 0 ? p.tdn[tap] : 0);
           if (wmn) bcol = p.wtap[tap] * p.N + n0 + (PAIR ? rank * (BN / 2) : 0);
         };
@@ -480,7 +493,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
                                  cbk * BLOCK_K);
             } else {
               tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], kb * BLOCK_K,
-                               n0 + rank * (BN / 2));
+                               brow0 + rank * (BN / 2));
             }
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -490,7 +503,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
               for (int c = 0; c < BN / 64; ++c)
                 tma_load_2d(smem_b + stage * Cfg::B_BYTES + c * 8192, &p.tmB, &full_bar[stage], bcol + c * 64, cbk * BLOCK_K);
             } else {
-              tma_load_2d(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
+              tma_load_2d(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], kb * BLOCK_K, brow0);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -579,7 +592,8 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
     for (int u = walker; u < total_tiles; u += walkers, ++it, tw.next()) {
       const int t = u;  // (the residual prefetch below is only used with splits == 1, where the unit is the tile)
       float* out_f32 = p.out_f32 + (long long)tw.sp * p.split_stride;
-      const int tile_m = PAIR ? 2 * tw.tile_m + rank : tw.tile_m, n0 = tw.n_idx * BN;
+      const int par = p.up2_all ? (tw.n_idx & 3) : 0;
+      const int tile_m = PAIR ? 2 * tw.tile_m + rank : tw.tile_m, n0 = (p.up2_all ? (tw.n_idx >> 2) : tw.n_idx) * BN;
       const int acc = it & 1;
       const long long m = (long long)tile_m * BLOCK_M + r;
       const bool row_ok = m < p.M;
@@ -743,8 +757,9 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
               int img0, h0;
               if (p.tiles_per_img > 0) { img0 = tile_m / p.tiles_per_img; h0 = (tile_m % p.tiles_per_img) * p.tile_h; }
               else { img0 = tile_m * p.tile_n; h0 = 0; }
+              const CUtensorMap* tc = par == 0 ? &p.tmC : &p.tmCx[par - 1];
               for (int bx = 0; bx < gcols / 64; ++bx)
-                tma_store_4d(&p.tmC, stage_c + bx * (BLOCK_M * 128), nc0 + bx * 64, 0, h0, img0);
+                tma_store_4d(tc, stage_c + bx * (BLOCK_M * 128), nc0 + bx * 64, 0, h0, img0);
             } else {
               for (int bx = 0; bx < gcols / 64; ++bx)
                 tma_store_2d(&p.tmC, stage_c + bx * (BLOCK_M * 128), nc0 + bx * 64, tile_m * BLOCK_M);
@@ -784,7 +799,7 @@ static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   if constexpr (PAIR) {
     // one cluster of two CTAs per TPC; the cluster walks the list of (M-tile pair, N tile, K split) units
-    const int units = ((m_tiles + 1) / 2) * (p.N / BN) * p.splits;
+    const int units = ((m_tiles + 1) / 2) * (p.N / BN) * p.splits * (p.up2_all ? 4 : 1);
     const int clusters = units < sm_count() / 2 ? units : sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
@@ -800,7 +815,7 @@ static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
     cfg.numAttrs = 2;
     return check_cuda(cudaLaunchKernelEx(&cfg, igemm_persist_kernel<BN, NSTG, EW, PAIR>, p), "igemm_persist pair launch");
   } else {
-    const int tiles = m_tiles * (p.N / BN) * p.splits;
+    const int tiles = m_tiles * (p.N / BN) * p.splits * (p.up2_all ? 4 : 1);
     const int grid = tiles < sm_count() ? tiles : sm_count();
     return check_cuda(launch_pdl(igemm_persist_kernel<BN, NSTG, EW, PAIR>, dim3(grid), dim3(64 + 128 * EW), Cfg::SMEM,
                                  stream, p),
@@ -901,13 +916,19 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     if (x.n != x0.n || x.h != x0.h || x.w != x0.w) return fail(IDF_ERR_ARG, "igemm: segments disagree on n/h/w");
     if (x.c <= 0 || x.c % BLOCK_K != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: channels %d not a multiple of 64", x.c);
     const bool custom = s == 0 && a->custom_taps != 0;
-    if (custom ? (a->taps[s] < 1 || a->taps[s] > 9) : (a->taps[s] != 1 && a->taps[s] != 9))
-      return fail(IDF_ERR_ARG, "igemm: taps must be 1 or 9 (1..9 with custom_taps)");
+    const bool up2_all_seg = s == 0 && a->out_up2 == 2 && !a->custom_taps && a->taps[0] == 4;
+    if (!up2_all_seg && (custom ? (a->taps[s] < 1 || a->taps[s] > 9) : (a->taps[s] != 1 && a->taps[s] != 9)))
+      return fail(IDF_ERR_ARG, "igemm: taps must be 1 or 9 (1..9 with custom_taps, 4 with out_up2 == 2)");
   }
   if (a->N <= 0 || a->N % BLOCK_N != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d not a multiple of %d", a->N, BLOCK_N);
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
+  const bool up2_all = a->out_up2 == 2;
+  if (up2_all && (a->custom_taps || a->taps[0] != 4 || a->a[1].ptr != nullptr || a->w_mn || a->ws != nullptr))
+    return fail(IDF_ERR_ARG, "igemm: out_up2 == 2 takes one 4-tap segment, stacked K-major weights and no workspace");
+  p.up2_all = up2_all ? 1 : 0;
+  const int par_tiles = up2_all ? 4 : 1;
   const int s2d = a->s2_direct ? 1 : 0;
   if (s2d && (a->s2_batch > 0 || a->taps[0] != 9 || nseg != 1 || a->custom_taps || (x0.h & 1) || (x0.w & 1)))
     return fail(IDF_ERR_ARG, "igemm: s2_direct needs one 9-tap segment over an even-sized full-resolution input");
@@ -986,7 +1007,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
       if (a->N % c != 0) continue;
       if (a->vt != nullptr && a->vt_col0 % c != 0) continue;
       if (bn == 0) bn = c;                                          // widest legal
-      if (m_tiles * (a->N / c) >= sm_count()) { bn = c; break; }    // widest that still fills the GPU
+      if (m_tiles * (a->N / c) * par_tiles >= sm_count()) { bn = c; break; }    // widest that still fills the GPU
       bn = c;                                                       // otherwise keep narrowing
     }
     if (bn == 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d has no legal tile width", a->N);
@@ -1021,13 +1042,13 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   static const int pair_mode = [] { const char* e = getenv("IDF_IGEMM_PAIR"); return e ? atoi(e) : 1; }();
   const bool pair_legal = !legacy && M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2;
   const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && bn == 256 && !short_k &&
-                                                      (M + BLOCK_M - 1) / BLOCK_M >= sm_count()));
+                                                      (M + BLOCK_M - 1) / BLOCK_M * par_tiles >= sm_count()));
   if (a->w_mn) {  // rows = the A operand's channels (K per tap), columns = (weight tap, output column)
     int maxt = 0;
     for (int t = 0; t < a->taps[0]; ++t) maxt = p.wtap[t] > maxt ? p.wtap[t] : maxt;
     if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)x0.c, (uint64_t)(maxt + 1) * a->N, (uint64_t)a->ldw, 64, 64)) != IDF_OK)
       return rc;
-  } else if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K,
+  } else if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N * par_tiles, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K,
                                 (uint32_t)(pair ? bn / 2 : bn))) != IDF_OK)
     return rc;
 
@@ -1084,16 +1105,20 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
       // sub-pixel store: row (img, h, w) of this GEMM lands at pixel (img, 2h + ph, 2w + pw) of the (n, 2h, 2w) output
       if (a->res != nullptr || a->vt != nullptr || is_matrix || legacy || a->s2_batch > 0 || s2d)
         return fail(IDF_ERR_UNSUPPORTED, "igemm: out_up2 excludes res / vt / matrix / stride-2 inputs");
-      if (a->out_ph < 0 || a->out_ph > 1 || a->out_pw < 0 || a->out_pw > 1) return fail(IDF_ERR_ARG, "igemm: bad output parity");
+      if (!up2_all && (a->out_ph < 0 || a->out_ph > 1 || a->out_pw < 0 || a->out_pw > 1))
+        return fail(IDF_ERR_ARG, "igemm: bad output parity");
       p.flags |= F_OUT_UP2;
       const long long ldo = a->ldo;
-      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a->out) + ((long long)a->out_ph * 2 * W + a->out_pw) * ldo;
       const uint64_t dims[4] = {(uint64_t)out_cols, (uint64_t)W, (uint64_t)H, (uint64_t)x0.n};
       const uint64_t strides[3] = {(uint64_t)(2 * ldo) * 2, (uint64_t)(4 * W * ldo) * 2, (uint64_t)(4LL * HW * ldo) * 2};
       const uint32_t box[4] = {64u, (uint32_t)p.tile_w, (uint32_t)p.tile_h, (uint32_t)p.tile_n};
-      if ((rc = encode_tmap(&p.tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 4, dims, strides, box,
-                            CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
-        return rc;
+      for (int par = 0; par < par_tiles; ++par) {  // one output map per parity (row parity * 2 + column parity)
+        const int ph = up2_all ? (par >> 1) : a->out_ph, pw = up2_all ? (par & 1) : a->out_pw;
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a->out) + ((long long)ph * 2 * W + pw) * ldo;
+        if ((rc = encode_tmap(par == 0 ? &p.tmC : &p.tmCx[par - 1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, 4, dims,
+                              strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) != IDF_OK)
+          return rc;
+      }
     } else if ((rc = make_mat_map(&p.tmC, a->out, (uint64_t)M, (uint64_t)out_cols, (uint64_t)a->ldo, 64, BLOCK_M)) != IDF_OK)
       return rc;
     if (a->res != nullptr) {

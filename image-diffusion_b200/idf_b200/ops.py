@@ -3,6 +3,7 @@ column slices of a wider buffer, so the row stride may exceed C). Nothing here c
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -61,7 +62,9 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
     if w_tap_ids is not None:
         for i, t in enumerate(w_tap_ids):
             a.w_tap_ids[i] = t
-    if out_up2 is not None:  # (row parity, column parity) of the 2x-resolution output this launch fills
+    if out_up2 == "all":  # all four parities in one launch (w = the four weight matrices stacked along rows)
+        a.out_up2 = 2
+    elif out_up2 is not None:  # (row parity, column parity) of the 2x-resolution output this launch fills
         a.out_up2, (a.out_ph, a.out_pw) = 1, out_up2
     if tap_offsets is not None:  # explicit (dh, dw) list for segment 0
         a.custom_taps = 1
@@ -386,9 +389,14 @@ def attention_bwd(qkv, o, d_out, lse, delta, dqkv, dq32, M, T, heads, head_dim):
 _UP2_ROWS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}
 
 
+class _UpsamplePack(list):
+    """[((p, q), tap offsets, (O, 4*I) bf16)] * 4, plus `.stacked`: the four matrices along rows, (4*O, 4*I)."""
+    stacked = None
+
+
 def pack_upsample_conv_weights(w: torch.Tensor):
     """OIHW fp32 3x3 -> [((p, q), tap offsets [(dh, dw)] * 4, (O, 4*I) bf16)] for the four output parities."""
-    out = []
+    out = _UpsamplePack()
     for p in (0, 1):
         for q in (0, 1):
             offs, mats = [], []
@@ -397,11 +405,18 @@ def pack_upsample_conv_weights(w: torch.Tensor):
                     offs.append((dh, dw))
                     mats.append(sum(w.detach()[:, :, kh, kw] for kh in khs for kw in kws))
             out.append(((p, q), offs, torch.cat(mats, dim=1).to(torch.bfloat16).contiguous()))
+    out.stacked = torch.cat([wp for _, _, wp in out], dim=0).contiguous()
     return out
 
 
 def upsample_conv3x3(x: torch.Tensor, grid, c: int, packed, n_out: int, out: torch.Tensor, bias=None):
     """out (B*2H*2W, ld) <- conv3x3(nearest2x(x)) + bias, x (B*H*W, c) at the low resolution `grid` = (B, H, W)."""
+    stacked = getattr(packed, "stacked", None)
+    if stacked is not None and os.environ.get("IDF_UP2_FUSED", "1") != "0":
+        # one launch for the four parities: 4x the tiles per launch (the per-parity launches leave SMs idle: 192 tiles
+        # on 148 SMs at the 16x16 -> 32x32 stage) and three launches fewer
+        igemm([(x, grid, c, 4)], stacked, n_out, out, bias=bias, out_up2="all")
+        return out
     for (p, q), offs, wp in packed:
         igemm([(x, grid, c, 4)], wp, n_out, out, bias=bias, tap_offsets=offs, out_up2=(p, q))
     return out

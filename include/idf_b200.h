@@ -101,7 +101,9 @@ typedef struct idf_igemm_args {
                            2w + out_pw) of an (n, 2h, 2w) image in `out` (row stride ldo). Four such launches, one per
                            parity, with 2x2 custom taps and pre-summed weights, ARE nearest-2x upsampling followed by a
                            3x3 conv (Upsample, components.py:124-130) at 4/9 of the FLOPs and without the upsampled
-                           tensor ever existing. */
+                           tensor ever existing. out_up2 == 2: ONE launch does all four parities: taps[0] = 4 (no custom
+                           taps: the 2x2 offsets follow from the parity), `w` holds the four pre-summed (N, 4*Cin) weight
+                           matrices stacked along rows in parity order (0,0) (0,1) (1,0) (1,1); out_ph / out_pw unused. */
   int32_t out_ph, out_pw;
   int32_t w_mn;         /* != 0: data-gradient mode. `w` is the FORWARD weight matrix of the layer, (a[0].c rows, ldw), whose
                            column block [t*N, (t+1)*N) holds tap t: out[m, n] = sum_t sum_k A[pixel(m)+tap_t, k] w[k, t*N+n].

@@ -366,6 +366,15 @@ def test_upsample_conv_as_subpixel_convs(B, C, H):
     got = unrows(cat[:, :C], B, 2 * H, 2 * H)
     assert rel_err(got, ref) < 8e-3, rel_err(got, ref)
     assert cat[:, C:].abs().max().item() == 0.0  # the other half of the buffer is untouched
+    # default: ONE launch for the four parities (out_up2 == 2); the four-launch form gives the same bits
+    import os
+    cat4 = torch.zeros_like(cat)
+    os.environ["IDF_UP2_FUSED"] = "0"
+    try:
+        ops.upsample_conv3x3(rows(x), (B, H, H), C, ops.pack_upsample_conv_weights(w), C, cat4[:, :C], bias=b)
+    finally:
+        del os.environ["IDF_UP2_FUSED"]
+    assert torch.equal(cat, cat4)
 
 
 @pytest.mark.parametrize("B,C,H", [(3, 256, 32), (5, 384, 16), (7, 512, 8), (96, 512, 8)])

@@ -23,8 +23,10 @@ with torch.no_grad():
         if name == "idf_conv2d_igemm":
             g = a[0]
             m = (g.s2_batch if g.s2_batch else g.a[0].n) * g.a[0].h * g.a[0].w
+            if g.s2_direct: m //= 4
             k = g.taps[0] * g.a[0].c + (g.taps[1] * g.a[1].c if g.a[1].ptr else 0)
-            desc = f"M={m} N={g.N} K={k} taps={g.taps[0]} res={bool(g.res)} vt={bool(g.vt)} f={2.0*m*g.N*k/1e9:.1f}GF"
+            n = g.N * (4 if g.out_up2 == 2 else 1)
+            desc = f"M={m} N={n} K={k} taps={g.taps[0]} res={bool(g.res)} vt={bool(g.vt)} f={2.0*m*n*k/1e9:.1f}GF"
         elif name == "idf_attention_fwd":
             desc = f"M={a[6]} T={a[7]} heads={a[8]} hd={a[9]}"
         elif name == "idf_groupnorm_silu":
