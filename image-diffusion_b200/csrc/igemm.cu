@@ -999,16 +999,34 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   // triple-buffered staging keep loads, residual prefetch and stores in flight together
   const bool short_k = !legacy && ktot <= 1024 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
   if (!legacy && !short_k) {
+    // Tile width by a small cost model, calibrated on B200 with the per-launch table of one sampling step
+    // (profiles/r01_sample_step_launches_events.txt): the busiest CTA works through waves(c) = ceil(units / SMs)
+    // tiles of K / 64 k-blocks; one k-block takes ~250 / 375 / 425 ns for 128- / 192- / 256-wide tiles (~395 ns on
+    // CTA pairs), i.e. the wide tiles are only ~15 % cheaper per FLOP, so they lose whenever they need more waves per
+    // FLOP (192 tiles of 256 columns on 148 SMs: two waves where 384 tiles of 128 columns need three half-size ones).
+    // The last tile's epilogue is exposed. IDF_IGEMM_TILE_MODEL=0: the former rule (widest width that fills the GPU).
+    static const int tile_model = [] { const char* e = getenv("IDF_IGEMM_TILE_MODEL"); return e ? atoi(e) : 1; }();
     const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     const int cands[3] = {256, 192, 128};
+    const double t_kb[3] = {425.0, 375.0, 250.0}, t_epi[3] = {3000.0, 2400.0, 1700.0};
+    const int fs = a->force_splits > 1 ? a->force_splits : 1;
+    double best = 0.0;
     bn = 0;
     for (int i = 0; i < 3; ++i) {
       const int c = cands[i];
       if (a->N % c != 0) continue;
       if (a->vt != nullptr && a->vt_col0 % c != 0) continue;
-      if (bn == 0) bn = c;                                          // widest legal
-      if (m_tiles * (a->N / c) * par_tiles >= sm_count()) { bn = c; break; }    // widest that still fills the GPU
-      bn = c;                                                       // otherwise keep narrowing
+      if (!tile_model) {
+        if (bn == 0) bn = c;                                                    // widest legal
+        if (m_tiles * (a->N / c) * par_tiles >= sm_count()) { bn = c; break; }  // widest that still fills the GPU
+        bn = c;                                                                 // otherwise keep narrowing
+        continue;
+      }
+      const long long units = m_tiles * (a->N / c) * par_tiles * fs;
+      const long long waves = (units + sm_count() - 1) / sm_count();
+      const bool pairs = c == 256 && m_tiles * par_tiles >= sm_count();
+      const double t = (double)waves * ((double)p.kb_total / fs) * (pairs ? 395.0 : t_kb[i]) + t_epi[i];
+      if (bn == 0 || t < best) { bn = c; best = t; }
     }
     if (bn == 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d has no legal tile width", a->N);
   }
