@@ -1155,7 +1155,19 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   }
   if (!legacy) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (short_k) return launch_persist<128, 3>(p, st, pair);  // (wider short-K tiles with a 2-stage ring measured slower)
+    if (short_k) {
+      // Without a residual to prefetch, K >= 256 and at least two waves of them, wide tiles with two staging buffers
+      // (3- / 4-stage ring) win 7-13 % (QKV projections of the 32x32 / 16x16 stages: fewer per-tile fixed costs in
+      // the epilogue-bound regime); with K = 128 or few tiles they lose as much, so those keep 128 x 128 tiles.
+      const int wbn = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : 128);
+      const long long wtiles = ((M + BLOCK_M - 1) / BLOCK_M) * (a->N / wbn);
+      if (wbn != 128 && a->res == nullptr && a->vt == nullptr && !a->w_mn && ktot >= 256 && wtiles >= 2 * sm_count()) {
+        if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, (uint32_t)wbn)) != IDF_OK)
+          return rc;
+        return wbn == 256 ? launch_persist<256, 2>(p, st, false) : launch_persist<192, 2>(p, st, false);
+      }
+      return launch_persist<128, 3>(p, st, pair);
+    }
     switch (bn) {
       case 256: rc = launch_persist<256, 1>(p, st, pair); break;
       case 192: rc = launch_persist<192, 1>(p, st, pair); break;
