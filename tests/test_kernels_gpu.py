@@ -145,6 +145,23 @@ def test_linear_residual_strided_output():
     assert cat[:, :N].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("M,K,N", [(49152, 256, 768), (24576, 384, 1152), (98304, 128, 384), (40000, 256, 256)])
+def test_linear_large_m_tile_paths(M, K, N):
+    """Projection GEMMs at the sizes of the 32x32 / 16x16 stages: with K >= 256 and two or more waves of tiles the
+    short-K kernel takes 256- / 192-wide tiles with two staging buffers, otherwise 128 x 128 tiles with three; the
+    last shape has a partial final M tile. Against an fp32 matmul of the same bf16 operands."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(M + K + N)
+    a = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    b = torch.randn(N, device=DEV, generator=g)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(a, (1, 1, M), K, 1)], w, N, out, bias=b)
+    ref = a.float() @ w.float().t() + b
+    assert rel_err(out.float(), ref) < 6e-3
+    assert (out.float() - ref).abs().max().item() < 0.08
+
+
 def test_gemm_small_m_and_f32_out():
     ops = _ops()
     M, K, N = 16, 512, 1536
