@@ -134,6 +134,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Before a CTA exits only the shared-memory READS of its bulk stores have to be complete (the staging buffer dies with
+// the CTA); the global writes are ordinary in-flight stores that grid completion makes visible. Waiting for full
+// completion instead costs every launch a global-write round trip (~1 us of the ~7 us fixed cost of a small GEMM).
+__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM loads

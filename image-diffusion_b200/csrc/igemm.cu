@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         }
       }
     }
-    if (issuer) tma_store_wait_all();
+    if (issuer) tma_store_wait_read_all();
   }
 
   tc_fence_before_sync();
