@@ -31,7 +31,7 @@ def timed(name, *a):
     elif name in ("idf_attention_fwd_train",):
         desc = f"M={a[6]} T={a[7]} heads={a[8]} hd={a[9]}"
     elif name == "idf_attention_bwd":
-        desc = f"M={a[11]} T={a[12]} heads={a[13]} hd={a[14]}"
+        desc = f"M={a[-5]} T={a[-4]} heads={a[-3]} hd={a[-2]}"
     elif name in ("idf_groupnorm_silu_train",):
         desc = f"B={a[6]} HW={a[7]} C={a[8]} silu={a[11]}"
     elif name == "idf_groupnorm_silu_bwd":
