@@ -404,7 +404,11 @@ static int groupnorm_impl(const void* x, int64_t ldx, void* y, int64_t ldy, cons
   }
   const int V = gps * cpg / 8;
   const int VP = V <= 4 ? 4 : 8;
-  int warps = GN_MAX_WARPS;
+  // CTA size by slab size (measured per shape, profiles/r01_groupnorm_warps_sweep.txt): 12 warps for the 128 KB slabs
+  // of the 32x32 stage, 8 for ~32 KB, 6 below that - small slabs on 12-warp CTAs run a few CTAs over one wave of
+  // resident CTAs (768 CTAs on 148 x 5 slots) and pay for two.
+  const long long slab_bytes = (long long)HW * V * 16;
+  int warps = slab_bytes >= 100 * 1024 ? GN_MAX_WARPS : (slab_bytes >= 30 * 1024 ? 8 : 6);
   while (warps > 1 && (warps - 1) * (32 / VP) >= HW) --warps;  // tiny images: no idle warps
   dim3 grid(B, groups / gps);
   const int threads = warps * 32;
