@@ -825,7 +825,10 @@ extern "C" int idf_groupnorm_silu_bwd(const void* x, int64_t ldx, const void* dy
       (add && (reinterpret_cast<uintptr_t>(add) & 15)))
     return fail(IDF_ERR_ARG, "groupnorm_bwd: 16-byte alignment required");
   const int VP = V <= 4 ? 4 : 8;
-  int warps = GNB_MAX_WARPS;
+  // CTA size by slab size, as in the forward kernel (norm.cu); IDF_GNB_WARPS_BY_SLAB=0: always 12 warps
+  static const int by_slab = [] { const char* e = getenv("IDF_GNB_WARPS_BY_SLAB"); return e ? atoi(e) : 1; }();
+  const long long slab_bytes = (long long)HW * V * 16;
+  int warps = (!by_slab || slab_bytes >= 100 * 1024) ? GNB_MAX_WARPS : (slab_bytes >= 30 * 1024 ? 8 : 6);
   while (warps > 1 && (warps - 1) * (32 / VP) >= HW) --warps;
   dim3 grid(B, groups / gps);
   const int threads = warps * 32;
