@@ -260,3 +260,36 @@ def test_image_grid_matches_make_grid():
     got = image_grid(imgs, nrow=3)
     assert got.dtype.name == "uint8" and got.shape == ref.shape
     assert abs(got.astype("float32") / 255.0 - ref).max() <= 0.5 / 255 + 1e-6
+
+
+def test_upsample_subpixel_weight_packing_matches_nearest2x_conv():
+    """Host side of the fused Upsample launch (idf_igemm_args.out_up2 == 2): the four pre-summed 2x2 weight matrices,
+    their stacking order (parity = row parity * 2 + column parity) and the tap offsets the kernel derives from the
+    parity, (dh, dw) = ((tap >> 1) - 1 + p, (tap & 1) - 1 + q), reproduce nearest-2x + conv3x3 (components.py:124-130)
+    in plain fp32 torch."""
+    import torch.nn.functional as F
+    from idf_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, C, Co, H = 2, 64, 128, 6
+    x = torch.randn(B, C, H, H, generator=g)
+    w = torch.randn(Co, C, 3, 3, generator=g) / (9 * C) ** 0.5
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, None, padding=1)
+    packed = ops.pack_upsample_conv_weights(w)
+    assert packed.stacked.shape == (4 * Co, 4 * C)
+    xp = F.pad(x, (1, 1, 1, 1))  # zero padding = TMA out-of-bounds fill
+    out = torch.zeros(B, Co, 2 * H, 2 * H)
+    for par in range(4):
+        p, q = par >> 1, par & 1
+        (pp, qq), offs, wp = packed[par]
+        assert (pp, qq) == (p, q)
+        wpar = packed.stacked[par * Co:(par + 1) * Co].float()  # (Co, 4 * C): tap-major, then channel
+        assert torch.equal(wpar, wp.float())
+        acc = torch.zeros(B, Co, H, H)
+        for tap in range(4):
+            dh, dw = (tap >> 1) - 1 + p, (tap & 1) - 1 + q
+            assert offs[tap] == (dh, dw)
+            xs = xp[:, :, 1 + dh:1 + dh + H, 1 + dw:1 + dw + H]
+            acc += torch.einsum("bchw,oc->bohw", xs, wpar[:, tap * C:(tap + 1) * C])
+        out[:, :, p::2, q::2] = acc
+    # the packed weights are bf16: compare at bf16 resolution of the weights
+    assert ((out - ref).norm() / ref.norm()).item() < 5e-3
