@@ -337,7 +337,7 @@ constexpr int PG_STG_BYTES = 2 * BLOCK_M * 128;  // one staging buffer: two (128
 struct TileWalk {
   int sp, n_idx, tile_m;
   int dsp, dn, dm, splits, n_tiles;
-  __device__ __forceinline__ void init(int u0, int stride, int splits_, int n_tiles_) {
+  __host__ __device__ __forceinline__ void init(int u0, int stride, int splits_, int n_tiles_) {
     splits = splits_; n_tiles = n_tiles_;
     int t = u0, g1 = stride;
     sp = 0; dsp = 0;
@@ -345,7 +345,7 @@ struct TileWalk {
     n_idx = t % n_tiles; tile_m = t / n_tiles;
     dn = g1 % n_tiles; dm = g1 / n_tiles;
   }
-  __device__ __forceinline__ void next() {
+  __host__ __device__ __forceinline__ void next() {
     int c = 0;
     sp += dsp;
     if (sp >= splits) { sp -= splits; c = 1; }
@@ -1187,4 +1187,18 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   dim3 grid((unsigned)((M + BLOCK_M - 1) / BLOCK_M), (unsigned)(a->N / BLOCK_N));
   igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_cuda(cudaGetLastError(), "igemm launch");
+}
+
+// Host-side test hook: the work-unit walk of the persistent kernel (TileWalk) for `steps` iterations of the walker that
+// starts at unit u0 and advances by `stride` units: out[3 i .. 3 i + 2] = (tile_m, n_idx, split) of its i-th unit.
+extern "C" int idf_tile_walk_trace(int32_t u0, int32_t stride, int32_t splits, int32_t n_tiles, int32_t steps,
+                                   int32_t* out, idf_stream_t /*stream*/) {
+  if (out == nullptr || u0 < 0 || stride <= 0 || splits <= 0 || n_tiles <= 0 || steps < 0)
+    return fail(IDF_ERR_ARG, "tile_walk_trace: bad argument");
+  TileWalk tw;
+  tw.init(u0, stride, splits, n_tiles);
+  for (int i = 0; i < steps; ++i, tw.next()) {
+    out[3 * i] = tw.tile_m; out[3 * i + 1] = tw.n_idx; out[3 * i + 2] = tw.sp;
+  }
+  return IDF_OK;
 }

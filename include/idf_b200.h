@@ -118,6 +118,17 @@ typedef struct idf_igemm_args {
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);
 
 /*
+ * idf_tile_walk_trace — HOST-side test hook (no GPU work, `out` is a host pointer, `stream` unused): the work-unit walk
+ * of the persistent implicit-GEMM kernel. A CTA (or CTA pair) starts at unit u0 = its index and advances by `stride` =
+ * the number of walkers; unit u = (tile_m * n_tiles + n_idx) * splits + split. The kernel decomposes the stride once
+ * and steps with compare-and-carry adds (the TMA-issuing thread cannot afford integer divisions per tile); this entry
+ * point returns what that walk yields so that CPU tests can hold it to the closed form:
+ * out[3 i .. 3 i + 2] = (tile_m, n_idx, split) of the walker's i-th unit.
+ */
+int idf_tile_walk_trace(int32_t u0, int32_t stride, int32_t splits, int32_t n_tiles, int32_t steps, int32_t* out,
+                        idf_stream_t stream);
+
+/*
  * idf_groupnorm_silu — GroupNorm(groups, C, eps, affine) optionally followed by SiLU, over a channels-last
  * (B, HW, C) bf16 tensor; fp32 statistics. Replaces nn.GroupNorm + nn.SiLU (components.py:31-35, 58, 453-454;
  * unet.py:98-99). x and y are (B*HW, ld) matrices; only C channels are read/written (lets the caller normalise

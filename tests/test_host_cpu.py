@@ -293,3 +293,24 @@ def test_upsample_subpixel_weight_packing_matches_nearest2x_conv():
         out[:, :, p::2, q::2] = acc
     # the packed weights are bf16: compare at bf16 resolution of the weights
     assert ((out - ref).norm() / ref.norm()).item() < 5e-3
+
+
+def test_persistent_kernel_tile_walk_matches_closed_form():
+    """The persistent implicit GEMM walks its work units with carry adds instead of divisions (csrc/igemm.cu: TileWalk);
+    idf_tile_walk_trace exposes that walk on the host. Unit u = (tile_m * n_tiles + n_idx) * splits + split."""
+    import ctypes as C
+    from idf_b200 import native
+    lib = native.load()
+    for stride in (1, 2, 7, 74, 148):
+        for splits in (1, 2, 3, 4):
+            for n_tiles in (1, 2, 3, 6, 9, 12):
+                for u0 in (0, 1, stride - 1):
+                    steps = 40
+                    out = (C.c_int32 * (3 * steps))()
+                    assert lib.idf_tile_walk_trace(u0, stride, splits, n_tiles, steps, out, None) == 0
+                    for i in range(steps):
+                        u = u0 + i * stride
+                        want = (u // splits // n_tiles, u // splits % n_tiles, u % splits)
+                        assert tuple(out[3 * i:3 * i + 3]) == want, (stride, splits, n_tiles, u0, i)
+    bad = (C.c_int32 * 3)()
+    assert lib.idf_tile_walk_trace(0, 0, 1, 1, 1, bad, None) != 0
