@@ -45,7 +45,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_constant__ AttnParams p) {
-  pdl_launch_dependents();
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);  // bytes per Q/K row in shared memory
   constexpr int QK_BYTES = 128 * SWZ;
   constexpr int V_BYTES = 2 * HD * 128;  // two boxes of (HD rows x 64 keys)
@@ -102,7 +101,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
-  pdl_wait();
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
@@ -347,7 +345,6 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* dst) {
 
 template <int HD>
 __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const __grid_constant__ AttnParams p) {
-  pdl_launch_dependents();
   constexpr int SWZ = HD <= 16 ? 32 : (HD <= 32 ? 64 : 128);
   constexpr int QK_BYTES = 128 * SWZ;
   const int V_BYTES = p.v_tok ? 128 * 128 : 2 * HD * 128;
@@ -415,7 +412,6 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
 
   // register re-balancing between warpgroups: the data-movement warpgroup gives its registers to the two softmax
   // warpgroups, which keep a whole 128-wide score row per thread
@@ -697,7 +693,7 @@ static int launch_attention_pipe(const AttnParams& p, int tiles, int heads, cuda
   }
   const int items = ((tiles + 1) / 2) * heads;
   const int grid = items < sm_count() ? items : sm_count();
-  return check_cuda(launch_pdl(attention_pipe_kernel<HD>, dim3(grid), dim3(ATTP_THREADS), smem, stream, p),
+  return check_cuda(launch_kernel(attention_pipe_kernel<HD>, dim3(grid), dim3(ATTP_THREADS), smem, stream, p),
                     "attention_pipe launch");
 }
 
@@ -712,7 +708,7 @@ static int launch_attention(const AttnParams& p, int tiles, int heads, cudaStrea
     if (rc != IDF_OK) return rc;
     smem_set = smem;
   }
-  return check_cuda(launch_pdl(attention_kernel<HD>, dim3(tiles, heads), dim3(ATT_THREADS), smem, stream, p),
+  return check_cuda(launch_kernel(attention_kernel<HD>, dim3(tiles, heads), dim3(ATT_THREADS), smem, stream, p),
                     "attention launch");
 }
 

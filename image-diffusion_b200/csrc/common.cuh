@@ -39,15 +39,6 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
 // ---------------------------------------------------------------------------------------------
-// programmatic dependent launch: a kernel calls pdl_launch_dependents() at its top so that the NEXT kernel of the
-// stream / graph may be scheduled while this one drains, and pdl_wait() before it first touches global memory (the
-// wait returns once every preceding grid has completed and flushed). Prologues (barrier init, TMEM allocation,
-// descriptor prefetch) and launch latency thereby overlap the previous kernel's tail.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

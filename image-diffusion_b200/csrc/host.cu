@@ -68,11 +68,6 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* ptr, in
   return IDF_OK;
 }
 
-bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("IDF_PDL"); return e != nullptr && atoi(e) != 0; }();
-  return on;
-}
-
 int sm_count() {
   static int n = 0;
   if (n == 0) {

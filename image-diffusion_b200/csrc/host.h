@@ -25,25 +25,15 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* ptr, in
 
 int sm_count();
 
-// IDF_PDL=1 enables programmatic dependent launch. Default off: measured no gain on the CUDA-graph replay of the
-// sampling step (4.28 vs 4.25 ms), the kernel-to-kernel gaps inside the graph are already short.
-bool pdl_enabled();
-
-// Launch with the programmatic-stream-serialization attribute: only for kernels that call pdl_wait() before their
-// first global-memory access.
+// cudaLaunchKernelEx wrapper: typed arguments, error returned instead of left in the runtime's sticky state.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              Args&&... args) {
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

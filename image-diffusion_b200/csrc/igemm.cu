@@ -23,12 +23,7 @@ namespace idf {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int STAGES = 3;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 16 KiB
-constexpr int TMEM_COLS = 128;
-constexpr int IGEMM_THREADS = 192;
-constexpr int IGEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 
 enum : int { F_RES = 1, F_ZERO_PAD = 2, F_VT = 4, F_OUT_F32 = 8, F_OUT_UP2 = 16 };
 
@@ -76,250 +71,6 @@ struct IgemmParams {
   float* out_f32;
   long long out_f32_ld;
 };
-
-__global__ void __launch_bounds__(IGEMM_THREADS, 2) igemm_kernel(const __grid_constant__ IgemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* smem_a = smem;                                  // [STAGES][16 KiB]
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;         // [STAGES][16 KiB]
-  uint8_t* stage_c = smem;                                 // epilogue staging aliases A stages 0..1 (32 KiB)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;
-  uint64_t* res_bar = bars + 2 * STAGES + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-
-  const int tile_m = blockIdx.x;
-  const int n0 = blockIdx.y * BLOCK_N;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA[0]);
-    tma_prefetch_desc(&p.tmB);
-    if (p.kb_total > p.kb_seg0) tma_prefetch_desc(&p.tmA[1]);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(res_bar, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    // (elect.sync, not `lane == 0`: ptxas then knows a single thread runs the loop and feeds the uniform datapath
-    //  of UTMALDG / UTCHMMA directly instead of wrapping every issue in a warp-uniformisation loop)
-    if (elect_one()) {
-      int img0, h0, w0 = 0;
-      if (p.matrix) {
-        img0 = 0;
-        h0 = 0;
-        w0 = tile_m * BLOCK_M;
-      } else if (p.tiles_per_img > 0) {
-        img0 = tile_m / p.tiles_per_img;
-        h0 = (tile_m % p.tiles_per_img) * p.tile_h;
-      } else {
-        img0 = tile_m * p.tile_n;
-        h0 = 0;
-      }
-      int seg = 0, tap = 0, cbk = 0;
-      for (int kb = 0; kb < p.kb_total; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
-        const int dh = p.tdh[seg][tap], dw = p.tdw[seg][tap], dn = seg == 0 ? p.tdn[tap] : 0;
-        tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[seg], &full_bar[s], cbk * BLOCK_K, w0 + dw, h0 + dh, img0 + dn);
-        tma_load_2d(smem_b + s * B_STAGE_BYTES, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
-        if (++cbk == p.cb[seg]) {
-          cbk = 0;
-          if (++tap == p.taps[seg]) {
-            tap = 0;
-            ++seg;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
-      for (int kb = 0; kb < p.kb_total; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after_sync();
-        const uint64_t da = umma_desc_kmajor(smem_u32(smem_a + s * A_STAGE_BYTES), 128);
-        const uint64_t db = umma_desc_kmajor(smem_u32(smem_b + s * B_STAGE_BYTES), 128);
-#pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advancing 16 bf16 (32 bytes) along K inside the swizzle row = +2 in the 16-byte address field
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-        }
-        umma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
-      }
-      umma_commit(tmem_full_bar);    // accumulator complete
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue (4 warps, 128 threads)
-    const int quad = warp & 3;             // TMEM lane quadrant this warp may touch
-    const int r = quad * 32 + lane;        // accumulator row within the tile
-    const int et = threadIdx.x - 64;       // 0..127
-    const long long m = (long long)tile_m * BLOCK_M + r;
-    const bool row_ok = m < p.M;
-
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after_sync();
-
-    const bool to_vt = (p.flags & F_VT) && n0 >= p.vt_col0;
-    const bool to_f32 = (p.flags & F_OUT_F32) != 0;
-    const bool staged = !to_vt && !to_f32;
-
-    if ((p.flags & F_RES) && staged) {
-      if (warp == 2 && elect_one()) {
-        mbar_expect_tx(res_bar, 2 * BLOCK_M * 128);
-        tma_load_2d(stage_c, &p.tmR, res_bar, n0, tile_m * BLOCK_M);
-        tma_load_2d(stage_c + BLOCK_M * 128, &p.tmR, res_bar, n0 + 64, tile_m * BLOCK_M);
-      }
-      mbar_wait(res_bar, 0);
-    }
-
-    int sample = 0;
-    bool zero_row = false;
-    if (p.rowbias != nullptr || (p.flags & F_ZERO_PAD)) {
-      const long long mm = row_ok ? m : 0;
-      sample = (int)(mm / p.HW);
-      const int pix = (int)(mm % p.HW);
-      if (p.flags & F_ZERO_PAD) zero_row = (pix / p.W == p.H - 1) || (pix % p.W == p.W - 1);
-    }
-    const float* rb = nullptr;
-    if (p.rowbias != nullptr) {
-      const int rrow = p.rowbias_idx ? p.rowbias_idx[sample] : sample;
-      rb = p.rowbias + (long long)rrow * p.rowbias_ld + n0;
-    }
-
-#pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      float acc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-      if (p.bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(b4 + j);
-          acc[4 * j + 0] += b.x;
-          acc[4 * j + 1] += b.y;
-          acc[4 * j + 2] += b.z;
-          acc[4 * j + 3] += b.w;
-        }
-      }
-      if (rb != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(rb + c * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b = __ldg(b4 + j);
-          acc[4 * j + 0] += b.x;
-          acc[4 * j + 1] += b.y;
-          acc[4 * j + 2] += b.z;
-          acc[4 * j + 3] += b.w;
-        }
-      }
-      if (staged) {
-        // staging layout = two TMA boxes of (128 rows x 64 cols), 128-byte swizzled
-        uint8_t* box = stage_c + (c >> 1) * (BLOCK_M * 128) + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
-          uint4* slot = reinterpret_cast<uint4*>(box + chunk * 16);
-          if (p.flags & F_RES) {
-            const uint4 rv = *slot;
-            acc[8 * q + 0] += bf16_lo(rv.x);
-            acc[8 * q + 1] += bf16_hi(rv.x);
-            acc[8 * q + 2] += bf16_lo(rv.y);
-            acc[8 * q + 3] += bf16_hi(rv.y);
-            acc[8 * q + 4] += bf16_lo(rv.z);
-            acc[8 * q + 5] += bf16_hi(rv.z);
-            acc[8 * q + 6] += bf16_lo(rv.w);
-            acc[8 * q + 7] += bf16_hi(rv.w);
-          }
-          uint4 o;
-          if (zero_row) {
-            o = make_uint4(0u, 0u, 0u, 0u);
-          } else {
-            o.x = pack_bf16x2(acc[8 * q + 0], acc[8 * q + 1]);
-            o.y = pack_bf16x2(acc[8 * q + 2], acc[8 * q + 3]);
-            o.z = pack_bf16x2(acc[8 * q + 4], acc[8 * q + 5]);
-            o.w = pack_bf16x2(acc[8 * q + 6], acc[8 * q + 7]);
-          }
-          *slot = o;
-        }
-      } else if (to_vt) {
-        // transpose through shared memory: stage_c is viewed as [128 columns][128 rows] bf16
-        __nv_bfloat16* tcol = reinterpret_cast<__nv_bfloat16*>(stage_c) + (c * 32) * BLOCK_M + r;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tcol[j * BLOCK_M] = __float2bfloat16_rn(acc[j]);
-      } else {
-        if (row_ok) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f32 + m * p.out_f32_ld + n0 + c * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(acc[4 * j + 0], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        }
-      }
-    }
-    if (to_vt) {
-      // coalesced write-out of the transposed tile: 16 threads cover one 256-byte channel row
-      named_bar_sync(1, 128);
-      const long long m0 = (long long)tile_m * BLOCK_M;
-      __nv_bfloat16* gbase = p.vt + (long long)(n0 - p.vt_col0) * p.vt_ld + m0;
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int q = i * 128 + et;
-        const int col = q >> 4, part = q & 15;
-        if (m0 + part * 8 < p.M) {
-          const uint4 v = *reinterpret_cast<const uint4*>(stage_c + col * (BLOCK_M * 2) + part * 16);
-          *reinterpret_cast<uint4*>(gbase + (long long)col * p.vt_ld + part * 8) = v;
-        }
-      }
-    }
-    if (staged) {
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (warp == 2 && elect_one()) {
-        tma_store_2d(&p.tmC, stage_c, n0, tile_m * BLOCK_M);
-        tma_store_2d(&p.tmC, stage_c + BLOCK_M * 128, n0 + 64, tile_m * BLOCK_M);
-        tma_store_commit();
-        tma_store_wait_all();
-      }
-    }
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // Persistent variant: one CTA per SM walks a static list of output tiles (128 x BN, BN in {128, 192, 256}).
@@ -378,7 +129,6 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
   constexpr int EPI_THREADS = 128 * EW;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int GPT = (BN + 127) / 128;  // column groups per tile
-  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -429,7 +179,6 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
   else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -806,18 +555,16 @@ static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
     cfg.blockDim = dim3(64 + 128 * EW);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 2;
+    cfg.numAttrs = 1;
     return check_cuda(cudaLaunchKernelEx(&cfg, igemm_persist_kernel<BN, NSTG, EW, PAIR>, p), "igemm_persist pair launch");
   } else {
     const int tiles = m_tiles * (p.N / BN) * p.splits * (p.up2_all ? 4 : 1);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    return check_cuda(launch_pdl(igemm_persist_kernel<BN, NSTG, EW, PAIR>, dim3(grid), dim3(64 + 128 * EW), Cfg::SMEM,
+    return check_cuda(launch_kernel(igemm_persist_kernel<BN, NSTG, EW, PAIR>, dim3(grid), dim3(64 + 128 * EW), Cfg::SMEM,
                                  stream, p),
                       "igemm_persist launch");
   }
@@ -839,8 +586,6 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
                                                             const float* __restrict__ rowbias,
                                                             const int* __restrict__ rowbias_idx, int rowbias_ld,
                                                             int H, int W, int zero_pad) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int vec = N / 8;
   const long long total = (long long)M * vec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -993,12 +738,11 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   } else if (a->ldw < ktot) return fail(IDF_ERR_ARG, "igemm: ldw %lld < K %d", (long long)a->ldw, ktot);
   // tile width: the persistent kernel takes 256 / 192 / 128 columns per tile; pick the widest that divides N (and
   // the V^T split point) unless that would leave SMs without a tile
-  static const int legacy = [] { const char* e = getenv("IDF_IGEMM_LEGACY"); return e ? atoi(e) : 0; }();
   int bn = BLOCK_N;
   // short-K GEMMs (K <= 1024: QKV / out_proj / skip projections) are epilogue- and memory-bound: narrow tiles with
   // triple-buffered staging keep loads, residual prefetch and stores in flight together
-  const bool short_k = !legacy && ktot <= 1024 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
-  if (!legacy && !short_k) {
+  const bool short_k = ktot <= 1024 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
+  if (!short_k) {
     // Tile width by a small cost model, calibrated on B200 with the per-launch table of one sampling step
     // (profiles/r01_sample_step_launches_events.txt): the busiest CTA works through waves(c) = ceil(units / SMs)
     // tiles of K / 64 k-blocks; one k-block takes ~250 / 375 / 425 ns for 128- / 192- / 256-wide tiles (~395 ns on
@@ -1034,7 +778,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   // tile over up to 4 work units; fp32 partials go to the caller's workspace and a finish kernel adds them in a
   // fixed order (deterministic) together with the epilogue terms.
   int splits = 1;
-  if (!legacy && !short_k && a->ws != nullptr && a->res == nullptr && a->vt == nullptr && !a->out_f32 && !a->out_up2) {
+  if (!short_k && a->ws != nullptr && a->res == nullptr && a->vt == nullptr && !a->out_f32 && !a->out_up2) {
     const long long units = ((M + BLOCK_M - 1) / BLOCK_M) * (a->N / bn);
     auto eff = [&](int sfac) {
       const long long u = units * sfac;
@@ -1058,7 +802,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   // 32x32 / 16x16 stages gain 5-9 %, 192-wide tiles lose 13-17 %, everything else is neutral or pays for the
   // cluster start-up: IDF_IGEMM_PAIR = 1 (default) pairs only the former, 2 = wherever legal, 0 = never.
   static const int pair_mode = [] { const char* e = getenv("IDF_IGEMM_PAIR"); return e ? atoi(e) : 1; }();
-  const bool pair_legal = !legacy && M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2;
+  const bool pair_legal = M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2;
   const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && bn == 256 && !short_k &&
                                                       (M + BLOCK_M - 1) / BLOCK_M * par_tiles >= sm_count()));
   if (a->w_mn) {  // rows = the A operand's channels (K per tap), columns = (weight tap, output column)
@@ -1121,7 +865,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     }
     if (a->out_up2) {
       // sub-pixel store: row (img, h, w) of this GEMM lands at pixel (img, 2h + ph, 2w + pw) of the (n, 2h, 2w) output
-      if (a->res != nullptr || a->vt != nullptr || is_matrix || legacy || a->s2_batch > 0 || s2d)
+      if (a->res != nullptr || a->vt != nullptr || is_matrix || a->s2_batch > 0 || s2d)
         return fail(IDF_ERR_UNSUPPORTED, "igemm: out_up2 excludes res / vt / matrix / stride-2 inputs");
       if (!up2_all && (a->out_ph < 0 || a->out_ph > 1 || a->out_pw < 0 || a->out_pw > 1))
         return fail(IDF_ERR_ARG, "igemm: bad output parity");
@@ -1146,47 +890,34 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     }
   }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    if ((rc = check_cuda(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IGEMM_SMEM),
-                         "igemm: cudaFuncSetAttribute")) != IDF_OK)
-      return rc;
-    attr_set = true;
-  }
-  if (!legacy) {
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (short_k) {
-      // Without a residual to prefetch, K >= 256 and at least two waves of them, wide tiles with two staging buffers
-      // (3- / 4-stage ring) win 7-13 % (QKV projections of the 32x32 / 16x16 stages: fewer per-tile fixed costs in
-      // the epilogue-bound regime); with K = 128 or few tiles they lose as much, so those keep 128 x 128 tiles.
-      const int wbn = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : 128);
-      const long long wtiles = ((M + BLOCK_M - 1) / BLOCK_M) * (a->N / wbn);
-      if (wbn != 128 && a->res == nullptr && a->vt == nullptr && !a->w_mn && ktot >= 256 && wtiles >= 2 * sm_count()) {
-        if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, (uint32_t)wbn)) != IDF_OK)
-          return rc;
-        return wbn == 256 ? launch_persist<256, 2>(p, st, false) : launch_persist<192, 2>(p, st, false);
-      }
-      return launch_persist<128, 3>(p, st, pair);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (short_k) {
+    // Without a residual to prefetch, K >= 256 and at least two waves of them, wide tiles with two staging buffers
+    // (3- / 4-stage ring) win 7-13 % (QKV projections of the 32x32 / 16x16 stages: fewer per-tile fixed costs in
+    // the epilogue-bound regime); with K = 128 or few tiles they lose as much, so those keep 128 x 128 tiles.
+    const int wbn = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : 128);
+    const long long wtiles = ((M + BLOCK_M - 1) / BLOCK_M) * (a->N / wbn);
+    if (wbn != 128 && a->res == nullptr && a->vt == nullptr && !a->w_mn && ktot >= 256 && wtiles >= 2 * sm_count()) {
+      if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, (uint32_t)wbn)) != IDF_OK)
+        return rc;
+      return wbn == 256 ? launch_persist<256, 2>(p, st, false) : launch_persist<192, 2>(p, st, false);
     }
-    switch (bn) {
-      case 256: rc = launch_persist<256, 1>(p, st, pair); break;
-      case 192: rc = launch_persist<192, 1>(p, st, pair); break;
-      default: rc = launch_persist<128, 1>(p, st, pair); break;
-    }
-    if (rc != IDF_OK || splits == 1) return rc;
-    const long long vecs = M * (a->N / 8);
-    long long blocks = (vecs + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    return check_cuda(launch_pdl(splitk_finish_kernel, dim3((unsigned)blocks), dim3(256), 0, st,
-                                 reinterpret_cast<const float*>(a->ws), p.split_stride, splits,
-                                 reinterpret_cast<__nv_bfloat16*>(a->out), (long long)a->ldo, (int)M, a->N, a->bias,
-                                 a->rowbias, a->rowbias_idx, a->rowbias_ld, p.H, p.W, a->zero_pad_last ? 1 : 0),
-                      "splitk_finish launch");
+    return launch_persist<128, 3>(p, st, pair);
   }
-  if (a->w_mn || a->out_up2 || a->s2_direct) return fail(IDF_ERR_UNSUPPORTED, "igemm: legacy kernel lacks this mode");
-  dim3 grid((unsigned)((M + BLOCK_M - 1) / BLOCK_M), (unsigned)(a->N / BLOCK_N));
-  igemm_kernel<<<grid, IGEMM_THREADS, IGEMM_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  return check_cuda(cudaGetLastError(), "igemm launch");
+  switch (bn) {
+    case 256: rc = launch_persist<256, 1>(p, st, pair); break;
+    case 192: rc = launch_persist<192, 1>(p, st, pair); break;
+    default: rc = launch_persist<128, 1>(p, st, pair); break;
+  }
+  if (rc != IDF_OK || splits == 1) return rc;
+  const long long vecs = M * (a->N / 8);
+  long long blocks = (vecs + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  return check_cuda(launch_kernel(splitk_finish_kernel, dim3((unsigned)blocks), dim3(256), 0, st,
+                               reinterpret_cast<const float*>(a->ws), p.split_stride, splits,
+                               reinterpret_cast<__nv_bfloat16*>(a->out), (long long)a->ldo, (int)M, a->N, a->bias,
+                               a->rowbias, a->rowbias_idx, a->rowbias_ld, p.H, p.W, a->zero_pad_last ? 1 : 0),
+                    "splitk_finish launch");
 }
 
 // Host-side test hook: the work-unit walk of the persistent kernel (TileWalk) for `steps` iterations of the walker that

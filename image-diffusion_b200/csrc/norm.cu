@@ -51,8 +51,6 @@ __global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv
   __shared__ float g_mean[GN_MAX_GPS];
   __shared__ float g_rstd[GN_MAX_GPS];
   constexpr int RPW = 32 / VP;  // pixel rows per warp per sweep
-  pdl_launch_dependents();
-  pdl_wait();
   const int b = blockIdx.x;
   const int c0 = blockIdx.y * gps * cpg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -163,132 +161,6 @@ __global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv
   for (; pix < HW; pix += rows_per_iter) apply_store(*reinterpret_cast<const uint4*>(xb + (long long)pix * ldx), pix);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Shared-memory staged variant. The whole (sample, slab) tile (HW rows x V vectors, <= ~64 KiB) is brought into shared
-// memory by a handful of TMA box loads issued up front - all of the CTA's DRAM/L2 traffic is in flight at once instead
-// of a register-staged loop of dependent load batches - and both passes (statistics, normalise + activate) then read
-// shared memory. Global memory is read exactly once. Same thread mapping, same fixed-order reductions and therefore
-// the same bits as groupnorm_kernel.
-// ---------------------------------------------------------------------------------------------------------------
-template <bool SILU, int VP>
-__global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_staged_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                                             __nv_bfloat16* __restrict__ y, long long ldy,
-                                                                             const float* __restrict__ gamma,
-                                                                             const float* __restrict__ beta, int HW,
-                                                                             int cpg, int gps, int V, int box_rows,
-                                                                             float eps, float* __restrict__ stats,
-                                                                             int groups) {
-  extern __shared__ uint8_t gn_smem_raw[];
-  __shared__ float ch_s[GN_MAX_WARPS][VP * 8];
-  __shared__ float ch_q[GN_MAX_WARPS][VP * 8];
-  __shared__ float ct_s[VP * 8];
-  __shared__ float ct_q[VP * 8];
-  __shared__ float g_mean[GN_MAX_GPS];
-  __shared__ float g_rstd[GN_MAX_GPS];
-  __shared__ uint64_t full_bar;
-  constexpr int RPW = 32 / VP;
-  const uint32_t raw_addr = smem_u32(gn_smem_raw);
-  uint8_t* slab = gn_smem_raw + ((128u - (raw_addr & 127u)) & 127u);
-  const int b = blockIdx.x;
-  const int c0 = blockIdx.y * gps * cpg;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int v = lane % VP, prl = lane / VP;
-  const bool active = v < V;
-  const int rows_per_iter = nwarps * RPW;
-  const int row_bytes = V * 16;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmX);
-    mbar_init(&full_bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&full_bar, (uint32_t)(HW * row_bytes));
-    for (int r0 = 0; r0 < HW; r0 += box_rows)
-      tma_load_2d(slab + (long long)r0 * row_bytes, &tmX, &full_bar, c0, b * HW + r0);
-  }
-  mbar_wait(&full_bar, 0);
-
-  const uint8_t* xs = slab + v * 16;
-  float s[8], q[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-  if (active) {
-    for (int pix = warp * RPW + prl; pix < HW; pix += rows_per_iter) {
-      const uint4 r0 = *reinterpret_cast<const uint4*>(xs + pix * row_bytes);
-      float f[8];
-      unpack8(r0, f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
-    }
-  }
-#pragma unroll
-  for (int off = VP; off < 32; off <<= 1) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      s[e] += __shfl_xor_sync(0xffffffffu, s[e], off);
-      q[e] += __shfl_xor_sync(0xffffffffu, q[e], off);
-    }
-  }
-  if (prl == 0) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { ch_s[warp][v * 8 + e] = s[e]; ch_q[warp][v * 8 + e] = q[e]; }
-  }
-  __syncthreads();
-  if (threadIdx.x < V * 8) {
-    float a = 0.f, c = 0.f;
-    for (int w = 0; w < nwarps; ++w) { a += ch_s[w][threadIdx.x]; c += ch_q[w][threadIdx.x]; }
-    ct_s[threadIdx.x] = a;
-    ct_q[threadIdx.x] = c;
-  }
-  __syncthreads();
-  if (threadIdx.x < gps) {
-    float a = 0.f, c = 0.f;
-    for (int k = 0; k < cpg; ++k) { a += ct_s[threadIdx.x * cpg + k]; c += ct_q[threadIdx.x * cpg + k]; }
-    const float inv_cnt = 1.f / ((float)HW * (float)cpg);
-    const float mean = a * inv_cnt;
-    const float var = fmaxf(c * inv_cnt - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    g_mean[threadIdx.x] = mean;
-    g_rstd[threadIdx.x] = rstd;
-    if (stats != nullptr) {
-      float* st = stats + ((long long)b * groups + blockIdx.y * gps + threadIdx.x) * 2;
-      st[0] = mean;
-      st[1] = rstd;
-    }
-  }
-  __syncthreads();
-  if (!active) return;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int cl = v * 8 + e;
-    const int g = cl / cpg;
-    const float ga = gamma[c0 + cl], be = beta[c0 + cl];
-    sc[e] = g_rstd[g] * ga;
-    sh[e] = be - g_mean[g] * g_rstd[g] * ga;
-  }
-  __nv_bfloat16* yb = y + (long long)b * HW * ldy + c0 + v * 8;
-  for (int pix = warp * RPW + prl; pix < HW; pix += rows_per_iter) {
-    const uint4 r0 = *reinterpret_cast<const uint4*>(xs + pix * row_bytes);
-    float f[8];
-    unpack8(r0, f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float t = fmaf(f[e], sc[e], sh[e]);
-      if (SILU) t = silu_tanh(t);
-      f[e] = t;
-    }
-    uint4 o;
-    o.x = pack_bf16x2(f[0], f[1]);
-    o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]);
-    o.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(yb + (long long)pix * ldy) = o;
-  }
-}
-
 // one CTA per row; cols <= 8 * blockDim * 4
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, long long ld_in,
                                                            __nv_bfloat16* __restrict__ out, long long ld_out,
@@ -360,48 +232,6 @@ static int groupnorm_impl(const void* x, int64_t ldx, void* y, int64_t ldy, cons
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
 
-  // ---- shared-memory staged path: slab = the widest whole-group span whose (HW x slab) tile is <= slab_kb KiB
-  static const int staged_kb = [] { const char* e = getenv("IDF_GN_STAGED_KB"); return e ? atoi(e) : 0; }();  // off: measured equal to the register-staged kernel (27-29 us at B=96, 32x32, C=256 either way)
-  if (staged_kb > 0) {
-    int sg = 0;
-    for (int d = 8; d >= 1; --d)
-      if (groups % d == 0 && (d * cpg) % 8 == 0 && d * cpg / 8 <= 8 && (long long)HW * d * cpg * 2 <= (long long)staged_kb * 1024) { sg = d; break; }
-    if (sg == 0)  // no slab fits the target: the narrowest legal one, if it still fits shared memory at all
-      for (int d = 1; d <= 8; ++d)
-        if (groups % d == 0 && (d * cpg) % 8 == 0 && d * cpg / 8 <= 8) { if ((long long)HW * d * cpg * 2 <= 200 * 1024) sg = d; break; }
-    if (sg > 0) {
-      const int Vs = sg * cpg / 8;
-      const int VPs = Vs <= 4 ? 4 : 8;
-      int box_rows = HW < 256 ? HW : 256;
-      while (HW % box_rows != 0) --box_rows;
-      CUtensorMap tm;
-      const uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * HW};
-      const uint64_t strides[1] = {(uint64_t)ldx * 2};
-      const uint32_t box[2] = {(uint32_t)(Vs * 8), (uint32_t)box_rows};
-      int rc = encode_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-      if (rc != IDF_OK) return rc;
-      int warps = GN_MAX_WARPS;
-      while (warps > 1 && (warps - 1) * (32 / VPs) >= HW) --warps;
-      const int smem = HW * Vs * 16 + 128;
-      dim3 grid(B, groups / sg);
-#define GN_STAGED(SILU_, VP_)                                                                                          \
-  do {                                                                                                                 \
-    static int attr = 0;                                                                                               \
-    if (smem > attr) {                                                                                                 \
-      rc = check_cuda(cudaFuncSetAttribute(groupnorm_staged_kernel<SILU_, VP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           200 * 1024 + 128), "groupnorm: cudaFuncSetAttribute");                      \
-      if (rc != IDF_OK) return rc;                                                                                     \
-      attr = 200 * 1024 + 128;                                                                                         \
-    }                                                                                                                  \
-    groupnorm_staged_kernel<SILU_, VP_><<<grid, warps * 32, smem, s>>>(tm, yp, ldy, gamma, beta, HW, cpg, sg, Vs,      \
-                                                                       box_rows, eps, stats, groups);                  \
-  } while (0)
-      if (VPs == 4) { if (apply_silu) GN_STAGED(true, 4); else GN_STAGED(false, 4); }
-      else { if (apply_silu) GN_STAGED(true, 8); else GN_STAGED(false, 8); }
-#undef GN_STAGED
-      return check_cuda(cudaGetLastError(), "groupnorm (staged) launch");
-    }
-  }
   const int V = gps * cpg / 8;
   const int VP = V <= 4 ? 4 : 8;
   // CTA size by slab size (measured per shape, profiles/r01_groupnorm_warps_sweep.txt): 12 warps for the 128 KB slabs
@@ -413,11 +243,11 @@ static int groupnorm_impl(const void* x, int64_t ldx, void* y, int64_t ldy, cons
   dim3 grid(B, groups / gps);
   const int threads = warps * 32;
   if (VP == 4) {
-    if (apply_silu) launch_pdl(groupnorm_kernel<true, 4>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
-    else launch_pdl(groupnorm_kernel<false, 4>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
+    if (apply_silu) launch_kernel(groupnorm_kernel<true, 4>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
+    else launch_kernel(groupnorm_kernel<false, 4>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
   } else {
-    if (apply_silu) launch_pdl(groupnorm_kernel<true, 8>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
-    else launch_pdl(groupnorm_kernel<false, 8>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
+    if (apply_silu) launch_kernel(groupnorm_kernel<true, 8>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
+    else launch_kernel(groupnorm_kernel<false, 8>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
   }
   return check_cuda(cudaGetLastError(), "groupnorm launch");
 }

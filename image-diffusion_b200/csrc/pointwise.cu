@@ -83,7 +83,8 @@ __global__ void cfg_posterior_kernel(const float* __restrict__ xt, const float* 
                                      const float* __restrict__ betas, const float* __restrict__ alphas,
                                      const float* __restrict__ acp, const float* __restrict__ sacp,
                                      const float* __restrict__ somacp, float* __restrict__ x_prev,
-                                     float* __restrict__ x_prev_dup, float* __restrict__ x0_out, int N, int chw) {
+                                     float* __restrict__ x_prev_dup, float* __restrict__ x0_out, int N, int chw,
+                                     int num_steps) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * chw) return;
   const int n = (int)(i / chw);
@@ -102,12 +103,46 @@ __global__ void cfg_posterior_kernel(const float* __restrict__ xt, const float* 
   mean = mean / sqrtf(alphas[tn]);
   float out = mean;
   if (t_first != 0) {
-    float var = (1.f - acp[tn - 1]) / (1.f - acp[tn]);
+    // per-sample t with t[0] != 0 but t[n] == 0: the reference indexes alpha_cum_prod[t - 1] = [-1], which torch
+    // wraps to the LAST table entry (components.py:419); same here instead of reading out of bounds
+    const int tp = tn > 0 ? tn - 1 : num_steps - 1;
+    float var = (1.f - acp[tp]) / (1.f - acp[tn]);
     var = var * b;
     out = mean + sqrtf(var) * z[i];
   }
   x_prev[i] = out;  // may alias xt: every thread reads its own element before writing it
   if (x_prev_dup != nullptr) x_prev_dup[i] = out;
+}
+
+// CFG mix + one step of the generalised (strided) sampler of Song et al., "Denoising Diffusion Implicit Models"
+// (ICLR 2021), eq. 12, from timestep t to an arbitrary earlier timestep t_prev (t_prev < 0: the final step, abar = 1):
+//   x0     = (x_t - sqrt(1 - abar_t) eps) / sqrt(abar_t)                     (optionally clamped to [-1, 1])
+//   sigma  = eta * sqrt((1 - abar_prev) / (1 - abar_t)) * sqrt(1 - abar_t / abar_prev)
+//   x_prev = sqrt(abar_prev) x0 + sqrt(1 - abar_prev - sigma^2) eps + sigma z
+// eta = 0: deterministic DDIM; eta = 1 with t_prev = t - 1 and no clamp: the reference's ancestral DDPM step
+// (components.py:405-424) in another algebraic form. Both timesteps are read on the device (graph replay safe).
+__global__ void cfg_ddim_kernel(const float* __restrict__ xt, const float* __restrict__ ec,
+                                const float* __restrict__ eu, const float* __restrict__ z,
+                                const float* __restrict__ cfg, const int64_t* __restrict__ t,
+                                const int64_t* __restrict__ t_prev, const float* __restrict__ acp, float eta,
+                                int clamp_x0, float* __restrict__ x_prev, float* __restrict__ x0_out, int N, int chw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * chw) return;
+  const int n = (int)(i / chw);
+  const int tn = (int)t[0];
+  const int tp = (int)t_prev[0];
+  const float x = xt[i];
+  const float u = eu[i];
+  const float eps = u + cfg[n] * (ec[i] - u);
+  const float a_t = acp[tn];
+  const float a_p = tp >= 0 ? acp[tp] : 1.f;
+  float x0 = (x - sqrtf(1.f - a_t) * eps) / sqrtf(a_t);
+  if (clamp_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+  if (x0_out != nullptr) x0_out[i] = x0;
+  const float sigma = eta * sqrtf((1.f - a_p) / (1.f - a_t)) * sqrtf(fmaxf(1.f - a_t / a_p, 0.f));
+  float out = sqrtf(a_p) * x0 + sqrtf(fmaxf(1.f - a_p - sigma * sigma, 0.f)) * eps;
+  if (sigma > 0.f) out += sigma * z[i];
+  x_prev[i] = out;  // may alias xt
 }
 
 __global__ void add_noise_kernel(const float* __restrict__ x, const float* __restrict__ noise,
@@ -163,7 +198,6 @@ __global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict_
   const int warps_per_block = blockDim.x >> 5;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
     float xv[DIM];
-#pragma unroll
     // hw > 0: z and zq are NCHW tensors with hw pixels per image (row = image * hw + pixel); else row-major rows
     const long long base = hw > 0 ? ((long long)(row / hw) * DIM * hw + row % hw) : (long long)row * DIM;
     const long long dstride = hw > 0 ? hw : 1;
@@ -503,27 +537,6 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, long long
   }
 }
 
-__global__ void im2col_s2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y,
-                                 int B, int H, int W, int C) {
-  const int OH = H / 2, OW = W / 2, vec = C / 8;
-  const long long total = (long long)B * OH * OW * 9 * vec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vec);
-    const int tap = (int)((i / vec) % 9);
-    const long long opix = i / ((long long)vec * 9);
-    const int ow = (int)(opix % OW);
-    const int oh = (int)((opix / OW) % OH);
-    const int b = (int)(opix / ((long long)OW * OH));
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (oh < OH - 1 && ow < OW - 1) {
-      const int hh = 2 * oh + tap / 3, ww = 2 * ow + tap % 3;
-      val = *reinterpret_cast<const uint4*>(x + (((long long)b * H + hh) * W + ww) * ldx + v * 8);
-    }
-    *reinterpret_cast<uint4*>(y + opix * (9LL * C) + (long long)tap * C + v * 8) = val;
-  }
-}
-
 // y[(ph*2+pw)*B + b][h][w][:] = x[b][2h+ph][2w+pw][:]  (16-byte vectors, four independent copies per thread)
 __global__ void __launch_bounds__(256) space_to_depth2_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                               __nv_bfloat16* __restrict__ y, int B, int H, int W,
@@ -639,15 +652,29 @@ extern "C" int idf_cfg_posterior_step(const float* xt, const float* eps_cond, co
                                       const float* betas, const float* alphas, const float* alpha_cum_prod,
                                       const float* sqrt_alpha_cum_prod, const float* sqrt_one_minus_alpha_cum_prod,
                                       float* x_prev, float* x_prev_dup, float* x0_out, int32_t N, int32_t chw,
-                                      idf_stream_t stream) {
+                                      int32_t num_steps, idf_stream_t stream) {
   if (!xt || !eps_cond || !eps_uncond || !noise || !cfg || !t || !betas || !alphas || !alpha_cum_prod ||
       !sqrt_alpha_cum_prod || !sqrt_one_minus_alpha_cum_prod || !x_prev)
     return fail(IDF_ERR_ARG, "cfg_posterior: null pointer");
+  if (num_steps < 1) return fail(IDF_ERR_ARG, "cfg_posterior: num_steps must be the schedule length");
   const long long n = (long long)N * chw;
   cfg_posterior_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       xt, eps_cond, eps_uncond, noise, cfg, t, t_stride, betas, alphas, alpha_cum_prod, sqrt_alpha_cum_prod,
-      sqrt_one_minus_alpha_cum_prod, x_prev, x_prev_dup, x0_out, N, chw);
+      sqrt_one_minus_alpha_cum_prod, x_prev, x_prev_dup, x0_out, N, chw, num_steps);
   return check_cuda(cudaGetLastError(), "cfg_posterior launch");
+}
+
+extern "C" int idf_cfg_ddim_step(const float* xt, const float* eps_cond, const float* eps_uncond, const float* noise,
+                                 const float* cfg, const int64_t* t, const int64_t* t_prev,
+                                 const float* alpha_cum_prod, float eta, int32_t clamp_x0, float* x_prev,
+                                 float* x0_out, int32_t N, int32_t chw, idf_stream_t stream) {
+  if (!xt || !eps_cond || !eps_uncond || !cfg || !t || !t_prev || !alpha_cum_prod || !x_prev)
+    return fail(IDF_ERR_ARG, "cfg_ddim: null pointer");
+  if (eta < 0.f || (eta > 0.f && !noise)) return fail(IDF_ERR_ARG, "cfg_ddim: eta > 0 needs a noise tensor");
+  const long long n = (long long)N * chw;
+  cfg_ddim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      xt, eps_cond, eps_uncond, noise, cfg, t, t_prev, alpha_cum_prod, eta, clamp_x0, x_prev, x0_out, N, chw);
+  return check_cuda(cudaGetLastError(), "cfg_ddim launch");
 }
 
 extern "C" int idf_add_noise(const float* x, const float* noise, const int64_t* t, const float* sqrt_alpha_cum_prod,
@@ -781,16 +808,6 @@ extern "C" int idf_upsample_nearest2x(const void* x, int64_t ldx, void* y, int64
   upsample2x_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, B, H, W, C);
   return check_cuda(cudaGetLastError(), "upsample launch");
-}
-
-extern "C" int idf_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
-                             idf_stream_t stream) {
-  if (!x || !y) return fail(IDF_ERR_ARG, "im2col_s2: null pointer");
-  if (C % 8 != 0 || ldx % 8 != 0 || H % 2 != 0 || W % 2 != 0) return fail(IDF_ERR_ARG, "im2col_s2: bad shape");
-  const long long total = (long long)B * (H / 2) * (W / 2) * 9 * (C / 8);
-  im2col_s2_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C);
-  return check_cuda(cudaGetLastError(), "im2col_s2 launch");
 }
 
 extern "C" int idf_space_to_depth2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t W, int32_t C,

@@ -65,11 +65,30 @@ class _Packed:
         self.w = {}
 
     def stale(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+        # `_weights_epoch` is bumped by writers that bypass torch's version counter (the fused Adam kernel updates
+        # the flat parameter buffer through a raw pointer: DiffusionTrainStep.step)
+        key = (getattr(self.module, "_weights_epoch", 0),) + tuple((p.data_ptr(), p._version)
+                                                                  for p in self.module.parameters())
         if key != self.key:
             self.key = key
             return True
         return False
+
+    def install(self, w):
+        """Refreshes the packed copies IN PLACE when the layout is unchanged, so that captured CUDA graphs (which hold
+        raw pointers to these tensors) keep reading valid, current weights."""
+        old = self.w
+        if old and old.keys() == w.keys() and all(old[k].shape == w[k].shape and old[k].dtype == w[k].dtype
+                                                   and type(old[k]) is type(w[k]) for k in w):
+            for k, v in w.items():
+                if isinstance(v, list):  # _UpsamplePack: per-parity matrices + the stacked matrix
+                    for (_, _, dst), (_, _, src) in zip(old[k], v):
+                        dst.copy_(src)
+                    old[k].stacked.copy_(v.stacked)
+                else:
+                    old[k].copy_(v)
+        else:
+            self.w = w
 
     def sd(self):
         return {k: v for k, v in self.module.state_dict().items()}
@@ -142,7 +161,7 @@ class UnetEngine:
         order = [(p, l) for p, _, _ in self.downs + self.mids + self.ups for l in range(self.L)]
         w["t.wp"] = _f32(torch.cat([sd[f"{p}.time_projs.{l}.1.weight"] for p, l in order], dim=0))
         w["t.bp"] = _f32(torch.cat([sd[f"{p}.time_projs.{l}.1.bias"] for p, l in order], dim=0))
-        self.packed.w = w
+        self.packed.install(w)
 
     # ---------------------------------------------------------------------------------------------
     def _tap(self, name, t2d):
@@ -297,7 +316,7 @@ class VaeEngine:
                     w[p + ".w"], w[p + ".b"] = pk(sd[f"{p}.{n}.weight"]), _f32(sd[f"{p}.{n}.bias"])
                 elif kind == "gn_silu":
                     w[p + ".gw"], w[p + ".gb"] = _f32(sd[p + ".weight"]), _f32(sd[p + ".bias"])
-        self.packed.w = w
+        self.packed.install(w)
 
     # ---- layer runners -------------------------------------------------------------------------
     def _res(self, p, x: Act, cout) -> Act:

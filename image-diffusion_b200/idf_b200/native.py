@@ -56,14 +56,15 @@ _SIGNATURES = {
     "idf_attention_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32],
     "idf_softmax_rows": [_vp, _i64, _vp, _i64, _i32, _i32, _f32],
     "idf_embed_time_class": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
-    "idf_cfg_posterior_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32],
+    "idf_cfg_posterior_step": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                               _i32],
+    "idf_cfg_ddim_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _i32, _i32],
     "idf_add_noise": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32],
     "idf_vq_argmin": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32],
     "idf_conv3x3_small_cin": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32],
     "idf_conv3x3_small_cout": [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32],
     "idf_conv1x1_small_f32": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32],
     "idf_upsample_nearest2x": [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32],
-    "idf_im2col_s2": [_vp, _i64, _vp, _i32, _i32, _i32, _i32],
     "idf_space_to_depth2": [_vp, _i64, _vp, _i32, _i32, _i32, _i32],
     "idf_nchw_f32_to_nhwc_bf16": [_vp, _vp, _i64, _i32, _i32, _i32],
     "idf_nhwc_bf16_to_nchw_f32": [_vp, _i64, _vp, _i32, _i32, _i32],

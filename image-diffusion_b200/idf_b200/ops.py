@@ -112,7 +112,17 @@ def cfg_posterior_step(xt, eps_c, eps_u, noise, cfg, t, sched, x_prev, x0_out=No
     call("idf_cfg_posterior_step", xt.data_ptr(), eps_c.data_ptr(), eps_u.data_ptr(), noise.data_ptr(), cfg.data_ptr(),
          t.data_ptr(), t_stride, sched.betas.data_ptr(), sched.alphas.data_ptr(), sched.alpha_cum_prod.data_ptr(),
          sched.sqrt_alpha_cum_prod.data_ptr(), sched.sqrt_one_minus_alpha_cum_prod.data_ptr(), x_prev.data_ptr(),
-         ptr(x_prev_dup), ptr(x0_out), N, chw)
+         ptr(x_prev_dup), ptr(x0_out), N, chw, sched.num_steps)
+    return x_prev
+
+
+def cfg_ddim_step(xt, eps_c, eps_u, noise, cfg, t, t_prev, sched, x_prev, eta: float = 0.0, clamp_x0: bool = False,
+                  x0_out=None):
+    """Guidance mix + one strided step t -> t_prev (device int64 scalars; t_prev < 0 = final step)."""
+    N = xt.shape[0]
+    call("idf_cfg_ddim_step", xt.data_ptr(), eps_c.data_ptr(), eps_u.data_ptr(), ptr(noise), cfg.data_ptr(),
+         t.data_ptr(), t_prev.data_ptr(), sched.alpha_cum_prod.data_ptr(), float(eta), 1 if clamp_x0 else 0,
+         x_prev.data_ptr(), ptr(x0_out), N, xt.numel() // N)
     return x_prev
 
 
@@ -161,11 +171,6 @@ def conv1x1_small_f32(x_nchw: torch.Tensor, w: torch.Tensor, bias, y_nchw: torch
 
 def upsample_nearest2x(x: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, C: int):
     call("idf_upsample_nearest2x", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), B, H, W, C)
-    return y
-
-
-def im2col_s2(x: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, C: int):
-    call("idf_im2col_s2", x.data_ptr(), x.stride(0), y.data_ptr(), B, H, W, C)
     return y
 
 

@@ -13,7 +13,14 @@ from . import native, ops
 
 
 class CfgSampler:
-    def __init__(self, unet, scheduler, labels: torch.Tensor, cfg_scales: torch.Tensor, latent_shape, use_graph=True):
+    def __init__(self, unet, scheduler, labels: torch.Tensor, cfg_scales: torch.Tensor, latent_shape, use_graph=True,
+                 kind: str = "ddpm", eta: float = 0.0, clamp_x0: bool = False):
+        """kind="ddpm": the reference's 1-step ancestral update (components.py:405-424). kind="ddim": the strided
+        update of idf_cfg_ddim_step - `steps` passed to run() may then be any decreasing subset of
+        the schedule; eta = 0 is deterministic, eta = 1 ancestral."""
+        if kind not in ("ddpm", "ddim"):
+            raise ValueError(f"CfgSampler: unknown kind {kind!r}")
+        self.kind, self.eta, self.clamp_x0 = kind, float(eta), clamp_x0
         dev = labels.device
         self.unet, self.sched = unet, scheduler._on(dev)
         self.N = N = labels.shape[0]
@@ -22,6 +29,7 @@ class CfgSampler:
         self.engine = unet.engine(2 * N, latent_shape[1], latent_shape[2])
         # embedding rows: classes 0..K-1 (conditional) and one masked row (unconditional)
         self.t_rows = torch.zeros(K + 1, device=dev, dtype=torch.int64)
+        self.t_prev = torch.full((1,), -1, device=dev, dtype=torch.int64)
         self.ctx_rows = torch.cat([torch.arange(K, device=dev), torch.zeros(1, device=dev, dtype=torch.int64)])
         self.mask_rows = torch.cat([torch.ones(K, device=dev), torch.zeros(1, device=dev)]).to(torch.float32)
         self.row_idx = torch.cat([labels.to(torch.int32), torch.full((N,), K, device=dev, dtype=torch.int32)])
@@ -31,6 +39,7 @@ class CfgSampler:
         self.rows_per_t = K + 1
         self.base_idx = self.row_idx.clone()
         self.table_all = None
+        self._epoch = -1
         self.cfg = cfg_scales.to(device=dev, dtype=torch.float32).contiguous()
         self.xx = torch.zeros(N, *latent_shape, device=dev, dtype=torch.float32)        # x_t (fp32 state)
         self.eps = torch.empty(2 * N, *latent_shape, device=dev, dtype=torch.float32)  # [eps_cond ; eps_uncond]
@@ -40,9 +49,12 @@ class CfgSampler:
         self.launches_per_step = None
 
     def _ensure_table(self):
-        """Cached on the engine (shared by every sampler of the same batch size), refreshed when the weights change."""
+        """Cached on the engine (shared by every sampler of the same batch size), refreshed when the weights change.
+        Both the packed weights (engine.prepare) and the table are rewritten IN PLACE, so a graph captured earlier
+        keeps reading valid, current data."""
         eng = self.engine
         eng.prepare()
+        self._epoch = getattr(self.unet, "_weights_epoch", 0)
         T, R = self.sched.num_steps, self.rows_per_t
         cache = eng.__dict__.setdefault("cfg_tables", {})
         entry = cache.get((T, R))
@@ -62,8 +74,12 @@ class CfgSampler:
                     self.row_idx.data_ptr(), 2 * N)
         self.engine.run(self.xx, self.t_rows, self.ctx_rows, self.mask_rows, self.row_idx, self.eps, dup_input=True,
                         table=self.table_all)
-        ops.cfg_posterior_step(self.xx, self.eps[:N], self.eps[N:], self.z, self.cfg, self.t_rows[:1], self.sched,
-                               self.xx)
+        if self.kind == "ddim":
+            ops.cfg_ddim_step(self.xx, self.eps[:N], self.eps[N:], self.z, self.cfg, self.t_rows[:1], self.t_prev,
+                              self.sched, self.xx, eta=self.eta, clamp_x0=self.clamp_x0)
+        else:
+            ops.cfg_posterior_step(self.xx, self.eps[:N], self.eps[N:], self.z, self.cfg, self.t_rows[:1], self.sched,
+                                   self.xx)
 
     def _ensure_graph(self):
         if self.graph is not None or not self.use_graph:
@@ -84,20 +100,24 @@ class CfgSampler:
         self.xx.copy_(keep)
 
     def set_latent(self, x_T: torch.Tensor):
+        self._ensure_table()  # start of a sampling run: full staleness check of the weights (load_state_dict, optimizer)
         self.xx.copy_(x_T)
 
     @property
     def latent(self) -> torch.Tensor:
         return self.xx
 
-    def step(self, i: int, noise: torch.Tensor | None = None):
-        """Advance x_i -> x_{i-1}. `noise` injects the step's N(0,1) draw; None draws it from the global CUDA
-        generator exactly where the reference does (components.py:423: randn_like(xt), skipped at i == 0)."""
-        if self.table_all is None:  # (weights are frozen for the lifetime of a sampler)
+    def step(self, i: int, noise: torch.Tensor | None = None, i_prev: int | None = None):
+        """Advance x_i -> x_{i-1} (kind="ddim": x_i -> x_{i_prev}; i_prev < 0 or None = the final step). `noise`
+        injects the step's N(0,1) draw; None draws it from the global CUDA generator exactly where the reference does
+        (components.py:423: randn_like(xt), skipped at i == 0; the deterministic eta = 0 sampler draws nothing)."""
+        if self.table_all is None or self._epoch != getattr(self.unet, "_weights_epoch", 0):
             self._ensure_table()
         self._ensure_graph()
         self.t_rows.fill_(i)
-        if i > 0:
+        if self.kind == "ddim":
+            self.t_prev.fill_(-1 if i_prev is None else i_prev)
+        if (i > 0 and self.kind == "ddpm") or (self.kind == "ddim" and self.eta > 0.0 and (i_prev or -1) >= 0):
             if noise is None:
                 self.z.normal_()
             else:
@@ -111,5 +131,5 @@ class CfgSampler:
         self.set_latent(x_T)
         steps = list(reversed(range(self.sched.num_steps))) if steps is None else list(steps)
         for k, i in enumerate(steps):
-            self.step(i, None if noises is None else noises[k])
+            self.step(i, None if noises is None else noises[k], steps[k + 1] if k + 1 < len(steps) else -1)
         return self.latent

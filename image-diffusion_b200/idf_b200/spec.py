@@ -8,6 +8,15 @@ from collections import OrderedDict
 import torch
 import torch.nn as nn
 
+# Architectures of the three shipped configurations (the values of the reference's YAML files).
+UNET_ARCH = dict(z_dim=3, channels=[128, 256, 384, 512], mid_channels=[512, 512], time_dim=512, num_res_layers=2,
+                 num_heads=8, num_groups=32, num_classes=3)  # configs/diff-kl-lin-32x32.yaml:2-9
+VAE_KL_ARCH = dict(in_channels=3, channels=[128, 256, 384], z_dim=3, bottleneck="kl", codebook_size=None,
+                   codebook_beta=None, codebook_gamma=None, enc_num_res_blocks=2, dec_num_res_blocks=2,
+                   attn_resolutions=[], num_heads=1, init_resolution=128, num_groups=32)  # configs/vae-kl-32x32.yaml:2-15
+VAE_VQ_ARCH = dict(VAE_KL_ARCH, bottleneck="vq", codebook_size=1024, codebook_beta=0.25,
+                   codebook_gamma=0.99)  # configs/vae-vq-32x32.yaml:2-15
+
 # kinds: conv/linear weight "w", its bias "b" (fan_in attached), norm gain "g", norm shift "z", embedding "e",
 # codebook "c", buffers "factor" / "zeros"
 

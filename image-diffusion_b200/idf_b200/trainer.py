@@ -20,6 +20,7 @@ import torch.distributed as dist
 from . import native, ops
 
 F32 = torch.float32
+HYPER_SLOTS = 8
 
 
 class GradBuckets:
@@ -89,6 +90,12 @@ class DiffusionTrainStep:
         self.step_count = 0
         self.buckets = GradBuckets(self.eng.flat_grad, self.eng.bucket_ends, group)
         self.world = self.buckets.world
+        if self.world > 1:
+            # replicas start from rank 0's parameters and optimizer state (what torch DDP does at construction);
+            # only gradients are exchanged afterwards
+            for buf in (self.flat_param, self.exp_avg, self.exp_avg_sq):
+                dist.broadcast(buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            self.eng.pkey = None
         C = latent_shape[0]
         z = lambda *s, dt=F32: torch.zeros(*s, device=dev, dtype=dt)
         self.latents = z(batch, (2 if sample_latents else 1) * C, *latent_shape[1:])
@@ -100,7 +107,12 @@ class DiffusionTrainStep:
         self.loss = z(1)
         self.norm_clip = z(2)
         self.hyper = z(4)
-        self.hyper_host = torch.zeros(4, dtype=F32).pin_memory()
+        # {lr, 1 - beta1^k, sqrt(1 - beta2^k)} of step k travel through a RING of pinned slots: the H2D copy of slot j
+        # is asynchronous, and the host may be several steps ahead of the GPU, so a slot is rewritten only after the
+        # event recorded behind its previous copy has completed (a single reused pinned buffer would let step k read
+        # step k+n's values).
+        self.hyper_ring = [torch.zeros(4, dtype=F32).pin_memory() for _ in range(HYPER_SLOTS)]
+        self.hyper_events = [None] * HYPER_SLOTS
         self.sq_scratch = z(2048)
         # One rank: the whole step is ONE CUDA graph. Several ranks: the step is captured as a CHAIN of graphs cut at
         # the gradient-bucket boundaries; the NCCL all-reduce of bucket k is issued eagerly on a side stream between
@@ -247,8 +259,18 @@ class DiffusionTrainStep:
         if draw:
             self.draw(generator)
         self.step_count += 1
-        self.hyper_host.copy_(torch.tensor(ops.adam_hyper(lr, self.step_count, *self.betas)))
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        slot = self.step_count % HYPER_SLOTS
+        if self.hyper_events[slot] is not None:
+            self.hyper_events[slot].synchronize()
+        host = self.hyper_ring[slot]
+        host.copy_(torch.tensor(ops.adam_hyper(lr, self.step_count, *self.betas)))
+        self.hyper.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.hyper_events[slot] = ev
+        # the fused Adam kernel writes the parameters through a raw pointer (no torch version bump): tell the
+        # inference engines / cached samplers of this module that their packed weights are stale
+        self.unet._weights_epoch = getattr(self.unet, "_weights_epoch", 0) + 1
         if self.graph is not None:
             self.graph.replay()
         elif self.segments is not None:

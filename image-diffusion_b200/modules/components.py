@@ -75,6 +75,24 @@ class Scheduler:
         return out, x0
 
 
+    def ddim_step(self, xt: torch.Tensor, noise_pred: torch.Tensor, t: int, t_prev: int, eta: float = 0.0,
+                  noise: torch.Tensor | None = None):
+        """Strided step x_t -> x_{t_prev} (t_prev < 0: final step) on this schedule's tables, returns (x_prev, x0):
+        Song et al. (DDIM) eq. 12; not in the reference, whose only sampler is the 1-step ancestral update above."""
+        _require_cuda(xt, "Scheduler.ddim_step")
+        self._on(xt.device)
+        xt_c, eps = _f32c(xt), _f32c(noise_pred)
+        if eta > 0.0 and t_prev >= 0 and noise is None:
+            noise = torch.randn_like(xt_c)
+        out, x0 = torch.empty_like(xt_c), torch.empty_like(xt_c)
+        zero = torch.zeros(xt_c.shape[0], device=xt.device, dtype=torch.float32)
+        tt = torch.tensor([t], device=xt.device, dtype=torch.int64)
+        tp = torch.tensor([t_prev], device=xt.device, dtype=torch.int64)
+        ops.cfg_ddim_step(xt_c, eps, eps, noise if noise is not None else xt_c, zero, tt, tp, self, out, eta=eta,
+                          x0_out=x0)
+        return out, x0
+
+
 class Codebook(nn.Module):
     """VQ codebook with EMA statistics; same parameters/buffers and return triple as components.py:249-315.
 

@@ -24,13 +24,17 @@ class Diffusion:
         self._samplers = {}
 
     @torch.no_grad()
-    def sample(self, cfg_scales, num_images: int = 10, seed: int = None):
+    def sample(self, cfg_scales, num_images: int = 10, seed: int = None, *, steps=None, sampler: str = "ddpm",
+               eta: float = 0.0):
         """`len(classes)` x `len(cfg_scales)` images (list) or `len(classes)` x `num_images` images (int scale),
         returned as the unclamped fp32 decoder output (N, 3, R, R) like diffusion.py:31-60.
 
         Class and scale are paired exactly as the reference pairs them (image k gets class k % B and scale
         cfg[k % C], diffusion.py:44,49). RNG: x_T and each step's noise are drawn from the global CUDA generator in
-        the reference's order, so a seed reproduces the reference's draws on the same device."""
+        the reference's order, so a seed reproduces the reference's draws on the same device.
+
+        Beyond the reference (keyword-only, defaults reproduce it): `steps` = a decreasing subset of the schedule and
+        `sampler="ddim"` (+ `eta`) run the strided sampler on the same kernels."""
         assert self.device == "cuda" and torch.cuda.is_available(), "You need a GPU to sample images."
         if seed is not None:
             torch.manual_seed(seed)
@@ -40,12 +44,16 @@ class Diffusion:
         cfg = torch.tensor(B * scales, device=self.device)
         xt = torch.randn(B * C, *self.latent_shape, device=self.device)
         labels = torch.tensor(list(range(B)) * C, device=self.device)
-        key = (B * C, tuple(labels.tolist()), tuple(cfg.tolist()))
-        sampler = self._samplers.get(key)
-        if sampler is None:
-            self._samplers = {key: CfgSampler(self.unet, self.scheduler, labels, cfg, self.latent_shape)}
-            sampler = self._samplers[key]
-        xt = sampler.run(xt)
+        if sampler == "ddpm" and steps is not None:
+            raise ValueError("Diffusion.sample: the ancestral DDPM update advances one timestep at a time; pass "
+                             "sampler='ddim' (eta=1.0 for the ancestral variance) to use a subset of the steps")
+        key = (B * C, tuple(labels.tolist()), tuple(cfg.tolist()), sampler, float(eta))
+        smp = self._samplers.get(key)
+        if smp is None:
+            self._samplers = {key: CfgSampler(self.unet, self.scheduler, labels, cfg, self.latent_shape, kind=sampler,
+                                              eta=eta)}
+            smp = self._samplers[key]
+        xt = smp.run(xt, steps=steps)
         return self.vae.decode(xt, quantize=self.vae.architecture["bottleneck"] == "vq")
 
     @classmethod

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IDF_B200_ABI_VERSION 2
+#define IDF_B200_ABI_VERSION 3
 
 typedef struct CUstream_st* idf_stream_t;
 
@@ -62,7 +62,7 @@ typedef struct idf_nhwc {
  *   zero_pad_last  when 1, rows whose pixel is in the last output row or column are written as exact zeros
  *                (Downsample's ConstantPad2d on the conv OUTPUT, components.py:110-117).
  *   epi_h/epi_w  image geometry for rowbias / zero_pad_last when the A operand is a flattened matrix
- *                (e.g. the im2col buffer of idf_im2col_s2); 0 means "use a[0].h / a[0].w".
+ *                (e.g. a pre-gathered patch matrix); 0 means "use a[0].h / a[0].w".
  */
 typedef struct idf_igemm_args {
   idf_nhwc_t a[2];
@@ -183,14 +183,30 @@ int idf_embed_time_class(const int64_t* t, const int64_t* ctx, const float* ctx_
  *   is decided by t[0]; tables are the Scheduler's fp32 [num_steps] vectors.
  *   x_prev may alias xt (in-place step). x_prev_dup (optional) receives a second copy of x_{t-1}: the
  *   unconditional half of the batch-doubled UNet input. x0_out may be NULL (the reference computes x0 and
- *   drops it).
+ *   drops it). num_steps = length of the schedule tables: a sample with t[n] == 0 in a batch whose t[0] != 0 reads
+ *   alpha_cum_prod[num_steps - 1], as the reference's negative index does (components.py:419).
  */
 int idf_cfg_posterior_step(const float* xt, const float* eps_cond, const float* eps_uncond, const float* noise,
                            const float* cfg, const int64_t* t, int32_t t_stride, const float* betas,
                            const float* alphas,
                            const float* alpha_cum_prod, const float* sqrt_alpha_cum_prod,
                            const float* sqrt_one_minus_alpha_cum_prod, float* x_prev, float* x_prev_dup,
-                           float* x0_out, int32_t N, int32_t chw, idf_stream_t stream);
+                           float* x0_out, int32_t N, int32_t chw, int32_t num_steps, idf_stream_t stream);
+
+/*
+ * idf_cfg_ddim_step — guidance mix fused with one step of the generalised (strided) sampler from timestep t[0] to
+ * an arbitrary earlier timestep t_prev[0] (< 0: final step, abar_prev = 1); SURVEY.md §8 row f4: step-skipping
+ * samplers on top of Scheduler's tables (components.py:364-397). Song et al., DDIM (ICLR 2021) eq. 12:
+ *   x0 = (x_t - sqrt(1 - abar_t) eps) / sqrt(abar_t), clamped to [-1, 1] when clamp_x0 != 0;
+ *   sigma = eta sqrt((1 - abar_prev) / (1 - abar_t)) sqrt(1 - abar_t / abar_prev);
+ *   x_prev = sqrt(abar_prev) x0 + sqrt(1 - abar_prev - sigma^2) eps + sigma * noise.
+ * eta = 0: deterministic (noise may be NULL); eta = 1, t_prev = t - 1, clamp_x0 = 0: the ancestral step of
+ * components.py:405-424. Both timesteps are device scalars (no host sync; CUDA-graph replay safe). x_prev may alias xt.
+ */
+int idf_cfg_ddim_step(const float* xt, const float* eps_cond, const float* eps_uncond, const float* noise,
+                      const float* cfg, const int64_t* t, const int64_t* t_prev, const float* alpha_cum_prod,
+                      float eta, int32_t clamp_x0, float* x_prev, float* x0_out, int32_t N, int32_t chw,
+                      idf_stream_t stream);
 
 /* idf_add_noise — sqrt(acp[t_n]) * x + sqrt(1 - acp[t_n]) * noise with per-sample t (components.py:399-403). */
 int idf_add_noise(const float* x, const float* noise, const int64_t* t, const float* sqrt_alpha_cum_prod,
@@ -231,14 +247,6 @@ int idf_conv1x1_small_f32(const float* x, const float* w, const float* bias, flo
 /* idf_upsample_nearest2x — nn.Upsample(scale_factor=2) (components.py:124,128) on channels-last bf16. */
 int idf_upsample_nearest2x(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t B, int32_t H, int32_t W,
                            int32_t C, idf_stream_t stream);
-
-/*
- * idf_im2col_s2 — gathers the 3x3 stride-2 pad-0 patches of Downsample (components.py:110) into a
- * (B*OH*OW, 9*C) bf16 matrix with OH = H/2, OW = W/2; rows of the padded last output row/column are zero. The
- * GEMM that follows runs with zero_pad_last = 1.
- */
-int idf_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t W, int32_t C,
-                  idf_stream_t stream);
 
 /*
  * idf_space_to_depth2 — splits a channels-last bf16 image into its four (row parity, column parity) planes:

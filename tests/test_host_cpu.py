@@ -18,7 +18,7 @@ def test_library_exports_every_symbol_of_the_header():
     declared = set(re.findall(r"\b(idf_[a-z0-9_]+)\s*\(", header))
     declared -= {"idf_nhwc", "idf_igemm_args"}
     lib = native.load()
-    assert lib.idf_abi_version() == 2
+    assert lib.idf_abi_version() == 3
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/idf_b200.h but not exported"
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)

@@ -15,7 +15,7 @@ dist.init_process_group("nccl", device_id=torch.device(dev))
 from idf_b200.trainer import DiffusionTrainStep
 from modules.components import Scheduler
 from modules.unet import Unet
-from oracle.ref_path import UNET_ARCH
+from idf_b200.spec import UNET_ARCH
 
 b = 6
 g = torch.Generator().manual_seed(7)
