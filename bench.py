@@ -1,14 +1,15 @@
 #!/usr/bin/env python
-"""bench.py — CFG UNet denoise throughput (img-steps/s) of the B200-native sampling path.
+"""bench.py — throughput of the B200-native hot path of jklimmek/image-diffusion.
 
-  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path (one rank per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K    # the reference algorithm on the host CPU (oracle port)
+  python bench.py --gpus N --steps K --warmup W                   # headline: CFG denoise img-steps/s (configs[1])
+  python bench.py --impl reference --gpus N --steps K --warmup W  # the reference algorithm on the host CPU cores
+  python bench.py --workload train|vq|shard ...                   # BASELINE configs[3] / [4] / [2]
 
-A "step" is one classifier-free-guided DDPM denoising step over one batch of 48 latents (BASELINE.json configs[1]:
-3 classes x 16 images, 32x32x3 latents, the ~60M-parameter diff-kl-lin-32x32 UNet): a batch-doubled UNet pass (96
-forwards) plus the fused guidance-mix / posterior update, i.e. 48 img-steps. With N GPUs every rank runs its own
-batch of 48 (batch-sharded sampling, no per-step cross-GPU traffic): weak scaling, value = total img-steps/s.
-Prints ONE JSON line on rank 0.
+Headline workload: a "step" is one classifier-free-guided DDPM denoising step over one batch of 48 latents
+(BASELINE.json configs[1]: 3 classes x 16 images, 32x32x3 latents, the ~60M-parameter diff-kl-lin-32x32 UNet): a
+batch-doubled UNet pass (96 forwards) plus the fused guidance-mix / posterior update, i.e. 48 img-steps. With N GPUs
+every rank runs its own batch of 48 (batch-sharded sampling, no per-step cross-GPU traffic): weak scaling, value =
+total img-steps/s. One rank per GPU under torchrun; rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -27,17 +28,33 @@ for p in (ROOT, os.path.join(ROOT, "image-diffusion_b200")):
 import torch  # noqa: E402
 
 GFLOP_PER_IMG_STEP = 45.510  # 2 UNet forwards, SURVEY.md §8(d) / BASELINE.md §3 (matmul-class FLOPs only)
+GFLOP_DECODE, GFLOP_ENCODE = 65.633, 141.3  # per image, SURVEY.md §8(d)
+TRAIN_GFLOP_PER_IMG = 3 * 22.755  # forward + data-gradient + weight-gradient GEMMs, SURVEY.md §8(d) config 4
 BATCH = 48
 README_IMG_STEPS_PER_S = 37.5  # 27 images x 1000 steps in "~12 minutes" on an unnamed GPU
+PARITY_TOL = 1e-2  # one CFG step (fp32 state, bf16 UNet interior) vs the fp32 oracle on the same GPU, rel-RMS
 
 
 def load_peaks():
+    """Roofline denominators: the driver-measured numbers of this pool's B200s, else the profiling recipe's fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fh:
             p = json.load(fh)
-        return p.get("bf16_tflops_sustained", 1373.8), p.get("hbm_gbs", 6546.9), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return {"burst": p.get("bf16_tflops", 1608.8), "sustained": p.get("bf16_tflops_sustained", 1373.8),
+                "hbm_gbs": p.get("hbm_gbs", 6546.9), "kind": "measured (MEASURED_PEAKS.json)"}
+    return {"burst": 1600.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "kind": "fallback (B200_PROFILING.md)"}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 class ClockSampler:
@@ -76,72 +93,147 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
-def build_models(dev):
+class Ranks:
+    """torchrun plumbing: one process per GPU, NCCL; barrier + max-over-ranks for every timed number."""
+
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = f"cuda:{self.local}"
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device(self.dev))
+            self.dist = dist
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def max(self, v: float) -> float:
+        if self.dist is None:
+            return v
+        t = torch.tensor([v], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def timed(self, fn):
+        """fn() between barrier + synchronize on both sides, CUDA events on the launching stream; max over ranks (ms)."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.barrier()
+        return self.max(e0.elapsed_time(e1))
+
+    def wall(self, fn):
+        self.barrier()
+        w0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        return self.max(time.perf_counter() - w0)
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def build_models(dev, vq=False):
+    from idf_b200.spec import UNET_ARCH, VAE_KL_ARCH, VAE_VQ_ARCH
     from modules.components import Scheduler
     from modules.unet import Unet
     from modules.vae import VAE
-    from oracle.ref_path import UNET_ARCH, VAE_KL_ARCH  # architecture constants only (configs/*.yaml values)
     torch.manual_seed(2018)  # configs/diff-kl-lin-32x32.yaml:32 — random-init weights, default init
     unet = Unet(**UNET_ARCH).to(dev).eval()
-    vae = VAE(**VAE_KL_ARCH).to(dev).eval()
+    vae = VAE(**(VAE_VQ_ARCH if vq else VAE_KL_ARCH)).to(dev).eval()
     return unet, vae, Scheduler(1000, 1e-4, 0.02, "linear", dev)
 
 
-def cpu_reference_rate(steps, warmup, batch=8, threads=None):
-    """The reference algorithm (oracle port, fp32 torch on CPU): img-steps/s of CFG steps on `batch` latents."""
+# =====================================================================================================================
+# reference arm / cpu_baseline leg: the oracle port of the reference algorithm on the host CPU cores
+# =====================================================================================================================
+def cpu_reference_rate(steps, warmup, batch=BATCH, threads=None, budget_s=300.0):
+    """The reference algorithm (oracle port, fp32 torch on CPU): img-steps/s of CFG steps on `batch` latents — the
+    same batch-48 step the GPU arm times. If the first warm-up step shows that warmup + steps would exceed
+    `budget_s`, the per-step sample shrinks to a smaller batch (stated in the returned description)."""
     from oracle import ref_path as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     with torch.no_grad():
-        torch.manual_seed(2018)
         sd = O.seeded_state_dict(O.unet_param_shapes(O.UNET_ARCH), 2018)
         sched = O.SchedulerTables(1000)
         g = torch.Generator().manual_seed(0)
-        x = torch.randn(batch, 3, 32, 32, generator=g)
-        labels = torch.tensor(([0, 1, 2] * batch)[:batch])
-        cfg = torch.full((batch,), 3)
+
+        def setup(b):
+            return (torch.randn(b, 3, 32, 32, generator=g), torch.tensor(([0, 1, 2] * b)[:b]), torch.full((b,), 3))
+
+        x, labels, cfg = setup(batch)
         times = []
-        for k in range(warmup + steps):
+        k = 0
+        while k < warmup + steps:
             z = torch.randn(batch, 3, 32, 32, generator=g)
             t0 = time.perf_counter()
             x = O.cfg_sample(sd, O.UNET_ARCH, sched, x, labels, cfg, [z], steps=[500])
+            dt = time.perf_counter() - t0
+            if k == 0 and dt * (warmup + steps) > budget_s and batch > 8:
+                batch = max(8, int(batch * budget_s / (dt * (warmup + steps))) // 3 * 3)
+                x, labels, cfg = setup(batch)
+                continue  # restart the warm-up with the bounded sample
             if k >= warmup:
-                times.append(time.perf_counter() - t0)
+                times.append(dt)
+            k += 1
     total = sum(times)
-    return batch * len(times) / total, total / len(times), threads
+    return batch * len(times) / total, total / len(times), threads, batch
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    rate, sec_per_step, threads = cpu_reference_rate(steps, 1)
-    sample = f"{steps} CFG steps (2 UNet fwd + mix + posterior) on batch 8, fp32 torch CPU, step i=500"
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    rate, sec_per_step, threads, batch = cpu_reference_rate(steps, warmup)
+    sample = (f"{steps} timed CFG steps after {warmup} warm-up (2 UNet forwards + guidance mix + posterior update each) "
+              f"on batch {batch}, fp32 torch on {threads} host threads ({cpu_model()}), timestep 500")
     line = {
         "impl": "reference", "metric": "CFG UNet denoise img-steps/s (32x32x3 latents, diff-kl-lin-32x32 UNet)",
-        "value": rate, "unit": "img-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "value": rate, "unit": "img-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] bounded sample: CFG DDPM denoise steps, batch 8 of 48, random-init UNet",
+        "config": {"workload": "configs[1]: CFG DDPM sampling steps, batch 48 (3 classes x 16), cfg scale 3, linear "
+                               "schedule, UNet 60.5M params random init" + ("" if batch == BATCH else
+                                                                           f" — bounded to batch {batch} per step"),
+                   "per_gpu_batch": batch, "cpu_model": cpu_model(),
                    "note": "reference algorithm = oracle/ref_path.py (functional restatement pinned on reference "
-                           "golden vectors); the reference itself is not pip-installable (no setup.py/pyproject)"},
-        "cpu_baseline": {"value": rate, "unit": "img-steps/s", "cores": threads, "kind": "port", "sample": sample},
+                           "golden vectors); the reference is plain Python modules with no setup.py/pyproject, so "
+                           "there is nothing to pip-install into baseline/_ref and /root/reference does not exist on "
+                           "the GPU box"},
+        "cpu_baseline": {"value": rate, "unit": "img-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                         "cpu_model": cpu_model()},
         "e2e": {"value": rate, "unit": "img-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# =====================================================================================================================
+# per-launch CUDA-event timing of one eager pass
+# =====================================================================================================================
 REPEATS = 3  # back-to-back repeats of each launch between one pair of CUDA events
 
 
 def timed_calls(run_eager, flops_of=None):
     """Runs one eager pass with every C-ABI call replaced by REPEATS back-to-back launches of it between ONE pair of
     CUDA events (duration = elapsed / REPEATS). A pair of events around a single launch also measures the event
-    records and the launch gap (~4-5 us per launch on this stack: the sum over a step was 15 % above the CUDA-graph
-    replay of the same step); with back-to-back repeats that overhead is amortised and the sum of the per-launch
-    durations reproduces the graph replay time, which bench reports next to it as the consistency check."""
+    records and the launch gap (~4-5 us per launch on this stack); with back-to-back repeats that overhead is
+    amortised and the sum of the per-launch durations reproduces the graph replay time, which bench reports next to
+    it as the consistency check."""
     from idf_b200 import native, ops
     records = []
     orig_call = native.call
@@ -173,6 +265,10 @@ def timed_calls(run_eager, flops_of=None):
 
 
 def igemm_flops(name, a):
+    if name == "idf_conv2d_wgrad":
+        g = a[0]
+        m = (g.s2_batch if g.s2_batch else g.x.n) * g.x.h * g.x.w
+        return 2.0 * m * g.cout * g.taps * g.x.c
     if name != "idf_conv2d_igemm":
         return 0.0
     g = a[0]
@@ -184,185 +280,76 @@ def igemm_flops(name, a):
     return 2.0 * m * n * k
 
 
-def igemm_roofline(sampler, peak_tflops, peak_kind):
-    """Live CUDA-event timing of every kernel of one eager step; returns the roofline object of the dominant kernel
-    (the tcgen05 implicit GEMM) plus a per-kernel time breakdown."""
-    keep = sampler.xx.clone()
-    try:
-        by = timed_calls(sampler._step, igemm_flops)
-    finally:
-        sampler.xx.copy_(keep)
+def roofline_of(by, peaks, entry="idf_conv2d_igemm", kernel="igemm_persist_kernel (tcgen05 implicit GEMM, all conv / "
+                "linear layers)", traffic_key="sample"):
+    """Roofline object of the dominant kernel from the per-launch table of one eager pass. `achieved` = algorithmic
+    FLOPs of the kernel's launches (2 M N K each) / their summed CUDA-event durations. `peak` is
+    the measured BURST bf16 figure: the launches are timed in short back-to-back groups at full clock, not inside a
+    long power-limited run; the fraction of the sustained figure is given next to it."""
     total = sum(v[0] for v in by.values())
-    ms, n, fl = by["idf_conv2d_igemm"]
+    ms, n, fl = by[entry]
     achieved = fl / (ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "igemm_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_launch")
-    roof = {"bound": "tensor", "kernel": "igemm_persist_kernel (tcgen05 implicit GEMM, all conv/linear layers)",
-            "achieved": achieved, "peak": peak_tflops, "peak_kind": f"bf16 dense sustained, of {peak_kind}",
-            "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
-            "launches_per_step": n, "avg_launch_ms": ms / n, "flops_per_launch": fl / n,
+            tj = json.load(fh)
+        traffic = tj.get(traffic_key, {}).get("dram_bytes_per_launch") if isinstance(tj.get(traffic_key), dict) else \
+            tj.get("dram_bytes_per_launch")
+    return {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peaks["burst"],
+            "peak_kind": f"bf16 dense burst, {peaks['kind']}", "unit": "TFLOP/s", "frac": achieved / peaks["burst"],
+            "frac_of_sustained_peak": achieved / peaks["sustained"], "sustained_peak": peaks["sustained"],
+            "traffic": traffic, "launches_per_step": n, "avg_launch_ms": ms / n, "flops_per_launch": fl / n,
             "share_of_step": ms / total, "sum_of_kernel_ms": total,
             "timing": f"CUDA events around {REPEATS} back-to-back repeats of each launch of one eager step, on the "
                       "launching stream; sum_of_kernel_ms should reproduce ms_per_step (graph replay)"}
-    breakdown = {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])}
-    return roof, breakdown
 
 
-TRAIN_GFLOP_PER_IMG = 3 * 22.755  # forward + data-gradient + weight-gradient GEMMs, SURVEY.md §8(d) config 4
-
-
-def kernel_breakdown(run_eager):
-    """CUDA-event time of every C-ABI call of one eager pass, summed per entry point (see timed_calls)."""
-    by = timed_calls(run_eager)
+def breakdown_of(by):
     return {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])}
 
 
-def run_train(args):
-    """BASELINE configs[3]: UNet training step (epsilon-MSE forward + backward + clip + Adam), batch 48 per GPU, bf16
-    interior, NCCL gradient all-reduce across ranks. value = images/s over all ranks."""
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = f"cuda:{local}"
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+# =====================================================================================================================
+# headline workload: CFG denoise steps, batch 48 per GPU
+# =====================================================================================================================
+def oracle_cfg_step(unet, sched, x, labels, cfg, z, i, autocast=False):
+    from oracle import ref_path as O
+    sd = {k: v.detach() for k, v in unet.state_dict().items()}
+    st = O.SchedulerTables(sched.num_steps, sched.beta_start, sched.beta_end, sched.type, device=x.device)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        return O.cfg_sample(sd, unet.architecture, st, x, labels, cfg, [z], steps=[i])
+
+
+def gpu_torch_baseline(unet, sched, dev):
+    """SURVEY §8(d) "same-box PyTorch bar": the reference algorithm (oracle port, plain torch ops = what the reference
+    ships for GPU) on THIS B200: fp32 eager with torch's default flags (cuDNN TF32 convolutions on, as the reference
+    runs) and under bf16 autocast, batch 48, CUDA-event timed."""
+    x = torch.randn(BATCH, 3, 32, 32, device=dev)
+    z = torch.randn(BATCH, 3, 32, 32, device=dev)
+    labels = torch.tensor([0, 1, 2] * (BATCH // 3), device=dev)
+    cfg = torch.full((BATCH,), 3, device=dev)
+    out = {}
+    for tag, ac in (("fp32_eager", False), ("bf16_autocast", True)):
+        oracle_cfg_step(unet, sched, x, labels, cfg, z, 500, ac)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            oracle_cfg_step(unet, sched, x, labels, cfg, z, 500, ac)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out[tag] = {"value": BATCH / ms * 1e3, "unit": "img-steps/s", "ms_per_step": ms}
+    out["what"] = ("oracle port of the reference (torch ops, 2 separate UNet forwards + elementwise mix/posterior) on "
+                   "the same GPU, batch 48, 3 timed steps after 1 warm-up; fp32 = torch defaults (cuDNN TF32 on)")
+    return out
+
+
+def run_sample(args):
+    R = Ranks()
+    dev, rank, world = R.dev, R.rank, R.world
     warmup = max(args.warmup, 3)
-    peak_tflops, _, peak_kind = load_peaks()
-    from idf_b200.trainer import DiffusionTrainStep
-    unet, _, sched = build_models(dev)
-    unet.train()
-    ts = DiffusionTrainStep(unet, sched, BATCH, (3, 32, 32), clip_grad=1.0)
-    gen = torch.Generator(device=dev).manual_seed(rank)
-    lat = torch.randn(BATCH, 6, 32, 32, device=dev, generator=gen)
-    lab = torch.randint(0, 3, (BATCH,), device=dev, generator=gen)
-    for _ in range(warmup):
-        ts.step(lat, lab, 1e-4)
-    torch.cuda.synchronize()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        ts.step(lat, lab, 1e-4)
-    e1.record()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    clock_info = clocks.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    # end to end: fp16 latents + labels from pinned host memory every step, loss read back every step
-    h_lat = torch.randn(BATCH, 6, 32, 32).half().pin_memory()
-    h_lab = torch.randint(0, 3, (BATCH,)).pin_memory()
-    d_lat, d_lab = torch.empty(BATCH, 6, 32, 32, device=dev, dtype=torch.float16), torch.empty(BATCH, device=dev, dtype=torch.int64)
-    h_loss = torch.empty(1).pin_memory()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    w0 = time.perf_counter()
-    for _ in range(args.steps):
-        d_lat.copy_(h_lat, non_blocking=True)
-        d_lab.copy_(h_lab, non_blocking=True)
-        loss = ts.step(d_lat, d_lab, 1e-4)
-        h_loss.copy_(loss, non_blocking=True)
-        torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
-    breakdown = None
-    if rank == 0 and world == 1:
-        keep = (ts.flat_param.clone(), ts.exp_avg.clone(), ts.exp_avg_sq.clone())
-        breakdown = kernel_breakdown(ts._whole_step)
-        for dst, src in zip((ts.flat_param, ts.exp_avg, ts.exp_avg_sq), keep):
-            dst.copy_(src)
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ts.eng.prepare(force=True)
-        torch.cuda.synchronize()
-        r0.record()
-        ts.eng.prepare(force=True)
-        r1.record()
-        torch.cuda.synchronize()
-        breakdown["weight_repack (eager torch ops, inside the graph when replayed)"] = {"ms": round(r0.elapsed_time(r1), 4), "launches": 0}
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-    value = world * BATCH * args.steps / (ms * 1e-3)
-    tfl = value / world * TRAIN_GFLOP_PER_IMG * 1e9 / 1e12
-    line = {
-        "metric": "UNet training step images/s (epsilon-MSE fwd+bwd+clip+Adam, diff-kl-lin-32x32 UNet, batch 48/GPU)",
-        "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[3]: UNet training step, batch 48 per GPU, 32x32x3 latents from stored (mean||logvar), "
-                               "random-init 60.5M-parameter UNet, fp32 master weights + Adam, bf16 interior; gradient "
-                               "all-reduce (NCCL) bucketed by backward stage when n_gpus > 1",
-                   "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                   "gflop_per_img": TRAIN_GFLOP_PER_IMG, "tflops_per_gpu": tfl,
-                   "pct_tensor_peak": tfl / peak_tflops, "loss": float(h_loss[0]), "graph": ts.graph is not None,
-                   "graph_segments": len(ts.segments) if ts.segments else 0},
-        "clocks": clock_info,
-        "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "img/s",
-                "h2d_bytes_per_step": h_lat.numel() * 2 + h_lab.numel() * 8, "d2h_bytes_per_step": 4,
-                "how": "per step: fp16 latents + labels pinned host -> device, DiffusionTrainStep.step, loss -> host, sync"},
-        "gpu_launches": (ts.launches_per_step or 0) * args.steps,
-        "kernel_breakdown_ms_per_step": breakdown,
-    }
-    print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
-                    help="sample: the headline CFG denoise metric (default); train: BASELINE configs[3] training step")
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--full-job", action="store_true", help="also time the full 1000-step sample + decode")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.workload == "train":
-        return run_train(args)
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = f"cuda:{local}"
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(dev))
-    warmup = max(args.warmup, 3)
-    peak_tflops, _, peak_kind = load_peaks()
-
-    from idf_b200 import native
+    peaks = load_peaks()
     from idf_b200.sampler import CfgSampler
     with torch.no_grad():
         unet, vae, sched = build_models(dev)
@@ -376,55 +363,56 @@ def main():
         timesteps = [999 - (k % 999) for k in range(total)]  # i = 999, 998, ... (never the noise-free i = 0)
         for k in range(warmup):
             sampler.step(timesteps[k])
-        torch.cuda.synchronize()
         # ---------------- device-timed region: K graph replays, inputs resident in HBM
-        clocks = ClockSampler(local)
+        clocks = ClockSampler(R.local)
         if rank == 0:
             clocks.start()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for k in range(warmup, total):
-            sampler.step(timesteps[k])
-        e1.record()
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
+
+        def region():
+            for k in range(warmup, total):
+                sampler.step(timesteps[k])
+
+        ms = R.timed(region)
         clock_info = clocks.stop() if rank == 0 else None
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
         # ---------------- end-to-end: host buffers, H2D noise + D2H latent every step, wall clock
         h_noise = torch.randn(BATCH, 3, 32, 32).pin_memory()
         h_out = torch.empty(BATCH, 3, 32, 32).pin_memory()
         d_noise = torch.empty(BATCH, 3, 32, 32, device=dev)
-        e2e_steps = args.steps
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        w0 = time.perf_counter()
-        for k in range(e2e_steps):
-            d_noise.copy_(h_noise, non_blocking=True)
-            sampler.step(timesteps[warmup + k], noise=d_noise)
-            h_out.copy_(sampler.latent, non_blocking=True)
-            torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - w0
-        if dist is not None:
-            t = torch.tensor([e2e_s], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = t.item()
+
+        def e2e_region():
+            for k in range(args.steps):
+                d_noise.copy_(h_noise, non_blocking=True)
+                sampler.step(timesteps[warmup + k], noise=d_noise)
+                h_out.copy_(sampler.latent, non_blocking=True)
+                torch.cuda.synchronize()
+
+        e2e_s = R.wall(e2e_region)
         finite = bool(torch.isfinite(h_out).all())
 
-        extra = {}
-        roof, breakdown = None, None
+        extra, roof, breakdown, parity, torch_base = {}, None, None, None, None
         if rank == 0:
-            roof, breakdown = igemm_roofline(sampler, peak_tflops, peak_kind)
-            # decode stage (once per job) timed for context
+            # ---- parity of what was just measured: one graph-replayed CFG step at batch 48 against the fp32 oracle
+            x0 = torch.randn(BATCH, 3, 32, 32, device=dev, generator=gen)
+            z0 = torch.randn(BATCH, 3, 32, 32, device=dev, generator=gen)
+            tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            ref = oracle_cfg_step(unet, sched, x0, labels, cfg, z0, 500)
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+            sampler.set_latent(x0)
+            sampler.step(500, noise=z0)
+            got = sampler.latent.clone()
+            err = ((got - ref).norm() / ref.norm()).item()
+            parity = {"check": "one CFG step (timestep 500, batch 48, graph replay) vs the fp32 oracle on the same GPU",
+                      "rel_rms": err, "tolerance": PARITY_TOL, "ok": err <= PARITY_TOL}
+            if not parity["ok"]:
+                raise SystemExit(f"bench.py: parity check failed: rel-RMS {err:.3e} > {PARITY_TOL}")
+            keep = sampler.xx.clone()
+            by = timed_calls(sampler._step, igemm_flops)
+            sampler.xx.copy_(keep)
+            roof, breakdown = roofline_of(by, peaks), breakdown_of(by)
+            # decode stage (once per job)
             z0 = sampler.latent.clone()
+            vae.decode(z0)
             vae.decode(z0)
             torch.cuda.synchronize()
             d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -432,22 +420,29 @@ def main():
             vae.decode(z0)
             d1.record()
             torch.cuda.synchronize()
-            extra["kl_decode_ms_batch48"] = d0.elapsed_time(d1)
-            if args.full_job:
+            dms = d0.elapsed_time(d1)
+            extra["kl_decode_ms_batch48"] = dms
+            extra["kl_decode_tflops"] = BATCH * GFLOP_DECODE / dms
+            if world == 1 and not args.no_full_job:
+                # the whole job of configs[1] through the public API: 1000 steps + KL decode of batch 48, images on host
                 from modules.diffusion import Diffusion
                 dfn = Diffusion(vae, unet, sched, "a,b,c", "cuda")
                 torch.cuda.synchronize()
                 f0 = time.perf_counter()
                 imgs = dfn.sample(3, num_images=16, seed=0).cpu()
-                extra["full_job_s_1000_steps_plus_decode"] = time.perf_counter() - f0
+                extra["full_job_s"] = time.perf_counter() - f0
+                extra["full_job_what"] = ("Diffusion.sample(3, num_images=16, seed=0): 1000 CFG DDPM steps + KL decode "
+                                          "of batch 48, decoded images copied to the host (wall clock)")
                 extra["full_job_finite"] = bool(torch.isfinite(imgs).all())
+            if world == 1 and not args.no_torch_baseline:
+                torch_base = gpu_torch_baseline(unet, sched, dev)
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        R.close()
         return
     value = world * BATCH * args.steps / (ms * 1e-3)
-    e2e_value = world * BATCH * e2e_steps / e2e_s
+    e2e_value = world * BATCH * args.steps / e2e_s
+    per_gpu_tflops = value / world * GFLOP_PER_IMG_STEP / 1e3
     line = {
         "metric": "CFG UNet denoise img-steps/s (32x32x3 latents, diff-kl-lin-32x32 UNet)",
         "value": value, "unit": "img-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -460,7 +455,9 @@ def main():
             "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"batch-sharded x{world}",
             "l2": "per-step working set (121 MB bf16 weights + >1 GB activations) exceeds the 126 MB L2",
             "vs_baseline_note": "README's ~37.5 img-steps/s: 27-image grid, unnamed GPU, fp32 eager",
-            "pct_tensor_peak": value / world * GFLOP_PER_IMG_STEP * 1e9 / (peak_tflops * 1e12),
+            "tflops_per_gpu": per_gpu_tflops,
+            "pct_tensor_peak_sustained": per_gpu_tflops / peaks["sustained"],
+            "pct_tensor_peak_burst": per_gpu_tflops / peaks["burst"],
             "gflop_per_img_step": GFLOP_PER_IMG_STEP, "finite": finite, **extra,
         },
         "clocks": clock_info,
@@ -469,17 +466,337 @@ def main():
                 "how": "per step: pinned-host noise -> device, CfgSampler.step (graph replay), latent -> pinned "
                        "host, stream sync; wall clock"},
         "gpu_launches": sampler.launches_per_step * args.steps,
+        "parity": parity,
         "roofline": roof,
         "kernel_breakdown_ms_per_step": breakdown,
     }
+    if torch_base is not None:
+        line["gpu_torch_baseline"] = torch_base
     if not args.no_cpu_baseline and world == 1:
-        rate, sec, threads = cpu_reference_rate(3, 1)
+        rate, sec, threads, b = cpu_reference_rate(4, 1, budget_s=40.0)
         line["cpu_baseline"] = {"value": rate, "unit": "img-steps/s", "cores": threads, "kind": "port",
-                                "sample": "3 CFG steps (2 UNet fwd + mix + posterior) on batch 8 of the same "
-                                          "workload, oracle port of the reference, fp32 torch on the host CPU"}
+                                "cpu_model": cpu_model(),
+                                "sample": f"4 timed CFG steps after 1 warm-up (2 UNet fwd + mix + posterior each) on "
+                                          f"batch {b} of the same workload, oracle port of the reference, fp32 torch "
+                                          "on the host CPU"}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    R.close()
+
+
+# =====================================================================================================================
+# BASELINE configs[3]: UNet training step, batch 48 per GPU, NCCL gradient all-reduce
+# =====================================================================================================================
+def run_train(args):
+    """value = images/s over all ranks; a step = epsilon-MSE forward + backward + clip + Adam + weight re-pack."""
+    R = Ranks()
+    dev, rank, world = R.dev, R.rank, R.world
+    warmup = max(args.warmup, 3)
+    peaks = load_peaks()
+    from idf_b200.trainer import DiffusionTrainStep
+    unet, _, sched = build_models(dev)
+    unet.train()
+    ts = DiffusionTrainStep(unet, sched, BATCH, (3, 32, 32), clip_grad=1.0)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    lat = torch.randn(BATCH, 6, 32, 32, device=dev, generator=gen)
+    lab = torch.randint(0, 3, (BATCH,), device=dev, generator=gen)
+    for _ in range(warmup):
+        ts.step(lat, lab, 1e-4)
+    clocks = ClockSampler(R.local)
+    if rank == 0:
+        clocks.start()
+
+    def region():
+        for _ in range(args.steps):
+            ts.step(lat, lab, 1e-4)
+
+    ms = R.timed(region)
+    clock_info = clocks.stop() if rank == 0 else None
+    exposed = None
+    if world > 1:
+        # the same K steps with the gradient all-reduce switched off (every rank then trains on its own gradients: a
+        # timing experiment, not a training mode): the difference is what the exchange costs a step
+        ts.buckets.enabled = False
+        region()
+        ms_local = R.timed(region)
+        ts.buckets.enabled = True
+        exposed = {"ms_per_step_without_allreduce": ms_local / args.steps,
+                   "allreduce_exposed_ms_per_step": (ms - ms_local) / args.steps,
+                   "allreduce_bytes_per_step": ts.eng.flat_numel * ts.buckets.elem_bytes,
+                   "allreduce_dtype": ts.buckets.dtype_name, "buckets": len(ts.buckets.plan())}
+    # end to end: fp16 latents + labels from pinned host memory every step, loss read back every step
+    h_lat = torch.randn(BATCH, 6, 32, 32).half().pin_memory()
+    h_lab = torch.randint(0, 3, (BATCH,)).pin_memory()
+    d_lat = torch.empty(BATCH, 6, 32, 32, device=dev, dtype=torch.float16)
+    d_lab = torch.empty(BATCH, device=dev, dtype=torch.int64)
+    h_loss = torch.empty(1).pin_memory()
+
+    def e2e_region():
+        for _ in range(args.steps):
+            d_lat.copy_(h_lat, non_blocking=True)
+            d_lab.copy_(h_lab, non_blocking=True)
+            loss = ts.step(d_lat, d_lab, 1e-4)
+            h_loss.copy_(loss, non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_s = R.wall(e2e_region)
+    breakdown, roof = None, None
+    if rank == 0 and world == 1:
+        keep = (ts.flat_param.clone(), ts.exp_avg.clone(), ts.exp_avg_sq.clone())
+        by = timed_calls(ts._whole_step, igemm_flops)
+        for dst, src in zip((ts.flat_param, ts.exp_avg, ts.exp_avg_sq), keep):
+            dst.copy_(src)
+        ts.eng.prepare(force=True)
+        breakdown = breakdown_of(by)
+        roof = roofline_of(by, peaks, kernel="igemm_persist_kernel (tcgen05 implicit GEMM: forward + data gradients)",
+                           traffic_key="train")
+        wg = by.get("idf_conv2d_wgrad")
+        if wg:
+            roof["wgrad_kernel"] = {"achieved": wg[2] / (wg[0] * 1e-3) / 1e12, "unit": "TFLOP/s", "launches": wg[1],
+                                    "ms": wg[0], "frac": wg[2] / (wg[0] * 1e-3) / 1e12 / peaks["burst"]}
+    if rank != 0:
+        R.close()
+        return
+    value = world * BATCH * args.steps / (ms * 1e-3)
+    tfl = value / world * TRAIN_GFLOP_PER_IMG * 1e9 / 1e12
+    line = {
+        "metric": "UNet training step images/s (epsilon-MSE fwd+bwd+clip+Adam, diff-kl-lin-32x32 UNet, batch 48/GPU)",
+        "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[3]: UNet training step, batch 48 per GPU, 32x32x3 latents from stored (mean||logvar), "
+                               "random-init 60.5M-parameter UNet, fp32 master weights + Adam, bf16 interior; gradient "
+                               "all-reduce (NCCL) bucketed by backward stage when n_gpus > 1",
+                   "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                   "gflop_per_img": TRAIN_GFLOP_PER_IMG, "tflops_per_gpu": tfl,
+                   "pct_tensor_peak_sustained": tfl / peaks["sustained"], "pct_tensor_peak_burst": tfl / peaks["burst"],
+                   "loss": float(h_loss[0]), "graph": ts.graph is not None,
+                   "graph_segments": len(ts.segments) if ts.segments else 0, "allreduce": exposed},
+        "clocks": clock_info,
+        "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "img/s",
+                "h2d_bytes_per_step": h_lat.numel() * 2 + h_lab.numel() * 8, "d2h_bytes_per_step": 4,
+                "how": "per step: fp16 latents + labels pinned host -> device, DiffusionTrainStep.step, loss -> host, sync"},
+        "gpu_launches": (ts.launches_per_step or 0) * args.steps,
+        "roofline": roof,
+        "kernel_breakdown_ms_per_step": breakdown,
+    }
+    print(json.dumps(line), flush=True)
+    R.close()
+
+
+# =====================================================================================================================
+# BASELINE configs[4]: VQ-VAE encode -> quantise -> decode of 128x128x3 images, batch 256
+# =====================================================================================================================
+def run_vq(args):
+    R = Ranks()
+    dev, rank, world = R.dev, R.rank, R.world
+    warmup = max(args.warmup, 3)
+    peaks = load_peaks()
+    B = args.batch or 256
+    with torch.no_grad():
+        _, vae, _ = build_models(dev, vq=True)
+        gen = torch.Generator(device=dev).manual_seed(rank)
+        img = torch.rand(B, 3, 128, 128, device=dev, generator=gen) * 2 - 1
+        for _ in range(warmup):
+            vae(img)
+        clocks = ClockSampler(R.local)
+        if rank == 0:
+            clocks.start()
+
+        def region():
+            for _ in range(args.steps):
+                vae(img)
+
+        ms = R.timed(region)
+        clock_info = clocks.stop() if rank == 0 else None
+        h_img = (torch.rand(B, 3, 128, 128) * 2 - 1).pin_memory()
+        h_out = torch.empty(B, 3, 128, 128).pin_memory()
+        d_img = torch.empty(B, 3, 128, 128, device=dev)
+
+        def e2e_region():
+            for _ in range(args.steps):
+                d_img.copy_(h_img, non_blocking=True)
+                h_out.copy_(vae(d_img), non_blocking=True)
+                torch.cuda.synchronize()
+
+        e2e_s = R.wall(e2e_region)
+        roof = breakdown = stage = cpu = None
+        if rank == 0:
+            from idf_b200 import native
+            before = native.launch_count
+            vae(img)
+            launches = native.launch_count - before
+            by = timed_calls(lambda: vae(img), igemm_flops)
+            roof, breakdown = roofline_of(by, peaks, traffic_key="vq"), breakdown_of(by)
+            # stage split: encoder / quantiser / decoder
+            z = torch.empty(B, 3, 32, 32, device=dev)
+            enc = vae._engine(("enc", B, 128, 128))
+            t_enc = R_time(lambda: enc.encode(img, z))
+            t_q = R_time(lambda: vae.codebook.quantize(z))
+            zq, _ = vae.codebook.quantize(z)
+            t_dec = R_time(lambda: vae.decode(zq))
+            stage = {"encode_ms": t_enc, "encode_tflops": B * GFLOP_ENCODE / t_enc, "quantize_ms": t_q,
+                     "decode_ms": t_dec, "decode_tflops": B * GFLOP_DECODE / t_dec}
+            if not args.no_cpu_baseline and world == 1:
+                cpu = cpu_vq_rate()
+    if rank != 0:
+        R.close()
+        return
+    value = world * B * args.steps / (ms * 1e-3)
+    tfl = value / world * (GFLOP_ENCODE + GFLOP_DECODE) / 1e3
+    line = {
+        "metric": "VQ-VAE encode+quantise+decode images/s (vae-vq-32x32, 128x128x3, batch 256)",
+        "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"configs[4]: VAE.forward (VQ bottleneck, 1024-entry codebook) on batch {B} of 128x128x3 "
+                               "images ~ U(-1,1), random-init weights: encoder -> nearest-code argmin -> decoder",
+                   "per_gpu_batch": B, "parallelism": f"replicas x{world}",
+                   "gflop_per_img": GFLOP_ENCODE + GFLOP_DECODE, "tflops_per_gpu": tfl,
+                   "pct_tensor_peak_sustained": tfl / peaks["sustained"], "pct_tensor_peak_burst": tfl / peaks["burst"],
+                   "stages": stage, "l2": "activations of one layer (256 x 128 x 128 x 256ch bf16 = 2.1 GB) exceed L2"},
+        "clocks": clock_info,
+        "e2e": {"value": world * B * args.steps / e2e_s, "unit": "img/s", "h2d_bytes_per_step": h_img.numel() * 4,
+                "d2h_bytes_per_step": h_out.numel() * 4,
+                "how": "per step: pinned fp32 images -> device, VAE.forward, reconstructions -> pinned host, sync"},
+        "gpu_launches": launches * args.steps,
+        "roofline": roof,
+        "kernel_breakdown_ms_per_step": breakdown,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    R.close()
+
+
+def R_time(fn, n=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def cpu_vq_rate(batch=4):
+    from oracle import ref_path as O
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        sd = O.seeded_state_dict(O.vae_param_shapes(O.VAE_VQ_ARCH), 2018)
+        img = torch.rand(batch, 3, 128, 128) * 2 - 1
+
+        def fwd():
+            z = O._run_program(sd, "encoder.down", O.encoder_program(O.VAE_VQ_ARCH), img, O.VAE_VQ_ARCH)
+            zq = O.codebook_forward(sd, "codebook", z, 0.25)[0]
+            return O.vae_decode(sd, O.VAE_VQ_ARCH, zq)
+
+        fwd()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 2 or time.perf_counter() - t0 < 10.0:
+            fwd()
+            n += 1
+        dt = time.perf_counter() - t0
+    return {"value": batch * n / dt, "unit": "img/s", "cores": threads, "kind": "port", "cpu_model": cpu_model(),
+            "sample": f"{n} VQ encode+quantise+decode passes on batch {batch} of the same workload after 1 warm-up, "
+                      "oracle port of the reference, fp32 torch on the host CPU"}
+
+
+# =====================================================================================================================
+# BASELINE configs[2]: batch-sharded sampling of 4096 latents with a CFG-scale sweep
+# =====================================================================================================================
+def run_shard(args):
+    """4096 latents (class labels 0,1,2 cycling; guidance scales cycling through --scales as a per-sample vector) are
+    split into contiguous shards of 4096/N latents; every rank walks its shard in micro-batches through ONE captured
+    graph. No per-step cross-GPU traffic. Strong scaling: the total is fixed. `--sample-steps` consecutive DDPM steps
+    starting at i = 999 are run per micro-batch (the full schedule is 1000), then the KL decode."""
+    R = Ranks()
+    dev, rank, world = R.dev, R.rank, R.world
+    peaks = load_peaks()
+    total, mb, nsteps = args.total, args.micro_batch, args.sample_steps
+    scales = [int(s) for s in args.scales.split(",")]
+    from idf_b200 import native
+    from idf_b200.dist import ShardedSampler, shard_bounds
+    from modules.diffusion import Diffusion
+    with torch.no_grad():
+        unet, vae, sched = build_models(dev)
+        d = Diffusion(vae, unet, sched, "a,b,c", "cuda")
+        labels = torch.tensor(([0, 1, 2] * total)[:total], device=dev)
+        cfg = torch.tensor((scales * total)[:total], device=dev)
+        steps = list(range(999, 999 - nsteps, -1))
+        ss = ShardedSampler(d, labels, cfg, mb, seed=0)
+        lo, hi = shard_bounds(total, world, rank, mb)
+        # warm-up: one micro-batch (graph capture, workspaces, embedding table, decoder engine)
+        ShardedSampler(d, labels[:mb], cfg[:mb], mb, seed=1).run(steps=steps[:3]) if rank == 0 or True else None
+        clocks = ClockSampler(R.local)
+        if rank == 0:
+            clocks.start()
+        before = native.launch_count
+        out = {}
+
+        def region():
+            out["img"] = ss.run(steps=steps, decode=True)
+
+        ms = R.timed(region)
+        launches = native.launch_count - before
+        clock_info = clocks.stop() if rank == 0 else None
+        finite = bool(torch.isfinite(out["img"]).all())
+        n_local = out["img"].shape[0]
+        # sampling only (no decode), for the img-steps/s figure
+        ms_nodecode = R.timed(lambda: ss.run(steps=steps, decode=False))
+    if rank != 0:
+        R.close()
+        return
+    value = total * nsteps / (ms_nodecode * 1e-3)
+    tfl = value / world * GFLOP_PER_IMG_STEP / 1e3
+    line = {
+        "metric": "CFG UNet denoise img-steps/s (32x32x3 latents, diff-kl-lin-32x32 UNet), batch-sharded job",
+        "value": value, "unit": "img-steps/s", "n_gpus": world, "steps": nsteps, "warmup": 3,
+        "ms_per_step": ms_nodecode / nsteps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"configs[2]: {total} latents in contiguous shards of {total // world} per GPU, micro-batch "
+                               f"{mb}, per-sample CFG scales cycling through {scales}, {nsteps} of the 1000 DDPM steps "
+                               "(i = 999 downwards) + KL decode; no per-step cross-GPU traffic",
+                   "total_latents": total, "micro_batch": mb, "cfg_scales": scales, "sample_steps": nsteps,
+                   "local_images": n_local, "tflops_per_gpu": tfl,
+                   "pct_tensor_peak_sustained": tfl / peaks["sustained"], "pct_tensor_peak_burst": tfl / peaks["burst"],
+                   "job_ms_with_decode": ms, "decode_ms_total": ms - ms_nodecode, "finite": finite,
+                   "l2": "per-step working set exceeds the 126 MB L2"},
+        "clocks": clock_info,
+        "e2e": {"value": total * nsteps / (ms * 1e-3), "unit": "img-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0,
+                "how": "the whole sharded job incl. x_T / noise generation on the device and the KL decode of every "
+                       "latent; nothing crosses PCIe per step (the job's inputs are a seed, labels and scales)"},
+        "gpu_launches": launches,
+    }
+    print(json.dumps(line), flush=True)
+    R.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "vq", "shard"],
+                    help="sample: the headline CFG denoise metric (default, configs[1]); train: configs[3]; "
+                         "vq: configs[4]; shard: configs[2] (4096 latents, batch-sharded)")
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-job", action="store_true", help="skip the 1000-step + decode job timing")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the same-GPU torch (oracle) timing")
+    ap.add_argument("--batch", type=int, default=0, help="vq: images per step (default 256)")
+    ap.add_argument("--total", type=int, default=4096, help="shard: latents in the job")
+    ap.add_argument("--micro-batch", type=int, default=96, help="shard: latents per graph replay")
+    ap.add_argument("--sample-steps", type=int, default=50, help="shard: DDPM steps per latent (of 1000)")
+    ap.add_argument("--scales", default="1,3,5,7,9", help="shard: CFG scales cycled over the samples")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return {"sample": run_sample, "train": run_train, "vq": run_vq, "shard": run_shard}[args.workload](args)
 
 
 if __name__ == "__main__":

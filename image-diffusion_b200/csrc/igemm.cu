@@ -57,6 +57,7 @@ struct IgemmParams {
                       //    selects the weight block (rows parity * N .. of the stacked weight matrix), the tap
                       //    offsets (dh, dw) = ((tap >> 1) - 1 + row parity, (tap & 1) - 1 + column parity) and
                       //    the output map
+  int bb_row, bb_col; // batched B operand: image i reads W rows + i * bb_row, columns + i * bb_col
   int splits;         // split-K factor (persistent kernel): partial sums go to out_f32 + split * split_stride
   long long split_stride;
   int M, N;
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
       for (int u = walker; u < total_tiles; u += walkers, tw.next()) {
         const int par = p.up2_all ? (tw.n_idx & 3) : 0;
         const int tile_m = PAIR ? 2 * tw.tile_m + rank : tw.tile_m, n0 = (p.up2_all ? (tw.n_idx >> 2) : tw.n_idx) * BN;
-        const int brow0 = par * p.N + n0;  // row of the (stacked) weight matrix
+        int brow0 = par * p.N + n0;  // row of the (stacked) weight matrix
         int img0, h0, w0 = 0;
         if (p.matrix) {
           img0 = 0; h0 = 0; w0 = tile_m * BLOCK_M;
@@ -206,6 +207,8 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         } else {
           img0 = tile_m * p.tile_n; h0 = 0;
         }
+        brow0 += img0 * p.bb_row;
+        const int bcol0 = img0 * p.bb_col;
         int kb0 = 0, kb1 = p.kb_total;
         int seg = 0, tap = 0, cbk = 0;
         if (splits > 1) {
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
                 tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES + c * 8192, &p.tmB, &full_bar[stage], bcol + c * 64,
                                  cbk * BLOCK_K);
             } else {
-              tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], kb * BLOCK_K,
+              tma_load_2d_pair(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], bcol0 + kb * BLOCK_K,
                                brow0 + rank * (BN / 2));
             }
           } else {
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
               for (int c = 0; c < BN / 64; ++c)
                 tma_load_2d(smem_b + stage * Cfg::B_BYTES + c * 8192, &p.tmB, &full_bar[stage], bcol + c * 64, cbk * BLOCK_K);
             } else {
-              tma_load_2d(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], kb * BLOCK_K, brow0);
+              tma_load_2d(smem_b + stage * Cfg::B_BYTES, &p.tmB, &full_bar[stage], bcol0 + kb * BLOCK_K, brow0);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -736,6 +739,18 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     if (a->ldw < (long long)(maxt + 1) * a->N) return fail(IDF_ERR_ARG, "igemm: ldw %lld too small for w_mn", (long long)a->ldw);
     p.w_mn = 1;
   } else if (a->ldw < ktot) return fail(IDF_ERR_ARG, "igemm: ldw %lld < K %d", (long long)a->ldw, ktot);
+  const bool batched = a->w_batch_row != 0 || a->w_batch_col != 0;
+  if (batched) {
+    if (a->w_mn || up2_all || nseg != 1 || a->taps[0] != 1 || a->custom_taps || p.tiles_per_img <= 0 || a->ws != nullptr ||
+        a->w_batch_row < 0 || a->w_batch_col < 0 || a->w_batch_row > 0x3fffffff || a->w_batch_col > 0x3fffffff)
+      return fail(IDF_ERR_ARG, "igemm: w_batch_* needs one 1-tap K-major segment whose images are multiples of 128 pixels");
+    p.bb_row = (int)a->w_batch_row;
+    p.bb_col = (int)a->w_batch_col;
+    if (a->ldw < ktot + (long long)(x0.n - 1) * p.bb_col) return fail(IDF_ERR_ARG, "igemm: ldw too small for w_batch_col");
+  }
+  // extent of the weight tensor map (all images' blocks when the second operand is batched)
+  const uint64_t w_rows = (uint64_t)a->N * par_tiles + (uint64_t)(x0.n - 1) * p.bb_row;
+  const uint64_t w_cols = (uint64_t)ktot + (uint64_t)(x0.n - 1) * p.bb_col;
   // tile width: the persistent kernel takes 256 / 192 / 128 columns per tile; pick the widest that divides N (and
   // the V^T split point) unless that would leave SMs without a tile
   int bn = BLOCK_N;
@@ -802,7 +817,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   // 32x32 / 16x16 stages gain 5-9 %, 192-wide tiles lose 13-17 %, everything else is neutral or pays for the
   // cluster start-up: IDF_IGEMM_PAIR = 1 (default) pairs only the former, 2 = wherever legal, 0 = never.
   static const int pair_mode = [] { const char* e = getenv("IDF_IGEMM_PAIR"); return e ? atoi(e) : 1; }();
-  const bool pair_legal = M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2;
+  const bool pair_legal = !batched && M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2;
   const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && bn == 256 && !short_k &&
                                                       (M + BLOCK_M - 1) / BLOCK_M * par_tiles >= sm_count()));
   if (a->w_mn) {  // rows = the A operand's channels (K per tap), columns = (weight tap, output column)
@@ -810,7 +825,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     for (int t = 0; t < a->taps[0]; ++t) maxt = p.wtap[t] > maxt ? p.wtap[t] : maxt;
     if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)x0.c, (uint64_t)(maxt + 1) * a->N, (uint64_t)a->ldw, 64, 64)) != IDF_OK)
       return rc;
-  } else if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N * par_tiles, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K,
+  } else if ((rc = make_mat_map(&p.tmB, a->w, w_rows, w_cols, (uint64_t)a->ldw, BLOCK_K,
                                 (uint32_t)(pair ? bn / 2 : bn))) != IDF_OK)
     return rc;
 
@@ -898,7 +913,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     const int wbn = a->N % 256 == 0 ? 256 : (a->N % 192 == 0 ? 192 : 128);
     const long long wtiles = ((M + BLOCK_M - 1) / BLOCK_M) * (a->N / wbn);
     if (wbn != 128 && a->res == nullptr && a->vt == nullptr && !a->w_mn && ktot >= 256 && wtiles >= 2 * sm_count()) {
-      if ((rc = make_mat_map(&p.tmB, a->w, (uint64_t)a->N, (uint64_t)ktot, (uint64_t)a->ldw, BLOCK_K, (uint32_t)wbn)) != IDF_OK)
+      if ((rc = make_mat_map(&p.tmB, a->w, w_rows, w_cols, (uint64_t)a->ldw, BLOCK_K, (uint32_t)wbn)) != IDF_OK)
         return rc;
       return wbn == 256 ? launch_persist<256, 2>(p, st, false) : launch_persist<192, 2>(p, st, false);
     }

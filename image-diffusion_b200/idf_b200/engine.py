@@ -283,6 +283,8 @@ class VaeEngine:
         self.packed = _Packed(module)
         self.ws = Workspace(device)
         self.G, self.heads = arch["num_groups"], arch["num_heads"]
+        self.use_graph = __import__("os").environ.get("IDF_VAE_GRAPH", "1") != "0"
+        self.graphs = {}
 
     def prepare(self):
         if not self.packed.stale():
@@ -311,9 +313,11 @@ class VaeEngine:
                                                 sd[p + ".to_v.weight"]], dim=0).to(BF16).contiguous()
                     w[p + ".bqkv"] = _f32(torch.cat([sd[p + ".to_q.bias"], sd[p + ".to_k.bias"], sd[p + ".to_v.bias"]]))
                     w[p + ".wo"], w[p + ".bo"] = sd[p + ".out_proj.weight"].detach().to(BF16).contiguous(), _f32(sd[p + ".out_proj.bias"])
-                elif kind in ("up", "down"):
-                    n = "conv" if kind == "up" else "down"
-                    w[p + ".w"], w[p + ".b"] = pk(sd[f"{p}.{n}.weight"]), _f32(sd[f"{p}.{n}.bias"])
+                elif kind == "up":
+                    w[p + ".w"] = ops.pack_upsample_conv_weights(sd[f"{p}.conv.weight"])
+                    w[p + ".b"] = _f32(sd[f"{p}.conv.bias"])
+                elif kind == "down":
+                    w[p + ".w"], w[p + ".b"] = pk(sd[f"{p}.down.weight"]), _f32(sd[f"{p}.down.bias"])
                 elif kind == "gn_silu":
                     w[p + ".gw"], w[p + ".gb"] = _f32(sd[p + ".weight"]), _f32(sd[p + ".bias"])
         self.packed.install(w)
@@ -354,18 +358,23 @@ class VaeEngine:
         else:
             if T % 128 or hd % 128:
                 raise ValueError(f"VaeEngine attention: T={T}, head_dim={hd} unsupported by the GEMM-pair path")
-            s = ws.get("scores", T, T, torch.float32)
-            pm = ws.get("probs", T, T)
+            # One launch per stage for a whole chunk of samples (igemm with a per-image second operand): S = Q K^T in
+            # fp32, row softmax to bf16, O = P V. Chunks of <= 64 samples bound the score workspace (64 x T x T fp32).
+            cb = min(B, 64)
+            s = ws.get("scores", cb * T, T, torch.float32)
+            pm = ws.get("probs", cb * T, T)
             scale = 1.0 / (hd ** 0.5)
-            for b in range(B):
+            for b0 in range(0, B, cb):
+                nb = min(cb, B - b0)
+                rows = slice(b0 * T, (b0 + nb) * T)
+                grid = (nb, T // 128, 128)
                 for hh in range(self.heads):
-                    rows = slice(b * T, (b + 1) * T)
                     q = qk[rows, hh * hd:(hh + 1) * hd]
                     kk = qk[rows, C + hh * hd:C + (hh + 1) * hd]
-                    ops.igemm([(q, (1, 1, T), hd, 1)], kk, T, s)                      # S = Q K^T  (fp32)
-                    ops.softmax_rows(s, pm, scale)                                     # P = softmax(S / sqrt(hd))
-                    ops.igemm([(pm, (1, 1, T), T, 1)], vt[hh * hd:(hh + 1) * hd, rows], hd,
-                              o[rows, hh * hd:(hh + 1) * hd])                          # O = P V
+                    ops.igemm([(q, grid, hd, 1)], kk, T, s[:nb * T], w_batch=(T, 0))          # S_i = Q_i K_i^T  (fp32)
+                    ops.softmax_rows(s[:nb * T], pm[:nb * T], scale)                           # P = softmax(S / sqrt(hd))
+                    ops.igemm([(pm[:nb * T], grid, T, 1)], vt[hh * hd:(hh + 1) * hd, b0 * T:], hd,
+                              o[rows, hh * hd:(hh + 1) * hd], w_batch=(0, T))                  # O_i = P_i V_i
         dst = ws.get("xa" if x.t is not self.ws.bufs.get(("xa", M, C, BF16)) else "xb", M, C)
         ops.igemm([(o, (1, 1, M), C, 1)], w[p + ".wo"], C, dst, bias=w[p + ".bo"], res=x.t)
         return Act(dst, B, H, W, C)
@@ -404,22 +413,46 @@ class VaeEngine:
                 ops.groupnorm_silu(x.t, h, w[p + ".gw"], w[p + ".gb"], x.B, x.H * x.W, x.C, self.G, True)
                 x = Act(h, x.B, x.H, x.W, x.C)
             elif kind == "up":
-                up = ws.get("up", 4 * x.M, x.C)
-                ops.upsample_nearest2x(x.t, up, x.B, x.H, x.W, x.C)
-                dst = ws.get("xa", 4 * x.M, cout)
-                ops.igemm([(up, (x.B, 2 * x.H, 2 * x.W), x.C, 9)], w[p + ".w"], cout, dst, bias=w[p + ".b"])
+                # nearest-2x + conv3x3 as four sub-pixel convolutions on the low-resolution tensor, one launch
+                # (4/9 of the FLOPs, the upsampled tensor never exists)
+                dst = ws.get("xu", 4 * x.M, cout)
+                ops.upsample_conv3x3(x.t, x.grid, x.C, w[p + ".w"], cout, dst, bias=w[p + ".b"])
                 x = Act(dst, x.B, 2 * x.H, 2 * x.W, cout)
             elif kind == "down":
-                planes = ws.get("s2d", x.M, x.C)
-                ops.space_to_depth2(x.t, planes, x.B, x.H, x.W, x.C)
-                dst = ws.get("xa", x.M // 4, cout)
-                ops.igemm([(planes, (4 * x.B, x.H // 2, x.W // 2), x.C, 9)], w[p + ".w"], cout, dst, bias=w[p + ".b"],
-                          zero_pad_last=True, s2_batch=x.B)
+                # stride-2 pad-0 conv read straight from the full-resolution tensor (TMA element strides)
+                dst = ws.get("xd", x.M // 4, cout)
+                ops.igemm([(x.t, x.grid, x.C, 9)], w[p + ".w"], cout, dst, bias=w[p + ".b"], zero_pad_last=True,
+                          s2_direct=True)
                 x = Act(dst, x.B, x.H // 2, x.W // 2, cout)
         return out_nchw
 
+    def _run_graphed(self, part, prefix, x_nchw, out_nchw):
+        """One CUDA-graph replay per call (the program is a fixed, allocation-free kernel sequence over persistent
+        workspaces): static input / output buffers, weights re-packed in place before the replay when they changed."""
+        if not self.use_graph:
+            return self._run(part, prefix, x_nchw, out_nchw)
+        self.prepare()
+        st = self.graphs.get(part)
+        if st is None:
+            sin, sout = x_nchw.clone(), torch.empty_like(out_nchw)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._run(part, prefix, sin, sout)  # warm-up: allocates workspaces, sets kernel attributes
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run(part, prefix, sin, sout)
+            st = self.graphs[part] = (g, sin, sout)
+        g, sin, sout = st
+        sin.copy_(x_nchw)
+        g.replay()
+        out_nchw.copy_(sout)
+        return out_nchw
+
     def decode(self, z_nchw, out_nchw):
-        return self._run("decoder", "decoder.up", z_nchw, out_nchw)
+        return self._run_graphed("decoder", "decoder.up", z_nchw, out_nchw)
 
     def encode(self, x_nchw, out_nchw):
-        return self._run("encoder", "encoder.down", x_nchw, out_nchw)
+        return self._run_graphed("encoder", "encoder.down", x_nchw, out_nchw)

@@ -26,7 +26,7 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
           res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0, ws=None,
           tap_offsets=None, splits: int = 0, out_up2=None, s2_direct: bool = False, w_mn: bool = False,
-          w_tap_ids=None) -> torch.Tensor:
+          w_tap_ids=None, w_batch=None) -> torch.Tensor:
     """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view."""
     a = IgemmArgs()
     if not 1 <= len(segs) <= 2:
@@ -59,6 +59,8 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
     a.force_splits = splits
     a.s2_direct = 1 if s2_direct else 0
     a.w_mn = 1 if w_mn else 0
+    if w_batch is not None:  # per-image (row, column) offset of the second operand: a batch of independent GEMMs
+        a.w_batch_row, a.w_batch_col = w_batch
     if w_tap_ids is not None:
         for i, t in enumerate(w_tap_ids):
             a.w_tap_ids[i] = t

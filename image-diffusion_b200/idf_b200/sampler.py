@@ -99,6 +99,14 @@ class CfgSampler:
         self.graph = g
         self.xx.copy_(keep)
 
+    def set_conditioning(self, labels: torch.Tensor, cfg_scales: torch.Tensor):
+        """New class labels / guidance scales for the same batch size, written IN PLACE: the captured graph (which
+        reads these device tensors) serves every micro-batch of a sharded run."""
+        if labels.shape[0] != self.N or cfg_scales.shape[0] != self.N:
+            raise ValueError(f"CfgSampler.set_conditioning: expected {self.N} labels and scales")
+        self.base_idx[: self.N].copy_(labels.to(torch.int32))
+        self.cfg.copy_(cfg_scales.to(torch.float32))
+
     def set_latent(self, x_T: torch.Tensor):
         self._ensure_table()  # start of a sampling run: full staleness check of the weights (load_state_dict, optimizer)
         self.xx.copy_(x_T)

@@ -43,12 +43,14 @@ class GradBuckets:
         assert last_end == flat_grad.numel() and lo == last_end
         self.side = torch.cuda.Stream() if flat_grad.is_cuda else None
         self.works = []
+        self.enabled = True  # False: skip the exchange (bench.py's "what does the all-reduce cost a step" experiment)
+        self.elem_bytes, self.dtype_name = flat_grad.element_size(), str(flat_grad.dtype).replace("torch.", "")
 
     def plan(self):
         return [self.ranges[s] for s in sorted(self.ranges)]
 
     def on_stage_done(self, stage: int):
-        if self.world == 1 or stage not in self.ranges:
+        if self.world == 1 or stage not in self.ranges or not self.enabled:
             return
         lo, hi = self.ranges[stage]
         view = self.flat[lo:hi]
@@ -207,7 +209,7 @@ class DiffusionTrainStep:
             if bucket is None:
                 b.finish()  # the update segment needs every bucket averaged
             g.replay()
-            if bucket is not None:
+            if bucket is not None and b.enabled:
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream())
                 with torch.cuda.stream(b.side):

@@ -113,6 +113,12 @@ typedef struct idf_igemm_args {
   int32_t s2_direct;    /* != 0: stride-2 pad-0 3x3 conv (Downsample, components.py:110) read straight from the
                            FULL-resolution input a[0] (n, 2h, 2w) through a TMA map with element strides (2, 2): no
                            parity-plane copy. The output grid is (n, h, w); use with zero_pad_last. */
+  int64_t w_batch_row;  /* batched second operand: image i of a[0] multiplies the (N, K) block of `w` that starts at row */
+  int64_t w_batch_col;  /* i * w_batch_row and column i * w_batch_col (both 0: one weight matrix for all images). One 1-tap
+                           segment whose images are whole multiples of 128 pixels. Used for the single 384-wide attention
+                           head of the VAE (components.py:87-95): S_i = Q_i K_i^T with w = K (w_batch_row = tokens per
+                           image) and O_i = P_i V_i with w = V^T (w_batch_col = tokens per image), one launch each for the
+                           whole batch. */
 } idf_igemm_args;
 
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);

@@ -102,6 +102,40 @@ def posterior_step(s: SchedulerTables, xt, eps, t, z):
     return mean + var ** 0.5 * z, x0
 
 
+def ddim_step(s: SchedulerTables, xt, eps, t: int, t_prev: int, eta: float, z=None, clamp_x0: bool = False):
+    """Strided step x_t -> x_{t_prev} (t_prev < 0: final step, abar_prev = 1). NOT in the reference (its only sampler
+    is the 1-step ancestral update above, components.py:405-424): SURVEY.md §8 row f4. Restates the published
+    algorithm, Song, Meng & Ermon, "Denoising Diffusion Implicit Models", ICLR 2021, eq. 12 / 16, on the reference's
+    tables (components.py:366-397). Pin: with eta = 1 and t_prev = t - 1 it must reproduce posterior_step (which is
+    pinned on the reference's golden vectors) up to fp32 round-off - tests/test_oracle_golden.py."""
+    a_t = s.alpha_cum_prod[t]
+    a_p = s.alpha_cum_prod[t_prev] if t_prev >= 0 else torch.ones_like(a_t)
+    x0 = (xt - torch.sqrt(1 - a_t) * eps) / torch.sqrt(a_t)
+    if clamp_x0:
+        x0 = x0.clamp(-1.0, 1.0)
+    sigma = eta * torch.sqrt((1 - a_p) / (1 - a_t)) * torch.sqrt(torch.clamp(1 - a_t / a_p, min=0))
+    out = torch.sqrt(a_p) * x0 + torch.sqrt(torch.clamp(1 - a_p - sigma ** 2, min=0)) * eps
+    if float(sigma) > 0:
+        out = out + sigma * z
+    return out, x0
+
+
+def cfg_sample_strided(unet_sd, unet_arch, sched: SchedulerTables, x_T, labels, cfg_scales, steps, eta=0.0, noises=None):
+    """diffusion.py:46-56 with the ancestral update replaced by ddim_step over a decreasing subset of timesteps."""
+    xt = x_T
+    N = xt.shape[0]
+    s4 = cfg_scales.view(-1, 1, 1, 1)
+    steps = list(steps)
+    for k, i in enumerate(steps):
+        t = torch.full((N,), i, dtype=torch.long, device=xt.device)
+        ec = unet_forward(unet_sd, unet_arch, xt, t, labels)
+        eu = unet_forward(unet_sd, unet_arch, xt, t)
+        eps = eu + s4 * (ec - eu)
+        xt, _ = ddim_step(sched, xt, eps, i, steps[k + 1] if k + 1 < len(steps) else -1, eta,
+                          None if noises is None else noises[k])
+    return xt
+
+
 # ---------------------------------------------------------------------------------------------
 # building blocks
 # ---------------------------------------------------------------------------------------------

@@ -403,3 +403,30 @@ def test_downsample_conv_strided_tma(B, C, H):
     got = unrows(out, B, H // 2, H // 2)
     assert rel_err(got, ref) < 6e-3, rel_err(got, ref)
     assert got[:, :, -1, :].abs().max().item() == 0.0 and got[:, :, :, -1].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B,T,hd", [(3, 1024, 384), (5, 256, 128), (70, 256, 128)])
+def test_igemm_batched_second_operand_is_a_batch_of_gemms(B, T, hd):
+    """w_batch_row / w_batch_col: image i of the A operand multiplies its own block of the second operand. The two
+    shapes of the VAE's single wide attention head (components.py:87-95): S_i = Q_i K_i^T (fp32 out) and O_i = P_i V_i
+    with V stored transposed (hd, B*T)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(B + T)
+    M = B * T
+    qk = torch.randn(M, 2 * hd, device=DEV, generator=g).to(torch.bfloat16)
+    vt = torch.randn(hd, M, device=DEV, generator=g).to(torch.bfloat16)
+    q, k = qk[:, :hd], qk[:, hd:]
+    s = torch.empty(M, T, device=DEV, dtype=torch.float32)
+    grid = (B, T // 128, 128)
+    ops.igemm([(q, grid, hd, 1)], k, T, s, w_batch=(T, 0))
+    ref = torch.bmm(q.float().view(B, T, hd), k.float().view(B, T, hd).transpose(1, 2)).view(M, T)
+    assert rel_err(s, ref) < 1e-5
+    pm = torch.empty(M, T, device=DEV, dtype=torch.bfloat16)
+    ops.softmax_rows(s, pm, 1.0 / math.sqrt(hd))
+    pref = torch.softmax(ref / math.sqrt(hd), dim=-1)
+    assert rel_err(pm.float(), pref) < 6e-3
+    o = torch.empty(M, 2 * hd, device=DEV, dtype=torch.bfloat16)
+    ops.igemm([(pm, grid, T, 1)], vt, hd, o[:, hd:], w_batch=(0, T))
+    v = vt.float().t().reshape(B, T, hd)
+    oref = torch.bmm(pm.float().view(B, T, T), v).view(M, hd)
+    assert rel_err(o[:, hd:].float(), oref) < 6e-3

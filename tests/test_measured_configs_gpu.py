@@ -1,0 +1,229 @@
+"""Parity AT THE CONFIGURATIONS bench.py MEASURES (BASELINE.json configs[1], [3], [4]): the batch sizes at which the
+engine takes its large-batch kernels (CTA-pair tiles, the tile-width cost model's choices, 12/8/6-warp GroupNorm
+CTAs, persistent attention with more work items than SMs). Same oracle, same tolerances as tests/test_modules_gpu.py
+(SURVEY.md §8d): eps rel-RMS <= 3e-2 / max-abs <= 5e-2, 20-step chain <= 1e-2, decoded pixels / latents <= 3.5e-2,
+train-step loss within 2e-2 and global gradient rel-RMS <= 2e-2, VQ indices bit-exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_path as O
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+DEV = "cuda"
+
+
+def gen(seed, *shape):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def rel_rms(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def to_dev(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+@pytest.fixture(scope="module")
+def unet_pair():
+    from modules.unet import Unet
+    sd = O.seeded_state_dict(O.unet_param_shapes(O.UNET_ARCH), 2018)
+    m = Unet(**O.UNET_ARCH)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), to_dev(sd)
+
+
+@torch.no_grad()
+def test_unet_forward_batch96_cfg_doubled(unet_pair):
+    """Unet.forward at the bench's CFG-doubled batch: rows [0, 48) conditional, rows [48, 96) class-masked."""
+    m, sd = unet_pair
+    N = 48
+    x = gen(4100, N, 3, 32, 32).to(DEV)
+    xx = torch.cat([x, x])
+    t = torch.full((2 * N,), 500, device=DEV)
+    ctx = torch.tensor([0, 1, 2] * (2 * N // 3), device=DEV)
+    mask = torch.cat([torch.ones(N, 1), torch.zeros(N, 1)]).to(DEV)
+    out = m(xx, t, ctx, mask)
+    ref = torch.cat([O.unet_forward(sd, O.UNET_ARCH, xx[i:i + 24], t[i:i + 24], ctx[i:i + 24], mask[i:i + 24])
+                     for i in range(0, 2 * N, 24)])
+    r, mx = rel_rms(out, ref), (out - ref).abs().max().item()
+    print(f"unet B=96 (CFG-doubled) vs fp32 oracle: rel-RMS {r:.3e} max-abs {mx:.3e}")
+    assert r <= 3e-2 and mx <= 5e-2, (r, mx)
+    # the conditional half of the doubled batch equals the plain batch-48 call bit for bit (deterministic kernels)
+    assert torch.equal(out[:N], m(x, t[:N], ctx[:N]))
+
+
+@torch.no_grad()
+def test_cfg_chain_20_steps_batch48(unet_pair):
+    """BASELINE configs[1] at its own batch (48 = 3 classes x 16, cfg scale 3): 20 free-running graph-replayed CFG
+    steps with injected noise against the oracle's loop."""
+    from idf_b200.sampler import CfgSampler
+    from modules.components import Scheduler
+    m, sd = unet_pair
+    N = 48
+    labels = torch.tensor([0, 1, 2] * 16, device=DEV)
+    cfg = torch.full((N,), 3, device=DEV)
+    sampler = CfgSampler(m, Scheduler(1000, device=DEV), labels, cfg, (3, 32, 32))
+    osched = O.SchedulerTables(1000, device=DEV)
+    steps = list(range(999, 979, -1))
+    x_T = gen(4200, N, 3, 32, 32).to(DEV)
+    noises = [gen(4201 + k, N, 3, 32, 32).to(DEV) for k in range(len(steps))]
+    got = sampler.run(x_T, steps=steps, noises=noises).clone()
+    ref = O.cfg_sample(sd, O.UNET_ARCH, osched, x_T, labels, cfg, noises, steps=steps)
+    r = rel_rms(got, ref)
+    print(f"20-step CFG chain, batch 48: rel-RMS {r:.3e}")
+    assert r <= 1e-2, r
+    assert sampler.graph is not None
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("T,hd", [(1024, 32), (1024, 16), (256, 48), (64, 64), (16, 64)])
+def test_qkv_attention_batch96(T, hd):
+    """The fused attention kernels at the bench batch (96 samples x 8 heads: more work items than SMs)."""
+    from idf_b200 import ops
+    B, heads = 96, 8
+    Cc, M = heads * hd, B * T
+    g = torch.Generator(device=DEV).manual_seed(T + hd)
+    qkv = (torch.randn(M, 3 * Cc, device=DEV, generator=g) * 1.2).to(torch.bfloat16)
+    out = torch.empty(M, Cc, device=DEV, dtype=torch.bfloat16)
+    ops.attention_qkv(qkv, out, M, T, heads, hd)
+    q, k, v = (qkv[:, i * Cc:(i + 1) * Cc].float().reshape(B, T, heads, hd).transpose(1, 2) for i in range(3))
+    ref = torch.cat([F.scaled_dot_product_attention(q[i:i + 16], k[i:i + 16], v[i:i + 16]) for i in range(0, B, 16)])
+    ref = ref.transpose(1, 2).reshape(M, Cc)
+    err = rel_rms(out.float(), ref)
+    print(f"attention B=96 T={T} hd={hd}: rel-RMS {err:.3e}")
+    assert err < 1.5e-2, err
+
+
+def test_train_step_batch48_full_arch():
+    """BASELINE configs[3] at its own batch: loss and the global gradient of the kernel training path at batch 48,
+    full architecture, against autograd through the fp32 oracle on the same GPU."""
+    from modules.unet import Unet
+    B = 48
+    with torch.enable_grad():
+        sd = O.seeded_state_dict(O.unet_param_shapes(O.UNET_ARCH), 11)
+        m = Unet(**O.UNET_ARCH)
+        m.load_state_dict(sd)
+        m = m.to(DEV).train()
+        g = torch.Generator().manual_seed(12)
+        x = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+        noise = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+        t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+        c = torch.randint(0, 3, (B,), generator=g).to(DEV)
+        mask = (torch.rand(B, generator=g) > 0.15).to(DEV).unsqueeze(1)
+        loss = F.mse_loss(m(x, t, context=c, context_mask=mask), noise)
+        loss.backward()
+        grads = {k: p.grad.float() for k, p in m.named_parameters()}
+        # oracle: gradient accumulation over chunks of 12 samples (mean over the whole batch = sum of chunk means / 4)
+        sdg = {k: v.to(DEV).clone().requires_grad_(v.is_floating_point() and k != "time_embedding.factor")
+               for k, v in sd.items()}
+        ref_loss = 0.0
+        for i in range(0, B, 12):
+            sl = slice(i, i + 12)
+            part = F.mse_loss(O.unet_forward(sdg, O.UNET_ARCH, x[sl], t[sl], c[sl], mask[sl]), noise[sl]) * (12 / B)
+            part.backward()
+            ref_loss += part.item()
+    ref = {k: v.grad for k, v in sdg.items() if v.requires_grad}
+    assert set(grads) == set(ref)
+    assert abs(loss.item() - ref_loss) <= 2e-2 * abs(ref_loss), (loss.item(), ref_loss)
+    num = sum(((grads[k] - r) ** 2).sum().item() for k, r in ref.items())
+    den = sum((r ** 2).sum().item() for r in ref.values())
+    glob = math.sqrt(num / den)
+    floor = 1e-4 * max(r.norm().item() for r in ref.values())
+    worst = max(((grads[k] - r).norm().item() / max(r.norm().item(), floor), k) for k, r in ref.items())
+    print(f"train step B=48 full arch: loss {loss.item():.6f} vs {ref_loss:.6f}; global grad rel-RMS {glob:.3e}; "
+          f"worst tensor {worst[1]} {worst[0]:.3e}")
+    assert glob <= 2e-2, glob
+    assert worst[0] <= 6e-2, worst
+
+
+@torch.no_grad()
+def test_fused_train_step_batch48_runs_ahead_of_gpu():
+    """DiffusionTrainStep at batch 48 with the host several steps ahead of the GPU (no sync between steps): every
+    step must use ITS OWN lr / bias-correction values (ring of pinned slots), i.e. the parameters equal those of a
+    run that synchronises after every step, bit for bit."""
+    from idf_b200.trainer import DiffusionTrainStep
+    from modules.components import Scheduler
+    from modules.unet import Unet
+    sched = Scheduler(1000, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(48, 6, 32, 32, generator=g).to(DEV)
+    lab = torch.randint(0, 3, (48,), generator=g).to(DEV)
+    results = []
+    for sync in (True, False):
+        torch.manual_seed(2018)
+        m = Unet(**O.UNET_ARCH).to(DEV).train()
+        ts = DiffusionTrainStep(m, sched, 48, (3, 32, 32), clip_grad=1.0)
+        gen_dev = torch.Generator(device=DEV).manual_seed(5)
+        for k in range(12):
+            ts.step(lat, lab, 1e-4 * (k + 1) / 12, generator=gen_dev)  # LR warm-up: a different lr every step
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        results.append(ts.flat_param.clone())
+        del ts, m
+    assert torch.equal(results[0], results[1])
+
+
+@torch.no_grad()
+def test_vq_config5_batch256_encode_quantize_decode():
+    """BASELINE config 5 at full size through the public API: VAE.forward (VQ) on [256, 3, 128, 128]. The encoder's
+    z and the decoded images are held to the oracle (computed in chunks: fp32 activations of 256 images at 128x128
+    are 4.3 GB per tensor); the codebook indices are BIT-EXACT against torch.cdist + argmin fed the same z, for the
+    default-init codebook (adversarial near-ties) and an N(0,1)-spread one."""
+    from modules.vae import VAE
+    B = 256
+    sd = O.seeded_state_dict(O.vae_param_shapes(O.VAE_VQ_ARCH), 7)
+    m = VAE(**O.VAE_VQ_ARCH)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    sdd = to_dev(sd)
+    img = (torch.rand(B, 3, 128, 128, generator=torch.Generator().manual_seed(55)) * 2 - 1).to(DEV)
+    z = torch.empty(B, 3, 32, 32, device=DEV)
+    m._engine(("enc", B, 128, 128)).encode(img, z)
+    z_ref = torch.cat([O._run_program(sdd, "encoder.down", O.encoder_program(O.VAE_VQ_ARCH), img[i:i + 16], O.VAE_VQ_ARCH)
+                       for i in range(0, B, 16)])
+    r = rel_rms(z, z_ref)
+    print(f"VQ encoder z, batch 256, vs oracle: rel-RMS {r:.3e}")
+    assert r <= 3.5e-2, r
+    for tag, w in (("default", sd["codebook.embeddings.weight"]), ("normal", gen(8, 1024, 3) * 0.5)):
+        m.codebook.embeddings.weight.data.copy_(w)
+        zq, idx = m.codebook.quantize(z)
+        flat = z.permute(0, 2, 3, 1).reshape(B, 1024, 3)
+        ref_idx = torch.cat([torch.cdist(flat[i:i + 32], w.to(DEV)[None].repeat(32, 1, 1)).argmin(-1).view(-1)
+                             for i in range(0, B, 32)])
+        assert torch.equal(idx, ref_idx), tag
+        assert torch.equal(zq, w.to(DEV)[idx].view(B, 32, 32, 3).permute(0, 3, 1, 2))
+    x_hat, loss, perp = m(img, return_metrics=True)   # public API: encode -> quantise -> decode
+    assert x_hat.shape == (B, 3, 128, 128) and torch.isfinite(x_hat).all()
+    zq, _ = m.codebook.quantize(z)
+    ref = torch.cat([O.vae_decode(sdd | {"codebook.embeddings.weight": m.codebook.embeddings.weight.data}, O.VAE_VQ_ARCH,
+                                  zq[i:i + 16]) for i in range(0, B, 16)])
+    r = rel_rms(x_hat, ref)
+    print(f"VQ decode of the quantised latents, batch 256, vs oracle: rel-RMS {r:.3e}; perplexity {float(perp):.1f}")
+    assert r <= 3.5e-2, r
+
+
+@torch.no_grad()
+def test_kl_decode_batch48(unet_pair):
+    """The decode stage of configs[1] at batch 48 against the oracle."""
+    from modules.vae import VAE
+    sd = O.seeded_state_dict(O.vae_param_shapes(O.VAE_KL_ARCH), 2018)
+    m = VAE(**O.VAE_KL_ARCH)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    sdd = to_dev(sd)
+    z = gen(4300, 48, 3, 32, 32).to(DEV)
+    out = m.decode(z)
+    ref = torch.cat([O.vae_decode(sdd, O.VAE_KL_ARCH, z[i:i + 16]) for i in range(0, 48, 16)])
+    r = rel_rms(out, ref)
+    print(f"KL decode batch 48 vs oracle: rel-RMS {r:.3e}")
+    assert r <= 3.5e-2, r
+    assert torch.equal(out, m.decode(z))  # second call (CUDA-graph replay when captured) gives the same bits
