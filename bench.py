@@ -730,23 +730,23 @@ def run_shard(args):
         ss = ShardedSampler(d, labels, cfg, mb, seed=0)
         lo, hi = shard_bounds(total, world, rank, mb)
         # warm-up: one micro-batch (graph capture, workspaces, embedding table, decoder engine)
-        ShardedSampler(d, labels[:mb], cfg[:mb], mb, seed=1).run(steps=steps[:3]) if rank == 0 or True else None
+        ShardedSampler(d, labels[:mb], cfg[:mb], mb, seed=1).run(steps=steps[:3])
         clocks = ClockSampler(R.local)
         if rank == 0:
             clocks.start()
         before = native.launch_count
-        out = {}
+        out, dec_ev = {}, []
 
         def region():
-            out["img"] = ss.run(steps=steps, decode=True)
+            out["img"] = ss.run(steps=steps, decode=True, decode_events=dec_ev)
 
-        ms = R.timed(region)
+        ms = R.timed(region)   # ONE timed run of the whole job; the decode share comes from events inside it
         launches = native.launch_count - before
         clock_info = clocks.stop() if rank == 0 else None
         finite = bool(torch.isfinite(out["img"]).all())
         n_local = out["img"].shape[0]
-        # sampling only (no decode), for the img-steps/s figure
-        ms_nodecode = R.timed(lambda: ss.run(steps=steps, decode=False))
+        ms_decode = R.max(sum(a.elapsed_time(b) for a, b in dec_ev))
+        ms_nodecode = ms - ms_decode
     if rank != 0:
         R.close()
         return
@@ -763,7 +763,9 @@ def run_shard(args):
                    "total_latents": total, "micro_batch": mb, "cfg_scales": scales, "sample_steps": nsteps,
                    "local_images": n_local, "tflops_per_gpu": tfl,
                    "pct_tensor_peak_sustained": tfl / peaks["sustained"], "pct_tensor_peak_burst": tfl / peaks["burst"],
-                   "job_ms_with_decode": ms, "decode_ms_total": ms - ms_nodecode, "finite": finite,
+                   "job_ms_with_decode": ms, "decode_ms_total": ms_decode, "finite": finite,
+                   "value_note": "img-steps/s over the sampling part of the job (job time minus the CUDA-event time of "
+                                 "the decode calls); e2e.value is over the whole job",
                    "l2": "per-step working set exceeds the 126 MB L2"},
         "clocks": clock_info,
         "e2e": {"value": total * nsteps / (ms * 1e-3), "unit": "img-steps/s", "h2d_bytes_per_step": 0,
@@ -790,7 +792,7 @@ def main():
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the same-GPU torch (oracle) timing")
     ap.add_argument("--batch", type=int, default=0, help="vq: images per step (default 256)")
     ap.add_argument("--total", type=int, default=4096, help="shard: latents in the job")
-    ap.add_argument("--micro-batch", type=int, default=96, help="shard: latents per graph replay")
+    ap.add_argument("--micro-batch", type=int, default=128, help="shard: latents per graph replay")
     ap.add_argument("--sample-steps", type=int, default=50, help="shard: DDPM steps per latent (of 1000)")
     ap.add_argument("--scales", default="1,3,5,7,9", help="shard: CFG scales cycled over the samples")
     args = ap.parse_args()

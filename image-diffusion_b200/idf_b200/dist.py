@@ -49,7 +49,8 @@ class ShardedSampler:
         self.total = labels.shape[0]
 
     @torch.no_grad()
-    def run(self, steps=None, decode: bool = True) -> torch.Tensor:
+    def run(self, steps=None, decode: bool = True, decode_events=None) -> torch.Tensor:
+        """decode_events: optional list that receives a (start, end) CUDA-event pair around every decode call."""
         from .sampler import CfgSampler
         rank, world = world_info()
         lo, hi = shard_bounds(self.total, world, rank, self.mb)
@@ -72,7 +73,13 @@ class ShardedSampler:
                     z.normal_(generator=gen)
                 sampler.step(i, noise=z)
             lat = sampler.latent.clone()
+            if decode and decode_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             outs.append(self.d.vae.decode(lat, quantize=self.d.vae.architecture["bottleneck"] == "vq") if decode else lat)
+            if decode and decode_events is not None:
+                ev[1].record()
+                decode_events.append(ev)
         if not outs:
             shape = (0, *self.d.latent_shape)
             return torch.empty(shape, device=dev)

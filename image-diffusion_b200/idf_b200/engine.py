@@ -78,8 +78,15 @@ class _Packed:
         """Refreshes the packed copies IN PLACE when the layout is unchanged, so that captured CUDA graphs (which hold
         raw pointers to these tensors) keep reading valid, current weights."""
         old = self.w
-        if old and old.keys() == w.keys() and all(old[k].shape == w[k].shape and old[k].dtype == w[k].dtype
-                                                   and type(old[k]) is type(w[k]) for k in w):
+
+        def same(a, b):
+            if type(a) is not type(b):
+                return False
+            if isinstance(a, list):  # _UpsamplePack
+                return len(a) == len(b) and a.stacked.shape == b.stacked.shape
+            return a.shape == b.shape and a.dtype == b.dtype and a.device == b.device
+
+        if old and old.keys() == w.keys() and all(same(old[k], w[k]) for k in w):
             for k, v in w.items():
                 if isinstance(v, list):  # _UpsamplePack: per-parity matrices + the stacked matrix
                     for (_, _, dst), (_, _, src) in zip(old[k], v):
@@ -108,7 +115,7 @@ class UnetEngine:
         # summation order - and the output bits - do not depend on the batch size. At 8x8 the fp32 partial traffic
         # eats the gain (measured).
         self.splitk = int(__import__("os").environ.get("IDF_SPLITK_4X4", "3"))
-        self.splitk_ws = None
+        self._B, self._rng = 0, (0, 0)
         self.downs, self.mids, self.ups = unet_blocks(arch)
         for _, cin, cout in self.downs + self.mids + self.ups:
             if cin % 64 or cout % 128:
@@ -169,38 +176,38 @@ class UnetEngine:
             self.taps[name] = t2d.float().clone()
 
     def _block(self, p, x: Act, cout, table, idx, final_dst=None) -> Act:
-        w, ws, G = self.packed.w, self.ws, self.G
+        w, G = self.packed.w, self.G
         B, H, W = x.grid
         M, HW = x.M, x.H * x.W
         hd = cout // self.heads
         sk = {}
         if self.splitk > 1 and HW <= 16:
-            sk = dict(ws=ws.get("splitk", 1, self.splitk * M * cout, torch.float32), splits=self.splitk)
+            sk = dict(ws=self._splitk_ws(M * cout), splits=self.splitk)
         for l in range(self.L):
             cin = x.C
             k = f"{p}.{l}"
-            h1 = ws.get("h1", M, cin)
+            h1 = self._buf("h1", HW, cin)
             ops.groupnorm_silu(x.t, h1, w[k + ".g1w"], w[k + ".g1b"], B, HW, cin, G, True)
-            y1 = ws.get("y1", M, cout)
+            y1 = self._buf("y1", HW, cout)
             off = self.tp_off[(p, l)]
             ops.igemm([(h1, x.grid, cin, 9)], w[k + ".w1"], cout, y1, bias=w[k + ".b1"],
                       rowbias=table[:, off:off + cout], rowbias_idx=idx, **sk)
-            h2 = ws.get("h2", M, cout)
+            h2 = self._buf("h2", HW, cout)
             ops.groupnorm_silu(y1, h2, w[k + ".g2w"], w[k + ".g2b"], B, HW, cout, G, True)
-            x2 = ws.get("x2", M, cout)
+            x2 = self._buf("x2", HW, cout)
             ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"], **sk)
-            h3 = ws.get("h3", M, cout)
+            h3 = self._buf("h3", HW, cout)
             ops.groupnorm_silu(x2, h3, w[k + ".g3w"], w[k + ".g3b"], B, HW, cout, G, False)
             # Q | K | V token-major in one buffer: the attention kernel takes V tiles as MN-major tcgen05 operands, so
             # the QKV GEMM has a plain TMA-store epilogue (no transposed V^T copy)
-            qk = ws.get("qkv", M, 3 * cout)
+            qk = self._buf("qkv", HW, 3 * cout)
             ops.igemm([(h3, (1, 1, M), cout, 1)], w[k + ".wqkv"], 3 * cout, qk, bias=w[k + ".bqkv"])
-            o = ws.get("o", M, cout)
+            o = self._buf("o", HW, cout)
             ops.attention_qkv(qk, o, M, HW, self.heads, hd)
             if l == self.L - 1 and final_dst is not None:
                 dst = final_dst
             else:
-                dst = ws.get("xa" if (l % 2 == 0) else "xb", M, cout)
+                dst = self._buf("xa" if (l % 2 == 0) else "xb", HW, cout)
             ops.igemm([(o, (1, 1, M), cout, 1)], w[k + ".wo"], cout, dst, bias=w[k + ".bo"], res=x2)
             if self.taps is not None:
                 for nm, tt in (("h1", h1), ("y1", y1), ("h2", h2), ("x2", x2), ("h3", h3), ("qk", qk), ("o", o),
@@ -237,40 +244,65 @@ class UnetEngine:
         if table is None:  # `table`: precomputed rows (e.g. every timestep of a sampling run), indexed by row_idx
             table = self.embedding_table(t_rows, ctx_rows, mask_rows)
         ch = list(self.arch["channels"])
-        a0 = ws.get("in", B * H * W, ch[0])
+        self._B, self._rng = B, (0, B)
+        a0 = self._buf("in", H * W, ch[0])
         ops.conv3x3_small_cin(x_nchw, w["in.w"], w["in.b"], a0, dup=dup_input)
         self._tap("table", table)
         self._tap("in", a0)
-        x = Act(a0, B, H, W, ch[0])
-        cats = []
-        for i, (p, cin, cout) in enumerate(self.downs):
-            cat = ws.get(f"cat{i}", x.M, 2 * cout)
-            cats.append(cat)
-            x = self._block(p, x, cout, table, row_idx, final_dst=cat[:, cout:])
-            nxt = ws.get("dn", x.M // 4, cout)
-            skd = {}
-            if self.splitk > 1 and (x.H // 2) * (x.W // 2) <= 16:
-                skd = dict(ws=ws.get("splitk", 1, self.splitk * (x.M // 4) * cout, torch.float32), splits=self.splitk)
-            # stride-2 pad-0 conv read straight from the block output (TMA element strides): no parity-plane copy
-            ops.igemm([(x.t, x.grid, cout, 9)], w[f"down.{i}.w"], cout, nxt, bias=w[f"down.{i}.b"], zero_pad_last=True,
-                      s2_direct=True, **skd)
-            self._tap(f"down.{i}", nxt)
-            x = Act(nxt, x.B, x.H // 2, x.W // 2, cout)
-        for p, cin, cout in self.mids:
-            x = self._block(p, x, cout, table, row_idx)
-        for i, (p, cin, cout) in enumerate(self.ups):
-            c = x.C
-            cat = cats.pop()
-            # nearest-2x + conv3x3 as four sub-pixel convolutions on the low-resolution tensor (4/9 of the FLOPs, no
-            # upsampled copy), stored straight into the left half of the concat buffer
-            ops.upsample_conv3x3(x.t, x.grid, c, w[f"up.{i}.w"], c, cat[:, :c], bias=w[f"up.{i}.b"])
-            self._tap(f"up.{i}", cat)
-            x = self._block(p, Act(cat, x.B, 2 * x.H, 2 * x.W, 2 * c), cout, table, row_idx)
-        h = ws.get("h1", x.M, x.C)
+        x = self._level(0, Act(a0, B, H, W, ch[0]), table, row_idx)
+        h = self._buf("h1", x.H * x.W, x.C)
         ops.groupnorm_silu(x.t, h, w["out.gw"], w["out.gb"], x.B, x.H * x.W, x.C, self.G, True)
         ops.conv3x3_small_cout(h, w["out.w"], w["out.b"], out_nchw)
         return out_nchw
 
+    # ---------------------------------------------------------------------------------------------
+    # Every operation of the network is per sample, so a sample range [b0, b0 + nb) of the batch can run as its own
+    # kernel chain on row slices of the same full-batch buffers (_rng). (Running the 8x8 / 4x4 interior as two
+    # half-batch chains on two streams was measured: 3.724 vs 3.729 ms per step - the one-CTA-per-SM persistent
+    # kernels do not overlap; not kept.)
+    # ---------------------------------------------------------------------------------------------
+    def _buf(self, name, HW, cols, dtype=BF16):
+        b0, nb = self._rng
+        return self.ws.get(name, self._B * HW, cols, dtype)[b0 * HW:(b0 + nb) * HW]
+
+    def _splitk_ws(self, elems):
+        return self.ws.get(f"splitk{self._rng[0]}", 1, self.splitk * elems, torch.float32)
+
+    def _level(self, i, x: Act, table, idx) -> Act:
+        """Down block i, everything below it, and the matching up block (unet.py:117-133)."""
+        n = len(self.downs)
+        p, _, cout = self.downs[i]
+        cat = self._buf(f"cat{i}", x.H * x.W, 2 * cout)
+        x = self._block(p, x, cout, table, idx, final_dst=cat[:, cout:])
+        self._inner(i, x, cat, table, idx)
+        pu, _, cu = self.ups[n - 1 - i]
+        return self._block(pu, Act(cat, x.B, x.H, x.W, 2 * cout), cu, table, idx)
+
+    def _inner(self, i, x: Act, cat, table, idx):
+        """Downsample i -> deeper levels (or the mid blocks) -> Upsample conv into the left half of level i's concat
+        buffer."""
+        w, n = self.packed.w, len(self.downs)
+        cout = x.C
+        Hd, Wd = x.H // 2, x.W // 2
+        nxt = self._buf("dn", Hd * Wd, cout)
+        skd = {}
+        if self.splitk > 1 and Hd * Wd <= 16:
+            skd = dict(ws=self._splitk_ws(x.B * Hd * Wd * cout), splits=self.splitk)
+        # stride-2 pad-0 conv read straight from the block output (TMA element strides): no parity-plane copy
+        ops.igemm([(x.t, x.grid, cout, 9)], w[f"down.{i}.w"], cout, nxt, bias=w[f"down.{i}.b"], zero_pad_last=True,
+                  s2_direct=True, **skd)
+        self._tap(f"down.{i}", nxt)
+        y = Act(nxt, x.B, Hd, Wd, cout)
+        if i + 1 < n:
+            y = self._level(i + 1, y, table, idx)
+        else:
+            for p, _, cm in self.mids:
+                y = self._block(p, y, cm, table, idx)
+        j = n - 1 - i
+        # nearest-2x + conv3x3 as four sub-pixel convolutions on the low-resolution tensor (4/9 of the FLOPs, no
+        # upsampled copy), stored straight into the left half of the concat buffer
+        ops.upsample_conv3x3(y.t, y.grid, y.C, w[f"up.{j}.w"], y.C, cat[:, :y.C], bias=w[f"up.{j}.b"])
+        self._tap(f"up.{j}", cat)
 
 # =================================================================================================
 # VAE encoder / decoder

@@ -318,7 +318,7 @@ def test_cfg_posterior_step():
     betas = torch.linspace(1e-4 ** 0.5, 0.02 ** 0.5, T, device=DEV) ** 2
     alphas = 1 - betas
     acp = torch.cumprod(alphas, 0)
-    sched = SimpleNamespace(betas=betas, alphas=alphas, alpha_cum_prod=acp, sqrt_alpha_cum_prod=acp.sqrt(),
+    sched = SimpleNamespace(num_steps=T, betas=betas, alphas=alphas, alpha_cum_prod=acp, sqrt_alpha_cum_prod=acp.sqrt(),
                             sqrt_one_minus_alpha_cum_prod=(1 - acp).sqrt())
     g = torch.Generator(device=DEV).manual_seed(9)
     N = 6

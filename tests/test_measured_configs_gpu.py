@@ -148,7 +148,11 @@ def test_train_step_batch48_full_arch():
 def test_fused_train_step_batch48_runs_ahead_of_gpu():
     """DiffusionTrainStep at batch 48 with the host several steps ahead of the GPU (no sync between steps): every
     step must use ITS OWN lr / bias-correction values (ring of pinned slots), i.e. the parameters equal those of a
-    run that synchronises after every step, bit for bit."""
+    run that synchronises after every step. Not bit for bit - the attention backward accumulates dQ with fp32
+    red.global.add, whose order varies - and parameters whose true gradient is zero (to_k.bias) follow the sign of that noise - but to a few percent of the
+    accumulated update (measured value printed; gate 5e-2); a step that read another step's
+    {lr, 1 - beta1^k, sqrt(1 - beta2^k)} (round-1 advisor finding: bc1 moves 0.1 -> 0.72 over these 12 steps, lr 12x)
+    changes the update by tens of percent."""
     from idf_b200.trainer import DiffusionTrainStep
     from modules.components import Scheduler
     from modules.unet import Unet
@@ -161,15 +165,18 @@ def test_fused_train_step_batch48_runs_ahead_of_gpu():
         torch.manual_seed(2018)
         m = Unet(**O.UNET_ARCH).to(DEV).train()
         ts = DiffusionTrainStep(m, sched, 48, (3, 32, 32), clip_grad=1.0)
+        init = ts.flat_param.clone()
         gen_dev = torch.Generator(device=DEV).manual_seed(5)
         for k in range(12):
             ts.step(lat, lab, 1e-4 * (k + 1) / 12, generator=gen_dev)  # LR warm-up: a different lr every step
             if sync:
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
-        results.append(ts.flat_param.clone())
+        results.append(ts.flat_param.clone() - init)
         del ts, m
-    assert torch.equal(results[0], results[1])
+    diff = ((results[0] - results[1]).norm() / results[0].norm()).item()
+    print(f"12 steps, host running ahead vs synchronised: update difference {diff:.3e}")
+    assert results[0].norm().item() > 0 and diff < 5e-2, diff
 
 
 @torch.no_grad()
