@@ -622,10 +622,18 @@ def run_vq(args):
         roof = breakdown = stage = cpu = None
         if rank == 0:
             from idf_b200 import native
+            for eng in vae._engines.values():
+                eng.use_graph = False
             before = native.launch_count
             vae(img)
-            launches = native.launch_count - before
+            launches = native.launch_count - before  # kernels per step (the timed steps replay them as CUDA graphs)
+            for eng in vae._engines.values():
+                eng.use_graph = True
+            for eng in vae._engines.values():  # per-launch timing needs the eager kernel sequence, not the graph replay
+                eng.use_graph = False
             by = timed_calls(lambda: vae(img), igemm_flops)
+            for eng in vae._engines.values():
+                eng.use_graph = True
             roof, breakdown = roofline_of(by, peaks, traffic_key="vq"), breakdown_of(by)
             # stage split: encoder / quantiser / decoder
             z = torch.empty(B, 3, 32, 32, device=dev)

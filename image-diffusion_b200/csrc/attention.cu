@@ -35,7 +35,22 @@ struct AttnParams {
   int heads;
   float* lse;  // optional (M, heads): log2-domain log-sum-exp of the scaled scores (training: consumed by the backward)
   int v_tok;   // 1: tmVT maps the token-major (M, 3C) QKV matrix, box (64, 128); V tiles are MN-major UMMA operands
+#ifdef IDF_ATTN_TRACE
+  long long* trace;  // debug build only (csrc/build.py --trace): clock64 stamps of CTA 0, [role][block][event]
+#endif
 };
+
+#ifdef IDF_ATTN_TRACE
+#define ATT_TRACE_BLOCKS 32
+#define ATT_TRACE_EVENTS 8
+#define ATT_STAMP(role, blk, evt)                                                                              \
+  do {                                                                                                         \
+    if (blockIdx.x == 0 && (blk) < ATT_TRACE_BLOCKS)                                                           \
+      p.trace[((role) * ATT_TRACE_BLOCKS + (blk)) * ATT_TRACE_EVENTS + (evt)] = clock64();                     \
+  } while (0)
+#else
+#define ATT_STAMP(role, blk, evt) do { } while (0)
+#endif
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -472,6 +487,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
             mbar_wait(&k_full[st], (e / ATTP_KSTAGES) & 1);
           }
           if (e > 0) mbar_wait(&s_empty[g], (e - 1) & 1);  // the group has pulled its previous S into registers
+          ATT_STAMP(0, e, g);  // S_g(e) issue
           tc_fence_after_sync();
           const uint64_t dq = umma_desc_kmajor(smem_u32(smem_q + ((item & 1) * 2 + g) * QK_BYTES), SWZ);
           const uint64_t dk = umma_desc_kmajor(smem_u32(smem_k + st * QK_BYTES), SWZ);
@@ -486,7 +502,9 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
         auto issue_pv = [&](int g, int e) {  // O_g (+)= P_g V_e
           const int item = e / n, j = e % n;
           const int vs = e % ATTP_VSTAGES;
+          ATT_STAMP(0, e, 2 + g);  // start waiting for P_g(e)
           mbar_wait(&p_full[g], e & 1);
+          ATT_STAMP(0, e, 4 + g);  // P_g(e) ready
           if (g == 0) mbar_wait(&v_full[vs], (e / ATTP_VSTAGES) & 1);
           if (j == 0 && item > 0) mbar_wait(&o_empty[g], (item - 1) & 1);  // previous item's output rows were read
           tc_fence_after_sync();
@@ -515,6 +533,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
               umma_bf16_ts(tmem_base + 256 + g * 64 + 48, tp + 8 * k, d1, idesc_l, (j > 0) || (k != 0));
           }
           umma_commit(&o_full[g]);
+          ATT_STAMP(0, e, 6 + g);  // P_g V(e) issued + committed
           if (g == 1) umma_commit(&v_empty[vs]);
         };
         if (E > 0) {
@@ -554,7 +573,15 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
     for (int item = 0; item < my_items; ++item) {
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n; ++j, ++e) {
+#ifdef IDF_ATTN_TRACE
+        const bool tr = quad == 0 && lane == 0;
+#define SM_STAMP(evt) do { if (tr) ATT_STAMP(1 + g, e, evt); } while (0)
+#else
+#define SM_STAMP(evt) do { } while (0)
+#endif
+        SM_STAMP(0);  // waiting for S(e)
         mbar_wait(&s_full[g], e & 1);
+        SM_STAMP(1);  // S(e) in TMEM
         tc_fence_after_sync();
         uint32_t sv[4][32];
 #pragma unroll
@@ -563,6 +590,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[g]);  // S now lives in registers
+        SM_STAMP(2);  // S(e) in registers
 
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -574,7 +602,9 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
         const float mrow = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
 
         // P_{j-1} V has to be complete before P is overwritten (and before the accumulator may be rescaled)
+        SM_STAMP(3);  // row max done, waiting for P V(e-1)
         if (j > 0) mbar_wait(&o_full[g], (e - 1) & 1);
+        SM_STAMP(4);  // P V(e-1) complete
         const bool grow = (mrow - m_run) * c > 8.0f;  // first block: m_run = -inf -> true
         if (__any_sync(0xffffffffu, grow)) {
           const float m_new = grow ? mrow : m_run;
@@ -625,10 +655,12 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
           }
           tmem_st_32x16(tmem_p + ch * 16, pk);
         }
+        SM_STAMP(5);  // exp phase issued
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
+        SM_STAMP(6);  // P(e) handed to the MMA thread
         l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
       }
       // all of this item's P V products for tile g are complete: fetch the output rows, free the accumulator
@@ -738,6 +770,18 @@ static int attention_fwd_impl(const void* qk, int64_t ld_qk, const void* vt, int
   p.heads = heads;
   p.lse = lse;
   p.v_tok = v_tok;
+#ifdef IDF_ATTN_TRACE
+  {
+    static long long* trace_buf = nullptr;
+    if (trace_buf == nullptr) {
+      cudaMalloc(&trace_buf, 3 * ATT_TRACE_BLOCKS * ATT_TRACE_EVENTS * sizeof(long long));
+      FILE* fh = fopen("/tmp/idf_attn_trace_ptr", "w");
+      if (fh) { fprintf(fh, "%llu", (unsigned long long)(uintptr_t)trace_buf); fclose(fh); }
+    }
+    cudaMemsetAsync(trace_buf, 0, 3 * ATT_TRACE_BLOCKS * ATT_TRACE_EVENTS * sizeof(long long), reinterpret_cast<cudaStream_t>(stream));
+    p.trace = trace_buf;
+  }
+#endif
 
   const int swz = head_dim <= 16 ? 32 : (head_dim <= 32 ? 64 : 128);
   const CUtensorMapSwizzle swz_enum = swz == 32 ? CU_TENSOR_MAP_SWIZZLE_32B

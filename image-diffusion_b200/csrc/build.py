@@ -39,6 +39,26 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
+def build_trace() -> str:
+    """Debug library with the attention kernel's clock64 trace hooks compiled in (tools/trace_attn.py): a separate
+    libidf_b200_trace.so selected with IDF_B200_LIB; the product library never contains the hooks."""
+    nvcc = _nvcc()
+    lib = os.path.join(PKG, "idf_b200", "libidf_b200_trace.so")
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, "trace_" + src.replace(".cu", ".o"))
+        res = subprocess.run([nvcc, *NVCC_FLAGS, "-DIDF_ATTN_TRACE", "-c", os.path.join(HERE, src), "-o", obj],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
+        objs.append(obj)
+    res = subprocess.run([nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     stamp_file = os.path.join(OBJ_DIR, "stamp.txt")
@@ -71,4 +91,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--trace" in sys.argv:
+        os.makedirs(OBJ_DIR, exist_ok=True)
+        print(build_trace())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -161,6 +161,134 @@ __global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv
   for (; pix < HW; pix += rows_per_iter) apply_store(*reinterpret_cast<const uint4*>(xb + (long long)pix * ldx), pix);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Large images (the VAE at 64x64 .. 128x128 pixels: 1 .. 8 MB per sample). The slab kernel above would hand each CTA
+// a 32-byte piece of every pixel row and re-read its 0.5 MB slab from HBM (hundreds of slabs in flight overflow the
+// 126 MB L2): measured 24 % of HBM peak over the VQ-VAE's 40 GroupNorms. Here a CTA owns a CHUNK OF WHOLE PIXEL ROWS
+// (fully coalesced 16-byte vectors):
+//   gn_rows_stats_kernel   per-(sample, chunk, group) partial sum / sum of squares (fp32, fixed order),
+//   gn_rows_apply_kernel   sums the sample's partials in chunk order, normalises (+ SiLU), writes bf16.
+// The host launches the pair for a few samples at a time, sized so that the group's input is still in L2 when the
+// apply kernel reads it again: HBM traffic = one read + one write. No atomics: bit-deterministic, batch invariant.
+// Thread t: vector v = t % V of row t / V (V = C / 8 vectors per row, R = blockDim / V rows per sweep).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GNR_THREADS = 256;
+constexpr int GNR_UNROLL = 4;
+
+__global__ void __launch_bounds__(GNR_THREADS) gn_rows_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                                    int HW, int C, int cpg, int rows_per_chunk,
+                                                                    float* __restrict__ part, int groups) {
+  __shared__ float red_s[GNR_THREADS * 8];
+  __shared__ float red_q[GNR_THREADS * 8];
+  __shared__ float ch_s[512], ch_q[512];
+  const int V = C / 8, R = blockDim.x / V;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  const int chunk = blockIdx.x, b = blockIdx.y, chunks = gridDim.x;
+  const int row0 = chunk * rows_per_chunk;
+  const int row1 = min(row0 + rows_per_chunk, HW);
+  const __nv_bfloat16* xb = x + ((long long)b * HW) * ldx + v * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  int row = row0 + r;
+  for (; row + (GNR_UNROLL - 1) * R < row1; row += GNR_UNROLL * R) {
+    uint4 t[GNR_UNROLL];
+#pragma unroll
+    for (int i = 0; i < GNR_UNROLL; ++i) t[i] = *reinterpret_cast<const uint4*>(xb + (long long)(row + i * R) * ldx);
+#pragma unroll
+    for (int i = 0; i < GNR_UNROLL; ++i) {
+      float f[8];
+      unpack8(t[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+    }
+  }
+  for (; row < row1; row += R) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xb + (long long)row * ldx), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { red_s[r * C + v * 8 + e] = s[e]; red_q[r * C + v * 8 + e] = q[e]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, d = 0.f;
+    for (int k = 0; k < R; ++k) { a += red_s[k * C + c]; d += red_q[k * C + c]; }
+    ch_s[c] = a; ch_q[c] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    float a = 0.f, d = 0.f;
+    for (int k = 0; k < cpg; ++k) { a += ch_s[threadIdx.x * cpg + k]; d += ch_q[threadIdx.x * cpg + k]; }
+    float* dst = part + (((long long)b * chunks + chunk) * groups + threadIdx.x) * 2;
+    dst[0] = a; dst[1] = d;
+  }
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(GNR_THREADS) gn_rows_apply_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                                    __nv_bfloat16* __restrict__ y, long long ldy,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, int HW, int C,
+                                                                    int cpg, int rows_per_chunk, float eps,
+                                                                    const float* __restrict__ part, int groups) {
+  __shared__ float g_mean[GN_MAX_GPS * 2], g_rstd[GN_MAX_GPS * 2];
+  const int V = C / 8, R = blockDim.x / V;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  const int chunk = blockIdx.x, b = blockIdx.y, chunks = gridDim.x;
+  float ga[8], be[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { ga[e] = gamma[v * 8 + e]; be[e] = beta[v * 8 + e]; }
+  if (threadIdx.x < groups) {
+    const float* src = part + ((long long)b * chunks * groups + threadIdx.x) * 2;
+    float a = 0.f, d = 0.f;
+    for (int k = 0; k < chunks; ++k) { a += src[(long long)k * groups * 2]; d += src[(long long)k * groups * 2 + 1]; }
+    const float inv_cnt = 1.f / ((float)HW * (float)cpg);
+    const float mean = a * inv_cnt;
+    const float var = fmaxf(d * inv_cnt - mean * mean, 0.f);
+    g_mean[threadIdx.x] = mean;
+    g_rstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int g = (v * 8 + e) / cpg;
+    sc[e] = g_rstd[g] * ga[e];
+    sh[e] = be[e] - g_mean[g] * g_rstd[g] * ga[e];
+  }
+  const int row0 = chunk * rows_per_chunk;
+  const int row1 = min(row0 + rows_per_chunk, HW);
+  const __nv_bfloat16* xb = x + ((long long)b * HW) * ldx + v * 8;
+  __nv_bfloat16* yb = y + ((long long)b * HW) * ldy + v * 8;
+  auto apply_store = [&](const uint4& t, int row) {
+    float f[8];
+    unpack8(t, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float u = fmaf(f[e], sc[e], sh[e]);
+      if (SILU) u = silu_tanh(u);
+      f[e] = u;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(yb + (long long)row * ldy) = o;
+  };
+  int row = row0 + r;
+  for (; row + (GNR_UNROLL - 1) * R < row1; row += GNR_UNROLL * R) {
+    uint4 t[GNR_UNROLL];
+#pragma unroll
+    for (int i = 0; i < GNR_UNROLL; ++i) t[i] = *reinterpret_cast<const uint4*>(xb + (long long)(row + i * R) * ldx);
+#pragma unroll
+    for (int i = 0; i < GNR_UNROLL; ++i) apply_store(t[i], row + i * R);
+  }
+  for (; row < row1; row += R) apply_store(*reinterpret_cast<const uint4*>(xb + (long long)row * ldx), row);
+}
+
 // one CTA per row; cols <= 8 * blockDim * 4
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, long long ld_in,
                                                            __nv_bfloat16* __restrict__ out, long long ld_out,
@@ -256,6 +384,48 @@ extern "C" int idf_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t l
                                   const float* beta, int32_t B, int32_t HW, int32_t C, int32_t groups, float eps,
                                   int32_t apply_silu, idf_stream_t stream) {
   return groupnorm_impl(x, ldx, y, ldy, gamma, beta, B, HW, C, groups, eps, apply_silu, nullptr, stream);
+}
+
+extern "C" int idf_groupnorm_silu_rows(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,
+                                       const float* beta, int32_t B, int32_t HW, int32_t C, int32_t groups, float eps,
+                                       int32_t apply_silu, float* ws, int64_t ws_bytes, int64_t l2_bytes,
+                                       idf_stream_t stream) {
+  if (!x || !y || !gamma || !beta || !ws) return fail(IDF_ERR_ARG, "groupnorm_rows: null pointer");
+  if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups != 0 || C % 8 != 0 || C > 512 || groups > 2 * GN_MAX_GPS ||
+      GNR_THREADS / (C / 8) < 1)
+    return fail(IDF_ERR_UNSUPPORTED, "groupnorm_rows: C = %d (multiple of 8, <= 512) in %d groups unsupported", C, groups);
+  if (ldx % 8 != 0 || ldy % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
+    return fail(IDF_ERR_ARG, "groupnorm_rows: 16-byte alignment required");
+  const int V = C / 8, R = GNR_THREADS / V, threads = V * R;
+  int rows_per_chunk = 4 * GNR_UNROLL * R;  // four unrolled sweeps per CTA ...
+  while (rows_per_chunk < 256) rows_per_chunk *= 2;  // ... and at least 256 rows
+  const int chunks = (HW + rows_per_chunk - 1) / rows_per_chunk;
+  if ((long long)B * chunks * groups * 2 * 4 > ws_bytes)
+    return fail(IDF_ERR_ARG, "groupnorm_rows: workspace needs %lld bytes", (long long)B * chunks * groups * 2 * 4);
+  // samples per launch pair: their input (read twice) should still be in L2 for the second read
+  const long long sample_bytes = (long long)HW * C * 2;
+  long long gsz = l2_bytes > 0 ? l2_bytes / sample_bytes : B;
+  if (gsz < 1) gsz = 1;
+  if (gsz > B) gsz = B;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const int cpg = C / groups;
+  for (int b0 = 0; b0 < B; b0 += (int)gsz) {
+    const int nb = (int)(B - b0 < gsz ? B - b0 : gsz);
+    dim3 grid(chunks, nb);
+    const __nv_bfloat16* xs = xp + (long long)b0 * HW * ldx;
+    __nv_bfloat16* ys = yp + (long long)b0 * HW * ldy;
+    float* part = ws + (long long)b0 * chunks * groups * 2;
+    gn_rows_stats_kernel<<<grid, threads, 0, st>>>(xs, (long long)ldx, HW, C, cpg, rows_per_chunk, part, groups);
+    if (apply_silu)
+      gn_rows_apply_kernel<true><<<grid, threads, 0, st>>>(xs, (long long)ldx, ys, (long long)ldy, gamma, beta, HW, C, cpg,
+                                                           rows_per_chunk, eps, part, groups);
+    else
+      gn_rows_apply_kernel<false><<<grid, threads, 0, st>>>(xs, (long long)ldx, ys, (long long)ldy, gamma, beta, HW, C,
+                                                            cpg, rows_per_chunk, eps, part, groups);
+  }
+  return check_cuda(cudaGetLastError(), "groupnorm_rows launch");
 }
 
 extern "C" int idf_groupnorm_silu_train(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma,

@@ -316,6 +316,8 @@ class VaeEngine:
         self.ws = Workspace(device)
         self.G, self.heads = arch["num_groups"], arch["num_heads"]
         self.use_graph = __import__("os").environ.get("IDF_VAE_GRAPH", "1") != "0"
+        self.gn_rows = __import__("os").environ.get("IDF_GN_ROWS", "1") != "0"
+        self.tc_tail = __import__("os").environ.get("IDF_VAE_TC_TAIL", "1") != "0"
         self.graphs = {}
 
     def prepare(self):
@@ -329,6 +331,14 @@ class VaeEngine:
                 p = f"{prefix}.{i}"
                 if kind in ("conv1x1", "conv3x3"):
                     w[p + ".w"], w[p + ".b"] = _f32(sd[p + ".weight"]), _f32(sd[p + ".bias"])
+                    if kind == "conv3x3" and cin % 64 == 0 and cout <= 128:
+                        # narrow tail conv (128 -> 3, 384 -> z) on the tensor cores: output channels zero-padded to one
+                        # 128-wide tile (the CUDA-core kernel runs at ~6 TFLOP/s: 15 % of a batch-48 decode)
+                        wp = torch.zeros(128, 9 * cin, device=sd[p + ".weight"].device, dtype=BF16)
+                        wp[:cout] = pk(sd[p + ".weight"])
+                        bp = torch.zeros(128, device=wp.device, dtype=torch.float32)
+                        bp[:cout] = sd[p + ".bias"].detach().float()
+                        w[p + ".wtc"], w[p + ".btc"] = wp, bp
                 elif kind == "res":
                     w[p + ".g1w"], w[p + ".g1b"] = _f32(sd[p + ".branch.0.weight"]), _f32(sd[p + ".branch.0.bias"])
                     w[p + ".g2w"], w[p + ".g2b"] = _f32(sd[p + ".branch.3.weight"]), _f32(sd[p + ".branch.3.bias"])
@@ -355,16 +365,24 @@ class VaeEngine:
         self.packed.install(w)
 
     # ---- layer runners -------------------------------------------------------------------------
+    def _gn(self, x_t, y_t, gw, gb, B, HW, C, silu):
+        """GroupNorm(+SiLU): tensors far beyond L2 (large batches at the 64x64 / 128x128 stages) take the whole-row
+        kernels (fully coalesced, two launches), everything else the slab kernel (one launch)."""
+        if B * HW * C * 2 >= ops.GN_ROWS_MIN_TOTAL_BYTES and self.gn_rows:
+            part = self.ws.get("gn_part", 1, B * ((HW + 255) // 256) * self.G * 2, torch.float32)
+            return ops.groupnorm_silu_rows(x_t, y_t, gw, gb, B, HW, C, self.G, silu, part)
+        return ops.groupnorm_silu(x_t, y_t, gw, gb, B, HW, C, self.G, silu)
+
     def _res(self, p, x: Act, cout) -> Act:
         w, ws, G = self.packed.w, self.ws, self.G
         B, H, W = x.grid
         M, HW, cin = x.M, x.H * x.W, x.C
         h1 = ws.get("h1", M, cin)
-        ops.groupnorm_silu(x.t, h1, w[p + ".g1w"], w[p + ".g1b"], B, HW, cin, G, True)
+        self._gn(x.t, h1, w[p + ".g1w"], w[p + ".g1b"], B, HW, cin, True)
         y1 = ws.get("y1", M, cout)
         ops.igemm([(h1, x.grid, cin, 9)], w[p + ".w1"], cout, y1, bias=w[p + ".b1"])
         h2 = ws.get("h2", M, cout)
-        ops.groupnorm_silu(y1, h2, w[p + ".g2w"], w[p + ".g2b"], B, HW, cout, G, True)
+        self._gn(y1, h2, w[p + ".g2w"], w[p + ".g2b"], B, HW, cout, True)
         dst = ws.get("xa" if x.t is not self.ws.bufs.get(("xa", M, cout, BF16)) else "xb", M, cout)
         if cin != cout:
             ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[p + ".w2"], cout, dst, bias=w[p + ".b2"])
@@ -380,7 +398,7 @@ class VaeEngine:
         M, T, C = x.M, x.H * x.W, x.C
         hd = C // self.heads
         h3 = ws.get("h3", M, C)
-        ops.groupnorm_silu(x.t, h3, w[p + ".gw"], w[p + ".gb"], B, T, C, self.G, False)
+        self._gn(x.t, h3, w[p + ".gw"], w[p + ".gb"], B, T, C, False)
         qk = ws.get("qk", M, 2 * C)
         vt = ws.get("vt", C, M)
         ops.igemm([(h3, (1, 1, M), C, 1)], w[p + ".wqkv"], 3 * C, qk, bias=w[p + ".bqkv"], vt=vt, vt_col0=2 * C)
@@ -434,7 +452,12 @@ class VaeEngine:
             elif kind == "conv3x3":  # last narrow conv: bf16 rows -> fp32 NCHW
                 last = n == len(prog) - 1
                 dst = out_nchw if last else ws.get("tail", B * cout, x.H * x.W, torch.float32).view(B, cout, x.H, x.W)
-                ops.conv3x3_small_cout(x.t, w[p + ".w"], w[p + ".b"], dst)
+                if self.tc_tail and (p + ".wtc") in w:
+                    wide = ws.get("tailw", x.M, 128)
+                    ops.igemm([(x.t, x.grid, x.C, 9)], w[p + ".wtc"], 128, wide, bias=w[p + ".btc"])
+                    ops.rows_to_nchw(wide, dst)  # first `cout` columns -> fp32 NCHW
+                else:
+                    ops.conv3x3_small_cout(x.t, w[p + ".w"], w[p + ".b"], dst)
                 cur = dst
             elif kind == "res":
                 x = self._res(p, x, cout)
@@ -442,7 +465,7 @@ class VaeEngine:
                 x = self._attn(p, x)
             elif kind == "gn_silu":
                 h = ws.get("h1", x.M, x.C)
-                ops.groupnorm_silu(x.t, h, w[p + ".gw"], w[p + ".gb"], x.B, x.H * x.W, x.C, self.G, True)
+                self._gn(x.t, h, w[p + ".gw"], w[p + ".gb"], x.B, x.H * x.W, x.C, True)
                 x = Act(h, x.B, x.H, x.W, x.C)
             elif kind == "up":
                 # nearest-2x + conv3x3 as four sub-pixel convolutions on the low-resolution tensor, one launch

@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libidf_b200.so")
+LIB_PATH = os.environ.get("IDF_B200_LIB") or os.path.join(_HERE, "libidf_b200.so")  # (override: debug builds)
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "idf_conv2d_igemm": [C.POINTER(IgemmArgs)],
     "idf_tile_walk_trace": [_i32, _i32, _i32, _i32, _i32, _vp],
     "idf_groupnorm_silu": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32],
+    "idf_groupnorm_silu_rows": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _i64, _i64],
     "idf_attention_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32],
     "idf_softmax_rows": [_vp, _i64, _vp, _i64, _i32, _i32, _f32],
     "idf_embed_time_class": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],

@@ -145,6 +145,18 @@ int idf_groupnorm_silu(const void* x, int64_t ldx, void* y, int64_t ldy, const f
                        idf_stream_t stream);
 
 /*
+ * idf_groupnorm_silu_rows — idf_groupnorm_silu for LARGE images (>= ~1 MB per sample: the VAE's 64x64 .. 128x128
+ * stages, components.py:31-35 inside Residual): CTAs own chunks of whole pixel rows (fully coalesced), statistics go
+ * through deterministic per-chunk partials in `ws` (fp32, at least B * ceil(HW / 256) * groups * 2 elements), and the
+ * work is issued a few samples at a time so that the second read of a sample is served by L2 (l2_bytes = budget for
+ * one group of samples, e.g. 48 MB; <= 0: all samples in one pair of launches). Same result contract as
+ * idf_groupnorm_silu (fp32 statistics, bit-deterministic, batch invariant). C <= 512, C % 8 == 0.
+ */
+int idf_groupnorm_silu_rows(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
+                            int32_t B, int32_t HW, int32_t C, int32_t groups, float eps, int32_t apply_silu, float* ws,
+                            int64_t ws_bytes, int64_t l2_bytes, idf_stream_t stream);
+
+/*
  * idf_attention_fwd — fused softmax(Q K^T * scale) V per (sample, head), flash style on tcgen05 with the score
  * tile in TMEM. Replaces components.py:86-94 (head split, QK^T / sqrt(hd), softmax, PV, head merge).
  *   qk   bf16 (M, ld_qk): columns [0, C) are Q, [C, 2C) are K, C = heads*head_dim, head-major channel blocks.

@@ -430,3 +430,30 @@ def test_igemm_batched_second_operand_is_a_batch_of_gemms(B, T, hd):
     v = vt.float().t().reshape(B, T, hd)
     oref = torch.bmm(pm.float().view(B, T, T), v).view(M, hd)
     assert rel_err(o[:, hd:].float(), oref) < 6e-3
+
+
+@pytest.mark.parametrize("B,C,H,silu", [(3, 128, 128, True), (2, 256, 64, True), (5, 384, 64, False), (2, 256, 128, True),
+                                        (7, 128, 20, True)])
+def test_groupnorm_rows_large_images(B, C, H, silu):
+    """Whole-row GroupNorm kernels (VAE stages): against F.group_norm, and bit-identical for any L2 grouping of the
+    samples (the statistics never mix samples and are summed in a fixed order)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(C + H)
+    x = torch.randn(B, C, H, H, device=DEV, generator=g) * 1.7 + 0.3
+    gamma = 1 + 0.2 * torch.randn(C, device=DEV, generator=g)
+    beta = 0.2 * torch.randn(C, device=DEV, generator=g)
+    xr = rows(x)
+    ws = torch.empty(B * ((H * H + 255) // 256) * 32 * 2, device=DEV)
+    y = torch.empty_like(xr)
+    ops.groupnorm_silu_rows(xr, y, gamma, beta, B, H * H, C, 32, silu, ws)
+    ref = F.group_norm(bf(x), 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_err(unrows(y, B, H, H), ref) < 6e-3
+    y1 = torch.empty_like(xr)
+    ops.call("idf_groupnorm_silu_rows", xr.data_ptr(), xr.stride(0), y1.data_ptr(), y1.stride(0), gamma.data_ptr(),
+             beta.data_ptr(), B, H * H, C, 32, 1e-5, 1 if silu else 0, ws.data_ptr(), ws.numel() * 4, 1)  # one sample per pair
+    assert torch.equal(y, y1)
+    y2 = torch.empty_like(xr)
+    ops.groupnorm_silu(xr, y2, gamma, beta, B, H * H, C, 32, silu)  # the slab kernel: same maths, other summation order
+    assert rel_err(y2.float(), y.float()) < 4e-3

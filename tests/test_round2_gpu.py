@@ -134,7 +134,7 @@ def test_sampling_follows_training_and_load_state_dict():
         ts.step(lat, lab, 3e-3)   # large lr: the weights move far beyond the parity tolerance
     m.eval()
     b = check("after 3 optimizer steps (same cached sampler and graph)", sampler)
-    assert rel_rms(a, b) > 5e-2  # the update really changed the output: a stale engine would fail the check above
+    assert rel_rms(a, b) > 2e-2  # the update moved the output beyond the parity gate: a stale engine fails the check above
     with torch.no_grad():
         out = m(x_T, torch.full((N,), 700, device=DEV), labels)   # plain Unet.forward sees the new weights too
         ref = O.unet_forward({k: v.detach() for k, v in m.state_dict().items()}, SMALL, x_T,
