@@ -74,6 +74,74 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restric
   }
 }
 
+// The same linear layer for MANY rows (the sampler's per-timestep table: R = num_steps * (classes + 1) = 4000 rows, 41 GFLOP
+// in all): a shared-memory tiled fp32 GEMM, 64 x 64 outputs per CTA, 4 x 4 per thread. The warp-per-column kernel above
+// streams each weight row once per 8 input rows - fine for a batch of rows, 2.4 TFLOP/s (15.5 ms per weight version) for
+// the table. fp32 throughout: the time bias keeps the accuracy of the reference's fp32 embedding path.
+constexpr int LT_BM = 64, LT_BN = 64, LT_BK = 16;
+template <bool SILU_OUT>
+__global__ void __launch_bounds__(256) linear_tiled_kernel(const float* __restrict__ X, int ldx,
+                                                           const float* __restrict__ W, const float* __restrict__ b,
+                                                           float* __restrict__ Y, int ldy, int R, int K, int J,
+                                                           const float* __restrict__ cls,
+                                                           const int64_t* __restrict__ ctx,
+                                                           const float* __restrict__ mask) {
+  __shared__ float As[LT_BK][LT_BM + 4];
+  __shared__ float Bs[LT_BK][LT_BN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int r0 = blockIdx.y * LT_BM, j0 = blockIdx.x * LT_BN;
+  const int lrow = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;  // this thread's float4 of each operand tile
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += LT_BK) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + lrow < R) a = *reinterpret_cast<const float4*>(X + (long long)(r0 + lrow) * ldx + k0 + lk);
+    if (j0 + lrow < J) w = __ldg(reinterpret_cast<const float4*>(W + (long long)(j0 + lrow) * K + k0 + lk));
+    As[lk + 0][lrow] = a.x; As[lk + 1][lrow] = a.y; As[lk + 2][lrow] = a.z; As[lk + 3][lrow] = a.w;
+    Bs[lk + 0][lrow] = w.x; Bs[lk + 1][lrow] = w.y; Bs[lk + 2][lrow] = w.z; Bs[lk + 3][lrow] = w.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LT_BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = j0 + tx * 4 + j;
+      if (col >= J) continue;
+      float v = acc[i][j] + b[col];
+      if (cls != nullptr && ctx != nullptr) v += (mask ? mask[r] : 1.f) * cls[(long long)ctx[r] * J + col];
+      Y[(long long)r * ldy + col] = SILU_OUT ? silu_f(v) : v;
+    }
+  }
+}
+
+template <bool SILU_OUT>
+static void launch_linear(const float* X, int ldx, const float* W, const float* b, float* Y, int ldy, int R, int K, int J,
+                          const float* cls, const int64_t* ctx, const float* mask, cudaStream_t s) {
+  if (R >= 256 && K % LT_BK == 0 && ldx % 4 == 0) {
+    dim3 grid((J + LT_BN - 1) / LT_BN, (R + LT_BM - 1) / LT_BM);
+    linear_tiled_kernel<SILU_OUT><<<grid, 256, 0, s>>>(X, ldx, W, b, Y, ldy, R, K, J, cls, ctx, mask);
+  } else {
+    const int wpb = 8;  // warps per block
+    linear_rows_kernel<SILU_OUT><<<(J + wpb - 1) / wpb, 256, 0, s>>>(X, ldx, W, b, Y, ldy, R, K, J, cls, ctx, mask);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // CFG mix + DDPM ancestral step (diffusion.py:55, components.py:405-424)
 // ---------------------------------------------------------------------------------------------
@@ -608,14 +676,10 @@ extern "C" int idf_embed_time_class(const int64_t* t, const int64_t* ctx, const 
   float* e = scratch;               // (R, D)    sin/cos, later silu(temb)
   float* h1 = scratch + (long long)R * D;  // (R, 4D)
   sincos_kernel<<<(R * D + 255) / 256, 256, 0, s>>>(t, factor, e, R, D);
-  const int wpb = 8;  // warps per block
-  linear_rows_kernel<true><<<(4 * D + wpb - 1) / wpb, 256, 0, s>>>(e, D, w1, b1, h1, 4 * D, R, D, 4 * D, nullptr,
-                                                                   nullptr, nullptr);
+  launch_linear<true>(e, D, w1, b1, h1, 4 * D, R, D, 4 * D, nullptr, nullptr, nullptr, s);
   // temb = Linear2(h1) + mask * class_w[ctx]; every consumer applies SiLU first (components.py:486), so store that
-  linear_rows_kernel<true><<<(D + wpb - 1) / wpb, 256, 0, s>>>(h1, 4 * D, w2, b2, e, D, R, 4 * D, D, class_w, ctx,
-                                                               ctx_mask);
-  linear_rows_kernel<false><<<(P + wpb - 1) / wpb, 256, 0, s>>>(e, D, wp, bp, out, P, R, D, P, nullptr, nullptr,
-                                                                nullptr);
+  launch_linear<true>(h1, 4 * D, w2, b2, e, D, R, 4 * D, D, class_w, ctx, ctx_mask, s);
+  launch_linear<false>(e, D, wp, bp, out, P, R, D, P, nullptr, nullptr, nullptr, s);
   return check_cuda(cudaGetLastError(), "embed launch");
 }
 

@@ -75,7 +75,9 @@ class GradBuckets:
 class DiffusionTrainStep:
     def __init__(self, unet, scheduler, batch: int, latent_shape=(3, 32, 32), clip_grad: float | None = 1.0,
                  cond_drop_prob: float = 0.15, sample_latents: bool = True, betas=(0.9, 0.999), eps: float = 1e-8,
-                 group=None, use_graph: bool = True):
+                 group=None, use_graph: bool = True, data_parallel: bool = True):
+        """data_parallel=False keeps the step local even when a process group is initialised (single-rank reference
+        runs next to a data-parallel job must not enter collectives the other ranks never call)."""
         self.unet = unet
         dev = unet.in_conv.weight.device
         if dev.type != "cuda":
@@ -91,6 +93,8 @@ class DiffusionTrainStep:
         self.exp_avg_sq = torch.zeros(n, device=dev, dtype=F32)
         self.step_count = 0
         self.buckets = GradBuckets(self.eng.flat_grad, self.eng.bucket_ends, group)
+        if not data_parallel:
+            self.buckets.world = 1
         self.world = self.buckets.world
         if self.world > 1:
             # replicas start from rank 0's parameters and optimizer state (what torch DDP does at construction);

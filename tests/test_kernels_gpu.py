@@ -252,6 +252,21 @@ def test_embed_time_class():
     temb = F.linear(F.silu(F.linear(e, w1, b1)), w2, b2)
     ref2 = F.linear(F.silu(temb), wp, bp)
     assert (out2 - ref2).abs().max().item() < 2e-3
+    # many rows (the sampler's per-timestep table): the shared-memory tiled fp32 GEMM path, ragged row / column counts
+    R = 1003
+    t = torch.randint(0, 1000, (R,), device=DEV, generator=g)
+    ctx = torch.randint(0, 3, (R,), device=DEV, generator=g)
+    mask = (torch.rand(R, device=DEV, generator=g) > 0.3).float()
+    Pr = 4840
+    out3 = torch.empty(R, Pr, device=DEV)
+    ops.embed_time_class(t, ctx, mask, factor, w1, b1, w2, b2, cw, wp[:Pr].contiguous(), bp[:Pr].contiguous(), out3,
+                         torch.empty(R * 5 * D, device=DEV))
+    with torch.no_grad():
+        e = t[:, None] / factor
+        e = torch.cat([torch.sin(e), torch.cos(e)], -1)
+        temb = F.linear(F.silu(F.linear(e, w1, b1)), w2, b2) + mask[:, None] * cw[ctx]
+        ref3 = F.linear(F.silu(temb), wp[:Pr], bp[:Pr])
+    assert (out3 - ref3).abs().max().item() < 2e-3, (out3 - ref3).abs().max().item()
 
 
 def test_small_channel_convs_and_movers():

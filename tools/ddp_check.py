@@ -28,10 +28,11 @@ mask = (torch.rand(world * b, generator=g) > 0.15).float().to(dev)
 sched = Scheduler(1000, device=dev)
 
 
-def make(batch):
-    torch.manual_seed(2018)
+def make(batch, data_parallel=True):
+    torch.manual_seed(2018 + (rank if data_parallel else 0))  # rank-dependent init: the constructor must broadcast rank 0's
     m = Unet(**UNET_ARCH).to(dev).train()
-    return m, DiffusionTrainStep(m, sched, batch, (3, 32, 32), clip_grad=1.0, use_graph=(os.environ.get("DDP_CHECK_GRAPH", "1") == "1"))
+    return m, DiffusionTrainStep(m, sched, batch, (3, 32, 32), clip_grad=1.0, data_parallel=data_parallel,
+                                 use_graph=(os.environ.get("DDP_CHECK_GRAPH", "1") == "1"))
 
 
 def load(ts, sl):
@@ -47,8 +48,7 @@ g_ddp = ts.eng.flat_grad.clone() / world
 ok = True
 if rank == 0:
     # single-GPU reference on the concatenated batch (no process group use: world forced to 1)
-    m1, ts1 = make(world * b)
-    ts1.world = 1; ts1.buckets.world = 1
+    m1, ts1 = make(world * b, data_parallel=False)
     load(ts1, slice(0, world * b))
     ts1.step(lat, lab, 1e-3, draw=False)
     torch.cuda.synchronize()
