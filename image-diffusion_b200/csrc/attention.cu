@@ -35,7 +35,6 @@ struct AttnParams {
   int heads;
   float* lse;  // optional (M, heads): log2-domain log-sum-exp of the scaled scores (training: consumed by the backward)
   int v_tok;   // 1: tmVT maps the token-major (M, 3C) QKV matrix, box (64, 128); V tiles are MN-major UMMA operands
-  int p_f16;   // pipelined kernel, head_dim <= 48: probabilities as fp16 pairs straight out of ex2.approx.f16x2
 #ifdef IDF_ATTN_TRACE
   long long* trace;  // debug build only (csrc/build.py --trace): clock64 stamps of CTA 0, [role][block][event]
 #endif
@@ -57,6 +56,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^x on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, relative error 7.5e-5: far below the
+// bf16 rounding of the probabilities): x = n + f, f in [-0.5, 0.5]; 2^f by Horner; n goes into the exponent field with
+// one integer multiply-add. 9 FMA-pipe instructions, no MUFU. IDF_ATTN_POLY (compile time) = how many of every 8
+// exponentials of the pipelined kernel's softmax take this path instead of MUFU.EX2.
+#ifndef IDF_ATTN_POLY
+#define IDF_ATTN_POLY 0
+#endif
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;  // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.055171460f, f, 0.24261086f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992812f);
+  return __uint_as_float(__float_as_uint(t) * 8388608u + __float_as_uint(p));  // p * 2^n
 }
 
 template <int HD>
@@ -478,10 +494,8 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
       // ------------------------------------------------------------------ MMA issuer
       if (elect_one()) {
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-        // P as fp16 (p_f16): A format F16 (0) instead of BF16 (1 << 7); V stays bf16 (kind::f16 takes mixed 16-bit types)
-        const uint32_t a_fmt_clear = p.p_f16 ? ~(1u << 7) : ~0u;
-        const uint32_t idesc_o = umma_idesc_bf16(128, HD) & a_fmt_clear;
-        const uint32_t idesc_o_mn = umma_idesc_bf16(128, HD, 0, 1) & a_fmt_clear;
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
+        constexpr uint32_t idesc_o_mn = umma_idesc_bf16(128, HD, 0, 1);
         auto issue_s = [&](int g, int e) {  // S_g = Q_g K_e^T
           const int item = e / n, j = e % n;
           const int st = e % ATTP_KSTAGES;
@@ -529,7 +543,7 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
                            (j > 0) || (k != 0));  // accumulate over the item's key blocks
           }
           if constexpr (LSUM) {
-            const uint32_t idesc_l = umma_idesc_bf16(128, 16) & a_fmt_clear;
+            constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16);
             const uint64_t d1 = umma_desc_kmajor(smem_u32(smem_ones), 128);
 #pragma unroll
             for (int k = 0; k < 8; ++k)  // l_g (+)= P_g x 1 into the accumulator's spare columns [48, 64)
@@ -595,6 +609,54 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
         if (lane == 0) mbar_arrive(&s_empty[g]);  // S now lives in registers
         SM_STAMP(2);  // S(e) in registers
 
+        // rescale of the output accumulator (and of the row sums kept next to it) by alpha = 2^((m_old - m_new) c)
+        auto rescale = [&](const float alpha) {
+          tc_fence_after_sync();
+#pragma unroll
+          for (int d0 = 0; d0 < HD; d0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_o + d0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
+            tmem_st_32x16(tmem_o + d0, v);
+          }
+          if constexpr (LSUM) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_o + 48, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
+            tmem_st_32x16(tmem_o + 48, v);
+          }
+          tmem_st_wait();
+          tc_fence_before_sync();
+        };
+        float ps[4];
+        // P = 2^(S c - mc) as packed bf16 pairs into tensor memory
+        auto exp_store = [&](const float mc) {
+          ps[0] = ps[1] = ps[2] = ps[3] = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t pk[16];  // 32 probabilities of this row as 16 packed bf16 pairs -> 16 TMEM columns
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float ev[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float arg = fmaf(__uint_as_float(sv[ch][8 * q + i]), c, -mc);
+                // (interleaved: every MUFU.EX2 of the pair that feeds one bf16 pack has a polynomial neighbour)
+                ev[i] = ((i * IDF_ATTN_POLY) % 8 < IDF_ATTN_POLY) ? poly_exp2(arg) : fast_exp2(arg);
+                if constexpr (!LSUM) ps[i & 3] += ev[i];
+              }
+              pk[4 * q + 0] = pack_bf16x2(ev[0], ev[1]);
+              pk[4 * q + 1] = pack_bf16x2(ev[2], ev[3]);
+              pk[4 * q + 2] = pack_bf16x2(ev[4], ev[5]);
+              pk[4 * q + 3] = pack_bf16x2(ev[6], ev[7]);
+            }
+            tmem_st_32x16(tmem_p + ch * 16, pk);
+          }
+        };
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)
@@ -614,75 +676,9 @@ __global__ void __launch_bounds__(ATTP_THREADS, 1) attention_pipe_kernel(const _
           const float alpha = fast_exp2((m_run - m_new) * c);  // 1 for rows that keep their maximum
           m_run = m_new;
           l_run *= alpha;
-          if (j > 0) {
-            tc_fence_after_sync();
-#pragma unroll
-            for (int d0 = 0; d0 < HD; d0 += 16) {
-              uint32_t v[16];
-              tmem_ld_32x16(tmem_o + d0, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
-              tmem_st_32x16(tmem_o + d0, v);
-            }
-            if constexpr (LSUM) {
-              uint32_t v[16];
-              tmem_ld_32x16(tmem_o + 48, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
-              tmem_st_32x16(tmem_o + 48, v);
-            }
-            tmem_st_wait();
-            tc_fence_before_sync();
-          }
+          if (j > 0) rescale(alpha);
         }
-        const float mc = m_run * c;
-
-        float ps[4] = {0.f, 0.f, 0.f, 0.f};
-        if (LSUM && p.p_f16) {
-          // Packed path: two scaled scores -> one fp16 pair (F2FP) -> ONE MUFU.EX2.F16x2 whose result IS the packed
-          // pair of probabilities that goes to tensor memory. Same MUFU time per element (the packed op is half
-          // rate), but nothing waits on a MUFU result any more: in the fp32 path every bf16 pack sits two MUFU issue
-          // slots (16 clk) behind its operands while the result takes ~26, and since a warp issues in order those
-          // stalls idle the MUFU pipe whenever the other softmax group is not in its exp phase too (intra-kernel
-          // trace: a group alone reached 56 % of the MUFU rate; the two groups overlap only ~half of the time).
-          // fp16 probabilities carry 11 mantissa bits (bf16: 8); the exponent argument is rounded to fp16 (|arg| <= ~8
-          // for every probability that matters: <= 2^-8 absolute, i.e. <= 0.3 % relative error in p); no flush to
-          // zero, so the tail down to 2^-24 of the row maximum survives as fp16 subnormals.
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a0 = fmaf(__uint_as_float(sv[ch][2 * i]), c, -mc);
-              const float a1 = fmaf(__uint_as_float(sv[ch][2 * i + 1]), c, -mc);
-              uint32_t h;
-              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(a1), "f"(a0));
-              asm("ex2.approx.f16x2 %0, %1;" : "=r"(pk[i]) : "r"(h));
-            }
-            tmem_st_32x16(tmem_p + ch * 16, pk);
-          }
-        } else {
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t pk[16];  // 32 probabilities of this row as 16 packed bf16 pairs -> 16 TMEM columns
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float ev[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                ev[i] = fast_exp2(fmaf(__uint_as_float(sv[ch][8 * q + i]), c, -mc));
-                if constexpr (!LSUM) ps[i & 3] += ev[i];
-              }
-              pk[4 * q + 0] = pack_bf16x2(ev[0], ev[1]);
-              pk[4 * q + 1] = pack_bf16x2(ev[2], ev[3]);
-              pk[4 * q + 2] = pack_bf16x2(ev[4], ev[5]);
-              pk[4 * q + 3] = pack_bf16x2(ev[6], ev[7]);
-            }
-            tmem_st_32x16(tmem_p + ch * 16, pk);
-          }
-        }
+        exp_store(m_run * c);
         SM_STAMP(5);  // exp phase issued
         tmem_st_wait();
         tc_fence_before_sync();
@@ -798,9 +794,6 @@ static int attention_fwd_impl(const void* qk, int64_t ld_qk, const void* vt, int
   p.heads = heads;
   p.lse = lse;
   p.v_tok = v_tok;
-  // IDF_ATTN_F16P=1: probabilities as fp16 pairs out of ex2.approx.f16x2 (experiment; default fp32 ex2 + bf16 pack)
-  static const int p_f16 = [] { const char* e = getenv("IDF_ATTN_F16P"); return e ? atoi(e) : 0; }();
-  p.p_f16 = p_f16;
 #ifdef IDF_ATTN_TRACE
   {
     static long long* trace_buf = nullptr;

@@ -39,15 +39,16 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
-def build_trace() -> str:
-    """Debug library with the attention kernel's clock64 trace hooks compiled in (tools/trace_attn.py): a separate
-    libidf_b200_trace.so selected with IDF_B200_LIB; the product library never contains the hooks."""
+def build_trace(tag: str = "trace", defines=("-DIDF_ATTN_TRACE",)) -> str:
+    """Variant library for experiments, selected at run time with IDF_B200_LIB (the product library is never touched):
+    `--trace`: the attention kernel's clock64 trace hooks (tools/trace_attn.py); `--variant TAG -DNAME=VALUE ...`: any
+    compile-time switch (e.g. -DIDF_ATTN_POLY=4)."""
     nvcc = _nvcc()
-    lib = os.path.join(PKG, "idf_b200", "libidf_b200_trace.so")
+    lib = os.path.join(PKG, "idf_b200", f"libidf_b200_{tag}.so")
     objs = []
     for src in SOURCES:
-        obj = os.path.join(OBJ_DIR, "trace_" + src.replace(".cu", ".o"))
-        res = subprocess.run([nvcc, *NVCC_FLAGS, "-DIDF_ATTN_TRACE", "-c", os.path.join(HERE, src), "-o", obj],
+        obj = os.path.join(OBJ_DIR, f"{tag}_" + src.replace(".cu", ".o"))
+        res = subprocess.run([nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(HERE, src), "-o", obj],
                              capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{res.stdout}\n{res.stderr}")
@@ -94,5 +95,9 @@ if __name__ == "__main__":
     if "--trace" in sys.argv:
         os.makedirs(OBJ_DIR, exist_ok=True)
         print(build_trace())
+    elif "--variant" in sys.argv:
+        os.makedirs(OBJ_DIR, exist_ok=True)
+        k = sys.argv.index("--variant")
+        print(build_trace(sys.argv[k + 1], tuple(a for a in sys.argv[k + 2:] if a.startswith("-D"))))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

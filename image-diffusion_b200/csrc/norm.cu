@@ -402,7 +402,8 @@ static int groupnorm_impl(const void* x, int64_t ldx, void* y, int64_t ldy, cons
   while (warps > 1 && (warps - 1) * (32 / VP) >= HW) --warps;  // tiny images: no idle warps
   dim3 grid(B, groups / gps);
   const int threads = warps * 32;
-  const bool res = HW <= GN_UNROLL * warps * (32 / VP);  // whole slab in registers between the passes
+  static const int gn_res = [] { const char* e = getenv("IDF_GN_RES"); return e ? atoi(e) : 1; }();  // (A/B switch)
+  const bool res = gn_res && HW <= GN_UNROLL * warps * (32 / VP);  // whole slab in registers between the passes
 #define GN_LAUNCH(SILU_, VP_, RES_)                                                                                     \
   launch_kernel(groupnorm_kernel<SILU_, VP_, RES_>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy,  \
                 gamma, beta, HW, cpg, gps, V, eps, stats, groups)

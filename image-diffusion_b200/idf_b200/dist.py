@@ -60,10 +60,14 @@ class ShardedSampler:
         sched_steps = list(reversed(range(self.d.scheduler.num_steps))) if steps is None else list(steps)
         for start in range(lo, hi, self.mb):
             lab, cfg = self.labels[start:start + self.mb], self.cfg[start:start + self.mb]
-            if sampler is None:  # one sampler (one captured graph) serves every micro-batch of the shard
-                sampler = CfgSampler(self.d.unet, self.d.scheduler, lab, cfg, self.d.latent_shape)
-            else:
-                sampler.set_conditioning(lab, cfg)
+            if sampler is None:
+                # one sampler (one captured graph) serves every micro-batch of the shard - and every later run of the
+                # same micro-batch size on this Diffusion object (labels / scales are rewritten in place)
+                cache = self.d.__dict__.setdefault("_shard_samplers", {})
+                sampler = cache.get(self.mb)
+                if sampler is None:
+                    sampler = cache[self.mb] = CfgSampler(self.d.unet, self.d.scheduler, lab, cfg, self.d.latent_shape)
+            sampler.set_conditioning(lab, cfg)
             gen = torch.Generator(device=dev).manual_seed(self.seed * 1000003 + start // self.mb)
             x_T = torch.randn(self.mb, *self.d.latent_shape, device=dev, generator=gen)
             sampler.set_latent(x_T)

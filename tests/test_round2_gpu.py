@@ -130,20 +130,20 @@ def test_sampling_follows_training_and_load_state_dict():
         sampler = CfgSampler(m.eval(), sched, labels, cfg, (3, 16, 16))
         a = check("before training", sampler)
     ts = DiffusionTrainStep(m.train(), sched, 4, (3, 16, 16), clip_grad=1.0)
-    for _ in range(3):
-        ts.step(lat, lab, 3e-3)   # large lr: the weights move far beyond the parity tolerance
+    for _ in range(4):
+        ts.step(lat, lab, 1e-2)   # large lr: the weights move far beyond the parity tolerance
     m.eval()
-    b = check("after 3 optimizer steps (same cached sampler and graph)", sampler)
-    assert rel_rms(a, b) > 2e-2  # the update moved the output beyond the parity gate: a stale engine fails the check above
+    b = check("after 4 optimizer steps (same cached sampler and graph)", sampler)
+    assert rel_rms(a, b) > 3e-2  # the update moved the output beyond the parity gate: a stale engine fails the check above
     with torch.no_grad():
         out = m(x_T, torch.full((N,), 700, device=DEV), labels)   # plain Unet.forward sees the new weights too
         ref = O.unet_forward({k: v.detach() for k, v in m.state_dict().items()}, SMALL, x_T,
                              torch.full((N,), 700, device=DEV), labels)
         assert rel_rms(out, ref) <= 3e-2
-    ts.step(lat, lab, 3e-3)
+    ts.step(lat, lab, 1e-2)
     check("after one more step", sampler)
     # load_state_dict into the same module (in-place copies: version counters bump)
     sd2 = O.seeded_state_dict(O.unet_param_shapes(SMALL), 77)
     m.load_state_dict(sd2)
     c = check("after load_state_dict", sampler)
-    assert rel_rms(b, c) > 5e-2
+    assert rel_rms(b, c) > 2e-2
