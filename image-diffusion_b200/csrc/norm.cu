@@ -37,7 +37,7 @@ __device__ __forceinline__ float silu_tanh(float t) {
   return fmaf(h, th, h);
 }
 
-template <bool SILU, int VP, bool RES>
+template <bool SILU, int VP>
 __global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv_bfloat16* __restrict__ x,
                                                                       long long ldx, __nv_bfloat16* __restrict__ y,
                                                                       long long ldy, const float* __restrict__ gamma,
@@ -59,36 +59,10 @@ __global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv
   const int rows_per_iter = nwarps * RPW;
 
   const __nv_bfloat16* xb = x + (long long)b * HW * ldx + c0 + v * 8;
-  // gamma / beta are fetched up front: their latency overlaps the statistics pass instead of following it
-  float ga[8], be[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { ga[e] = active ? gamma[c0 + v * 8 + e] : 0.f; be[e] = active ? beta[c0 + v * 8 + e] : 0.f; }
-  // Small slabs (HW <= GN_UNROLL sweeps: the 16x16 / 8x8 / 4x4 stages) stay in registers between the two passes: those
-  // launches are pure latency chains (load -> reduce -> load again -> store) and lose the second round trip.
-  // (RES is a template parameter: the register-resident variant needs 80 registers, the streaming one 56 - and the
-  // large slabs of the 32x32 stage want three 12-warp CTAs per SM)
-  constexpr bool resident = RES;
-  uint4 keep[RES ? GN_UNROLL : 1];
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-  if constexpr (resident) {
-   if (active) {
-    const int pix0 = warp * RPW + prl;
-#pragma unroll
-    for (int i = 0; i < GN_UNROLL; ++i) {
-      const int pix = pix0 + i * rows_per_iter;
-      keep[i] = pix < HW ? *reinterpret_cast<const uint4*>(xb + (long long)pix * ldx) : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int i = 0; i < GN_UNROLL; ++i) {
-      float f[8];
-      unpack8(keep[i], f);  // (rows beyond HW are zeros: they add nothing to either sum)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
-    }
-   }
-  } else if (active) {
+  if (active) {
     int pix = warp * RPW + prl;
     for (; pix + (GN_UNROLL - 1) * rows_per_iter < HW; pix += GN_UNROLL * rows_per_iter) {
       uint4 r[GN_UNROLL];
@@ -153,8 +127,9 @@ __global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv
   for (int e = 0; e < 8; ++e) {
     const int cl = v * 8 + e;
     const int g = cl / cpg;
-    sc[e] = g_rstd[g] * ga[e];
-    sh[e] = be[e] - g_mean[g] * g_rstd[g] * ga[e];
+    const float ga = gamma[c0 + cl], be = beta[c0 + cl];
+    sc[e] = g_rstd[g] * ga;
+    sh[e] = be - g_mean[g] * g_rstd[g] * ga;
   }
   __nv_bfloat16* yb = y + (long long)b * HW * ldy + c0 + v * 8;
   auto apply_store = [&](const uint4& r0, int pix) {
@@ -173,13 +148,6 @@ __global__ void __launch_bounds__(GN_MAX_WARPS * 32) groupnorm_kernel(const __nv
     o.w = pack_bf16x2(f[6], f[7]);
     *reinterpret_cast<uint4*>(yb + (long long)pix * ldy) = o;
   };
-  if constexpr (resident) {
-    const int pix0 = warp * RPW + prl;
-#pragma unroll
-    for (int i = 0; i < GN_UNROLL; ++i)
-      if (pix0 + i * rows_per_iter < HW) apply_store(keep[i], pix0 + i * rows_per_iter);
-    return;
-  }
   // four independent 16-byte loads in flight per thread (a one-load-per-iteration loop is latency-bound: ncu showed
   // 26-31 % DRAM and 34 % SM throughput with every CTA resident for the whole kernel)
   int pix = warp * RPW + prl;
@@ -402,19 +370,13 @@ static int groupnorm_impl(const void* x, int64_t ldx, void* y, int64_t ldy, cons
   while (warps > 1 && (warps - 1) * (32 / VP) >= HW) --warps;  // tiny images: no idle warps
   dim3 grid(B, groups / gps);
   const int threads = warps * 32;
-  static const int gn_res = [] { const char* e = getenv("IDF_GN_RES"); return e ? atoi(e) : 1; }();  // (A/B switch)
-  const bool res = gn_res && HW <= GN_UNROLL * warps * (32 / VP);  // whole slab in registers between the passes
-#define GN_LAUNCH(SILU_, VP_, RES_)                                                                                     \
-  launch_kernel(groupnorm_kernel<SILU_, VP_, RES_>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy,  \
-                gamma, beta, HW, cpg, gps, V, eps, stats, groups)
   if (VP == 4) {
-    if (apply_silu) { if (res) GN_LAUNCH(true, 4, true); else GN_LAUNCH(true, 4, false); }
-    else { if (res) GN_LAUNCH(false, 4, true); else GN_LAUNCH(false, 4, false); }
+    if (apply_silu) launch_kernel(groupnorm_kernel<true, 4>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
+    else launch_kernel(groupnorm_kernel<false, 4>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
   } else {
-    if (apply_silu) { if (res) GN_LAUNCH(true, 8, true); else GN_LAUNCH(true, 8, false); }
-    else { if (res) GN_LAUNCH(false, 8, true); else GN_LAUNCH(false, 8, false); }
+    if (apply_silu) launch_kernel(groupnorm_kernel<true, 8>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
+    else launch_kernel(groupnorm_kernel<false, 8>, grid, dim3(threads), 0, s, xp, (long long)ldx, yp, (long long)ldy, gamma, beta, HW, cpg, gps, V, eps, stats, groups);
   }
-#undef GN_LAUNCH
   return check_cuda(cudaGetLastError(), "groupnorm launch");
 }
 

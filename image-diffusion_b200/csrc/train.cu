@@ -249,14 +249,25 @@ __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(
   }
 }
 
-// out[c] (+)= sum_r in[r, c]  (rows summed in order)
-__global__ void reduce_rows_kernel(const float* __restrict__ in, long long ld, int rows, int cols,
-                                   float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// out[c] (+)= sum_r in[r, c]. 32 columns x 8 row groups per CTA: row group k sums rows k, k+8, ... (independent loads in
+// flight instead of one dependent chain over all rows), the eight partials are then added in order: fixed summation
+// order, bit-deterministic.
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ in, long long ld, int rows, int cols,
+                                                          float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float a = 0.f;
-  for (int r = 0; r < rows; ++r) a += in[(long long)r * ld + c];
-  out[c] = accumulate ? out[c] + a : a;
+  if (c < cols)
+    for (int r = rg; r < rows; r += 8) a += in[(long long)r * ld + c];
+  red[rg][cl] = a;
+  __syncthreads();
+  if (rg == 0 && c < cols) {
+    float s0 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s0 += red[k][cl];
+    out[c] = accumulate ? out[c] + s0 : s0;
+  }
 }
 
 // per_sample[b, c] = sum over the HW pixel rows of sample b of x[., c]. CTA = (sample, 64 channels), 256 threads =
@@ -856,7 +867,7 @@ extern "C" int idf_groupnorm_bwd_finalize(const float* dgamma_part, const float*
 extern "C" int idf_reduce_rows_f32(const float* in, int64_t ld, int32_t rows, int32_t cols, float* out,
                                    int32_t accumulate, idf_stream_t stream) {
   if (!in || !out || rows <= 0 || cols <= 0) return fail(IDF_ERR_ARG, "reduce_rows: bad argument");
-  reduce_rows_kernel<<<(cols + 127) / 128, 128, 0, S(stream)>>>(in, ld, rows, cols, out, accumulate);
+  reduce_rows_kernel<<<(cols + 31) / 32, 256, 0, S(stream)>>>(in, ld, rows, cols, out, accumulate);
   return check_cuda(cudaGetLastError(), "reduce_rows launch");
 }
 
@@ -866,7 +877,7 @@ extern "C" int idf_colsum_bf16(const void* x, int64_t ldx, int32_t B, int32_t HW
   if (C % 8 != 0 || ldx % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return fail(IDF_ERR_ARG, "colsum: alignment");
   colsum_kernel<<<dim3(B, (C + 63) / 64), 256, 0, S(stream)>>>(BF(x), ldx, HW, C, per_sample, ld_ps);
   if (total != nullptr)
-    reduce_rows_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(per_sample, ld_ps, B, C, total, accumulate_total);
+    reduce_rows_kernel<<<(C + 31) / 32, 256, 0, S(stream)>>>(per_sample, ld_ps, B, C, total, accumulate_total);
   return check_cuda(cudaGetLastError(), "colsum launch");
 }
 
@@ -905,7 +916,7 @@ extern "C" int idf_conv3x3_small_cin_wgrad(const float* x, const void* dy, int64
   if ((long long)nparts * Cout * 27 * 4 > part_bytes) return fail(IDF_ERR_ARG, "small_cin_wgrad: scratch too small");
   const int smem = 3 * (RB + 2) * (W + 2) * 4;
   small_cin_wgrad_kernel<3, 2><<<dim3(nparts, Cout / 128), 128, smem, S(stream)>>>(x, BF(dy), lddy, part, H, W, Cout);
-  reduce_rows_kernel<<<(Cout * 27 + 127) / 128, 128, 0, S(stream)>>>(part, (long long)Cout * 27, nparts, Cout * 27, grad_w, 0);
+  reduce_rows_kernel<<<(Cout * 27 + 31) / 32, 256, 0, S(stream)>>>(part, (long long)Cout * 27, nparts, Cout * 27, grad_w, 0);
   return check_cuda(cudaGetLastError(), "small_cin_wgrad launch");
 }
 
@@ -921,7 +932,7 @@ extern "C" int idf_conv3x3_small_cout_bwd(const void* h, int64_t ldh, const floa
   if ((long long)nparts * Cout * C * 9 * 4 > part_bytes) return fail(IDF_ERR_ARG, "small_cout_bwd: scratch too small");
   small_cout_dgrad_kernel<3, 2><<<dim3(nparts, C / 128), 128, 3 * (RB + 2) * (W + 2) * 4, S(stream)>>>(dout, w, BF(dh), lddh, H, W, C);
   small_cout_wgrad_kernel<3, 2><<<dim3(nparts, C / 128), 128, 3 * RB * W * 4, S(stream)>>>(BF(h), ldh, dout, part, H, W, C);
-  reduce_rows_kernel<<<(Cout * C * 9 + 127) / 128, 128, 0, S(stream)>>>(part, (long long)Cout * C * 9, nparts, Cout * C * 9, grad_w, 0);
+  reduce_rows_kernel<<<(Cout * C * 9 + 31) / 32, 256, 0, S(stream)>>>(part, (long long)Cout * C * 9, nparts, Cout * C * 9, grad_w, 0);
   nchw_channel_sum_kernel<<<Cout, 256, 0, S(stream)>>>(dout, B, Cout, H * W, grad_b);
   return check_cuda(cudaGetLastError(), "small_cout_bwd launch");
 }
