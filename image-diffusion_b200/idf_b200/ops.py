@@ -87,9 +87,9 @@ def groupnorm_silu(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: 
 
 # Whole-row GroupNorm kernels: measured on B200 (VQ-VAE forward, batch 256: 75.6 -> 63.9 ms) they win once the tensor is
 # far beyond the 126 MB L2 (the slab kernel's second pass then comes from HBM in 32-byte pieces); below that the slab
-# kernel's single launch wins (KL decode of batch 48: 4.03 vs 4.23 ms). Issuing the work in L2-sized sample groups
+# kernel's single launch wins (KL decode of batch 48: 4.03 vs 4.23 ms; 403 MB tensor: 129 vs 168 us): threshold 1 GB. Issuing the work in L2-sized sample groups
 # (IDF_GN_L2_MB > 0) was measured slower than all samples at once (67.1 vs 63.9 ms): default off.
-GN_ROWS_MIN_TOTAL_BYTES = 256 << 20
+GN_ROWS_MIN_TOTAL_BYTES = 1 << 30
 GN_ROWS_L2_BYTES = int(os.environ.get("IDF_GN_L2_MB", "0")) << 20
 
 
