@@ -71,6 +71,8 @@ struct IgemmParams {
   long long vt_ld;
   float* out_f32;
   long long out_f32_ld;
+  float* out_nchw;    // narrow tile (BN = 16): columns [0, nchw_c) written as fp32 NCHW planes (the network's last conv)
+  int nchw_c;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -342,6 +344,33 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
     TileWalk tw;
     tw.init(walker, walkers, splits, n_tiles);
     for (int u = walker; u < total_tiles; u += walkers, ++it, tw.next()) {
+      if constexpr (BN == 16) {
+        // Narrow tile: the <= 16 output channels of the network's last convolution (128 -> 3, 384 -> z), one row per
+        // thread, written straight as fp32 NCHW planes (consecutive lanes = consecutive pixels: coalesced per plane).
+        const int acc = it & 1;
+        const int tile_m = tw.tile_m;
+        const long long m = (long long)tile_m * BLOCK_M + r;
+        mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+        tc_fence_after_sync();
+        uint32_t v[16];
+        if (wg == 0) {
+          tmem_ld_32x16(tmem_base + acc * BN + lane_addr, v);
+          tmem_ld_wait();
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (wg == 0 && m < p.M) {
+          int sample, pix;
+          if (p.hw_shift >= 0) { sample = (int)(m >> p.hw_shift); pix = (int)m & (p.HW - 1); }
+          else { sample = (int)(m / p.HW); pix = (int)(m % p.HW); }
+          float* dst = p.out_nchw + ((long long)sample * p.nchw_c) * p.HW + pix;
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < p.nchw_c) dst[(long long)c * p.HW] = __uint_as_float(v[c]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+        }
+        continue;
+      }
       const int t = u;  // (the residual prefetch below is only used with splits == 1, where the unit is the tile)
       float* out_f32 = p.out_f32 + (long long)tw.sp * p.split_stride;
       const int par = p.up2_all ? (tw.n_idx & 3) : 0;
@@ -655,7 +684,7 @@ static int make_mat_map(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_
 using namespace idf;
 
 extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
-  if (a == nullptr || a->a[0].ptr == nullptr || a->w == nullptr || a->out == nullptr)
+  if (a == nullptr || a->a[0].ptr == nullptr || a->w == nullptr)
     return fail(IDF_ERR_ARG, "idf_conv2d_igemm: null argument");
   const idf_nhwc_t& x0 = a->a[0];
   const int nseg = a->a[1].ptr != nullptr ? 2 : 1;
@@ -668,7 +697,16 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     if (!up2_all_seg && (custom ? (a->taps[s] < 1 || a->taps[s] > 9) : (a->taps[s] != 1 && a->taps[s] != 9)))
       return fail(IDF_ERR_ARG, "igemm: taps must be 1 or 9 (1..9 with custom_taps, 4 with out_up2 == 2)");
   }
-  if (a->N <= 0 || a->N % BLOCK_N != 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d not a multiple of %d", a->N, BLOCK_N);
+  const bool narrow = a->out_nchw != nullptr;
+  if (narrow) {
+    if (a->N != 16 || a->out_nchw_c < 1 || a->out_nchw_c > 16 || a->res || a->vt || a->ws || a->out_up2 || a->w_mn ||
+        a->s2_batch || a->s2_direct || a->rowbias || a->zero_pad_last || a->a[1].ptr || a->w_batch_row || a->w_batch_col)
+      return fail(IDF_ERR_ARG, "igemm: out_nchw takes one plain segment, N == 16 (zero-padded weights) and 1..16 channels");
+  } else if (a->out == nullptr) {
+    return fail(IDF_ERR_ARG, "idf_conv2d_igemm: null output");
+  }
+  if (!narrow && (a->N <= 0 || a->N % BLOCK_N != 0))
+    return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d not a multiple of %d", a->N, BLOCK_N);
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -756,8 +794,10 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   int bn = BLOCK_N;
   // short-K GEMMs (K <= 1024: QKV / out_proj / skip projections) are epilogue- and memory-bound: narrow tiles with
   // triple-buffered staging keep loads, residual prefetch and stores in flight together
-  const bool short_k = ktot <= 1024 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
-  if (!short_k) {
+  const bool short_k = !narrow && ktot <= 1024 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
+  if (narrow) {
+    bn = 16;
+  } else if (!short_k) {
     // Tile width by a small cost model, calibrated on B200 with the per-launch table of one sampling step
     // (profiles/r01_sample_step_launches_events.txt): the busiest CTA works through waves(c) = ceil(units / SMs)
     // tiles of K / 64 k-blocks; one k-block takes ~250 / 375 / 425 ns for 128- / 192- / 256-wide tiles (~395 ns on
@@ -817,7 +857,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   // 32x32 / 16x16 stages gain 5-9 %, 192-wide tiles lose 13-17 %, everything else is neutral or pays for the
   // cluster start-up: IDF_IGEMM_PAIR = 1 (default) pairs only the former, 2 = wherever legal, 0 = never.
   static const int pair_mode = [] { const char* e = getenv("IDF_IGEMM_PAIR"); return e ? atoi(e) : 1; }();
-  const bool pair_legal = !batched && M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2;
+  const bool pair_legal = !narrow && !batched && M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2;
   const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && bn == 256 && !short_k &&
                                                       (M + BLOCK_M - 1) / BLOCK_M * par_tiles >= sm_count()));
   if (a->w_mn) {  // rows = the A operand's channels (K per tap), columns = (weight tap, output column)
@@ -851,7 +891,11 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   if (a->bias != nullptr && (reinterpret_cast<uintptr_t>(a->bias) & 15))
     return fail(IDF_ERR_ARG, "igemm: bias must be 16-byte aligned");
   if (a->zero_pad_last) p.flags |= F_ZERO_PAD;
-  if (splits > 1) {
+  if (narrow) {
+    if (a->bias != nullptr && is_matrix) return fail(IDF_ERR_UNSUPPORTED, "igemm: out_nchw needs an image-shaped input");
+    p.out_nchw = a->out_nchw;
+    p.nchw_c = a->out_nchw_c;
+  } else if (splits > 1) {
     // the GEMM writes raw fp32 partials; bias / time bias / padding mask move to the finish kernel
     if ((reinterpret_cast<uintptr_t>(a->ws) & 15) || a->N % 8 != 0 || a->ldo % 8 != 0 || (reinterpret_cast<uintptr_t>(a->out) & 15))
       return fail(IDF_ERR_ARG, "igemm: split-K alignment");
@@ -920,6 +964,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     return launch_persist<128, 3>(p, st, pair);
   }
   switch (bn) {
+    case 16: return launch_persist_ew<16, 1, 2, false>(p, st);
     case 256: rc = launch_persist<256, 1>(p, st, pair); break;
     case 192: rc = launch_persist<192, 1>(p, st, pair); break;
     default: rc = launch_persist<128, 1>(p, st, pair); break;

@@ -55,6 +55,17 @@ def _f32(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+def _narrow_pack(weight, bias):
+    """(Cout <= 16, Cin, 3, 3) conv -> bf16 (16, 9*Cin) weight rows (zero beyond Cout) + fp32 bias[16]: the operands of
+    the implicit GEMM's 16-wide tile (idf_igemm_args.out_nchw)."""
+    cout = weight.shape[0]
+    wp = torch.zeros(16, weight.shape[1] * weight.shape[2] * weight.shape[3], device=weight.device, dtype=BF16)
+    wp[:cout] = ops.pack_conv_weight(weight)
+    bp = torch.zeros(16, device=weight.device, dtype=torch.float32)
+    bp[:cout] = bias.detach().float()
+    return wp, bp
+
+
 class _Packed:
     """bf16 / fp32 device copies of a module's parameters in the layouts the kernels consume; rebuilt whenever a
     parameter has been modified in place or replaced (optimizer step, load_state_dict, .to())."""
@@ -116,6 +127,7 @@ class UnetEngine:
         # eats the gain (measured).
         self.splitk = int(__import__("os").environ.get("IDF_SPLITK_4X4", "3"))
         self._B, self._rng = 0, (0, 0)
+        self.tc_tail = __import__("os").environ.get("IDF_TC_TAIL", "1") != "0"
         self.downs, self.mids, self.ups = unet_blocks(arch)
         for _, cin, cout in self.downs + self.mids + self.ups:
             if cin % 64 or cout % 128:
@@ -161,6 +173,7 @@ class UnetEngine:
         w["in.w"], w["in.b"] = _f32(sd["in_conv.weight"]), _f32(sd["in_conv.bias"])
         w["out.gw"], w["out.gb"] = _f32(sd["out_conv.0.weight"]), _f32(sd["out_conv.0.bias"])
         w["out.w"], w["out.b"] = _f32(sd["out_conv.2.weight"]), _f32(sd["out_conv.2.bias"])
+        w["out.wtc"], w["out.btc"] = _narrow_pack(sd["out_conv.2.weight"], sd["out_conv.2.bias"])
         w["t.factor"] = _f32(sd["time_embedding.factor"])
         w["t.w1"], w["t.b1"] = _f32(sd["time_embedding.embeddings.0.weight"]), _f32(sd["time_embedding.embeddings.0.bias"])
         w["t.w2"], w["t.b2"] = _f32(sd["time_embedding.embeddings.2.weight"]), _f32(sd["time_embedding.embeddings.2.bias"])
@@ -252,7 +265,11 @@ class UnetEngine:
         x = self._level(0, Act(a0, B, H, W, ch[0]), table, row_idx)
         h = self._buf("h1", x.H * x.W, x.C)
         ops.groupnorm_silu(x.t, h, w["out.gw"], w["out.gb"], x.B, x.H * x.W, x.C, self.G, True)
-        ops.conv3x3_small_cout(h, w["out.w"], w["out.b"], out_nchw)
+        if self.tc_tail and x.C % 64 == 0 and out_nchw.shape[1] <= 16:
+            # 128 -> z_dim conv on the tensor cores: one 16-wide tile, epilogue writes fp32 NCHW planes
+            ops.igemm([(h, x.grid, x.C, 9)], w["out.wtc"], 16, None, bias=w["out.btc"], out_nchw=out_nchw)
+        else:
+            ops.conv3x3_small_cout(h, w["out.w"], w["out.b"], out_nchw)
         return out_nchw
 
     # ---------------------------------------------------------------------------------------------
@@ -331,14 +348,10 @@ class VaeEngine:
                 p = f"{prefix}.{i}"
                 if kind in ("conv1x1", "conv3x3"):
                     w[p + ".w"], w[p + ".b"] = _f32(sd[p + ".weight"]), _f32(sd[p + ".bias"])
-                    if kind == "conv3x3" and cin % 64 == 0 and cout <= 128:
-                        # narrow tail conv (128 -> 3, 384 -> z) on the tensor cores: output channels zero-padded to one
-                        # 128-wide tile (the CUDA-core kernel runs at ~6 TFLOP/s: 15 % of a batch-48 decode)
-                        wp = torch.zeros(128, 9 * cin, device=sd[p + ".weight"].device, dtype=BF16)
-                        wp[:cout] = pk(sd[p + ".weight"])
-                        bp = torch.zeros(128, device=wp.device, dtype=torch.float32)
-                        bp[:cout] = sd[p + ".bias"].detach().float()
-                        w[p + ".wtc"], w[p + ".btc"] = wp, bp
+                    if kind == "conv3x3" and cin % 64 == 0 and cout <= 16:
+                        # narrow tail conv (128 -> 3, 384 -> z) on the tensor cores: one 16-wide tile (the CUDA-core
+                        # kernel runs at ~6 TFLOP/s: 15 % of a batch-48 decode)
+                        w[p + ".wtc"], w[p + ".btc"] = _narrow_pack(sd[p + ".weight"], sd[p + ".bias"])
                 elif kind == "res":
                     w[p + ".g1w"], w[p + ".g1b"] = _f32(sd[p + ".branch.0.weight"]), _f32(sd[p + ".branch.0.bias"])
                     w[p + ".g2w"], w[p + ".g2b"] = _f32(sd[p + ".branch.3.weight"]), _f32(sd[p + ".branch.3.bias"])
@@ -453,9 +466,7 @@ class VaeEngine:
                 last = n == len(prog) - 1
                 dst = out_nchw if last else ws.get("tail", B * cout, x.H * x.W, torch.float32).view(B, cout, x.H, x.W)
                 if self.tc_tail and (p + ".wtc") in w:
-                    wide = ws.get("tailw", x.M, 128)
-                    ops.igemm([(x.t, x.grid, x.C, 9)], w[p + ".wtc"], 128, wide, bias=w[p + ".btc"])
-                    ops.rows_to_nchw(wide, dst)  # first `cout` columns -> fp32 NCHW
+                    ops.igemm([(x.t, x.grid, x.C, 9)], w[p + ".wtc"], 16, None, bias=w[p + ".btc"], out_nchw=dst)
                 else:
                     ops.conv3x3_small_cout(x.t, w[p + ".w"], w[p + ".b"], dst)
                 cur = dst

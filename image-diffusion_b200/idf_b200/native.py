@@ -36,6 +36,7 @@ class IgemmArgs(C.Structure):
         ("out_up2", _i32), ("out_ph", _i32), ("out_pw", _i32),
         ("w_mn", _i32), ("w_tap_ids", C.c_int8 * 9), ("s2_direct", _i32),
         ("w_batch_row", _i64), ("w_batch_col", _i64),
+        ("out_nchw", _vp), ("out_nchw_c", _i32),
     ]
 
 

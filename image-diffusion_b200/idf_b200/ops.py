@@ -26,8 +26,9 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
           res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0, ws=None,
           tap_offsets=None, splits: int = 0, out_up2=None, s2_direct: bool = False, w_mn: bool = False,
-          w_tap_ids=None, w_batch=None) -> torch.Tensor:
-    """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view."""
+          w_tap_ids=None, w_batch=None, out_nchw=None) -> torch.Tensor:
+    """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view; with `out_nchw`
+    (fp32 (B, C <= 16, H, W), weights / bias zero-padded to n_out = 16) the result goes there instead and `out` is None."""
     a = IgemmArgs()
     if not 1 <= len(segs) <= 2:
         raise ValueError("igemm takes one or two input segments")
@@ -40,8 +41,12 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
         a.taps[1] = 1
     _check_bf16_rows(w, "igemm weight")
     a.w, a.ldw, a.N = w.data_ptr(), w.stride(0), n_out
-    a.out, a.ldo = out.data_ptr(), out.stride(0)
-    a.out_f32 = 1 if out.dtype == torch.float32 else 0
+    if out_nchw is not None:
+        a.out, a.ldo, a.out_f32 = None, 0, 0
+        a.out_nchw, a.out_nchw_c = out_nchw.data_ptr(), out_nchw.shape[1]
+    else:
+        a.out, a.ldo = out.data_ptr(), out.stride(0)
+        a.out_f32 = 1 if out.dtype == torch.float32 else 0
     a.bias = ptr(bias)
     a.rowbias = ptr(rowbias)
     a.rowbias_idx = ptr(rowbias_idx)
@@ -73,7 +78,7 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
         for i, (dh, dw) in enumerate(tap_offsets):
             a.tap_dh[i], a.tap_dw[i] = dh, dw
     call("idf_conv2d_igemm", a)
-    return out
+    return out if out_nchw is None else out_nchw
 
 
 def groupnorm_silu(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, B: int, HW: int, C: int,

@@ -123,9 +123,10 @@ class CfgSampler:
             self._ensure_table()
         self._ensure_graph()
         self.t_rows.fill_(i)
+        ip = -1 if i_prev is None else int(i_prev)
         if self.kind == "ddim":
-            self.t_prev.fill_(-1 if i_prev is None else i_prev)
-        if (i > 0 and self.kind == "ddpm") or (self.kind == "ddim" and self.eta > 0.0 and (i_prev or -1) >= 0):
+            self.t_prev.fill_(ip)
+        if (i > 0 and self.kind == "ddpm") or (self.kind == "ddim" and self.eta > 0.0 and ip >= 0):
             if noise is None:
                 self.z.normal_()
             else:

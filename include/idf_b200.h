@@ -119,6 +119,12 @@ typedef struct idf_igemm_args {
                            head of the VAE (components.py:87-95): S_i = Q_i K_i^T with w = K (w_batch_row = tokens per
                            image) and O_i = P_i V_i with w = V^T (w_batch_col = tokens per image), one launch each for the
                            whole batch. */
+  float* out_nchw;      /* narrow output (the network's last convolutions: 128 -> 3 of unet.py:100 / components.py:244, 384 -> z
+                           of components.py:183): N must be 16 (weight rows beyond the real channel count zero, bias padded
+                           to 16 floats) and columns [0, out_nchw_c) are written as fp32 NCHW planes
+                           out_nchw[(img * out_nchw_c + c) * h * w + pixel]; `out` is unused and may be NULL. One plain
+                           9- or 1-tap segment. */
+  int32_t out_nchw_c;
 } idf_igemm_args;
 
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);

@@ -472,3 +472,23 @@ def test_groupnorm_rows_large_images(B, C, H, silu):
     y2 = torch.empty_like(xr)
     ops.groupnorm_silu(xr, y2, gamma, beta, B, H * H, C, 32, silu)  # the slab kernel: same maths, other summation order
     assert rel_err(y2.float(), y.float()) < 4e-3
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H", [(3, 128, 3, 32), (2, 384, 6, 32), (1, 128, 3, 128), (5, 128, 3, 8), (96, 128, 3, 32)])
+def test_igemm_narrow_tile_writes_fp32_nchw(B, Cin, Cout, H):
+    """The network's last convolutions (128 -> 3, 384 -> z) on one 16-wide tcgen05 tile, fp32 NCHW planes out."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(Cin + H + B)
+    x = torch.randn(B, Cin, H, H, device=DEV, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, device=DEV, generator=g)
+    wp = torch.zeros(16, 9 * Cin, device=DEV, dtype=torch.bfloat16)
+    wp[:Cout] = ops.pack_conv_weight(w)
+    bp = torch.zeros(16, device=DEV)
+    bp[:Cout] = b
+    out = torch.full((B, Cout, H, H), float("nan"), device=DEV)
+    ops.igemm([(rows(x), (B, H, H), Cin, 9)], wp, 16, None, bias=bp, out_nchw=out)
+    ref = F.conv2d(bf(x), bf(w), b, padding=1)
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 2e-5 * 100, rel_err(out, ref)   # fp32 accumulation order only (inputs are bf16-exact)
+    assert rel_err(out, ref) < 1e-4
