@@ -1,7 +1,7 @@
 """Parity AT THE CONFIGURATIONS bench.py MEASURES (BASELINE.json configs[1], [3], [4]): the batch sizes at which the
 engine takes its large-batch kernels (CTA-pair tiles, the tile-width cost model's choices, 12/8/6-warp GroupNorm
 CTAs, persistent attention with more work items than SMs). Same oracle, same tolerances as tests/test_modules_gpu.py
-(SURVEY.md §8d): eps rel-RMS <= 3e-2 / max-abs <= 5e-2, 20-step chain <= 1e-2, decoded pixels / latents <= 3.5e-2,
+(measured values of the last run in profiles/r02_parity_measured_values.txt): eps rel-RMS <= 3e-2 / max-abs <= 5e-2, 20-step chain <= 1e-2, decoded pixels / latents <= 3.5e-2,
 train-step loss within 2e-2 and global gradient rel-RMS <= 2e-2, VQ indices bit-exact.
 """
 import math
