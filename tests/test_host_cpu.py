@@ -314,3 +314,30 @@ def test_persistent_kernel_tile_walk_matches_closed_form():
                         assert tuple(out[3 * i:3 * i + 3]) == want, (stride, splits, n_tiles, u0, i)
     bad = (C.c_int32 * 3)()
     assert lib.idf_tile_walk_trace(0, 0, 1, 1, 1, bad, None) != 0
+
+
+def test_packed_weights_refresh_in_place_and_follow_the_weights_epoch():
+    """Round-1 advisor findings, host side (no GPU needed): the packed operand copies are rewritten IN PLACE when the
+    layout is unchanged (captured graphs hold raw pointers to them), and a writer that bypasses torch's version
+    counter (the fused Adam kernel) invalidates them by bumping `_weights_epoch`."""
+    import torch
+    from idf_b200.engine import _Packed
+
+    m = torch.nn.Linear(4, 3)
+    pk = _Packed(m)
+    assert pk.stale() and not pk.stale()
+    first = {"w": m.weight.detach().to(torch.bfloat16).clone(), "b": m.bias.detach().clone()}
+    pk.install(first)
+    ptrs = {k: v.data_ptr() for k, v in pk.w.items()}
+    m.weight.data.add_(1.0)               # raw write: no version bump, same storage -> not detected by itself
+    assert not pk.stale()
+    m._weights_epoch = getattr(m, "_weights_epoch", 0) + 1
+    assert pk.stale()
+    pk.install({"w": m.weight.detach().to(torch.bfloat16).clone(), "b": m.bias.detach().clone()})
+    assert {k: v.data_ptr() for k, v in pk.w.items()} == ptrs          # same buffers ...
+    assert torch.equal(pk.w["w"].float(), m.weight.detach().to(torch.bfloat16).float())  # ... new values
+    with torch.no_grad():
+        m.weight.mul_(2.0)                # in-place op through torch: version counter moves
+    assert pk.stale()
+    pk.install({"w": torch.zeros(5, 4, dtype=torch.bfloat16), "b": m.bias.detach().clone()})  # layout changed: replaced
+    assert pk.w["w"].shape == (5, 4)
