@@ -653,6 +653,63 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, long lo
   y[i] = __bfloat162float(x[((long long)b * HW + p) * ldx + c]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Codebook.forward, eval mode, after the argmin (components.py:301-313): commitment loss beta * mean((z_q - z)^2), the
+// straight-through output z + (z_q - z) (same arithmetic as the reference, so the same bits), code usage histogram and
+// perplexity exp(-sum p log(p + 1e-6)). Integer histogram (exact, order independent); the squared-error sum goes
+// through per-CTA partials added in CTA order: bit-deterministic.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int VQS_MAX_CODES = 4096;
+__global__ void __launch_bounds__(256) vq_stats_kernel(const float* __restrict__ z, const float* __restrict__ zq,
+                                                       const int64_t* __restrict__ idx, float* __restrict__ st_out,
+                                                       long long elems, int rows, int size, int* __restrict__ counts,
+                                                       float* __restrict__ part) {
+  extern __shared__ int s_hist[];  // [size]
+  __shared__ float s_red[256];
+  for (int i = threadIdx.x; i < size; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&s_hist[(int)idx[r]], 1);
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (long long)gridDim.x * blockDim.x) {
+    const float a = z[i], d = zq[i] - a;
+    acc = fmaf(d, d, acc);
+    st_out[i] = a + d;
+  }
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = s_red[0];
+  for (int i = threadIdx.x; i < size; i += blockDim.x)
+    if (s_hist[i] != 0) atomicAdd(&counts[i], s_hist[i]);
+}
+
+__global__ void __launch_bounds__(1024) vq_stats_finish_kernel(const int* __restrict__ counts, const float* __restrict__ part,
+                                                               int nparts, int size, int rows, long long elems, float beta,
+                                                               float* __restrict__ loss, float* __restrict__ perplexity) {
+  __shared__ float s_red[1024];
+  float e = 0.f;
+  for (int i = threadIdx.x; i < size; i += blockDim.x) {
+    const float pr = (float)counts[i] / (float)rows;
+    e += pr * logf(pr + 1e-6f);
+  }
+  s_red[threadIdx.x] = e;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *perplexity = expf(-s_red[0]);
+    float sse = 0.f;
+    for (int i = 0; i < nparts; ++i) sse += part[i];
+    *loss = beta * (sse / (float)elems);
+  }
+}
+
 static inline unsigned blocks_for(long long n, int threads, int cap = 148 * 16) {
   long long b = (n + threads - 1) / threads;
   if (b > cap) b = cap;
@@ -766,6 +823,25 @@ extern "C" int idf_vq_argmin(const float* z, const float* codebook, int64_t* idx
     default: return fail(IDF_ERR_UNSUPPORTED, "vq_argmin: dim %d not in {3,4,8}", dim);
   }
   return check_cuda(cudaGetLastError(), "vq_argmin launch");
+}
+
+extern "C" int idf_vq_loss_perplexity(const float* z, const float* zq, const int64_t* idx, float* quant_out,
+                                      int32_t rows, int32_t dim, int32_t size, float beta, float* loss,
+                                      float* perplexity, void* ws, int64_t ws_bytes, idf_stream_t stream) {
+  if (!z || !zq || !idx || !quant_out || !loss || !perplexity || !ws) return fail(IDF_ERR_ARG, "vq_loss_perplexity: null pointer");
+  if (rows <= 0 || dim <= 0 || size <= 0 || size > VQS_MAX_CODES) return fail(IDF_ERR_ARG, "vq_loss_perplexity: bad shape");
+  const long long elems = (long long)rows * dim;
+  const int grid = (int)blocks_for(elems, 256, 148 * 4);
+  if ((long long)size * 4 + (long long)grid * 4 > ws_bytes)
+    return fail(IDF_ERR_ARG, "vq_loss_perplexity: workspace needs %lld bytes", (long long)size * 4 + (long long)grid * 4);
+  int* counts = reinterpret_cast<int*>(ws);
+  float* part = reinterpret_cast<float*>(counts + size);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc = check_cuda(cudaMemsetAsync(counts, 0, (size_t)size * 4, s), "vq_loss_perplexity: memset");
+  if (rc != IDF_OK) return rc;
+  vq_stats_kernel<<<grid, 256, size * 4, s>>>(z, zq, idx, quant_out, elems, rows, size, counts, part);
+  vq_stats_finish_kernel<<<1, 1024, 0, s>>>(counts, part, grid, size, rows, elems, beta, loss, perplexity);
+  return check_cuda(cudaGetLastError(), "vq_loss_perplexity launch");
 }
 
 extern "C" int idf_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int64_t ldy,

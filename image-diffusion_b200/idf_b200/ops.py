@@ -171,6 +171,18 @@ def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, idx_out: torch.Tensor, zq
     return idx_out
 
 
+def vq_loss_perplexity(z: torch.Tensor, zq: torch.Tensor, idx: torch.Tensor, size: int, beta: float):
+    """Eval-mode tail of Codebook.forward: (straight-through output, commitment loss, perplexity) - the last two as
+    0-dim device tensors."""
+    out = torch.empty_like(z)
+    stats = torch.empty(2, device=z.device, dtype=torch.float32)
+    ws = torch.empty(size + 592, device=z.device, dtype=torch.int32)
+    rows = idx.numel()
+    call("idf_vq_loss_perplexity", z.data_ptr(), zq.data_ptr(), idx.data_ptr(), out.data_ptr(), rows, z.numel() // rows,
+         size, float(beta), stats.data_ptr(), stats.data_ptr() + 4, ws.data_ptr(), ws.numel() * 4)
+    return out, stats[0], stats[1]
+
+
 def conv3x3_small_cin(x_nchw: torch.Tensor, w: torch.Tensor, bias, y: torch.Tensor, dup: bool = False):
     """dup=True also writes the result to rows [B*H*W, 2*B*H*W) of y (batch-doubled CFG input)."""
     B, Cin, H, W = x_nchw.shape

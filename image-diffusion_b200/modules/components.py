@@ -121,17 +121,19 @@ class Codebook(nn.Module):
 
     def forward(self, x):
         zq, idx = self.quantize(x)
-        z = x.to(torch.float32)
-        if self.training:
-            with torch.no_grad():
-                flat = z.permute(0, 2, 3, 1).reshape(-1, self.dim)
-                counts = torch.bincount(idx, minlength=self.size).to(torch.float32)
-                self.ema_cluster_size = self.ema_cluster_size * self.gamma + (1 - self.gamma) * counts
-                n = torch.sum(self.ema_cluster_size)
-                self.ema_cluster_size = (self.ema_cluster_size + self.epsilon) / (n + self.size * self.epsilon) * n
-                dw = torch.zeros_like(self.ema_w).index_add_(0, idx, flat)
-                self.ema_w = nn.Parameter(self.ema_w * self.gamma + (1 - self.gamma) * dw)
-                self.embeddings.weight = nn.Parameter(self.ema_w / self.ema_cluster_size.unsqueeze(1))
+        z = _f32c(x)
+        if not self.training:
+            # eval: commitment loss, straight-through output and perplexity in one fused kernel pair (no torch arithmetic)
+            return ops.vq_loss_perplexity(z, zq, idx, self.size, self.beta)
+        with torch.no_grad():  # EMA codebook update (components.py:284-298): host-orchestrated, off the hot path
+            flat = z.permute(0, 2, 3, 1).reshape(-1, self.dim)
+            counts = torch.bincount(idx, minlength=self.size).to(torch.float32)
+            self.ema_cluster_size = self.ema_cluster_size * self.gamma + (1 - self.gamma) * counts
+            n = torch.sum(self.ema_cluster_size)
+            self.ema_cluster_size = (self.ema_cluster_size + self.epsilon) / (n + self.size * self.epsilon) * n
+            dw = torch.zeros_like(self.ema_w).index_add_(0, idx, flat)
+            self.ema_w = nn.Parameter(self.ema_w * self.gamma + (1 - self.gamma) * dw)
+            self.embeddings.weight = nn.Parameter(self.ema_w / self.ema_cluster_size.unsqueeze(1))
         quant_loss = self.beta * torch.mean((zq - z) ** 2)
         quant_out = z + (zq - z).detach()  # straight-through (components.py:305)
         probs = torch.bincount(idx, minlength=self.size).to(torch.float32) / idx.numel()

@@ -248,6 +248,18 @@ int idf_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, float
                   int32_t dim, int32_t size, int32_t nchw_hw, idf_stream_t stream);
 
 /*
+ * idf_vq_loss_perplexity — the rest of Codebook.forward in eval mode (components.py:301-313), after idf_vq_argmin:
+ * loss = beta * mean((zq - z)^2), quant_out = z + (zq - z) (the straight-through output, same arithmetic and bits as
+ * the reference), perplexity = exp(-sum_k p_k log(p_k + 1e-6)) with p = code usage histogram / rows. z, zq, quant_out
+ * are fp32 tensors of rows * dim elements in the SAME layout (elementwise); idx int64 [rows]; loss / perplexity are
+ * device scalars; ws = scratch of at least (size + 592) * 4 bytes. Integer histogram + ordered partial sums:
+ * deterministic.
+ */
+int idf_vq_loss_perplexity(const float* z, const float* zq, const int64_t* idx, float* quant_out, int32_t rows,
+                           int32_t dim, int32_t size, float beta, float* loss, float* perplexity, void* ws,
+                           int64_t ws_bytes, idf_stream_t stream);
+
+/*
  * idf_conv3x3_small_cin — direct 3x3 s1 p1 convolution for tiny Cin (the 3-channel latent): fp32 NCHW in,
  * bf16 NHWC out. Replaces unet.py:45,116 (in_conv) and components.py:207-208 (decoder 1x1 folded by the
  * caller + 3x3). w is fp32 OIHW, bias fp32 [Cout]; Cout % 128 == 0, Cin in {3, 4}. With dup != 0 the B*H*W output

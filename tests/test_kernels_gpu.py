@@ -492,3 +492,22 @@ def test_igemm_narrow_tile_writes_fp32_nchw(B, Cin, Cout, H):
     assert torch.isfinite(out).all()
     assert rel_err(out, ref) < 2e-5 * 100, rel_err(out, ref)   # fp32 accumulation order only (inputs are bf16-exact)
     assert rel_err(out, ref) < 1e-4
+
+
+def test_vq_loss_perplexity_matches_torch():
+    """Eval-mode tail of Codebook.forward (components.py:301-313) in one fused kernel pair vs the torch expressions."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(21)
+    B, D, H, size = 7, 3, 32, 1024
+    z = torch.randn(B, D, H, H, device=DEV, generator=g)
+    cb = torch.randn(size, D, device=DEV, generator=g) * 0.7
+    idx = torch.empty(B * H * H, device=DEV, dtype=torch.int64)
+    zq = torch.empty_like(z)
+    ops.vq_argmin(z, cb, idx, zq)
+    out, loss, perp = ops.vq_loss_perplexity(z, zq, idx, size, 0.25)
+    assert torch.equal(out, z + (zq - z))
+    ref_loss = 0.25 * torch.mean((zq - z) ** 2)
+    probs = torch.bincount(idx, minlength=size).float() / idx.numel()
+    ref_perp = torch.exp(-torch.sum(probs * torch.log(probs + 1e-6)))
+    assert abs(loss.item() - ref_loss.item()) <= 1e-6 * max(1.0, abs(ref_loss.item()))
+    assert abs(perp.item() - ref_perp.item()) <= 1e-4 * ref_perp.item()
