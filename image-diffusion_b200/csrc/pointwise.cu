@@ -710,6 +710,42 @@ __global__ void __launch_bounds__(1024) vq_stats_finish_kernel(const int* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// KL bottleneck of VAE.encode (vae.py:99-113): z6 = (mean || log_var) per sample; log_var clamped to [-30, 20];
+// kl[b] = -0.5 * sum(1 + lv - mean^2 - exp(lv)) over the sample, loss = mean_b kl[b]; optional reparametrised
+// sample z = mean + noise * exp(0.5 lv). One CTA per sample, fixed-order reductions (deterministic).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kl_stats_kernel(const float* __restrict__ z6, const float* __restrict__ noise,
+                                                       float* __restrict__ z_out, float* __restrict__ kl_per_sample,
+                                                       int half) {
+  __shared__ float s_red[256];
+  const int b = blockIdx.x;
+  const float* mean = z6 + (long long)b * 2 * half;
+  const float* lvp = mean + half;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float m = mean[i];
+    const float lv = fminf(fmaxf(lvp[i], -30.f), 20.f);
+    acc += 1.f + lv - m * m - expf(lv);
+    if (z_out != nullptr) z_out[(long long)b * half + i] = m + noise[(long long)b * half + i] * expf(0.5f * lv);
+  }
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) kl_per_sample[b] = -0.5f * s_red[0];
+}
+
+__global__ void kl_mean_kernel(const float* __restrict__ kl_per_sample, int B, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a += kl_per_sample[b];
+    *loss = a / (float)B;
+  }
+}
+
 static inline unsigned blocks_for(long long n, int threads, int cap = 148 * 16) {
   long long b = (n + threads - 1) / threads;
   if (b > cap) b = cap;
@@ -842,6 +878,16 @@ extern "C" int idf_vq_loss_perplexity(const float* z, const float* zq, const int
   vq_stats_kernel<<<grid, 256, size * 4, s>>>(z, zq, idx, quant_out, elems, rows, size, counts, part);
   vq_stats_finish_kernel<<<1, 1024, 0, s>>>(counts, part, grid, size, rows, elems, beta, loss, perplexity);
   return check_cuda(cudaGetLastError(), "vq_loss_perplexity launch");
+}
+
+extern "C" int idf_kl_loss_reparam(const float* z6, const float* noise, float* z_out, float* kl_per_sample, float* loss,
+                                   int32_t B, int32_t half, idf_stream_t stream) {
+  if (!z6 || !kl_per_sample || !loss || B <= 0 || half <= 0) return fail(IDF_ERR_ARG, "kl_loss_reparam: bad argument");
+  if ((z_out != nullptr) != (noise != nullptr)) return fail(IDF_ERR_ARG, "kl_loss_reparam: z_out and noise go together");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  kl_stats_kernel<<<B, 256, 0, s>>>(z6, noise, z_out, kl_per_sample, half);
+  kl_mean_kernel<<<1, 32, 0, s>>>(kl_per_sample, B, loss);
+  return check_cuda(cudaGetLastError(), "kl_loss_reparam launch");
 }
 
 extern "C" int idf_conv3x3_small_cin(const float* x, const float* w, const float* bias, void* y, int64_t ldy,

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "idf_cfg_ddim_step": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _i32, _i32],
     "idf_add_noise": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32],
     "idf_vq_argmin": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32],
+    "idf_kl_loss_reparam": [_vp, _vp, _vp, _vp, _vp, _i32, _i32],
     "idf_vq_loss_perplexity": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _i64],
     "idf_conv3x3_small_cin": [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32],
     "idf_conv3x3_small_cout": [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32],

@@ -183,6 +183,17 @@ def vq_loss_perplexity(z: torch.Tensor, zq: torch.Tensor, idx: torch.Tensor, siz
     return out, stats[0], stats[1]
 
 
+def kl_loss_reparam(z6: torch.Tensor, noise=None):
+    """KL bottleneck (vae.py:99-113) on the encoder's (B, 2*z, H, W) output: returns (mean KL loss as a 0-dim device
+    tensor, reparametrised sample (B, z, H, W) or None when `noise` is None)."""
+    B = z6.shape[0]
+    half = z6.numel() // B // 2
+    kl = torch.empty(B + 1, device=z6.device, dtype=torch.float32)
+    z_out = None if noise is None else torch.empty(B, z6.shape[1] // 2, *z6.shape[2:], device=z6.device, dtype=torch.float32)
+    call("idf_kl_loss_reparam", z6.data_ptr(), ptr(noise), ptr(z_out), kl.data_ptr(), kl.data_ptr() + 4 * B, B, half)
+    return kl[B], z_out
+
+
 def conv3x3_small_cin(x_nchw: torch.Tensor, w: torch.Tensor, bias, y: torch.Tensor, dup: bool = False):
     """dup=True also writes the result to rows [B*H*W, 2*B*H*W) of y (batch-doubled CFG input)."""
     B, Cin, H, W = x_nchw.shape

@@ -7,6 +7,7 @@ import os
 import torch
 import torch.nn as nn
 
+from idf_b200 import ops
 from idf_b200.engine import VaeEngine
 from idf_b200.spec import register_tree, vae_param_spec
 
@@ -61,12 +62,11 @@ class VAE(nn.Module):
         self._engine(("enc", B, H, W)).encode(xin, z)
         if self.bottleneck == "vq":
             return self.codebook(z)
-        mean, log_var = torch.chunk(z, chunks=2, dim=1)
-        log_var = torch.clamp(log_var, -30.0, 20.0)
-        kl_loss = -0.5 * torch.sum(1 + log_var - mean.pow(2) - log_var.exp(), dim=[1, 2, 3])
-        if sample:
-            z = mean + torch.randn_like(mean) * torch.exp(0.5 * log_var)
-        return z, kl_loss.mean(), 0.0
+        # KL loss (+ reparametrised sample) in one fused kernel pair (vae.py:99-113); the noise comes from torch's
+        # global CUDA generator exactly where the reference draws it (randn_like(mean))
+        noise = torch.randn(B, zc // 2, H // f, W // f, device=x.device, dtype=torch.float32) if sample else None
+        kl_loss, zs = ops.kl_loss_reparam(z, noise)
+        return (zs if sample else z), kl_loss, 0.0
 
     def decode(self, z, quantize=False):
         if self.bottleneck == "kl" and quantize:

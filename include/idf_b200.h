@@ -260,6 +260,15 @@ int idf_vq_loss_perplexity(const float* z, const float* zq, const int64_t* idx, 
                            int64_t ws_bytes, idf_stream_t stream);
 
 /*
+ * idf_kl_loss_reparam — the KL bottleneck of VAE.encode (vae.py:99-113). z6 fp32 (B, 2*half): per sample the mean
+ * block followed by the log-variance block ((B, 2*z_dim, H, W) NCHW, half = z_dim*H*W). log_var is clamped to [-30, 20];
+ * kl_per_sample[b] = -0.5 * sum(1 + lv - mean^2 - exp(lv)); *loss = mean over the batch. With noise / z_out (both or
+ * neither; fp32 (B, half)) also z_out = mean + noise * exp(0.5 * lv) (reparametrised sample). Deterministic.
+ */
+int idf_kl_loss_reparam(const float* z6, const float* noise, float* z_out, float* kl_per_sample, float* loss, int32_t B,
+                        int32_t half, idf_stream_t stream);
+
+/*
  * idf_conv3x3_small_cin — direct 3x3 s1 p1 convolution for tiny Cin (the 3-channel latent): fp32 NCHW in,
  * bf16 NHWC out. Replaces unet.py:45,116 (in_conv) and components.py:207-208 (decoder 1x1 folded by the
  * caller + 3x3). w is fp32 OIHW, bias fp32 [Cout]; Cout % 128 == 0, Cin in {3, 4}. With dup != 0 the B*H*W output

@@ -511,3 +511,23 @@ def test_vq_loss_perplexity_matches_torch():
     ref_perp = torch.exp(-torch.sum(probs * torch.log(probs + 1e-6)))
     assert abs(loss.item() - ref_loss.item()) <= 1e-6 * max(1.0, abs(ref_loss.item()))
     assert abs(perp.item() - ref_perp.item()) <= 1e-4 * ref_perp.item()
+
+
+def test_kl_loss_reparam_matches_torch():
+    """KL bottleneck of VAE.encode (vae.py:99-113): clamp, per-sample KL sum, batch mean, reparametrised sample."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(22)
+    B, zd, H = 5, 3, 32
+    z6 = torch.randn(B, 2 * zd, H, H, device=DEV, generator=g)
+    z6[0, zd, 0, 0] = 35.0      # above the clamp
+    z6[1, zd + 1, 3, 3] = -50.0  # below it
+    noise = torch.randn(B, zd, H, H, device=DEV, generator=g)
+    mean, lv = torch.chunk(z6, 2, dim=1)
+    lv = torch.clamp(lv, -30.0, 20.0)
+    ref_kl = (-0.5 * torch.sum(1 + lv - mean.pow(2) - lv.exp(), dim=[1, 2, 3])).mean()
+    ref_z = mean + noise * torch.exp(0.5 * lv)
+    kl, z = ops.kl_loss_reparam(z6, noise)
+    assert abs(kl.item() - ref_kl.item()) <= 2e-6 * abs(ref_kl.item())
+    assert (z - ref_z).abs().max().item() <= 2e-6 * ref_z.abs().max().item()
+    kl2, none = ops.kl_loss_reparam(z6)
+    assert none is None and kl2.item() == kl.item()
