@@ -11,6 +11,7 @@
 // residual / padding mask, and hand a bf16 tile to a TMA store.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -73,7 +74,51 @@ struct IgemmParams {
   long long out_f32_ld;
   float* out_nchw;    // narrow tile (BN = 16): columns [0, nchw_c) written as fp32 NCHW planes (the network's last conv)
   int nchw_c;
+  // GroupNorm-fused epilogue (GN template instances): see the kernel's GN branch
+  int gn_mode;        // 1: tmC receives GroupNorm(+SiLU)(result); 2: tmC receives the raw result and tmG the normalised one
+  int gn_silu;
+  int gn_qpg;         // quad-columns (4 channels) per group
+  int gn_groups;
+  int gn_T;           // tiles per image = tiles_per_img * n_tiles: arrivals that complete an image's statistics
+  float gn_inv_cnt;   // 1 / (HW * channels per group)
+  float gn_eps;
+  const float* gn_gamma;
+  const float* gn_beta;
+  float2* gn_part;    // [images][groups][tiles per image][gn_qpg] per-tile (sum, sum of squares) of every quad-column
+  unsigned* gn_cnt;   // [images] arrival (low 16 bits) / departure (high 16 bits) counters; zero between launches
+  CUtensorMap tmG;
+#ifdef IDF_GN_TRACE
+  long long* trace;   // debug build only (csrc/build.py --variant gntrace -DIDF_GN_TRACE): clock64 stamps of CTA 0
+#endif
 };
+
+#ifdef IDF_GN_TRACE
+#define GN_TRACE_TILES 8
+#define GN_TRACE_EVENTS 8
+#define GN_STAMP(role, tile, evt)                                                                     \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && (tile) < GN_TRACE_TILES)                                                   \
+      p.trace[((role) * GN_TRACE_TILES + (tile)) * GN_TRACE_EVENTS + (evt)] = clock64();              \
+  } while (0)
+#else
+#define GN_STAMP(role, tile, evt) do { } while (0)
+#endif
+
+constexpr int GN_SMEM = 1536;  // per-column tables of the current 128-column group: bias (512 B), (scale, shift) (1 KiB)
+
+// silu(t) = t * sigmoid(t) = h + h * tanh(h), h = t / 2 (one MUFU op; same form as the standalone GroupNorm kernel)
+__device__ __forceinline__ float igemm_silu(float t) {
+  const float h = 0.5f * t;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
+
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Persistent variant: one CTA per SM walks a static list of output tiles (128 x BN, BN in {128, 192, 256}).
@@ -126,7 +171,22 @@ struct PgCfg {
 // covers all 128 rows; the warpgroups split the 32-column chunks of each column group between them. With one warp
 // per scheduler (EW = 1) nothing hides the TMEM / L1 / shared-memory latencies of the epilogue, which is what bounds
 // the short-K GEMMs and the single-tile-per-CTA launches of the 8x8 / 4x4 stages.
-template <int BN, int NSTG, int EW, bool PAIR>
+//
+// GN = true: GroupNorm(+SiLU) of the convolution result is applied in the epilogue, so the standalone GroupNorm pass
+// (read + write of the whole tensor and a launch) between two convolutions disappears (components.py:448-460: the
+// second ConvBlock's GroupNorm reads only what the first one's conv wrote). A tile covers 128 pixels of ONE image
+// (HW % 128 == 0) and BN of its channels, the statistics need the whole image: every tile reduces its accumulator
+// (+ bias + time bias) to per-quad-column (sum, sum of squares) - fixed shuffle tree over the 32 rows of a warp, the
+// four warps added in order - publishes them to global memory, bumps the image's arrival counter and waits until all
+// of the image's tiles have arrived; the tiles of an image are consecutive work units, i.e. they run on neighbouring
+// CTAs at the same time, and an image never has two units on one CTA (host-checked), so the wait cannot deadlock:
+// by induction over the image index every image's tiles get their accumulators. Each tile then sums the partials of
+// its groups in a fixed order (bit-reproducible, independent of the batch size), reads its accumulator from tensor
+// memory a second time and stores the normalised tile (mode 2: the raw tile as well, stored between the arrival and the
+// wait so that the exchange latency is hidden). The last tile to leave resets the counter, so the workspace is ready for
+// the next launch. Per-column constants (bias + time bias, gamma, beta; scale and shift once the statistics are known)
+// live in one register of "their" thread and are handed to the row-per-thread loops through small shared tables.
+template <int BN, int NSTG, int EW, bool PAIR, bool GN = false>
 __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = PgCfg<BN, NSTG, PAIR>;
   constexpr int EPI_THREADS = 128 * EW;
@@ -284,7 +344,9 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           if (sp >= splits) sp -= splits;
         }
         const int acc = it & 1;
+        if constexpr (GN) GN_STAMP(0, it, 0);
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        if constexpr (GN) GN_STAMP(0, it, 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -313,6 +375,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         }
         if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);
         else umma_commit(&tmem_full[acc]);
+        if constexpr (GN) GN_STAMP(0, it, 2);
       }
     }
   } else {
@@ -369,6 +432,218 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           for (int c = 0; c < 16; ++c)
             if (c < p.nchw_c) dst[(long long)c * p.HW] = __uint_as_float(v[c]) + (p.bias ? __ldg(p.bias + c) : 0.f);
         }
+        continue;
+      }
+      if constexpr (GN) {
+        constexpr int QC = BN / 4;
+        float* cbt = reinterpret_cast<float*>(stage_base + NSTG * PG_STG_BYTES + 256);  // [128] bias + time bias of the
+        float2* sct = reinterpret_cast<float2*>(cbt + 128);                               // current column group; [128] (scale, shift)
+        float* red = reinterpret_cast<float*>(stage_base);  // [4 warps][BN / 4][2]: staging buffer 0 during pass 1
+        const int tile_m = PAIR ? 2 * tw.tile_m + rank : tw.tile_m, n0 = tw.n_idx * BN;
+        const int acc = it & 1;
+        const int tpi = p.tiles_per_img, qpg = p.gn_qpg;
+        const int img = p.tpi_shift >= 0 ? (tile_m >> p.tpi_shift) : (tile_m / tpi);
+        // this thread's column (thread et <-> column n0 + et): bias + time bias, gamma, beta - fetched while the MMAs run
+        float cb_r = 0.f, ga_r = 0.f, be_r = 0.f;
+        if (et < BN) {
+          const int col = n0 + et;
+          if (p.bias != nullptr) cb_r = __ldg(p.bias + col);
+          if (p.rowbias != nullptr)
+            cb_r += __ldg(p.rowbias + (long long)(p.rowbias_idx ? p.rowbias_idx[img] : img) * p.rowbias_ld + col);
+          ga_r = __ldg(p.gn_gamma + col);
+          be_r = __ldg(p.gn_beta + col);
+        }
+        if (issuer) tma_store_wait_read_all();  // the previous tile's stores have finished reading the staging buffer
+        if (issuer) GN_STAMP(1, it, 0);
+        mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+        tc_fence_after_sync();
+        if (issuer) GN_STAMP(1, it, 1);
+        const uint32_t tmem_d = tmem_base + acc * BN + lane_addr;
+        // ---- pass 1: per-quad-column (sum, sum of squares) over this tile's 128 rows
+#pragma unroll 1
+        for (int cg = 0; cg < GPT; ++cg) {
+          const int gcols = group_cols(cg);
+          const int my_nch = (gcols / 32) / EW;
+          named_bar_sync(1, EPI_THREADS);  // staging buffer (red) and cbt free
+          if (et >= cg * 128 && et < cg * 128 + gcols) cbt[et - cg * 128] = cb_r;
+          named_bar_sync(1, EPI_THREADS);
+#pragma unroll 1
+          for (int i0 = 0; i0 < my_nch; i0 += 2) {
+            const bool two = i0 + 1 < my_nch;
+            const int c0 = wg * my_nch + i0;
+            uint32_t v[2][32];
+            tmem_ld_32x32(tmem_d + cg * 128 + c0 * 32, v[0]);
+            if (two) tmem_ld_32x32(tmem_d + cg * 128 + (c0 + 1) * 32, v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !two) break;
+              const int c = c0 + h;
+              float w16[16];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 cb4 = *reinterpret_cast<const float4*>(cbt + c * 32 + 4 * q);
+                const float a0 = __uint_as_float(v[h][4 * q + 0]) + cb4.x, a1 = __uint_as_float(v[h][4 * q + 1]) + cb4.y;
+                const float a2 = __uint_as_float(v[h][4 * q + 2]) + cb4.z, a3 = __uint_as_float(v[h][4 * q + 3]) + cb4.w;
+                w16[q] = (a0 + a1) + (a2 + a3);
+                w16[8 + q] = fmaf(a3, a3, fmaf(a2, a2, fmaf(a1, a1, a0 * a0)));
+              }
+              // halving butterfly over the 32 rows of the warp: 16 values -> lane l ends with the total of value l >> 1
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const bool up = (lane & 16) != 0;
+                const float send = up ? w16[k] : w16[k + 8], keep = up ? w16[k + 8] : w16[k];
+                w16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const bool up = (lane & 8) != 0;
+                const float send = up ? w16[k] : w16[k + 4], keep = up ? w16[k + 4] : w16[k];
+                w16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const bool up = (lane & 4) != 0;
+                const float send = up ? w16[k] : w16[k + 2], keep = up ? w16[k + 2] : w16[k];
+                w16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              {
+                const bool up = (lane & 2) != 0;
+                const float send = up ? w16[0] : w16[1], keep = up ? w16[1] : w16[0];
+                w16[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+              }
+              w16[0] += __shfl_xor_sync(0xffffffffu, w16[0], 1);
+              if ((lane & 1) == 0) {
+                const int idx = lane >> 1;  // 0..7: sum of quad idx, 8..15: sum of squares of quad idx - 8
+                red[((quad * QC) + ((cg * 128 + c * 32) >> 2) + (idx & 7)) * 2 + (idx >> 3)] = w16[0];
+              }
+            }
+          }
+        }
+        named_bar_sync(1, EPI_THREADS);
+        if (issuer) GN_STAMP(1, it, 2);
+        if (et < QC) {  // partials laid out [image][group][tile of the image][quad-column of the group]
+          float s_ = 0.f, q_ = 0.f;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) { s_ += red[(w4 * QC + et) * 2]; q_ += red[(w4 * QC + et) * 2 + 1]; }
+          const int qc = (n0 >> 2) + et;
+          const int g = qc / qpg;
+          p.gn_part[(((long long)img * p.gn_groups + g) * tpi + (tile_m - img * tpi)) * qpg + (qc - g * qpg)] = make_float2(s_, q_);
+        }
+        named_bar_sync(1, EPI_THREADS);
+        if (issuer) {  // release: the CTA's partials (ordered by the barrier) before the arrival
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          atomicAdd(&p.gn_cnt[img], 1u);
+          GN_STAMP(1, it, 3);
+        }
+        // one pass over the accumulator through the staging buffer: raw (+ bias) tile or normalised tile
+        float sc_r = 0.f, sh_r = 0.f;
+        auto store_pass = [&](const bool norm, const CUtensorMap* tc) {
+#pragma unroll 1
+          for (int cg = 0; cg < GPT; ++cg) {
+            const int gcols = group_cols(cg);
+            const int my_nch = (gcols / 32) / EW;
+            if (issuer) tma_store_wait_read_all();
+            named_bar_sync(1, EPI_THREADS);  // staging buffer and tables free
+            if (et >= cg * 128 && et < cg * 128 + gcols) {
+              if (norm) sct[et - cg * 128] = make_float2(sc_r, sh_r);
+              else cbt[et - cg * 128] = cb_r;
+            }
+            named_bar_sync(1, EPI_THREADS);
+#pragma unroll 1
+            for (int i0 = 0; i0 < my_nch; i0 += 2) {
+              const bool two = i0 + 1 < my_nch;
+              const int c0 = wg * my_nch + i0;
+              uint32_t v[2][32];
+              tmem_ld_32x32(tmem_d + cg * 128 + c0 * 32, v[0]);
+              if (two) tmem_ld_32x32(tmem_d + cg * 128 + (c0 + 1) * 32, v[1]);
+              tmem_ld_wait();
+              if (norm && cg == GPT - 1 && i0 + 2 >= my_nch) {  // this warp's last TMEM read of the tile
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                  if constexpr (PAIR) mbar_arrive_even_cta(&tmem_empty[acc]);
+                  else mbar_arrive(&tmem_empty[acc]);
+                }
+              }
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !two) break;
+                const int c = c0 + h;
+                float a[32];
+                if (norm) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 2) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(sct + c * 32 + j);  // (scale, shift) of two columns
+                    a[j] = fmaf(__uint_as_float(v[h][j]), t4.x, t4.y);
+                    a[j + 1] = fmaf(__uint_as_float(v[h][j + 1]), t4.z, t4.w);
+                  }
+                  if (p.gn_silu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) a[j] = igemm_silu(a[j]);
+                  }
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 cb4 = *reinterpret_cast<const float4*>(cbt + c * 32 + 4 * q);
+                    a[4 * q + 0] = __uint_as_float(v[h][4 * q + 0]) + cb4.x; a[4 * q + 1] = __uint_as_float(v[h][4 * q + 1]) + cb4.y;
+                    a[4 * q + 2] = __uint_as_float(v[h][4 * q + 2]) + cb4.z; a[4 * q + 3] = __uint_as_float(v[h][4 * q + 3]) + cb4.w;
+                  }
+                }
+                uint8_t* box = stage_base + (c >> 1) * (BLOCK_M * 128) + r * 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+                  uint4 o;
+                  o.x = pack_bf16x2(a[8 * q + 0], a[8 * q + 1]);
+                  o.y = pack_bf16x2(a[8 * q + 2], a[8 * q + 3]);
+                  o.z = pack_bf16x2(a[8 * q + 4], a[8 * q + 5]);
+                  o.w = pack_bf16x2(a[8 * q + 6], a[8 * q + 7]);
+                  *reinterpret_cast<uint4*>(box + chunk * 16) = o;
+                }
+              }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, EPI_THREADS);
+            if (issuer) {
+              for (int bx = 0; bx < gcols / 64; ++bx)
+                tma_store_2d(tc, stage_base + bx * (BLOCK_M * 128), n0 + cg * 128 + bx * 64, tile_m * BLOCK_M);
+              tma_store_commit();
+            }
+          }
+        };
+        if (p.gn_mode == 2) store_pass(false, &p.tmC);  // the raw tile goes out while the other tiles' partials arrive
+        if (issuer) {
+          GN_STAMP(1, it, 4);
+          while ((ld_relaxed_gpu(&p.gn_cnt[img]) & 0xffffu) != (unsigned)p.gn_T) __nanosleep(20);
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          GN_STAMP(1, it, 5);
+        }
+        named_bar_sync(1, EPI_THREADS);
+        if (et < BN) {  // statistics of this thread's column's group: the image's partials in a fixed order
+          const int g = (n0 + et) / (4 * qpg);
+          const int n = tpi * qpg;
+          const float2* src = p.gn_part + ((long long)img * p.gn_groups + g) * n;
+          float s_ = 0.f, q_ = 0.f;
+          for (int i0 = 0; i0 < n; i0 += 16) {
+            float2 v2[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v2[k] = (i0 + k < n) ? __ldcg(src + i0 + k) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { s_ += v2[k].x; q_ += v2[k].y; }
+          }
+          const float mean = s_ * p.gn_inv_cnt;
+          const float var = fmaxf(q_ * p.gn_inv_cnt - mean * mean, 0.f);
+          sc_r = rsqrtf(var + p.gn_eps) * ga_r;
+          sh_r = fmaf(cb_r, sc_r, be_r - mean * sc_r);  // (acc + cb - mean) * rstd * gamma + beta = acc * sc + sh
+        }
+        if (issuer) {  // leave: the last tile of the image to do so zeroes the counter for the next launch
+          GN_STAMP(1, it, 6);
+          const unsigned old = atomicAdd(&p.gn_cnt[img], 0x10000u);
+          if ((old >> 16) == (unsigned)p.gn_T - 1u) atomicExch(&p.gn_cnt[img], 0u);
+        }
+        store_pass(true, p.gn_mode == 2 ? &p.tmG : &p.tmC);
+        if (issuer) GN_STAMP(1, it, 7);
         continue;
       }
       const int t = u;  // (the residual prefetch below is only used with splits == 1, where the unit is the tile)
@@ -566,13 +841,22 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
   }
 }
 
-template <int BN, int NSTG, int EW, bool PAIR>
+// GN-fused launches: a walker count that is a whole number of images per wave, so that the tiles of an image always
+// run in the same wave (an image split over two waves makes its first tiles wait a whole tile time for the others, and
+// the delay then spreads through the images those CTAs share later: measured +17 us on a 48 us conv)
+static int gn_walkers(int walkers, int per_img) {
+  return per_img > 0 && walkers >= per_img ? walkers / per_img * per_img : walkers;
+}
+
+template <int BN, int NSTG, int EW, bool PAIR, bool GN = false>
 static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
   using Cfg = PgCfg<BN, NSTG, PAIR>;
+  constexpr int SMEM = Cfg::SMEM + (GN ? GN_SMEM : 0);
+  static_assert(SMEM <= 232448, "shared memory");
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(igemm_persist_kernel<BN, NSTG, EW, PAIR>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM),
+    int rc = check_cuda(cudaFuncSetAttribute(igemm_persist_kernel<BN, NSTG, EW, PAIR, GN>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM),
                         "igemm_persist: cudaFuncSetAttribute");
     if (rc != IDF_OK) return rc;
     attr_set = true;
@@ -581,22 +865,24 @@ static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
   if constexpr (PAIR) {
     // one cluster of two CTAs per TPC; the cluster walks the list of (M-tile pair, N tile, K split) units
     const int units = ((m_tiles + 1) / 2) * (p.N / BN) * p.splits * (p.up2_all ? 4 : 1);
-    const int clusters = units < sm_count() / 2 ? units : sm_count() / 2;
+    int clusters = units < sm_count() / 2 ? units : sm_count() / 2;
+    if constexpr (GN) clusters = gn_walkers(clusters, (p.tiles_per_img / 2) * (p.N / BN));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(64 + 128 * EW);
-    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return check_cuda(cudaLaunchKernelEx(&cfg, igemm_persist_kernel<BN, NSTG, EW, PAIR>, p), "igemm_persist pair launch");
+    return check_cuda(cudaLaunchKernelEx(&cfg, igemm_persist_kernel<BN, NSTG, EW, PAIR, GN>, p), "igemm_persist pair launch");
   } else {
     const int tiles = m_tiles * (p.N / BN) * p.splits * (p.up2_all ? 4 : 1);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    return check_cuda(launch_kernel(igemm_persist_kernel<BN, NSTG, EW, PAIR>, dim3(grid), dim3(64 + 128 * EW), Cfg::SMEM,
+    int grid = tiles < sm_count() ? tiles : sm_count();
+    if constexpr (GN) grid = gn_walkers(grid, p.tiles_per_img * (p.N / BN));
+    return check_cuda(launch_kernel(igemm_persist_kernel<BN, NSTG, EW, PAIR, GN>, dim3(grid), dim3(64 + 128 * EW), SMEM,
                                  stream, p),
                       "igemm_persist launch");
   }
@@ -794,7 +1080,8 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   int bn = BLOCK_N;
   // short-K GEMMs (K <= 1024: QKV / out_proj / skip projections) are epilogue- and memory-bound: narrow tiles with
   // triple-buffered staging keep loads, residual prefetch and stores in flight together
-  const bool short_k = !narrow && ktot <= 1024 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
+  const bool gn = a->gn_mode != 0;
+  const bool short_k = !narrow && !gn && ktot <= 1024 && a->taps[0] == 1 && (nseg == 1 || a->taps[1] == 1);
   if (narrow) {
     bn = 16;
   } else if (!short_k) {
@@ -857,9 +1144,58 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   // 32x32 / 16x16 stages gain 5-9 %, 192-wide tiles lose 13-17 %, everything else is neutral or pays for the
   // cluster start-up: IDF_IGEMM_PAIR = 1 (default) pairs only the former, 2 = wherever legal, 0 = never.
   static const int pair_mode = [] { const char* e = getenv("IDF_IGEMM_PAIR"); return e ? atoi(e) : 1; }();
-  const bool pair_legal = !narrow && !batched && M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2;
+  const bool pair_legal = !narrow && !batched && M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2 &&
+                          !(gn && (p.tiles_per_img & 1));
   const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && bn == 256 && !short_k &&
                                                       (M + BLOCK_M - 1) / BLOCK_M * par_tiles >= sm_count()));
+  if (gn) {
+    // GroupNorm-fused epilogue: whole images of 128-pixel tiles, plain bf16 output, no split-K
+    if ((a->gn_mode != 1 && a->gn_mode != 2) || narrow || is_matrix || p.tiles_per_img <= 0 || a->res || a->vt || a->out_f32 ||
+        a->out_up2 || a->w_mn || a->ws || a->zero_pad_last || batched || a->s2_batch || a->epi_h || a->epi_w)
+      return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode needs an image-shaped conv (H*W %% 128 == 0) with a plain bf16 output");
+    if (a->gn_groups <= 0 || a->N % a->gn_groups != 0 || (a->N / a->gn_groups) % 4 != 0)
+      return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode needs channels per group %% 4 == 0 (N = %d, groups = %d)", a->N, a->gn_groups);
+    if (!a->gn_gamma || !a->gn_beta || (reinterpret_cast<uintptr_t>(a->gn_gamma) & 15) || (reinterpret_cast<uintptr_t>(a->gn_beta) & 15))
+      return fail(IDF_ERR_ARG, "igemm: gn_gamma / gn_beta must be 16-byte aligned fp32 vectors");
+    if (a->gn_mode == 2 && (a->gn_out == nullptr || a->gn_ldo < a->N)) return fail(IDF_ERR_ARG, "igemm: gn_mode 2 needs gn_out");
+    const long long m_tiles = M / BLOCK_M;
+    const long long cnt_bytes = ((long long)x0.n * 4 + 255) / 256 * 256;
+    const long long need = cnt_bytes + m_tiles * (a->N / 4) * 8;
+    if (a->gn_ws == nullptr || (reinterpret_cast<uintptr_t>(a->gn_ws) & 255) || a->gn_ws_bytes < need)
+      return fail(IDF_ERR_ARG, "igemm: gn_ws must be 256-byte aligned and hold %lld bytes", need);
+    const long long n_tiles = a->N / bn;
+    const long long units = (pair ? m_tiles / 2 : m_tiles) * n_tiles;
+    const long long walkers = pair ? (units < sm_count() / 2 ? units : sm_count() / 2) : (units < sm_count() ? units : sm_count());
+    const long long per_img = (pair ? p.tiles_per_img / 2 : p.tiles_per_img) * n_tiles;
+    if (per_img > walkers || p.tiles_per_img * n_tiles > 0xffff)
+      return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode: an image's %lld tiles do not fit one wave of %lld walkers", per_img, walkers);
+    p.gn_mode = a->gn_mode;
+    p.gn_silu = a->gn_silu ? 1 : 0;
+    p.gn_qpg = a->N / a->gn_groups / 4;
+    p.gn_groups = a->gn_groups;
+    p.gn_T = (int)(p.tiles_per_img * n_tiles);
+    p.gn_inv_cnt = 1.0f / ((float)HW * (float)(a->N / a->gn_groups));
+    p.gn_eps = a->gn_eps;
+    p.gn_gamma = a->gn_gamma;
+    p.gn_beta = a->gn_beta;
+    p.gn_cnt = reinterpret_cast<unsigned*>(a->gn_ws);
+    p.gn_part = reinterpret_cast<float2*>(reinterpret_cast<char*>(a->gn_ws) + cnt_bytes);
+    if (a->gn_mode == 2 &&
+        (rc = make_mat_map(&p.tmG, a->gn_out, (uint64_t)M, (uint64_t)a->N, (uint64_t)a->gn_ldo, 64, BLOCK_M)) != IDF_OK)
+      return rc;
+#ifdef IDF_GN_TRACE
+    {
+      static long long* trace_buf = nullptr;
+      if (trace_buf == nullptr) {
+        cudaMalloc(&trace_buf, 2 * GN_TRACE_TILES * GN_TRACE_EVENTS * sizeof(long long));
+        FILE* fh = fopen("/tmp/idf_gn_trace_ptr", "w");
+        if (fh) { fprintf(fh, "%llu", (unsigned long long)(uintptr_t)trace_buf); fclose(fh); }
+      }
+      cudaMemsetAsync(trace_buf, 0, 2 * GN_TRACE_TILES * GN_TRACE_EVENTS * sizeof(long long), reinterpret_cast<cudaStream_t>(stream));
+      p.trace = trace_buf;
+    }
+#endif
+  }
   if (a->w_mn) {  // rows = the A operand's channels (K per tap), columns = (weight tap, output column)
     int maxt = 0;
     for (int t = 0; t < a->taps[0]; ++t) maxt = p.wtap[t] > maxt ? p.wtap[t] : maxt;
@@ -962,6 +1298,13 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
       return wbn == 256 ? launch_persist<256, 2>(p, st, false) : launch_persist<192, 2>(p, st, false);
     }
     return launch_persist<128, 3>(p, st, pair);
+  }
+  if (gn) {
+    switch (bn) {
+      case 256: return pair ? launch_persist_ew<256, 1, 2, true, true>(p, st) : launch_persist_ew<256, 1, 2, false, true>(p, st);
+      case 192: return pair ? launch_persist_ew<192, 1, 2, true, true>(p, st) : launch_persist_ew<192, 1, 2, false, true>(p, st);
+      default: return pair ? launch_persist_ew<128, 1, 2, true, true>(p, st) : launch_persist_ew<128, 1, 2, false, true>(p, st);
+    }
   }
   switch (bn) {
     case 16: return launch_persist_ew<16, 1, 2, false>(p, st);

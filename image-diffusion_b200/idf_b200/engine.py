@@ -128,6 +128,10 @@ class UnetEngine:
         self.splitk = int(__import__("os").environ.get("IDF_SPLITK_4X4", "3"))
         self._B, self._rng = 0, (0, 0)
         self.tc_tail = __import__("os").environ.get("IDF_TC_TAIL", "1") != "0"
+        # GroupNorm fused into the producing conv's epilogue where an image is a whole number of 128-pixel tiles
+        # (32x32 / 16x16 stages): 1 = GN2 (y1 -> h2, y1 never stored), 2 = also GN3 (conv2 stores x2 and h3)
+        self.gn_fuse = int(__import__("os").environ.get("IDF_GN_FUSE", "2"))
+        self._gn_ws = {}
         self.downs, self.mids, self.ups = unet_blocks(arch)
         for _, cin, cout in self.downs + self.mids + self.ups:
             if cin % 64 or cout % 128:
@@ -188,11 +192,24 @@ class UnetEngine:
         if self.taps is not None:
             self.taps[name] = t2d.float().clone()
 
+    def _gn_fused(self, key, B, M, cout, silu, out=None):
+        """Arguments of the GroupNorm-fused igemm epilogue (idf_igemm_args.gn_*) for GroupNorm `key` of the module."""
+        w = self.packed.w
+        nbytes = ops.gn_workspace_bytes(B, M, cout)
+        ws = self._gn_ws.get(nbytes)
+        if ws is None:  # counters start at zero; every launch leaves them zero
+            ws = self._gn_ws[nbytes] = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
+        g = dict(gamma=w[key + "w"], beta=w[key + "b"], groups=self.G, silu=silu, ws=ws)
+        if out is not None:
+            g["out"] = out
+        return g
+
     def _block(self, p, x: Act, cout, table, idx, final_dst=None) -> Act:
         w, G = self.packed.w, self.G
         B, H, W = x.grid
         M, HW = x.M, x.H * x.W
         hd = cout // self.heads
+        fuse = self.gn_fuse if (self.taps is None and HW % 128 == 0 and (cout // G) % 4 == 0 and cout % G == 0) else 0
         sk = {}
         if self.splitk > 1 and HW <= 16:
             sk = dict(ws=self._splitk_ws(M * cout), splits=self.splitk)
@@ -201,16 +218,24 @@ class UnetEngine:
             k = f"{p}.{l}"
             h1 = self._buf("h1", HW, cin)
             ops.groupnorm_silu(x.t, h1, w[k + ".g1w"], w[k + ".g1b"], B, HW, cin, G, True)
-            y1 = self._buf("y1", HW, cout)
             off = self.tp_off[(p, l)]
-            ops.igemm([(h1, x.grid, cin, 9)], w[k + ".w1"], cout, y1, bias=w[k + ".b1"],
-                      rowbias=table[:, off:off + cout], rowbias_idx=idx, **sk)
             h2 = self._buf("h2", HW, cout)
-            ops.groupnorm_silu(y1, h2, w[k + ".g2w"], w[k + ".g2b"], B, HW, cout, G, True)
+            y1 = None if fuse >= 1 else self._buf("y1", HW, cout)
+            if fuse >= 1:  # conv1's epilogue normalises: y1 is never written
+                ops.igemm([(h1, x.grid, cin, 9)], w[k + ".w1"], cout, h2, bias=w[k + ".b1"],
+                          rowbias=table[:, off:off + cout], rowbias_idx=idx, gn=self._gn_fused(k + ".g2", B, M, cout, True))
+            else:
+                ops.igemm([(h1, x.grid, cin, 9)], w[k + ".w1"], cout, y1, bias=w[k + ".b1"],
+                          rowbias=table[:, off:off + cout], rowbias_idx=idx, **sk)
+                ops.groupnorm_silu(y1, h2, w[k + ".g2w"], w[k + ".g2b"], B, HW, cout, G, True)
             x2 = self._buf("x2", HW, cout)
-            ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"], **sk)
             h3 = self._buf("h3", HW, cout)
-            ops.groupnorm_silu(x2, h3, w[k + ".g3w"], w[k + ".g3b"], B, HW, cout, G, False)
+            if fuse >= 2:  # conv2 stores the raw x2 (attention residual) and GroupNorm(x2) (QKV input)
+                ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"],
+                          gn=self._gn_fused(k + ".g3", B, M, cout, False, out=h3))
+            else:
+                ops.igemm([(h2, x.grid, cout, 9), (x.t, x.grid, cin, 1)], w[k + ".w2"], cout, x2, bias=w[k + ".b2"], **sk)
+                ops.groupnorm_silu(x2, h3, w[k + ".g3w"], w[k + ".g3b"], B, HW, cout, G, False)
             # Q | K | V token-major in one buffer: the attention kernel takes V tiles as MN-major tcgen05 operands, so
             # the QKV GEMM has a plain TMA-store epilogue (no transposed V^T copy)
             qk = self._buf("qkv", HW, 3 * cout)

@@ -37,6 +37,8 @@ class IgemmArgs(C.Structure):
         ("w_mn", _i32), ("w_tap_ids", C.c_int8 * 9), ("s2_direct", _i32),
         ("w_batch_row", _i64), ("w_batch_col", _i64),
         ("out_nchw", _vp), ("out_nchw_c", _i32),
+        ("gn_mode", _i32), ("gn_groups", _i32), ("gn_silu", _i32), ("gn_eps", _f32),
+        ("gn_gamma", _vp), ("gn_beta", _vp), ("gn_out", _vp), ("gn_ldo", _i64), ("gn_ws", _vp), ("gn_ws_bytes", _i64),
     ]
 
 

@@ -26,9 +26,12 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
 def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, rowbias=None, rowbias_idx=None,
           res=None, vt=None, vt_col0: int = 0, zero_pad_last: bool = False, epi_hw=None, s2_batch: int = 0, ws=None,
           tap_offsets=None, splits: int = 0, out_up2=None, s2_direct: bool = False, w_mn: bool = False,
-          w_tap_ids=None, w_batch=None, out_nchw=None) -> torch.Tensor:
+          w_tap_ids=None, w_batch=None, out_nchw=None, gn=None) -> torch.Tensor:
     """segs: list of (tensor2d, (n, h, w), channels, taps). `out` is a 2-D bf16 (or fp32) matrix view; with `out_nchw`
-    (fp32 (B, C <= 16, H, W), weights / bias zero-padded to n_out = 16) the result goes there instead and `out` is None."""
+    (fp32 (B, C <= 16, H, W), weights / bias zero-padded to n_out = 16) the result goes there instead and `out` is None.
+    gn = dict(gamma, beta, groups, silu, ws[, out, eps]): GroupNorm(+SiLU) of the result in the epilogue; without `out`
+    the normalised tensor replaces the raw one in `out`, with it `out` keeps the raw result and gn["out"] gets the
+    normalised one. ws: zero-initialised byte scratch from gn_workspace_bytes()."""
     a = IgemmArgs()
     if not 1 <= len(segs) <= 2:
         raise ValueError("igemm takes one or two input segments")
@@ -73,12 +76,26 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
         a.out_up2 = 2
     elif out_up2 is not None:  # (row parity, column parity) of the 2x-resolution output this launch fills
         a.out_up2, (a.out_ph, a.out_pw) = 1, out_up2
+    if gn is not None:
+        g_out = gn.get("out")
+        a.gn_mode = 2 if g_out is not None else 1
+        a.gn_groups, a.gn_silu, a.gn_eps = gn["groups"], 1 if gn["silu"] else 0, gn.get("eps", 1e-5)
+        a.gn_gamma, a.gn_beta = gn["gamma"].data_ptr(), gn["beta"].data_ptr()
+        if g_out is not None:
+            _check_bf16_rows(g_out, "igemm gn out")
+            a.gn_out, a.gn_ldo = g_out.data_ptr(), g_out.stride(0)
+        a.gn_ws, a.gn_ws_bytes = gn["ws"].data_ptr(), gn["ws"].numel() * gn["ws"].element_size()
     if tap_offsets is not None:  # explicit (dh, dw) list for segment 0
         a.custom_taps = 1
         for i, (dh, dw) in enumerate(tap_offsets):
             a.tap_dh[i], a.tap_dw[i] = dh, dw
     call("idf_conv2d_igemm", a)
     return out if out_nchw is None else out_nchw
+
+
+def gn_workspace_bytes(images: int, rows: int, n_out: int) -> int:
+    """Scratch of the GroupNorm-fused igemm epilogue (idf_igemm_args.gn_ws): image counters + per-tile partial sums."""
+    return (images * 4 + 255) // 256 * 256 + (rows // 128) * (n_out // 4) * 8
 
 
 def groupnorm_silu(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, B: int, HW: int, C: int,

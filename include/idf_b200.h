@@ -125,6 +125,24 @@ typedef struct idf_igemm_args {
                            out_nchw[(img * out_nchw_c + c) * h * w + pixel]; `out` is unused and may be NULL. One plain
                            9- or 1-tap segment. */
   int32_t out_nchw_c;
+  int32_t gn_mode;      /* != 0: GroupNorm (+ SiLU) of the convolution result (+ bias + rowbias) applied in the epilogue, i.e.
+                           the GroupNorm that opens the NEXT ConvBlock (components.py:448-460) without its own pass over the
+                           tensor. 1: `out` receives the normalised tensor only; 2: `out` receives the raw result and `gn_out`
+                           the normalised one (the raw tensor is also a residual / skip input). Needs an image-shaped input
+                           with h*w a multiple of 128, N / gn_groups a multiple of 4, a plain bf16 output (no res / vt / ws /
+                           up2 / zero_pad_last). Statistics are taken from the fp32 accumulators over the whole (sample,
+                           group), summed in a fixed order: results do not depend on the batch size. */
+  int32_t gn_groups;
+  int32_t gn_silu;
+  float gn_eps;
+  const float* gn_gamma; /* fp32 (N), 16-byte aligned */
+  const float* gn_beta;
+  void* gn_out;         /* gn_mode 2: bf16 (M, N) matrix, row stride gn_ldo */
+  int64_t gn_ldo;
+  void* gn_ws;          /* 256-byte aligned scratch: ceil(4 * a[0].n / 256) * 256 bytes of image counters, which must be ZERO
+                           before the first use and are left zero by every launch, then 8 * (M / 128) * (N / 4) bytes of
+                           per-tile partial sums. One launch at a time per workspace. */
+  int64_t gn_ws_bytes;
 } idf_igemm_args;
 
 int idf_conv2d_igemm(const idf_igemm_args* args, idf_stream_t stream);
