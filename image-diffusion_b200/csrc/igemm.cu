@@ -79,13 +79,13 @@ struct IgemmParams {
   int gn_silu;
   int gn_qpg;         // quad-columns (4 channels) per group
   int gn_groups;
-  int gn_T;           // tiles per image = tiles_per_img * n_tiles: arrivals that complete an image's statistics
   float gn_inv_cnt;   // 1 / (HW * channels per group)
   float gn_eps;
   const float* gn_gamma;
   const float* gn_beta;
-  float2* gn_part;    // [images][groups][tiles per image][gn_qpg] per-tile (sum, sum of squares) of every quad-column
-  unsigned* gn_cnt;   // [images] arrival (low 16 bits) / departure (high 16 bits) counters; zero between launches
+  float4* gn_part;    // [images][groups][tiles per image][gn_qpg] per-tile (sum, sum of squares, launch tag, -) of every
+                      // quad-column: one 16-byte record, written and read with single vector accesses
+  unsigned* gn_epoch; // [0] launch epoch of this workspace (records of this launch carry epoch + 1), [1] finished CTAs
   CUtensorMap tmG;
 #ifdef IDF_GN_TRACE
   long long* trace;   // debug build only (csrc/build.py --variant gntrace -DIDF_GN_TRACE): clock64 stamps of CTA 0
@@ -114,6 +114,14 @@ __device__ __forceinline__ float igemm_silu(float t) {
   return fmaf(h, th, h);
 }
 
+__device__ __forceinline__ float4 ld_relaxed_gpu_v4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_v4(float4* p, const float4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -177,14 +185,15 @@ struct PgCfg {
 // second ConvBlock's GroupNorm reads only what the first one's conv wrote). A tile covers 128 pixels of ONE image
 // (HW % 128 == 0) and BN of its channels, the statistics need the whole image: every tile reduces its accumulator
 // (+ bias + time bias) to per-quad-column (sum, sum of squares) - fixed shuffle tree over the 32 rows of a warp, the
-// four warps added in order - publishes them to global memory, bumps the image's arrival counter and waits until all
-// of the image's tiles have arrived; the tiles of an image are consecutive work units, i.e. they run on neighbouring
+// four warps added in order - and publishes them to global memory as 16-byte records that carry the launch's tag; a
+// tile then polls the records of its groups until all of the image's tiles have written theirs (no counters, fences
+// or atomics on the path); the tiles of an image are consecutive work units, i.e. they run on neighbouring
 // CTAs at the same time, and an image never has two units on one CTA (host-checked), so the wait cannot deadlock:
 // by induction over the image index every image's tiles get their accumulators. Each tile then sums the partials of
 // its groups in a fixed order (bit-reproducible, independent of the batch size), reads its accumulator from tensor
 // memory a second time and stores the normalised tile (mode 2: the raw tile as well, stored between the arrival and the
-// wait so that the exchange latency is hidden). The last tile to leave resets the counter, so the workspace is ready for
-// the next launch. Per-column constants (bias + time bias, gamma, beta; scale and shift once the statistics are known)
+// wait so that the exchange latency is hidden). The tag is the workspace's launch epoch + 1; the last CTA to finish
+// advances the epoch, so stale records of earlier launches (or of other layers sharing the workspace) never match. Per-column constants (bias + time bias, gamma, beta; scale and shift once the statistics are known)
 // live in one register of "their" thread and are handed to the row-per-thread loops through small shared tables.
 template <int BN, int NSTG, int EW, bool PAIR, bool GN = false>
 __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
@@ -402,6 +411,11 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         tma_load_2d(dst + bx * (BLOCK_M * 128), &p.tmR, &res_bar[bufi], nc0 + bx * 64, tm * BLOCK_M);
     };
     int it = 0, gc = 0;
+    unsigned tag = 0;
+    if constexpr (GN) {  // records of this launch carry epoch + 1 (never 0: fresh workspaces are zero-filled)
+      tag = ld_relaxed_gpu(p.gn_epoch) + 1u;
+      if (tag == 0u) tag = 1u;
+    }
     if (has_res && issuer && walker < total_tiles && !((p.flags & F_VT) || to_f32))
       load_res((PAIR ? 2 : 1) * (walker / n_tiles) + rank, walker % n_tiles, 0, 0);  // (residual path: splits == 1)
     TileWalk tw;
@@ -522,20 +536,16 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         }
         named_bar_sync(1, EPI_THREADS);
         if (issuer) GN_STAMP(1, it, 2);
-        if (et < QC) {  // partials laid out [image][group][tile of the image][quad-column of the group]
+        if (et < QC) {  // records laid out [image][group][tile of the image][quad-column of the group]
           float s_ = 0.f, q_ = 0.f;
 #pragma unroll
           for (int w4 = 0; w4 < 4; ++w4) { s_ += red[(w4 * QC + et) * 2]; q_ += red[(w4 * QC + et) * 2 + 1]; }
           const int qc = (n0 >> 2) + et;
           const int g = qc / qpg;
-          p.gn_part[(((long long)img * p.gn_groups + g) * tpi + (tile_m - img * tpi)) * qpg + (qc - g * qpg)] = make_float2(s_, q_);
+          st_relaxed_gpu_v4(p.gn_part + (((long long)img * p.gn_groups + g) * tpi + (tile_m - img * tpi)) * qpg + (qc - g * qpg),
+                            make_float4(s_, q_, __uint_as_float(tag), 0.f));
         }
-        named_bar_sync(1, EPI_THREADS);
-        if (issuer) {  // release: the CTA's partials (ordered by the barrier) before the arrival
-          asm volatile("fence.acq_rel.gpu;" ::: "memory");
-          atomicAdd(&p.gn_cnt[img], 1u);
-          GN_STAMP(1, it, 3);
-        }
+        if (issuer) GN_STAMP(1, it, 3);
         // one pass over the accumulator through the staging buffer: raw (+ bias) tile or normalised tile
         float sc_r = 0.f, sh_r = 0.f;
         auto store_pass = [&](const bool norm, const CUtensorMap* tc) {
@@ -612,36 +622,49 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
             }
           }
         };
-        if (p.gn_mode == 2) store_pass(false, &p.tmC);  // the raw tile goes out while the other tiles' partials arrive
-        if (issuer) {
-          GN_STAMP(1, it, 4);
-          while ((ld_relaxed_gpu(&p.gn_cnt[img]) & 0xffffu) != (unsigned)p.gn_T) __nanosleep(20);
-          asm volatile("fence.acq_rel.gpu;" ::: "memory");
-          GN_STAMP(1, it, 5);
-        }
-        named_bar_sync(1, EPI_THREADS);
-        if (et < BN) {  // statistics of this thread's column's group: the image's partials in a fixed order
-          const int g = (n0 + et) / (4 * qpg);
-          const int n = tpi * qpg;
-          const float2* src = p.gn_part + ((long long)img * p.gn_groups + g) * n;
-          float s_ = 0.f, q_ = 0.f;
+        if (p.gn_mode == 2) store_pass(false, &p.tmC);  // the raw tile goes out while the other tiles' records arrive
+        if (issuer) GN_STAMP(1, it, 4);
+        // statistics of this thread's column's group: the records of all of the image's tiles, summed in a fixed order.
+        // A record is valid once it carries this launch's tag (data and tag travel in one 16-byte access, so no
+        // separate flag, fence or counter is needed). One thread waits for the records of its own group first - the
+        // other tiles write all of theirs at the same moment - so that a waiting CTA polls with one thread, not 256
+        // (measured: all threads polling slowed the TMA loads of every CTA); then each thread loads and checks its own.
+        const int n = tpi * qpg;
+        float s_ = 0.f, q_ = 0.f;
+        // the group's n records, 16 per batch (one round trip): sums them in order once every tag matches
+        auto sum_group = [&](const float4* src, const unsigned backoff_ns) {
+          s_ = 0.f; q_ = 0.f;
           for (int i0 = 0; i0 < n; i0 += 16) {
-            float2 v2[16];
+            float4 v4[16];
+            bool ok;
+            unsigned ns = backoff_ns;
+            do {
+              ok = true;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v2[k] = (i0 + k < n) ? __ldcg(src + i0 + k) : make_float2(0.f, 0.f);
+              for (int k = 0; k < 16; ++k)
+                v4[k] = (i0 + k < n) ? ld_relaxed_gpu_v4(src + i0 + k) : make_float4(0.f, 0.f, __uint_as_float(tag), 0.f);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { s_ += v2[k].x; q_ += v2[k].y; }
+              for (int k = 0; k < 16; ++k) ok = ok && (__float_as_uint(v4[k].z) == tag);
+              if (!ok) {
+                __nanosleep(ns);
+                if (ns < 256) ns *= 2;
+              }
+            } while (!ok);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { s_ += v4[k].x; q_ += v4[k].y; }
           }
+        };
+        const float4* gsrc = p.gn_part + ((long long)img * p.gn_groups + (n0 + et) / (4 * qpg)) * n;
+        if (issuer) sum_group(gsrc, 32);
+        named_bar_sync(1, EPI_THREADS);
+        if (et < BN) {
+          sum_group(gsrc, 256);
           const float mean = s_ * p.gn_inv_cnt;
           const float var = fmaxf(q_ * p.gn_inv_cnt - mean * mean, 0.f);
           sc_r = rsqrtf(var + p.gn_eps) * ga_r;
           sh_r = fmaf(cb_r, sc_r, be_r - mean * sc_r);  // (acc + cb - mean) * rstd * gamma + beta = acc * sc + sh
         }
-        if (issuer) {  // leave: the last tile of the image to do so zeroes the counter for the next launch
-          GN_STAMP(1, it, 6);
-          const unsigned old = atomicAdd(&p.gn_cnt[img], 0x10000u);
-          if ((old >> 16) == (unsigned)p.gn_T - 1u) atomicExch(&p.gn_cnt[img], 0u);
-        }
+        if (issuer) GN_STAMP(1, it, 6);
         store_pass(true, p.gn_mode == 2 ? &p.tmG : &p.tmC);
         if (issuer) GN_STAMP(1, it, 7);
         continue;
@@ -828,6 +851,14 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
       }
     }
     if (issuer) tma_store_wait_read_all();
+    if constexpr (GN) {
+      // the last CTA to finish advances the workspace's epoch: every CTA has read it by then, and the next launch on
+      // this workspace (stream order) sees the new value
+      if (issuer && atomicAdd(p.gn_epoch + 1, 1u) == gridDim.x - 1u) {
+        p.gn_epoch[1] = 0u;
+        p.gn_epoch[0] = tag;
+      }
+    }
   }
 
   tc_fence_before_sync();
@@ -1159,27 +1190,26 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
       return fail(IDF_ERR_ARG, "igemm: gn_gamma / gn_beta must be 16-byte aligned fp32 vectors");
     if (a->gn_mode == 2 && (a->gn_out == nullptr || a->gn_ldo < a->N)) return fail(IDF_ERR_ARG, "igemm: gn_mode 2 needs gn_out");
     const long long m_tiles = M / BLOCK_M;
-    const long long cnt_bytes = ((long long)x0.n * 4 + 255) / 256 * 256;
-    const long long need = cnt_bytes + m_tiles * (a->N / 4) * 8;
+    const long long cnt_bytes = 256;
+    const long long need = cnt_bytes + m_tiles * (a->N / 4) * 16;
     if (a->gn_ws == nullptr || (reinterpret_cast<uintptr_t>(a->gn_ws) & 255) || a->gn_ws_bytes < need)
       return fail(IDF_ERR_ARG, "igemm: gn_ws must be 256-byte aligned and hold %lld bytes", need);
     const long long n_tiles = a->N / bn;
     const long long units = (pair ? m_tiles / 2 : m_tiles) * n_tiles;
     const long long walkers = pair ? (units < sm_count() / 2 ? units : sm_count() / 2) : (units < sm_count() ? units : sm_count());
     const long long per_img = (pair ? p.tiles_per_img / 2 : p.tiles_per_img) * n_tiles;
-    if (per_img > walkers || p.tiles_per_img * n_tiles > 0xffff)
+    if (per_img > walkers)
       return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode: an image's %lld tiles do not fit one wave of %lld walkers", per_img, walkers);
     p.gn_mode = a->gn_mode;
     p.gn_silu = a->gn_silu ? 1 : 0;
     p.gn_qpg = a->N / a->gn_groups / 4;
     p.gn_groups = a->gn_groups;
-    p.gn_T = (int)(p.tiles_per_img * n_tiles);
     p.gn_inv_cnt = 1.0f / ((float)HW * (float)(a->N / a->gn_groups));
     p.gn_eps = a->gn_eps;
     p.gn_gamma = a->gn_gamma;
     p.gn_beta = a->gn_beta;
-    p.gn_cnt = reinterpret_cast<unsigned*>(a->gn_ws);
-    p.gn_part = reinterpret_cast<float2*>(reinterpret_cast<char*>(a->gn_ws) + cnt_bytes);
+    p.gn_epoch = reinterpret_cast<unsigned*>(a->gn_ws);
+    p.gn_part = reinterpret_cast<float4*>(reinterpret_cast<char*>(a->gn_ws) + cnt_bytes);
     if (a->gn_mode == 2 &&
         (rc = make_mat_map(&p.tmG, a->gn_out, (uint64_t)M, (uint64_t)a->N, (uint64_t)a->gn_ldo, 64, BLOCK_M)) != IDF_OK)
       return rc;

@@ -131,7 +131,9 @@ typedef struct idf_igemm_args {
                            the normalised one (the raw tensor is also a residual / skip input). Needs an image-shaped input
                            with h*w a multiple of 128, N / gn_groups a multiple of 4, a plain bf16 output (no res / vt / ws /
                            up2 / zero_pad_last). Statistics are taken from the fp32 accumulators over the whole (sample,
-                           group), summed in a fixed order: results do not depend on the batch size. */
+                           group), summed in a fixed order: results do not depend on the batch size. The tiles of a sample
+                           exchange their partial sums through gn_ws while the kernel runs, which relies on all of the
+                           launch's CTAs being resident (one per SM; the launch never has more CTAs than SMs). */
   int32_t gn_groups;
   int32_t gn_silu;
   float gn_eps;
@@ -139,9 +141,10 @@ typedef struct idf_igemm_args {
   const float* gn_beta;
   void* gn_out;         /* gn_mode 2: bf16 (M, N) matrix, row stride gn_ldo */
   int64_t gn_ldo;
-  void* gn_ws;          /* 256-byte aligned scratch: ceil(4 * a[0].n / 256) * 256 bytes of image counters, which must be ZERO
-                           before the first use and are left zero by every launch, then 8 * (M / 128) * (N / 4) bytes of
-                           per-tile partial sums. One launch at a time per workspace. */
+  void* gn_ws;          /* 256-byte aligned scratch of 256 + 16 * (M / 128) * (N / 4) bytes, ZERO-filled before its first use:
+                           a launch epoch (advanced by every launch) and one 16-byte record of partial sums per (tile,
+                           4 channels), tagged with the epoch. One launch at a time per workspace; launches of different
+                           shapes may share one. */
   int64_t gn_ws_bytes;
 } idf_igemm_args;
 

@@ -41,5 +41,5 @@ for t in range(NT):
     if m[2] == 0 and e[7] == 0:
         continue
     print(f"tile {t}: MMA wait acc {m[1] - m[0]:6d} | mainloop {m[2] - m[1]:6d} (ends {m[2] - t0:7d}) || epilogue: wait acc {e[1] - e[0]:6d} | "
-          f"pass 1 {e[2] - e[1]:5d} | publish {e[3] - e[2]:5d} | raw pass {e[4] - e[3]:5d} | spin+fence {e[5] - e[4]:6d} | stats {e[6] - e[5]:5d} | "
+          f"pass 1 {e[2] - e[1]:5d} | publish {e[3] - e[2]:5d} | raw pass {e[4] - e[3]:5d} | poll + statistics {e[6] - e[4]:6d} | "
           f"norm pass {e[7] - e[6]:5d} | total {e[7] - e[1]:6d} (ends {e[7] - t0:7d})")
