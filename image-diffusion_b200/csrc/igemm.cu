@@ -79,6 +79,8 @@ struct IgemmParams {
   int gn_silu;
   int gn_qpg;         // quad-columns (4 channels) per group
   int gn_groups;
+  int gn_ipt;         // images per tile: 1 (H*W % 128 == 0) or 2 (8x8 images, 128-wide tiles only)
+  int gn_tpi;         // tiles per image (1 when gn_ipt == 2)
   float gn_inv_cnt;   // 1 / (HW * channels per group)
   float gn_eps;
   const float* gn_gamma;
@@ -104,7 +106,6 @@ struct IgemmParams {
 #define GN_STAMP(role, tile, evt) do { } while (0)
 #endif
 
-constexpr int GN_SMEM = 1536;  // per-column tables of the current 128-column group: bias (512 B), (scale, shift) (1 KiB)
 
 // silu(t) = t * sigmoid(t) = h + h * tanh(h), h = t / 2 (one MUFU op; same form as the standalone GroupNorm kernel)
 __device__ __forceinline__ float igemm_silu(float t) {
@@ -165,14 +166,18 @@ struct TileWalk {
 // BN: tile width; NSTG: epilogue staging buffers (1: long-K tiles whose epilogue hides under the next mainloop;
 // 3: short-K, epilogue-bound tiles - store of group g-1, fill of group g and residual prefetch of group g+1 overlap)
 // PAIR: two CTAs of a cluster share one 256-row MMA (cta_group::2); each stages half of the B tile
-template <int BN, int NSTG, bool PAIR = false>
+// GN: the GroupNorm-fused epilogue keeps per-column tables of the current 128-column group behind the barriers: bias
+// (512 B) and (scale, shift) (1 KiB) per image of the tile; GN = 2: two 8x8 images per tile (one ring stage less)
+template <int BN, int NSTG, bool PAIR = false, int GN = 0>
 struct PgCfg {
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
+  static constexpr int GN_IPT = GN == 2 ? 2 : 1;  // images per tile
+  static constexpr int GN_BYTES = GN ? GN_IPT * 1536 : 0;
   // as many ring stages as fit beside the staging buffers in the 227 KiB of shared memory
-  static constexpr int STAGES = (232448 - 1024 - 256 - NSTG * PG_STG_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = (232448 - 1024 - 256 - GN_BYTES - NSTG * PG_STG_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (BN == 128) ? 256 : 512;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + NSTG * PG_STG_BYTES + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + NSTG * PG_STG_BYTES + 1024 + 256 + GN_BYTES;
 };
 
 // EW: epilogue warpgroups (warps 2 .. 2 + 4 EW - 1). Warp w reads TMEM lanes 32 (w % 4) .. +31, so every warpgroup
@@ -180,7 +185,7 @@ struct PgCfg {
 // per scheduler (EW = 1) nothing hides the TMEM / L1 / shared-memory latencies of the epilogue, which is what bounds
 // the short-K GEMMs and the single-tile-per-CTA launches of the 8x8 / 4x4 stages.
 //
-// GN = true: GroupNorm(+SiLU) of the convolution result is applied in the epilogue, so the standalone GroupNorm pass
+// GN != 0: GroupNorm(+SiLU) of the convolution result is applied in the epilogue, so the standalone GroupNorm pass
 // (read + write of the whole tensor and a launch) between two convolutions disappears (components.py:448-460: the
 // second ConvBlock's GroupNorm reads only what the first one's conv wrote). A tile covers 128 pixels of ONE image
 // (HW % 128 == 0) and BN of its channels, the statistics need the whole image: every tile reduces its accumulator
@@ -195,9 +200,9 @@ struct PgCfg {
 // wait so that the exchange latency is hidden). The tag is the workspace's launch epoch + 1; the last CTA to finish
 // advances the epoch, so stale records of earlier launches (or of other layers sharing the workspace) never match. Per-column constants (bias + time bias, gamma, beta; scale and shift once the statistics are known)
 // live in one register of "their" thread and are handed to the row-per-thread loops through small shared tables.
-template <int BN, int NSTG, int EW, bool PAIR, bool GN = false>
+template <int BN, int NSTG, int EW, bool PAIR, int GN = 0>
 __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const __grid_constant__ IgemmParams p) {
-  using Cfg = PgCfg<BN, NSTG, PAIR>;
+  using Cfg = PgCfg<BN, NSTG, PAIR, GN>;
   constexpr int EPI_THREADS = 128 * EW;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int GPT = (BN + 127) / 128;  // column groups per tile
@@ -353,9 +358,9 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           if (sp >= splits) sp -= splits;
         }
         const int acc = it & 1;
-        if constexpr (GN) GN_STAMP(0, it, 0);
+        if constexpr (GN != 0) GN_STAMP(0, it, 0);
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
-        if constexpr (GN) GN_STAMP(0, it, 1);
+        if constexpr (GN != 0) GN_STAMP(0, it, 1);
         tc_fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -384,7 +389,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         }
         if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);
         else umma_commit(&tmem_full[acc]);
-        if constexpr (GN) GN_STAMP(0, it, 2);
+        if constexpr (GN != 0) GN_STAMP(0, it, 2);
       }
     }
   } else {
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
     };
     int it = 0, gc = 0;
     unsigned tag = 0;
-    if constexpr (GN) {  // records of this launch carry epoch + 1 (never 0: fresh workspaces are zero-filled)
+    if constexpr (GN != 0) {  // records of this launch carry epoch + 1 (never 0: fresh workspaces are zero-filled)
       tag = ld_relaxed_gpu(p.gn_epoch) + 1u;
       if (tag == 0u) tag = 1u;
     }
@@ -448,22 +453,31 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         }
         continue;
       }
-      if constexpr (GN) {
+      if constexpr (GN != 0) {
         constexpr int QC = BN / 4;
-        float* cbt = reinterpret_cast<float*>(stage_base + NSTG * PG_STG_BYTES + 256);  // [128] bias + time bias of the
-        float2* sct = reinterpret_cast<float2*>(cbt + 128);                               // current column group; [128] (scale, shift)
+        // tables of the current column group, per image of the tile: [ipt][128] bias + time bias, [ipt][128] (scale, shift)
+        float* cbt = reinterpret_cast<float*>(stage_base + NSTG * PG_STG_BYTES + 256);
+        float2* sct = reinterpret_cast<float2*>(cbt + Cfg::GN_IPT * 128);
         float* red = reinterpret_cast<float*>(stage_base);  // [4 warps][BN / 4][2]: staging buffer 0 during pass 1
         const int tile_m = PAIR ? 2 * tw.tile_m + rank : tw.tile_m, n0 = tw.n_idx * BN;
         const int acc = it & 1;
-        const int tpi = p.tiles_per_img, qpg = p.gn_qpg;
-        const int img = p.tpi_shift >= 0 ? (tile_m >> p.tpi_shift) : (tile_m / tpi);
-        // this thread's column (thread et <-> column n0 + et): bias + time bias, gamma, beta - fetched while the MMAs run
+        // ipt = 2: the tile holds two 8x8 images (rows 0..63 / 64..127 = TMEM quadrants 0,1 / 2,3); statistics stay
+        // per image, the exchange is between the N tiles of the same 128 rows
+        constexpr int ipt = Cfg::GN_IPT;
+        const int tpi = p.gn_tpi, qpg = p.gn_qpg;
+        const int img = ipt == 2 ? 2 * tile_m : (p.tpi_shift >= 0 ? (tile_m >> p.tpi_shift) : (tile_m / tpi));  // first image
+        // column role: thread et <-> (image tsel of the tile, column n0 + colr); row role: this thread's row is in image rsel
+        const int colr = ipt == 2 ? (et & 127) : et;
+        const int tsel = ipt == 2 ? (et >> 7) : 0;
+        const int rsel = ipt == 2 ? (quad >> 1) : 0;
+        const bool col_thread = et < BN * ipt;
+        // bias + time bias, gamma, beta of this thread's column - fetched while the MMAs run
         float cb_r = 0.f, ga_r = 0.f, be_r = 0.f;
-        if (et < BN) {
-          const int col = n0 + et;
+        if (col_thread) {
+          const int col = n0 + colr;
           if (p.bias != nullptr) cb_r = __ldg(p.bias + col);
           if (p.rowbias != nullptr)
-            cb_r += __ldg(p.rowbias + (long long)(p.rowbias_idx ? p.rowbias_idx[img] : img) * p.rowbias_ld + col);
+            cb_r += __ldg(p.rowbias + (long long)(p.rowbias_idx ? p.rowbias_idx[img + tsel] : img + tsel) * p.rowbias_ld + col);
           ga_r = __ldg(p.gn_gamma + col);
           be_r = __ldg(p.gn_beta + col);
         }
@@ -479,7 +493,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           const int gcols = group_cols(cg);
           const int my_nch = (gcols / 32) / EW;
           named_bar_sync(1, EPI_THREADS);  // staging buffer (red) and cbt free
-          if (et >= cg * 128 && et < cg * 128 + gcols) cbt[et - cg * 128] = cb_r;
+          if (col_thread && colr >= cg * 128 && colr < cg * 128 + gcols) cbt[tsel * 128 + colr - cg * 128] = cb_r;
           named_bar_sync(1, EPI_THREADS);
 #pragma unroll 1
           for (int i0 = 0; i0 < my_nch; i0 += 2) {
@@ -496,7 +510,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
               float w16[16];
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const float4 cb4 = *reinterpret_cast<const float4*>(cbt + c * 32 + 4 * q);
+                const float4 cb4 = *reinterpret_cast<const float4*>(cbt + rsel * 128 + c * 32 + 4 * q);
                 const float a0 = __uint_as_float(v[h][4 * q + 0]) + cb4.x, a1 = __uint_as_float(v[h][4 * q + 1]) + cb4.y;
                 const float a2 = __uint_as_float(v[h][4 * q + 2]) + cb4.z, a3 = __uint_as_float(v[h][4 * q + 3]) + cb4.w;
                 w16[q] = (a0 + a1) + (a2 + a3);
@@ -536,13 +550,16 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         }
         named_bar_sync(1, EPI_THREADS);
         if (issuer) GN_STAMP(1, it, 2);
-        if (et < QC) {  // records laid out [image][group][tile of the image][quad-column of the group]
+        if (et < QC * ipt) {  // records laid out [image][group][tile of the image][quad-column of the group]
+          const int isel = ipt == 2 ? et / QC : 0, ql = et - isel * QC;
           float s_ = 0.f, q_ = 0.f;
 #pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) { s_ += red[(w4 * QC + et) * 2]; q_ += red[(w4 * QC + et) * 2 + 1]; }
-          const int qc = (n0 >> 2) + et;
+          for (int w4 = 0; w4 < 4; ++w4)  // the warps holding this image's rows, in order
+            if (ipt == 1 || (w4 >> 1) == isel) { s_ += red[(w4 * QC + ql) * 2]; q_ += red[(w4 * QC + ql) * 2 + 1]; }
+          const int qc = (n0 >> 2) + ql;
           const int g = qc / qpg;
-          st_relaxed_gpu_v4(p.gn_part + (((long long)img * p.gn_groups + g) * tpi + (tile_m - img * tpi)) * qpg + (qc - g * qpg),
+          const int tin = ipt == 2 ? 0 : tile_m - img * tpi;
+          st_relaxed_gpu_v4(p.gn_part + (((long long)(img + isel) * p.gn_groups + g) * tpi + tin) * qpg + (qc - g * qpg),
                             make_float4(s_, q_, __uint_as_float(tag), 0.f));
         }
         if (issuer) GN_STAMP(1, it, 3);
@@ -555,9 +572,9 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
             const int my_nch = (gcols / 32) / EW;
             if (issuer) tma_store_wait_read_all();
             named_bar_sync(1, EPI_THREADS);  // staging buffer and tables free
-            if (et >= cg * 128 && et < cg * 128 + gcols) {
-              if (norm) sct[et - cg * 128] = make_float2(sc_r, sh_r);
-              else cbt[et - cg * 128] = cb_r;
+            if (col_thread && colr >= cg * 128 && colr < cg * 128 + gcols) {
+              if (norm) sct[tsel * 128 + colr - cg * 128] = make_float2(sc_r, sh_r);
+              else cbt[tsel * 128 + colr - cg * 128] = cb_r;
             }
             named_bar_sync(1, EPI_THREADS);
 #pragma unroll 1
@@ -584,7 +601,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
                 if (norm) {
 #pragma unroll
                   for (int j = 0; j < 32; j += 2) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(sct + c * 32 + j);  // (scale, shift) of two columns
+                    const float4 t4 = *reinterpret_cast<const float4*>(sct + rsel * 128 + c * 32 + j);  // (scale, shift) of two columns
                     a[j] = fmaf(__uint_as_float(v[h][j]), t4.x, t4.y);
                     a[j + 1] = fmaf(__uint_as_float(v[h][j + 1]), t4.z, t4.w);
                   }
@@ -595,7 +612,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
                 } else {
 #pragma unroll
                   for (int q = 0; q < 8; ++q) {
-                    const float4 cb4 = *reinterpret_cast<const float4*>(cbt + c * 32 + 4 * q);
+                    const float4 cb4 = *reinterpret_cast<const float4*>(cbt + rsel * 128 + c * 32 + 4 * q);
                     a[4 * q + 0] = __uint_as_float(v[h][4 * q + 0]) + cb4.x; a[4 * q + 1] = __uint_as_float(v[h][4 * q + 1]) + cb4.y;
                     a[4 * q + 2] = __uint_as_float(v[h][4 * q + 2]) + cb4.z; a[4 * q + 3] = __uint_as_float(v[h][4 * q + 3]) + cb4.w;
                   }
@@ -654,10 +671,10 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
             for (int k = 0; k < 16; ++k) { s_ += v4[k].x; q_ += v4[k].y; }
           }
         };
-        const float4* gsrc = p.gn_part + ((long long)img * p.gn_groups + (n0 + et) / (4 * qpg)) * n;
+        const float4* gsrc = p.gn_part + ((long long)(img + tsel) * p.gn_groups + (n0 + colr) / (4 * qpg)) * n;
         if (issuer) sum_group(gsrc, 32);
         named_bar_sync(1, EPI_THREADS);
-        if (et < BN) {
+        if (col_thread) {
           sum_group(gsrc, 256);
           const float mean = s_ * p.gn_inv_cnt;
           const float var = fmaxf(q_ * p.gn_inv_cnt - mean * mean, 0.f);
@@ -851,7 +868,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
       }
     }
     if (issuer) tma_store_wait_read_all();
-    if constexpr (GN) {
+    if constexpr (GN != 0) {
       // the last CTA to finish advances the workspace's epoch: every CTA has read it by then, and the next launch on
       // this workspace (stream order) sees the new value
       if (issuer && atomicAdd(p.gn_epoch + 1, 1u) == gridDim.x - 1u) {
@@ -879,10 +896,10 @@ static int gn_walkers(int walkers, int per_img) {
   return per_img > 0 && walkers >= per_img ? walkers / per_img * per_img : walkers;
 }
 
-template <int BN, int NSTG, int EW, bool PAIR, bool GN = false>
+template <int BN, int NSTG, int EW, bool PAIR, int GN = 0>
 static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
-  using Cfg = PgCfg<BN, NSTG, PAIR>;
-  constexpr int SMEM = Cfg::SMEM + (GN ? GN_SMEM : 0);
+  using Cfg = PgCfg<BN, NSTG, PAIR, GN>;
+  constexpr int SMEM = Cfg::SMEM;
   static_assert(SMEM <= 232448, "shared memory");
   static bool attr_set = false;
   if (!attr_set) {
@@ -897,7 +914,7 @@ static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
     // one cluster of two CTAs per TPC; the cluster walks the list of (M-tile pair, N tile, K split) units
     const int units = ((m_tiles + 1) / 2) * (p.N / BN) * p.splits * (p.up2_all ? 4 : 1);
     int clusters = units < sm_count() / 2 ? units : sm_count() / 2;
-    if constexpr (GN) clusters = gn_walkers(clusters, (p.tiles_per_img / 2) * (p.N / BN));
+    if constexpr (GN != 0) clusters = gn_walkers(clusters, (p.gn_tpi / 2) * (p.N / BN));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(64 + 128 * EW);
@@ -912,7 +929,7 @@ static int launch_persist_ew(const IgemmParams& p, cudaStream_t stream) {
   } else {
     const int tiles = m_tiles * (p.N / BN) * p.splits * (p.up2_all ? 4 : 1);
     int grid = tiles < sm_count() ? tiles : sm_count();
-    if constexpr (GN) grid = gn_walkers(grid, p.tiles_per_img * (p.N / BN));
+    if constexpr (GN != 0) grid = gn_walkers(grid, p.gn_tpi * (p.N / BN));
     return check_cuda(launch_kernel(igemm_persist_kernel<BN, NSTG, EW, PAIR, GN>, dim3(grid), dim3(64 + 128 * EW), SMEM,
                                  stream, p),
                       "igemm_persist launch");
@@ -1146,6 +1163,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
       if (bn == 0 || t < best) { bn = c; best = t; }
     }
     if (bn == 0) return fail(IDF_ERR_UNSUPPORTED, "igemm: N = %d has no legal tile width", a->N);
+    if (gn && p.tiles_per_img == 0) bn = BLOCK_N;  // two 8x8 images per tile: 128-wide tiles (table layout of the epilogue)
   }
   // split-K: when the tile list leaves a large part of the GPU idle (8x8 / 4x4 stages), split the K range of each
   // tile over up to 4 work units; fp32 partials go to the caller's workspace and a finish kernel adds them in a
@@ -1176,14 +1194,17 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
   // cluster start-up: IDF_IGEMM_PAIR = 1 (default) pairs only the former, 2 = wherever legal, 0 = never.
   static const int pair_mode = [] { const char* e = getenv("IDF_IGEMM_PAIR"); return e ? atoi(e) : 1; }();
   const bool pair_legal = !narrow && !batched && M > BLOCK_M && (!a->w_mn || bn != 192) && sm_count() >= 2 &&
-                          !(gn && (p.tiles_per_img & 1));
+                          !(gn && ((p.tiles_per_img & 1) || p.tiles_per_img == 0));
   const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && bn == 256 && !short_k &&
                                                       (M + BLOCK_M - 1) / BLOCK_M * par_tiles >= sm_count()));
   if (gn) {
     // GroupNorm-fused epilogue: whole images of 128-pixel tiles, plain bf16 output, no split-K
-    if ((a->gn_mode != 1 && a->gn_mode != 2) || narrow || is_matrix || p.tiles_per_img <= 0 || a->res || a->vt || a->out_f32 ||
-        a->out_up2 || a->w_mn || a->ws || a->zero_pad_last || batched || a->s2_batch || a->epi_h || a->epi_w)
-      return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode needs an image-shaped conv (H*W %% 128 == 0) with a plain bf16 output");
+    const bool two_img = !is_matrix && p.tiles_per_img == 0 && p.tile_n == 2 && x0.n % 2 == 0;
+    if ((a->gn_mode != 1 && a->gn_mode != 2) || narrow || is_matrix || (p.tiles_per_img <= 0 && !two_img) || a->res || a->vt ||
+        a->out_f32 || a->out_up2 || a->w_mn || a->ws || a->zero_pad_last || batched || a->s2_batch || a->epi_h || a->epi_w)
+      return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode needs an image-shaped conv (H*W %% 128 == 0, or H*W == 64 with an even "
+                                       "batch) with a plain bf16 output");
+    const int ipt = two_img ? 2 : 1, tpi = two_img ? 1 : p.tiles_per_img;
     if (a->gn_groups <= 0 || a->N % a->gn_groups != 0 || (a->N / a->gn_groups) % 4 != 0)
       return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode needs channels per group %% 4 == 0 (N = %d, groups = %d)", a->N, a->gn_groups);
     if (!a->gn_gamma || !a->gn_beta || (reinterpret_cast<uintptr_t>(a->gn_gamma) & 15) || (reinterpret_cast<uintptr_t>(a->gn_beta) & 15))
@@ -1191,19 +1212,21 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     if (a->gn_mode == 2 && (a->gn_out == nullptr || a->gn_ldo < a->N)) return fail(IDF_ERR_ARG, "igemm: gn_mode 2 needs gn_out");
     const long long m_tiles = M / BLOCK_M;
     const long long cnt_bytes = 256;
-    const long long need = cnt_bytes + m_tiles * (a->N / 4) * 16;
+    const long long need = cnt_bytes + m_tiles * ipt * (a->N / 4) * 16;
     if (a->gn_ws == nullptr || (reinterpret_cast<uintptr_t>(a->gn_ws) & 255) || a->gn_ws_bytes < need)
       return fail(IDF_ERR_ARG, "igemm: gn_ws must be 256-byte aligned and hold %lld bytes", need);
     const long long n_tiles = a->N / bn;
     const long long units = (pair ? m_tiles / 2 : m_tiles) * n_tiles;
     const long long walkers = pair ? (units < sm_count() / 2 ? units : sm_count() / 2) : (units < sm_count() ? units : sm_count());
-    const long long per_img = (pair ? p.tiles_per_img / 2 : p.tiles_per_img) * n_tiles;
+    const long long per_img = (pair ? tpi / 2 : tpi) * n_tiles;
     if (per_img > walkers)
       return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode: an image's %lld tiles do not fit one wave of %lld walkers", per_img, walkers);
     p.gn_mode = a->gn_mode;
     p.gn_silu = a->gn_silu ? 1 : 0;
     p.gn_qpg = a->N / a->gn_groups / 4;
     p.gn_groups = a->gn_groups;
+    p.gn_ipt = ipt;
+    p.gn_tpi = tpi;
     p.gn_inv_cnt = 1.0f / ((float)HW * (float)(a->N / a->gn_groups));
     p.gn_eps = a->gn_eps;
     p.gn_gamma = a->gn_gamma;
@@ -1330,10 +1353,11 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     return launch_persist<128, 3>(p, st, pair);
   }
   if (gn) {
+    if (p.gn_ipt == 2) return launch_persist_ew<128, 1, 2, false, 2>(p, st);
     switch (bn) {
-      case 256: return pair ? launch_persist_ew<256, 1, 2, true, true>(p, st) : launch_persist_ew<256, 1, 2, false, true>(p, st);
-      case 192: return pair ? launch_persist_ew<192, 1, 2, true, true>(p, st) : launch_persist_ew<192, 1, 2, false, true>(p, st);
-      default: return pair ? launch_persist_ew<128, 1, 2, true, true>(p, st) : launch_persist_ew<128, 1, 2, false, true>(p, st);
+      case 256: return pair ? launch_persist_ew<256, 1, 2, true, 1>(p, st) : launch_persist_ew<256, 1, 2, false, 1>(p, st);
+      case 192: return pair ? launch_persist_ew<192, 1, 2, true, 1>(p, st) : launch_persist_ew<192, 1, 2, false, 1>(p, st);
+      default: return pair ? launch_persist_ew<128, 1, 2, true, 1>(p, st) : launch_persist_ew<128, 1, 2, false, 1>(p, st);
     }
   }
   switch (bn) {

@@ -128,8 +128,8 @@ class UnetEngine:
         self.splitk = int(__import__("os").environ.get("IDF_SPLITK_4X4", "3"))
         self._B, self._rng = 0, (0, 0)
         self.tc_tail = __import__("os").environ.get("IDF_TC_TAIL", "1") != "0"
-        # GroupNorm fused into the producing conv's epilogue where an image is a whole number of 128-pixel tiles
-        # (32x32 / 16x16 stages): 1 = GN2 (y1 -> h2, y1 never stored), 2 = also GN3 (conv2 stores x2 and h3)
+        # GroupNorm fused into the producing conv's epilogue where an image is a whole number of 128-pixel tiles or half
+        # of one (32x32 / 16x16 / 8x8 stages): 1 = GN2 (y1 -> h2, y1 never stored), 2 = also GN3 (conv2 stores x2 and h3)
         self.gn_fuse = int(__import__("os").environ.get("IDF_GN_FUSE", "2"))
         self._gn_ws = {}
         self.downs, self.mids, self.ups = unet_blocks(arch)
@@ -209,7 +209,12 @@ class UnetEngine:
         B, H, W = x.grid
         M, HW = x.M, x.H * x.W
         hd = cout // self.heads
-        fuse = self.gn_fuse if (self.taps is None and HW % 128 == 0 and (cout // G) % 4 == 0 and cout % G == 0) else 0
+        tiles_ok = HW % 128 == 0 or (HW == 64 and B % 2 == 0)   # whole images per 128-pixel tile, or two 8x8 images
+        fuse = self.gn_fuse if (self.taps is None and tiles_ok and (cout // G) % 4 == 0 and cout % G == 0) else 0
+        if HW == 64 and cout >= 512:
+            # 512-channel convs of the 8x8 stage: the fused launch is held to 128-wide tiles; measured per layer
+            # (profiles/r02_gn_fused_per_layer.txt) the double-output form gains nothing there, the single one 1-3 us
+            fuse = min(fuse, 1)
         sk = {}
         if self.splitk > 1 and HW <= 16:
             sk = dict(ws=self._splitk_ws(M * cout), splits=self.splitk)

@@ -1,7 +1,7 @@
 """GroupNorm fused into the implicit-GEMM epilogue (idf_igemm_args.gn_mode) on the B200: conv3x3 (+ bias + time bias)
 -> GroupNorm (+ SiLU) against conv2d + F.group_norm in fp32 on the same bf16-rounded inputs. Covers single tiles and CTA
-pairs, all three tile widths, groups that straddle tiles (384 channels: 12 per group), both output modes, the counter
-reset between launches and batch invariance of the statistics (components.py:448-460)."""
+pairs, all three tile widths, 8x8 images (two per tile), groups that straddle tiles (384 channels: 12 per group), both
+output modes, workspace reuse between launches and batch invariance of the statistics (components.py:448-460)."""
 import math
 
 import pytest
@@ -99,6 +99,9 @@ def run_case(B, Cin, Cout, H, silu, dual, seed=0, skip_c=0):
     (96, 64, 384, 16, False, True),     # both outputs, the bench's batch
     (20, 128, 256, 32, False, True),    # both outputs on CTA pairs
     (4, 64, 1024, 16, True, True),      # 32 channels per group
+    (96, 128, 512, 8, True, False),     # 8x8: two images per 128-pixel tile, statistics per half tile
+    (96, 128, 384, 8, False, True),     # 8x8, 12 channels per group: groups straddle the 128-wide tiles; both outputs
+    (2, 64, 128, 8, True, True),        # 8x8, one tile
 ])
 def test_conv_groupnorm_fused(B, Cin, Cout, H, silu, dual):
     run_case(B, Cin, Cout, H, silu, dual)
@@ -108,6 +111,7 @@ def test_conv_groupnorm_fused_two_segments():
     """conv3x3 (+) 1x1 skip projection as one two-segment GEMM, raw and normalised outputs (the block's conv2)."""
     run_case(12, 256, 256, 32, False, True, skip_c=128)
     run_case(24, 384, 384, 16, False, True, skip_c=256)
+    run_case(30, 512, 512, 8, False, True, skip_c=384)
 
 
 def test_conv_groupnorm_fused_batch_invariance():
@@ -131,6 +135,11 @@ def test_conv_groupnorm_fused_batch_invariance():
 
     big, small = run(B), run(2)
     assert torch.equal(big[:2 * H * H], small)
+    # 8x8 images (two per tile)
+    H = 8
+    x = torch.randn(B, Cin, H, H, device=DEV, generator=g)
+    big, small = run(B), run(4)
+    assert torch.equal(big[:4 * H * H], small)
 
 
 def test_conv_groupnorm_fused_rejects_unsupported_shapes():
@@ -140,8 +149,11 @@ def test_conv_groupnorm_fused_rejects_unsupported_shapes():
     out = torch.empty(2 * 64, 128, device=DEV, dtype=torch.bfloat16)
     ws = torch.zeros(1 << 16, device=DEV, dtype=torch.uint8)
     gam = torch.ones(128, device=DEV)
-    with pytest.raises(RuntimeError):   # 8x8 images: several samples per 128-pixel tile
-        ops.igemm([(x, (2, 8, 8), 128, 9)], w, 128, out, gn=dict(gamma=gam, beta=gam, groups=32, silu=True, ws=ws))
+    with pytest.raises(RuntimeError):   # 4x4 images: eight samples per 128-pixel tile
+        ops.igemm([(x, (8, 4, 4), 128, 9)], w, 128, out, gn=dict(gamma=gam, beta=gam, groups=32, silu=True, ws=ws))
+    x3 = torch.zeros(3 * 64, 128, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):   # 8x8 images, odd batch: the last tile would hold one image
+        ops.igemm([(x3, (3, 8, 8), 128, 9)], w, 128, torch.empty_like(x3), gn=dict(gamma=gam, beta=gam, groups=32, silu=True, ws=ws))
     x = torch.zeros(256, 128, device=DEV, dtype=torch.bfloat16)
     out = torch.empty(256, 128, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError):   # 2 channels per group

@@ -17,7 +17,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 96
 # (H, Cin of the 3x3 segment, skip channels of the 1x1 segment, Cout)
 SHAPES = [(32, 128, 0, 256), (32, 256, 128, 256), (32, 256, 0, 256), (32, 256, 256, 256), (32, 512, 0, 128), (32, 128, 512, 128),
           (32, 128, 0, 128), (32, 128, 128, 128), (16, 256, 0, 384), (16, 384, 256, 384), (16, 384, 0, 384), (16, 384, 384, 384),
-          (16, 768, 0, 256), (16, 256, 768, 256), (16, 256, 0, 256), (16, 256, 256, 256)]
+          (16, 768, 0, 256), (16, 256, 768, 256), (16, 256, 0, 256), (16, 256, 256, 256),
+          (8, 384, 0, 512), (8, 512, 384, 512), (8, 512, 0, 512), (8, 512, 512, 512),
+          (8, 1024, 0, 384), (8, 384, 1024, 384), (8, 384, 0, 384), (8, 384, 384, 384)]
 
 
 def timeit(fn, n=12, warm=3):
