@@ -81,6 +81,7 @@ struct IgemmParams {
   int gn_groups;
   int gn_ipt;         // images per tile: 1 (H*W % 128 == 0) or 2 (8x8 images, 128-wide tiles only)
   int gn_tpi;         // tiles per image (1 when gn_ipt == 2)
+  int gn_images;      // images in the batch (gn_ipt == 2 with an odd batch: the last tile's second half is empty)
   float gn_inv_cnt;   // 1 / (HW * channels per group)
   float gn_eps;
   const float* gn_gamma;
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         const int colr = ipt == 2 ? (et & 127) : et;
         const int tsel = ipt == 2 ? (et >> 7) : 0;
         const int rsel = ipt == 2 ? (quad >> 1) : 0;
-        const bool col_thread = et < BN * ipt;
+        const bool col_thread = et < BN * ipt && img + tsel < p.gn_images;
         // bias + time bias, gamma, beta of this thread's column - fetched while the MMAs run
         float cb_r = 0.f, ga_r = 0.f, be_r = 0.f;
         if (col_thread) {
@@ -550,7 +551,8 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         }
         named_bar_sync(1, EPI_THREADS);
         if (issuer) GN_STAMP(1, it, 2);
-        if (et < QC * ipt) {  // records laid out [image][group][tile of the image][quad-column of the group]
+        if (et < QC * ipt && img + (ipt == 2 ? et / QC : 0) < p.gn_images) {
+          // records laid out [image][group][tile of the image][quad-column of the group]
           const int isel = ipt == 2 ? et / QC : 0, ql = et - isel * QC;
           float s_ = 0.f, q_ = 0.f;
 #pragma unroll
@@ -654,7 +656,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           for (int i0 = 0; i0 < n; i0 += 16) {
             float4 v4[16];
             bool ok;
-            unsigned ns = backoff_ns;
+            unsigned ns = backoff_ns, spins = 0;
             do {
               ok = true;
 #pragma unroll
@@ -665,6 +667,9 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
               if (!ok) {
                 __nanosleep(ns);
                 if (ns < 256) ns *= 2;
+                // ~4 s without the other tiles' records: their CTAs are not running (the launch shares the GPU with
+                // another resident kernel that waits in the same way) - fail loudly instead of hanging
+                if (++spins > (1u << 24)) __trap();
               }
             } while (!ok);
 #pragma unroll
@@ -1199,20 +1204,20 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
                                                       (M + BLOCK_M - 1) / BLOCK_M * par_tiles >= sm_count()));
   if (gn) {
     // GroupNorm-fused epilogue: whole images of 128-pixel tiles, plain bf16 output, no split-K
-    const bool two_img = !is_matrix && p.tiles_per_img == 0 && p.tile_n == 2 && x0.n % 2 == 0;
+    const bool two_img = !is_matrix && p.tiles_per_img == 0 && p.tile_n == 2;
     if ((a->gn_mode != 1 && a->gn_mode != 2) || narrow || is_matrix || (p.tiles_per_img <= 0 && !two_img) || a->res || a->vt ||
         a->out_f32 || a->out_up2 || a->w_mn || a->ws || a->zero_pad_last || batched || a->s2_batch || a->epi_h || a->epi_w)
-      return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode needs an image-shaped conv (H*W %% 128 == 0, or H*W == 64 with an even "
-                                       "batch) with a plain bf16 output");
+      return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode needs an image-shaped conv (H*W %% 128 == 0 or H*W == 64) with a plain "
+                                       "bf16 output");
     const int ipt = two_img ? 2 : 1, tpi = two_img ? 1 : p.tiles_per_img;
     if (a->gn_groups <= 0 || a->N % a->gn_groups != 0 || (a->N / a->gn_groups) % 4 != 0)
       return fail(IDF_ERR_UNSUPPORTED, "igemm: gn_mode needs channels per group %% 4 == 0 (N = %d, groups = %d)", a->N, a->gn_groups);
     if (!a->gn_gamma || !a->gn_beta || (reinterpret_cast<uintptr_t>(a->gn_gamma) & 15) || (reinterpret_cast<uintptr_t>(a->gn_beta) & 15))
       return fail(IDF_ERR_ARG, "igemm: gn_gamma / gn_beta must be 16-byte aligned fp32 vectors");
     if (a->gn_mode == 2 && (a->gn_out == nullptr || a->gn_ldo < a->N)) return fail(IDF_ERR_ARG, "igemm: gn_mode 2 needs gn_out");
-    const long long m_tiles = M / BLOCK_M;
+    const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     const long long cnt_bytes = 256;
-    const long long need = cnt_bytes + m_tiles * ipt * (a->N / 4) * 16;
+    const long long need = cnt_bytes + (m_tiles > x0.n ? m_tiles : (long long)x0.n) * (a->N / 4) * 16;
     if (a->gn_ws == nullptr || (reinterpret_cast<uintptr_t>(a->gn_ws) & 255) || a->gn_ws_bytes < need)
       return fail(IDF_ERR_ARG, "igemm: gn_ws must be 256-byte aligned and hold %lld bytes", need);
     const long long n_tiles = a->N / bn;
@@ -1227,6 +1232,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     p.gn_groups = a->gn_groups;
     p.gn_ipt = ipt;
     p.gn_tpi = tpi;
+    p.gn_images = x0.n;
     p.gn_inv_cnt = 1.0f / ((float)HW * (float)(a->N / a->gn_groups));
     p.gn_eps = a->gn_eps;
     p.gn_gamma = a->gn_gamma;

@@ -209,7 +209,7 @@ class UnetEngine:
         B, H, W = x.grid
         M, HW = x.M, x.H * x.W
         hd = cout // self.heads
-        tiles_ok = HW % 128 == 0 or (HW == 64 and B % 2 == 0)   # whole images per 128-pixel tile, or two 8x8 images
+        tiles_ok = HW % 128 == 0 or HW == 64   # whole images per 128-pixel tile, or two 8x8 images
         fuse = self.gn_fuse if (self.taps is None and tiles_ok and (cout // G) % 4 == 0 and cout % G == 0) else 0
         if HW == 64 and cout >= 512:
             # 512-channel convs of the 8x8 stage: the fused launch is held to 128-wide tiles; measured per layer

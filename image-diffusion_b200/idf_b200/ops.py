@@ -95,7 +95,7 @@ def igemm(segs, w: torch.Tensor, n_out: int, out: torch.Tensor, *, bias=None, ro
 
 def gn_workspace_bytes(images: int, rows: int, n_out: int) -> int:
     """Scratch of the GroupNorm-fused igemm epilogue (idf_igemm_args.gn_ws): launch epoch + per-tile partial records."""
-    return 256 + max(rows // 128, images) * (n_out // 4) * 16
+    return 256 + max((rows + 127) // 128, images) * (n_out // 4) * 16
 
 
 def groupnorm_silu(x: torch.Tensor, y: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, B: int, HW: int, C: int,

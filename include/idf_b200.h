@@ -129,7 +129,7 @@ typedef struct idf_igemm_args {
                            the GroupNorm that opens the NEXT ConvBlock (components.py:448-460) without its own pass over the
                            tensor. 1: `out` receives the normalised tensor only; 2: `out` receives the raw result and `gn_out`
                            the normalised one (the raw tensor is also a residual / skip input). Needs an image-shaped input
-                           with h*w a multiple of 128 (or h*w == 64 and an even number of images), N / gn_groups a multiple of 4, a plain bf16 output (no res / vt / ws /
+                           with h*w a multiple of 128 (or h*w == 64: two images per tile), N / gn_groups a multiple of 4, a plain bf16 output (no res / vt / ws /
                            up2 / zero_pad_last). Statistics are taken from the fp32 accumulators over the whole (sample,
                            group), summed in a fixed order: results do not depend on the batch size. The tiles of a sample
                            exchange their partial sums through gn_ws while the kernel runs, which relies on all of the

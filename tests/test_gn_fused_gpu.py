@@ -102,6 +102,8 @@ def run_case(B, Cin, Cout, H, silu, dual, seed=0, skip_c=0):
     (96, 128, 512, 8, True, False),     # 8x8: two images per 128-pixel tile, statistics per half tile
     (96, 128, 384, 8, False, True),     # 8x8, 12 channels per group: groups straddle the 128-wide tiles; both outputs
     (2, 64, 128, 8, True, True),        # 8x8, one tile
+    (5, 128, 384, 8, True, True),       # 8x8, odd batch: the last tile holds one image and an empty half
+    (1, 64, 128, 8, False, False),      # 8x8, a single image
 ])
 def test_conv_groupnorm_fused(B, Cin, Cout, H, silu, dual):
     run_case(B, Cin, Cout, H, silu, dual)
@@ -138,8 +140,8 @@ def test_conv_groupnorm_fused_batch_invariance():
     # 8x8 images (two per tile)
     H = 8
     x = torch.randn(B, Cin, H, H, device=DEV, generator=g)
-    big, small = run(B), run(4)
-    assert torch.equal(big[:4 * H * H], small)
+    big, small = run(B), run(3)
+    assert torch.equal(big[:3 * H * H], small)
 
 
 def test_conv_groupnorm_fused_rejects_unsupported_shapes():
@@ -151,9 +153,6 @@ def test_conv_groupnorm_fused_rejects_unsupported_shapes():
     gam = torch.ones(128, device=DEV)
     with pytest.raises(RuntimeError):   # 4x4 images: eight samples per 128-pixel tile
         ops.igemm([(x, (8, 4, 4), 128, 9)], w, 128, out, gn=dict(gamma=gam, beta=gam, groups=32, silu=True, ws=ws))
-    x3 = torch.zeros(3 * 64, 128, device=DEV, dtype=torch.bfloat16)
-    with pytest.raises(RuntimeError):   # 8x8 images, odd batch: the last tile would hold one image
-        ops.igemm([(x3, (3, 8, 8), 128, 9)], w, 128, torch.empty_like(x3), gn=dict(gamma=gam, beta=gam, groups=32, silu=True, ws=ws))
     x = torch.zeros(256, 128, device=DEV, dtype=torch.bfloat16)
     out = torch.empty(256, 128, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError):   # 2 channels per group
