@@ -83,3 +83,13 @@ int sm_count() {
 extern "C" const char* idf_last_error(void) { return idf::g_err; }
 
 extern "C" int idf_abi_version(void) { return IDF_B200_ABI_VERSION; }
+
+extern "C" int idf_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(idf_nhwc_t);
+    case 1: return (int)sizeof(idf_igemm_args);
+    case 2: return (int)sizeof(idf_wgrad_args);
+    case 3: return (int)sizeof(idf_pack_job);
+    default: return -1;
+  }
+}

@@ -104,7 +104,8 @@ _SIGNATURES = {
     "idf_pack_weights": [_vp, _vp, _i32, _i32],
     "idf_rowidx_from_timestep": [_vp, _vp, _i32, _vp, _i32],
 }
-EXPORTS = sorted(list(_SIGNATURES) + ["idf_last_error", "idf_abi_version"])
+EXPORTS = sorted(list(_SIGNATURES) + ["idf_last_error", "idf_abi_version", "idf_struct_size"])
+ABI_VERSION = 4  # include/idf_b200.h: IDF_B200_ABI_VERSION this binding was written against
 
 _lib = None
 launch_count = 0  # kernels-launching C-ABI calls made through this module (bench.py reports it)
@@ -124,6 +125,15 @@ def load() -> C.CDLL:
     lib.idf_last_error.argtypes = []
     lib.idf_abi_version.restype = C.c_int
     lib.idf_abi_version.argtypes = []
+    lib.idf_struct_size.restype = C.c_int
+    lib.idf_struct_size.argtypes = [C.c_int]
+    if lib.idf_abi_version() != ABI_VERSION:
+        raise NativeError(f"{LIB_PATH} has ABI version {lib.idf_abi_version()}, this binding expects {ABI_VERSION}: rebuild "
+                          "the library (python __graft_entry__.py build)")
+    for which, struct in enumerate((NHWC, IgemmArgs, WgradArgs, PackJob)):
+        if lib.idf_struct_size(which) != C.sizeof(struct):
+            raise NativeError(f"{struct.__name__}: ctypes layout has {C.sizeof(struct)} bytes, the library's struct "
+                              f"{lib.idf_struct_size(which)}: native.py and include/idf_b200.h disagree")
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int

@@ -24,12 +24,19 @@
 extern "C" {
 #endif
 
-#define IDF_B200_ABI_VERSION 3
+#define IDF_B200_ABI_VERSION 4
 
 typedef struct CUstream_st* idf_stream_t;
 
 const char* idf_last_error(void);
 int idf_abi_version(void);
+
+/*
+ * idf_struct_size — sizeof() of the argument structs as this library was compiled, for bindings that re-declare them
+ * (ctypes / cgo / JNI): which = 0 idf_nhwc_t, 1 idf_igemm_args, 2 idf_wgrad_args, 3 idf_pack_job; -1 for anything else.
+ * A binding whose own layout gives a different size must refuse to call the library.
+ */
+int idf_struct_size(int which);
 
 /* A channels-last activation view: element (n, h, w, c) lives at ptr[n*sn + h*sh + w*sw + c]. A plain
  * (rows, cols) matrix is the view n = 1, h = 1, w = rows, c = cols, sw = row stride. */

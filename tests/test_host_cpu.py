@@ -18,7 +18,12 @@ def test_library_exports_every_symbol_of_the_header():
     declared = set(re.findall(r"\b(idf_[a-z0-9_]+)\s*\(", header))
     declared -= {"idf_nhwc", "idf_igemm_args"}
     lib = native.load()
-    assert lib.idf_abi_version() == 3
+    assert lib.idf_abi_version() == 4 == native.ABI_VERSION
+    # the ctypes re-declarations of the argument structs have the library's sizes (native.load refuses to run otherwise)
+    import ctypes
+    for which, struct in enumerate((native.NHWC, native.IgemmArgs, native.WgradArgs, native.PackJob)):
+        assert lib.idf_struct_size(which) == ctypes.sizeof(struct), struct.__name__
+    assert lib.idf_struct_size(99) == -1
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/idf_b200.h but not exported"
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
