@@ -281,7 +281,8 @@ def igemm_flops(name, a):
 
 
 def roofline_of(by, peaks, entry="idf_conv2d_igemm", kernel="igemm_persist_kernel (tcgen05 implicit GEMM, all conv / "
-                "linear layers)", traffic_key="sample"):
+                "linear layers; in the sampling step the launches that feed a GroupNorm also apply it in their epilogue, "
+                "and that time is counted here against GEMM FLOPs only)", traffic_key="sample"):
     """Roofline object of the dominant kernel from the per-launch table of one eager pass. `achieved` = algorithmic
     FLOPs of the kernel's launches (2 M N K each) / their summed CUDA-event durations. `peak` is
     the measured BURST bf16 figure: the launches are timed in short back-to-back groups at full clock, not inside a
@@ -659,7 +660,8 @@ def run_vq(args):
             by = timed_calls(lambda: vae(img), igemm_flops)
             for eng in vae._engines.values():
                 eng.use_graph = True
-            roof, breakdown = roofline_of(by, peaks, traffic_key="vq"), breakdown_of(by)
+            roof, breakdown = roofline_of(by, peaks, kernel="igemm_persist_kernel (tcgen05 implicit GEMM, all conv / linear layers of the "
+                                              "VQ-VAE)", traffic_key="vq"), breakdown_of(by)
             # stage split: encoder / quantiser / decoder
             z = torch.empty(B, 3, 32, 32, device=dev)
             enc = vae._engine(("enc", B, 128, 128))
