@@ -1,11 +1,11 @@
 #!/bin/bash
-# final one-GPU pass after the GroupNorm-fused epilogue: everything of r2_final1.sh, then the ncu launch list of one
-# eager sampling step and a --set full capture of the fused conv kernels. Outputs gpurun_out/f1_* and gpurun_out/p3_*.
+# final one-GPU pass of round 2: everything of r2_final1.sh (GPU tests, smoke, every bench workload, reference arm), then
+# the per-layer A/B and the intra-kernel trace of the GroupNorm-fused epilogue. Outputs gpurun_out/f1_*, gn_layers.txt, gn_trace.txt
 tools/r2_final1.sh
-M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum"
-timeout 300 python tools/profile_step.py 3 > gpurun_out/p3_step_plain.log 2>&1 || { echo "profile_step failed"; tail gpurun_out/p3_step_plain.log; exit 0; }
-timeout 600 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/p3_launches_sample.csv \
-  python tools/profile_step.py 3 > gpurun_out/p3_ncu_sample.log 2>&1; echo "ncu sample list rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"igemm_persist" -c 6 \
-  -o gpurun_out/p3_full_sample -f python tools/profile_step.py 3 > gpurun_out/p3_ncu_full.log 2>&1; echo "ncu full rc=$?"
-ls -la gpurun_out/p3_* | cut -c1-150
+timeout 300 python tools/time_gn_fused.py 96 > gpurun_out/gn_layers.txt 2>&1; echo "layers rc=$?"; tail -n 1 gpurun_out/gn_layers.txt
+rm -f gpurun_out/gn_trace.txt
+export IDF_B200_LIB=image-diffusion_b200/idf_b200/libidf_b200_gntrace.so
+for args in "32 128 256 1" "32 128 256 2" "32 256 256 1" "32 128 128 1" "8 384 512 1"; do
+  timeout 120 python tools/trace_gn.py $args >> gpurun_out/gn_trace.txt 2>&1 || echo "trace $args failed"
+done
+grep -c tile gpurun_out/gn_trace.txt
