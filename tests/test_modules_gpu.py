@@ -131,7 +131,7 @@ def test_cfg_sampling_20_steps_free_running(unet_pair):
         r = rel_rms(got, ref)
         print(f"20-step chain from i={steps[0]}: rel-RMS {r:.3e}")
         assert r <= 1e-2, r
-    assert sampler.graph is not None and sampler.launches_per_step > 100
+    assert sampler.graph is not None and sampler.launches_per_step > 90
 
 
 def test_graph_replay_equals_eager(unet_pair):
