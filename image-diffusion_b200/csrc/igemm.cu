@@ -1383,6 +1383,46 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
                     "splitk_finish launch");
 }
 
+// Host-side test hook: the launch plan of a GroupNorm-fused launch and the two properties its wait-for-the-image's-tiles
+// step relies on, checked by walking every walker's unit list exactly as the kernel does (TileWalk): (1) no walker ever
+// holds two units of the same image (a CTA waiting for a tile it has not started yet would wait forever); (2) all units
+// of an image fall into the same wave (same position in their walkers' lists), so no tile waits a whole tile time.
+// out = {walkers, units per image, waves, violations of (1), images split over two waves}.
+extern "C" int idf_gn_plan_check(int32_t m_tiles, int32_t tiles_per_img, int32_t n_tiles, int32_t pair, int32_t sms,
+                                 int32_t* out, idf_stream_t /*stream*/) {
+  if (out == nullptr || m_tiles <= 0 || tiles_per_img <= 0 || n_tiles <= 0 || sms <= 0 || m_tiles % tiles_per_img != 0 ||
+      (pair && ((tiles_per_img & 1) || sms < 2)))
+    return fail(IDF_ERR_ARG, "gn_plan_check: bad argument");
+  const int units = (pair ? m_tiles / 2 : m_tiles) * n_tiles;
+  const int per_img = (pair ? tiles_per_img / 2 : tiles_per_img) * n_tiles;
+  int walkers = pair ? sms / 2 : sms;
+  if (units < walkers) walkers = units;
+  if (per_img > walkers) return fail(IDF_ERR_UNSUPPORTED, "gn_plan_check: an image's %d units exceed %d walkers", per_img, walkers);
+  walkers = gn_walkers(walkers, per_img);
+  const int images = m_tiles / tiles_per_img;
+  int* wave_of = static_cast<int*>(malloc(sizeof(int) * (size_t)images));
+  if (wave_of == nullptr) return fail(IDF_ERR_ARG, "gn_plan_check: out of memory");
+  for (int i = 0; i < images; ++i) wave_of[i] = -1;
+  int same_walker = 0, split = 0, waves = 0;
+  for (int w = 0; w < walkers; ++w) {
+    TileWalk tw;
+    tw.init(w, walkers, 1, n_tiles);
+    int prev_img = -1, it = 0;
+    for (int u = w; u < units; u += walkers, tw.next(), ++it) {
+      const int tile_m = pair ? 2 * tw.tile_m : tw.tile_m;
+      const int img = tile_m / tiles_per_img;
+      if (img == prev_img) ++same_walker;
+      prev_img = img;
+      if (wave_of[img] < 0) wave_of[img] = it;
+      else if (wave_of[img] != it && wave_of[img] != -2) { ++split; wave_of[img] = -2; }
+      if (it + 1 > waves) waves = it + 1;
+    }
+  }
+  free(wave_of);
+  out[0] = walkers; out[1] = per_img; out[2] = waves; out[3] = same_walker; out[4] = split;
+  return IDF_OK;
+}
+
 // Host-side test hook: the work-unit walk of the persistent kernel (TileWalk) for `steps` iterations of the walker that
 // starts at unit u0 and advances by `stride` units: out[3 i .. 3 i + 2] = (tile_m, n_idx, split) of its i-th unit.
 extern "C" int idf_tile_walk_trace(int32_t u0, int32_t stride, int32_t splits, int32_t n_tiles, int32_t steps,

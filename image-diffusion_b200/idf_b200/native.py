@@ -56,6 +56,7 @@ class PackJob(C.Structure):
 _SIGNATURES = {
     "idf_conv2d_igemm": [C.POINTER(IgemmArgs)],
     "idf_tile_walk_trace": [_i32, _i32, _i32, _i32, _i32, _vp],
+    "idf_gn_plan_check": [_i32, _i32, _i32, _i32, _i32, _vp],
     "idf_groupnorm_silu": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32],
     "idf_groupnorm_silu_rows": [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _i64, _i64],
     "idf_attention_fwd": [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _f32],

@@ -169,6 +169,17 @@ int idf_tile_walk_trace(int32_t u0, int32_t stride, int32_t splits, int32_t n_ti
                         idf_stream_t stream);
 
 /*
+ * idf_gn_plan_check — HOST-side test hook (no GPU work, `out` is a host pointer to 5 ints, `stream` unused): the launch
+ * plan of a gn_mode launch over m_tiles M tiles (tiles_per_img per image), n_tiles N tiles, on CTA pairs or not, on a GPU
+ * with `sms` SMs, and the two properties the in-kernel wait for an image's tiles relies on, verified by walking every
+ * walker's unit list as the kernel does: out = {walkers, units per image, waves, times a walker holds two consecutive
+ * units of one image (must be 0: such a CTA would wait for a tile it has not started), images whose units fall into two
+ * waves (0 when the walker count is a whole number of images)}.
+ */
+int idf_gn_plan_check(int32_t m_tiles, int32_t tiles_per_img, int32_t n_tiles, int32_t pair, int32_t sms, int32_t* out,
+                      idf_stream_t stream);
+
+/*
  * idf_groupnorm_silu — GroupNorm(groups, C, eps, affine) optionally followed by SiLU, over a channels-last
  * (B, HW, C) bf16 tensor; fp32 statistics. Replaces nn.GroupNorm + nn.SiLU (components.py:31-35, 58, 453-454;
  * unet.py:98-99). x and y are (B*HW, ld) matrices; only C channels are read/written (lets the caller normalise

@@ -321,6 +321,39 @@ def test_persistent_kernel_tile_walk_matches_closed_form():
     assert lib.idf_tile_walk_trace(0, 0, 1, 1, 1, bad, None) != 0
 
 
+def test_groupnorm_fused_launch_plan_never_makes_a_cta_wait_for_itself():
+    """GroupNorm-fused igemm launches (idf_igemm_args.gn_mode): a tile waits inside the kernel until all tiles of its
+    image have published their partial sums. That is deadlock-free only if no CTA (walker) ever holds two units of one
+    image, and free of whole-tile stalls only if an image's units share a wave. idf_gn_plan_check walks the unit lists
+    as the kernel does; checked for every stage shape of the UNet over batch sizes, tile widths and SM counts."""
+    import ctypes as C
+    from idf_b200 import native
+    lib = native.load()
+    out = (C.c_int32 * 5)()
+    seen = 0
+    for sms in (148, 132, 64):
+        for batch in (1, 2, 3, 5, 6, 8, 48, 96, 128, 256):
+            # (tiles per image, N tiles): 32x32 / 16x16 stages, and 8x8 (two images per tile: one tile row block per "image")
+            shapes = [(8, 1, batch * 8), (8, 2, batch * 8), (2, 1, batch * 2), (2, 2, batch * 2), (2, 3, batch * 2),
+                      (1, 3, (batch + 1) // 2), (1, 4, (batch + 1) // 2)]
+            for tpi, n_tiles, m_tiles in shapes:
+                for pair in (0, 1):
+                    if pair and (tpi & 1):
+                        continue
+                    rc = lib.idf_gn_plan_check(m_tiles, tpi, n_tiles, pair, sms, out, None)
+                    assert rc == 0, (sms, batch, tpi, n_tiles, pair, lib.idf_last_error())
+                    walkers, per_img, waves, same_walker, split = list(out)
+                    units = (m_tiles // 2 if pair else m_tiles) * n_tiles
+                    assert same_walker == 0 and split == 0, (sms, batch, tpi, n_tiles, pair, list(out))
+                    assert walkers % per_img == 0 and walkers <= (sms // 2 if pair else sms)
+                    assert waves == -(-units // walkers)
+                    seen += 1
+    assert seen > 300
+    # an image with more units than the GPU has walkers cannot be fused (128x128 image, two N tiles)
+    assert lib.idf_gn_plan_check(256, 128, 2, 0, 148, out, None) != 0
+    assert lib.idf_gn_plan_check(16, 3, 1, 0, 148, out, None) != 0   # M tiles not a whole number of images
+
+
 def test_packed_weights_refresh_in_place_and_follow_the_weights_epoch():
     """Round-1 advisor findings, host side (no GPU needed): the packed operand copies are rewritten IN PLACE when the
     layout is unchanged (captured graphs hold raw pointers to them), and a writer that bypasses torch's version
