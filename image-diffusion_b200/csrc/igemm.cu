@@ -28,6 +28,9 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 
 enum : int { F_RES = 1, F_ZERO_PAD = 2, F_VT = 4, F_OUT_F32 = 8, F_OUT_UP2 = 16 };
 
+// A partial-sum record of the GroupNorm-fused epilogue (see gn_record_load / gn_record_store)
+struct GnRecord { unsigned long long lo, hi; };
+
 struct IgemmParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
@@ -86,8 +89,8 @@ struct IgemmParams {
   float gn_eps;
   const float* gn_gamma;
   const float* gn_beta;
-  float4* gn_part;    // [images][groups][tiles per image][gn_qpg] per-tile (sum, sum of squares, launch tag, -) of every
-                      // quad-column: one 16-byte record, written and read with single vector accesses
+  GnRecord* gn_part;  // [images][groups][tiles per image][gn_qpg] per-tile {sum, tag}, {sum of squares, tag} of every
+                      // quad-column: one 16-byte record
   unsigned* gn_epoch; // [0] launch epoch of this workspace (records of this launch carry epoch + 1), [1] finished CTAs
   CUtensorMap tmG;
 #ifdef IDF_GN_TRACE
@@ -116,13 +119,21 @@ __device__ __forceinline__ float igemm_silu(float t) {
   return fmaf(h, th, h);
 }
 
-__device__ __forceinline__ float4 ld_relaxed_gpu_v4(const float4* p) {
-  float4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+// A partial-sum record: two 64-bit words {sum, tag} and {sum of squares, tag}. Each word is one scalar 64-bit access
+// (single-copy atomic in the PTX memory model), so a value can never be seen without the tag it was written with, however
+// the two words of the 16-byte vector access are ordered.
+__device__ __forceinline__ GnRecord gn_record_load(const GnRecord* p) {
+  GnRecord v;
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_relaxed_gpu_v4(float4* p, const float4 v) {
-  asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ void gn_record_store(GnRecord* p, float sum, float sumsq, unsigned tag) {
+  const unsigned long long lo = ((unsigned long long)tag << 32) | __float_as_uint(sum);
+  const unsigned long long hi = ((unsigned long long)tag << 32) | __float_as_uint(sumsq);
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ bool gn_record_valid(const GnRecord& v, unsigned tag) {
+  return (unsigned)(v.lo >> 32) == tag && (unsigned)(v.hi >> 32) == tag;
 }
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
@@ -191,7 +202,7 @@ struct PgCfg {
 // second ConvBlock's GroupNorm reads only what the first one's conv wrote). A tile covers 128 pixels of ONE image
 // (HW % 128 == 0) and BN of its channels, the statistics need the whole image: every tile reduces its accumulator
 // (+ bias + time bias) to per-quad-column (sum, sum of squares) - fixed shuffle tree over the 32 rows of a warp, the
-// four warps added in order - and publishes them to global memory as 16-byte records that carry the launch's tag; a
+// four warps added in order - and publishes them to global memory as records whose 64-bit words carry the launch's tag; a
 // tile then polls the records of its groups until all of the image's tiles have written theirs (no counters, fences
 // or atomics on the path); the tiles of an image are consecutive work units, i.e. they run on neighbouring
 // CTAs at the same time, and an image never has two units on one CTA (host-checked), so the wait cannot deadlock:
@@ -561,8 +572,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
           const int qc = (n0 >> 2) + ql;
           const int g = qc / qpg;
           const int tin = ipt == 2 ? 0 : tile_m - img * tpi;
-          st_relaxed_gpu_v4(p.gn_part + (((long long)(img + isel) * p.gn_groups + g) * tpi + tin) * qpg + (qc - g * qpg),
-                            make_float4(s_, q_, __uint_as_float(tag), 0.f));
+          gn_record_store(p.gn_part + (((long long)(img + isel) * p.gn_groups + g) * tpi + tin) * qpg + (qc - g * qpg), s_, q_, tag);
         }
         if (issuer) GN_STAMP(1, it, 3);
         // one pass over the accumulator through the staging buffer: raw (+ bias) tile or normalised tile
@@ -644,26 +654,26 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
         if (p.gn_mode == 2) store_pass(false, &p.tmC);  // the raw tile goes out while the other tiles' records arrive
         if (issuer) GN_STAMP(1, it, 4);
         // statistics of this thread's column's group: the records of all of the image's tiles, summed in a fixed order.
-        // A record is valid once it carries this launch's tag (data and tag travel in one 16-byte access, so no
+        // A record is valid once both of its 64-bit words carry this launch's tag (value and tag share a word, so no
         // separate flag, fence or counter is needed). One thread waits for the records of its own group first - the
         // other tiles write all of theirs at the same moment - so that a waiting CTA polls with one thread, not 256
         // (measured: all threads polling slowed the TMA loads of every CTA); then each thread loads and checks its own.
         const int n = tpi * qpg;
         float s_ = 0.f, q_ = 0.f;
         // the group's n records, 16 per batch (one round trip): sums them in order once every tag matches
-        auto sum_group = [&](const float4* src, const unsigned backoff_ns) {
+        auto sum_group = [&](const GnRecord* src, const unsigned backoff_ns) {
           s_ = 0.f; q_ = 0.f;
+          const GnRecord none = {(unsigned long long)tag << 32, (unsigned long long)tag << 32};  // (0, 0), valid
           for (int i0 = 0; i0 < n; i0 += 16) {
-            float4 v4[16];
+            GnRecord v4[16];
             bool ok;
             unsigned ns = backoff_ns, spins = 0;
             do {
               ok = true;
 #pragma unroll
-              for (int k = 0; k < 16; ++k)
-                v4[k] = (i0 + k < n) ? ld_relaxed_gpu_v4(src + i0 + k) : make_float4(0.f, 0.f, __uint_as_float(tag), 0.f);
+              for (int k = 0; k < 16; ++k) v4[k] = (i0 + k < n) ? gn_record_load(src + i0 + k) : none;
 #pragma unroll
-              for (int k = 0; k < 16; ++k) ok = ok && (__float_as_uint(v4[k].z) == tag);
+              for (int k = 0; k < 16; ++k) ok = ok && gn_record_valid(v4[k], tag);
               if (!ok) {
                 __nanosleep(ns);
                 if (ns < 256) ns *= 2;
@@ -673,10 +683,10 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) igemm_persist_kernel(const _
               }
             } while (!ok);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { s_ += v4[k].x; q_ += v4[k].y; }
+            for (int k = 0; k < 16; ++k) { s_ += __uint_as_float((unsigned)v4[k].lo); q_ += __uint_as_float((unsigned)v4[k].hi); }
           }
         };
-        const float4* gsrc = p.gn_part + ((long long)(img + tsel) * p.gn_groups + (n0 + colr) / (4 * qpg)) * n;
+        const GnRecord* gsrc = p.gn_part + ((long long)(img + tsel) * p.gn_groups + (n0 + colr) / (4 * qpg)) * n;
         if (issuer) sum_group(gsrc, 32);
         named_bar_sync(1, EPI_THREADS);
         if (col_thread) {
@@ -1238,7 +1248,7 @@ extern "C" int idf_conv2d_igemm(const idf_igemm_args* a, idf_stream_t stream) {
     p.gn_gamma = a->gn_gamma;
     p.gn_beta = a->gn_beta;
     p.gn_epoch = reinterpret_cast<unsigned*>(a->gn_ws);
-    p.gn_part = reinterpret_cast<float4*>(reinterpret_cast<char*>(a->gn_ws) + cnt_bytes);
+    p.gn_part = reinterpret_cast<GnRecord*>(reinterpret_cast<char*>(a->gn_ws) + cnt_bytes);
     if (a->gn_mode == 2 &&
         (rc = make_mat_map(&p.tmG, a->gn_out, (uint64_t)M, (uint64_t)a->N, (uint64_t)a->gn_ldo, 64, BLOCK_M)) != IDF_OK)
       return rc;

@@ -150,7 +150,7 @@ typedef struct idf_igemm_args {
   int64_t gn_ldo;
   void* gn_ws;          /* 256-byte aligned scratch of 256 + 16 * max(M / 128, images) * (N / 4) bytes, ZERO-filled before its first use:
                            a launch epoch (advanced by every launch) and one 16-byte record of partial sums per (tile,
-                           4 channels), tagged with the epoch. One launch at a time per workspace; launches of different
+                           4 channels), each 64-bit word of it tagged with the epoch. One launch at a time per workspace; launches of different
                            shapes may share one. */
   int64_t gn_ws_bytes;
 } idf_igemm_args;
